@@ -1,0 +1,410 @@
+/* oracle/cpu_ref.c -- TEST INFRASTRUCTURE ONLY (see cpu_ref.h for the contract).
+ *
+ * Plain-C restatement of the reference's hot path.  Every function cites the
+ * reference file:line it follows (paths relative to /root/reference/src).
+ * Not a copy: the reference expresses these as chains of CuMatrix method calls
+ * (one kernel/BLAS call each); here each is written as the explicit loop nest
+ * it denotes, in the same operation order where rounding could matter.
+ */
+#include "cpu_ref.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define LOG_ZERO ((REAL)(sizeof(REAL) == 4 ? -1e30 : -1e100)) /* ctc-utils.h:36,45 */
+#define LOG_INF ((REAL)(sizeof(REAL) == 4 ? 1e30 : 1e100))
+#define EXP_LIMIT ((REAL)(sizeof(REAL) == 4 ? 88.722839 : 709.78271289338397))
+#define REAL_MAX ((REAL)(sizeof(REAL) == 4 ? 3.4028235e+38 : 1.7976931348623157e+308))
+
+int oracle_real_size(void) { return (int)sizeof(REAL); }
+
+static REAL r_exp(REAL x) { return sizeof(REAL) == 4 ? (REAL)expf((float)x) : (REAL)exp((double)x); }
+static REAL r_log(REAL x) { return sizeof(REAL) == 4 ? (REAL)logf((float)x) : (REAL)log((double)x); }
+
+/* ---- GEMM helpers (cpucompute/matrix.cc:158-174 AddMatMat -> cblas_Xgemm) ---- */
+
+/* C[M x N] (ldc) = alpha * A[M x K] (lda) * Bt[K x N] (ldb) + beta * C */
+static void gemm_nn(int M, int N, int K, REAL alpha, const REAL *A, int lda, const REAL *B, int ldb,
+                    REAL beta, REAL *Cm, int ldc) {
+#pragma omp parallel for schedule(static) if ((long)M * N * K > 200000)
+  for (int m = 0; m < M; m++) {
+    REAL *c = Cm + (long)m * ldc;
+    if (beta == (REAL)0) for (int n = 0; n < N; n++) c[n] = 0;
+    else if (beta != (REAL)1) for (int n = 0; n < N; n++) c[n] *= beta;
+    const REAL *a = A + (long)m * lda;
+    for (int k = 0; k < K; k++) {
+      REAL av = alpha * a[k];
+      const REAL *b = B + (long)k * ldb;
+      for (int n = 0; n < N; n++) c[n] += av * b[n];
+    }
+  }
+}
+
+/* C[M x N] = alpha * A[M x K] * B[N x K]^T + beta * C   (x * W^T) */
+static void gemm_nt(int M, int N, int K, REAL alpha, const REAL *A, int lda, const REAL *B, int ldb,
+                    REAL beta, REAL *Cm, int ldc) {
+  REAL *Bt = (REAL *)malloc(sizeof(REAL) * (size_t)K * N);
+  for (int n = 0; n < N; n++)
+    for (int k = 0; k < K; k++) Bt[(long)k * N + n] = B[(long)n * ldb + k];
+  gemm_nn(M, N, K, alpha, A, lda, Bt, N, beta, Cm, ldc);
+  free(Bt);
+}
+
+/* C[M x N] = alpha * A[K x M]^T * B[K x N] + beta * C   (D^T * X) */
+static void gemm_tn(int M, int N, int K, REAL alpha, const REAL *A, int lda, const REAL *B, int ldb,
+                    REAL beta, REAL *Cm, int ldc) {
+#pragma omp parallel for schedule(static) if ((long)M * N * K > 200000)
+  for (int m = 0; m < M; m++) {
+    REAL *c = Cm + (long)m * ldc;
+    if (beta == (REAL)0) for (int n = 0; n < N; n++) c[n] = 0;
+    else if (beta != (REAL)1) for (int n = 0; n < N; n++) c[n] *= beta;
+    for (int k = 0; k < K; k++) {
+      REAL av = alpha * A[(long)k * lda + m];
+      if (av == (REAL)0) continue; /* padded rows carry exact zeros */
+      const REAL *b = B + (long)k * ldb;
+      for (int n = 0; n < N; n++) c[n] += av * b[n];
+    }
+  }
+}
+
+/* cpucompute/vector.cc:820-840 (non-MKL Sigmoid) */
+static REAL sigmoid_ref(REAL x) {
+  if (x > (REAL)0) return (REAL)1 / ((REAL)1 + r_exp(-x));
+  REAL ex = r_exp(x);
+  return ex / (ex + (REAL)1);
+}
+/* cpucompute/vector.cc:789-803 (non-MKL Tanh) */
+static REAL tanh_ref(REAL x) {
+  if (x > (REAL)0) {
+    REAL e = r_exp(-x);
+    return (REAL)-1 + (REAL)2 / ((REAL)1 + e * e);
+  }
+  REAL e = r_exp(x);
+  return (REAL)1 - (REAL)2 / ((REAL)1 + e * e);
+}
+
+/* One direction of the vanilla forward pass.
+ * dir=+1: bilstm-parallel-layer.h:97-150 (t=1..T, prev=t-1, no masking)
+ * dir=-1: bilstm-parallel-layer.h:152-206 (t=T..1, prev=t+1, rows with t>len[s] zeroed :201-204) */
+static void lstm_dir_forward(int dir, int T, int S, int I, int C, const int *len, const REAL *x,
+                             const REAL *wx, const REAL *wm, const REAL *bias, const REAL *pi,
+                             const REAL *pf, const REAL *po, REAL *buf) {
+  const int W = 7 * C;
+  memset(buf, 0, sizeof(REAL) * (size_t)(T + 2) * S * W); /* Resize(kSetZero) :393-394 */
+  /* YGIFO[1S..(T+1)S) = in * Wx^T  (:109 / :163), then += bias (:110 / :164) */
+  gemm_nt(T * S, 4 * C, I, (REAL)1, x, I, wx, I, (REAL)0, buf + (long)S * W, W);
+  for (long r = S; r < (long)(T + 1) * S; r++) {
+    REAL *row = buf + r * W;
+    for (int j = 0; j < 4 * C; j++) row[j] += bias[j];
+  }
+  REAL *wmT = (REAL *)malloc(sizeof(REAL) * (size_t)C * 4 * C); /* Wm^T, transposed once */
+  for (int n = 0; n < 4 * C; n++)
+    for (int k = 0; k < C; k++) wmT[(long)k * 4 * C + n] = wm[(long)n * C + k];
+  for (int step = 0; step < T; step++) {
+    int t = dir > 0 ? 1 + step : T - step;
+    int tp = t - dir;
+    REAL *cur = buf + (long)t * S * W;
+    const REAL *prev = buf + (long)tp * S * W;
+    /* y_GIFO(t) += YM(prev) * Wm^T  (:125 / :177) */
+    gemm_nn(S, 4 * C, C, (REAL)1, prev + 6 * C, W, wmT, 4 * C, (REAL)1, cur, W);
+    for (int s = 0; s < S; s++) {
+      REAL *y = cur + (long)s * W;
+      const REAL *yp = prev + (long)s * W;
+      for (int j = 0; j < C; j++) {
+        REAL cp = yp[4 * C + j];
+        REAL yi = y[C + j] + cp * pi[j];     /* :127 */
+        REAL yf = y[2 * C + j] + cp * pf[j]; /* :129 */
+        REAL i_ = sigmoid_ref(yi), f_ = sigmoid_ref(yf), g_ = tanh_ref(y[j]); /* :131-133 */
+        REAL c_ = g_ * i_;                                                    /* :136 */
+        c_ = c_ + cp * f_;                                                    /* :137 */
+        REAL h_ = tanh_ref(c_);                                               /* :140 */
+        REAL o_ = sigmoid_ref(y[3 * C + j] + c_ * po[j]);                     /* :143-144 */
+        y[j] = g_; y[C + j] = i_; y[2 * C + j] = f_; y[3 * C + j] = o_;
+        y[4 * C + j] = c_; y[5 * C + j] = h_; y[6 * C + j] = h_ * o_; /* :147 */
+      }
+      if (dir < 0 && t > len[s]) memset(y, 0, sizeof(REAL) * W); /* :201-204 */
+    }
+  }
+  free(wmT);
+}
+
+void oracle_bilstm_forward(int T, int S, int I, int C, const int *len, const REAL *x,
+                           const REAL *const *p, REAL *buf_fw, REAL *buf_bw, REAL *out) {
+  lstm_dir_forward(+1, T, S, I, C, len, x, p[0], p[1], p[2], p[3], p[4], p[5], buf_fw);
+  lstm_dir_forward(-1, T, S, I, C, len, x, p[6], p[7], p[8], p[9], p[10], p[11], buf_bw);
+  /* out = [ YM_fw | YM_bw ] rows S..(T+1)S  (:409-419) */
+  const int W = 7 * C;
+  for (long r = 0; r < (long)T * S; r++) {
+    memcpy(out + r * 2 * C, buf_fw + (r + S) * W + 6 * C, sizeof(REAL) * C);
+    memcpy(out + r * 2 * C + C, buf_bw + (r + S) * W + 6 * C, sizeof(REAL) * C);
+  }
+}
+
+/* One direction of BPTT.
+ * dir=+1 (forward cells): bilstm-parallel-layer.h:422-512 (t=T..1, next=t+1, prev=t-1)
+ * dir=-1 (backward cells): :514-602 (t=1..T, next=t-1, prev=t+1) */
+static void lstm_dir_backward(int dir, int T, int S, int I, int C, const REAL *x, const REAL *wx,
+                              const REAL *wm, const REAL *pi, const REAL *pf, const REAL *po,
+                              const REAL *buf, const REAL *out_diff, int diff_off, REAL *dbuf,
+                              REAL *in_diff, REAL in_beta, REAL *const *corr, REAL mmt) {
+  const int W = 7 * C;
+  memset(dbuf, 0, sizeof(REAL) * (size_t)(T + 2) * S * W); /* :899-900 */
+  /* DM rows 1S..(T+1)S <- out_diff half (:448 / :539) */
+  for (long r = 0; r < (long)T * S; r++)
+    memcpy(dbuf + (r + S) * W + 6 * C, out_diff + r * 2 * C + diff_off, sizeof(REAL) * C);
+  for (int step = 0; step < T; step++) {
+    int t = dir > 0 ? T - step : 1 + step;
+    int tn = t + dir, tp = t - dir;
+    REAL *d = dbuf + (long)t * S * W;
+    const REAL *dn = dbuf + (long)tn * S * W;
+    const REAL *y = buf + (long)t * S * W, *yn = buf + (long)tn * S * W, *yp = buf + (long)tp * S * W;
+    /* d_m += DGIFO(next) * Wm  (:470 / :561) */
+    gemm_nn(S, C, 4 * C, (REAL)1, dn, W, wm, C, (REAL)1, d + 6 * C, W);
+    for (int s = 0; s < S; s++) {
+      REAL *dd = d + (long)s * W;
+      const REAL *ddn = dn + (long)s * W;
+      const REAL *yy = y + (long)s * W, *yyn = yn + (long)s * W, *yyp = yp + (long)s * W;
+      for (int j = 0; j < C; j++) {
+        REAL g = yy[j], i_ = yy[C + j], f = yy[2 * C + j], o = yy[3 * C + j], h = yy[5 * C + j];
+        REAL dm = dd[6 * C + j];
+        REAL dh = dm * o;                      /* :473 */
+        dh = dh * ((REAL)1 - h * h);           /* :474 DiffTanh */
+        REAL dO = dm * h;                      /* :477 */
+        dO = dO * o * ((REAL)1 - o);           /* :478 DiffSigmoid: e*y*(1-y) */
+        REAL dc = dh;                          /* :481 (d_c starts at 0) */
+        dc += ddn[4 * C + j] * yyn[2 * C + j]; /* :482 */
+        dc += ddn[C + j] * pi[j];              /* :483 */
+        dc += ddn[2 * C + j] * pf[j];          /* :484 */
+        dc += dO * po[j];                      /* :485 */
+        REAL df = dc * yyp[4 * C + j];         /* :488 */
+        df = df * f * ((REAL)1 - f);           /* :489 */
+        REAL di = dc * g;                      /* :492 */
+        di = di * i_ * ((REAL)1 - i_);         /* :493 */
+        REAL dg = dc * i_;                     /* :496 */
+        dg = dg * ((REAL)1 - g * g);           /* :497 */
+        dd[j] = dg; dd[C + j] = di; dd[2 * C + j] = df; dd[3 * C + j] = dO;
+        dd[4 * C + j] = dc; dd[5 * C + j] = dh;
+      }
+    }
+  }
+  const REAL *DG = dbuf + (long)S * W; /* DGIFO rows 1S..(T+1)S */
+  /* in_diff (=|+=) DGIFO * Wx  (:502 beta=0 / :593 beta=1) */
+  gemm_nn(T * S, I, 4 * C, (REAL)1, DG, W, wx, I, in_beta, in_diff, I);
+  /* Wx_corr = DGIFO^T * in + mmt * Wx_corr (:505 / :596) */
+  gemm_tn(4 * C, I, T * S, (REAL)1, DG, W, x, I, mmt, corr[0], I);
+  /* Wm_corr = DGIFO^T * YM(prev slots) + mmt*...  fw: slots 0..T-1 (:506); bw: slots 2..T+1 (:597) */
+  const REAL *Yprev = buf + (long)(dir > 0 ? 0 : 2) * S * W;
+  gemm_tn(4 * C, C, T * S, (REAL)1, DG, W, Yprev + 6 * C, W, mmt, corr[1], C);
+  /* bias_corr = colsum(DGIFO) + mmt*... (:507 / :598) */
+  for (int j = 0; j < 4 * C; j++) {
+    REAL s_ = 0;
+    for (long r = 0; r < (long)T * S; r++) s_ += DG[r * W + j];
+    corr[2][j] = s_ + mmt * corr[2][j];
+  }
+  /* peepholes (:508-510 / :599-601): p_i,p_f use c of prev slots; p_o uses c of the same slot */
+  const REAL *Ycur = buf + (long)S * W;
+  for (int j = 0; j < C; j++) {
+    REAL si = 0, sf = 0, so = 0;
+    for (long r = 0; r < (long)T * S; r++) {
+      si += DG[r * W + C + j] * Yprev[r * W + 4 * C + j];
+      sf += DG[r * W + 2 * C + j] * Yprev[r * W + 4 * C + j];
+      so += DG[r * W + 3 * C + j] * Ycur[r * W + 4 * C + j];
+    }
+    corr[3][j] = si + mmt * corr[3][j];
+    corr[4][j] = sf + mmt * corr[4][j];
+    corr[5][j] = so + mmt * corr[5][j];
+  }
+}
+
+void oracle_bilstm_backward(int T, int S, int I, int C, const REAL *x, const REAL *const *p,
+                            const REAL *buf_fw, const REAL *buf_bw, const REAL *out_diff,
+                            REAL *dbuf_fw, REAL *dbuf_bw, REAL *in_diff, REAL *const *corr,
+                            REAL momentum) {
+  lstm_dir_backward(+1, T, S, I, C, x, p[0], p[1], p[3], p[4], p[5], buf_fw, out_diff, 0, dbuf_fw,
+                    in_diff, (REAL)0, corr, momentum);
+  lstm_dir_backward(-1, T, S, I, C, x, p[6], p[7], p[9], p[10], p[11], buf_bw, out_diff, C, dbuf_bw,
+                    in_diff, (REAL)1, corr + 6, momentum);
+}
+
+void oracle_affine_forward(int N, int D, int K, const REAL *in, const REAL *Wt, const REAL *b, REAL *out) {
+  for (long r = 0; r < N; r++)
+    for (int k = 0; k < K; k++) out[r * K + k] = b[k]; /* AddVecToRows(1.0, bias_, 0.0) :163 */
+  gemm_nt(N, K, D, (REAL)1, in, D, Wt, D, (REAL)1, out, K); /* :165 */
+}
+
+void oracle_affine_backward(int N, int D, int K, const REAL *out_diff, const REAL *Wt, REAL *in_diff) {
+  gemm_nn(N, D, K, (REAL)1, out_diff, K, Wt, D, (REAL)0, in_diff, D); /* :171 */
+}
+
+void oracle_affine_grad(int N, int D, int K, const REAL *in, const REAL *diff, REAL *Wc, REAL *bc, REAL mmt) {
+  gemm_tn(K, D, N, (REAL)1, diff, K, in, D, mmt, Wc, D); /* :182 */
+  for (int k = 0; k < K; k++) {                          /* :183 */
+    REAL s_ = 0;
+    for (long r = 0; r < N; r++) s_ += diff[r * K + k];
+    bc[k] = s_ + mmt * bc[k];
+  }
+}
+
+/* cuda-kernels.cu:744-808 (_softmax_reduce): max-subtract, exp, sum, divide. */
+void oracle_softmax(int N, int K, const REAL *in, REAL *out) {
+  for (long r = 0; r < N; r++) {
+    const REAL *x = in + r * K;
+    REAL *y = out + r * K;
+    REAL mx = x[0];
+    for (int k = 1; k < K; k++) if (mx < x[k]) mx = x[k];
+    REAL sum = 0;
+    for (int k = 0; k < K; k++) { y[k] = r_exp(x[k] - mx); sum += y[k]; }
+    for (int k = 0; k < K; k++) y[k] = y[k] / sum;
+  }
+}
+
+/* ---- log-domain helpers: gpucompute/ctc-utils.h:53-96 ---- */
+static REAL AddAB(REAL a, REAL b) { return (a == LOG_ZERO || b == LOG_ZERO) ? LOG_ZERO : a + b; }
+static REAL SubAB(REAL a, REAL b) {
+  if (a == LOG_ZERO) return LOG_ZERO;
+  if (b == LOG_ZERO) return LOG_INF;
+  return a - b;
+}
+static REAL ExpA(REAL a) {
+  if (a <= LOG_ZERO) return 0;
+  if (a >= EXP_LIMIT) return REAL_MAX;
+  return r_exp(a);
+}
+static REAL LogAPlusB(REAL a, REAL b) {
+  if (b < a) return AddAB(a, r_log((REAL)1 + ExpA(SubAB(b, a))));
+  return AddAB(b, r_log((REAL)1 + ExpA(SubAB(a, b))));
+}
+
+void oracle_ctc_eval_parallel(int T, int S, int K, const int *len, const int *labels, const int *lab_len,
+                              const REAL *y, REAL *pzx, REAL *diff, REAL *alpha_out, REAL *beta_out) {
+  /* label expansion: ctc-loss.cc:111-129 */
+  int maxlab = 0;
+  for (int s = 0; s < S; s++) if (lab_len[s] > maxlab) maxlab = lab_len[s];
+  const int Lp = 2 * maxlab + 1;
+  int *lab = (int *)malloc(sizeof(int) * (size_t)S * Lp);
+  int *Ls = (int *)malloc(sizeof(int) * S);
+  for (long i = 0; i < (long)S * Lp; i++) lab[i] = -1;
+  {
+    long off = 0;
+    for (int s = 0; s < S; s++) {
+      Ls[s] = 2 * lab_len[s] + 1;
+      for (int l = 0; l < lab_len[s]; l++) {
+        lab[(long)s * Lp + 2 * l] = 0;
+        lab[(long)s * Lp + 2 * l + 1] = labels[off + l];
+      }
+      lab[(long)s * Lp + 2 * lab_len[s]] = 0;
+      off += lab_len[s];
+    }
+  }
+  const long N = (long)T * S;
+  /* log of the softmax output: ctc-loss.cc:132-133 */
+  REAL *lg = (REAL *)malloc(sizeof(REAL) * (size_t)N * K);
+  for (long i = 0; i < N * K; i++) lg[i] = r_log(y[i]);
+  REAL *alpha = (REAL *)malloc(sizeof(REAL) * (size_t)N * Lp);
+  REAL *beta = (REAL *)malloc(sizeof(REAL) * (size_t)N * Lp);
+  for (long i = 0; i < N * Lp; i++) { alpha[i] = LOG_ZERO; beta[i] = LOG_ZERO; } /* :138-139 */
+
+  /* alpha: cuda-kernels.cu:1369-1408, one time row per launch (ctc-loss.cc:140-142) */
+  for (int t = 0; t < T; t++)
+    for (int s = 0; s < S; s++)
+      for (int j = 0; j < Lp; j++) {
+        REAL *a = alpha + ((long)t * S + s) * Lp;
+        int cls = lab[(long)s * Lp + j];
+        if (cls == -1 || t >= len[s]) { a[j] = LOG_ZERO; continue; }
+        REAL lp = lg[((long)t * S + s) * K + cls];
+        if (t == 0) { a[j] = j < 2 ? lp : LOG_ZERO; continue; }
+        const REAL *ap = alpha + ((long)(t - 1) * S + s) * Lp;
+        if (j > 1) {
+          if (j % 2 == 0 || lab[(long)s * Lp + j - 2] == cls) {
+            a[j] = AddAB(lp, LogAPlusB(ap[j - 1], ap[j]));
+          } else {
+            REAL tmp = LogAPlusB(ap[j - 1], ap[j]);
+            a[j] = AddAB(lp, LogAPlusB(ap[j - 2], tmp));
+          }
+        } else if (j == 1) {
+          a[j] = AddAB(lp, LogAPlusB(ap[j - 1], ap[j]));
+        } else {
+          a[j] = AddAB(lp, ap[j]);
+        }
+      }
+  /* beta: cuda-kernels.cu:1484-1544 (per-sequence label_len variant), ctc-loss.cc:143-145 */
+  for (int t = T - 1; t >= 0; t--)
+    for (int s = 0; s < S; s++)
+      for (int j = 0; j < Lp; j++) {
+        REAL *b = beta + ((long)t * S + s) * Lp;
+        int cls = lab[(long)s * Lp + j];
+        if (cls == -1 || t >= len[s]) { b[j] = LOG_ZERO; continue; }
+        REAL lp = lg[((long)t * S + s) * K + cls];
+        int L = Ls[s];
+        if (t == len[s] - 1) { b[j] = (j > L - 3) ? lp : LOG_ZERO; continue; }
+        const REAL *bn = beta + ((long)(t + 1) * S + s) * Lp;
+        if (j < L - 2) {
+          if (j % 2 == 0 || lab[(long)s * Lp + j + 2] == cls) {
+            b[j] = AddAB(lp, LogAPlusB(bn[j + 1], bn[j]));
+          } else {
+            REAL tmp = LogAPlusB(bn[j + 1], bn[j]);
+            b[j] = AddAB(lp, LogAPlusB(bn[j + 2], tmp));
+          }
+        } else if (j == L - 2) {
+          b[j] = AddAB(lp, LogAPlusB(bn[j + 1], bn[j]));
+        } else {
+          b[j] = AddAB(lp, bn[j]);
+        }
+      }
+  /* pzx: ctc-loss.cc:146-153.  |l_s| = 0 (L=1) reads alpha(.., -1) in the reference
+   * (undefined); defined here as pzx = alpha(L-1). */
+  for (int s = 0; s < S; s++) {
+    int L = Ls[s];
+    const REAL *a = alpha + ((long)(len[s] - 1) * S + s) * Lp;
+    REAL t1 = a[L - 1];
+    REAL t2 = L >= 2 ? a[L - 2] : LOG_ZERO;
+    pzx[s] = t1 + r_log((REAL)1 + ExpA(t2 - t1));
+  }
+  /* error: cuda-kernels.cu:1605-1627; then softmax back-prop ctc-loss.cc:160-168 */
+  memset(diff, 0, sizeof(REAL) * (size_t)N * K);
+  REAL *err = (REAL *)malloc(sizeof(REAL) * K);
+  for (long r = 0; r < N; r++) {
+    int s = (int)(r % S), t = (int)(r / S);
+    if (t >= len[s]) continue; /* ctc_err_ stays 0 -> diff row = 0 */
+    const REAL *a = alpha + r * Lp, *b = beta + r * Lp, *yr = y + r * K;
+    REAL rowsum = 0;
+    for (int k = 0; k < K; k++) {
+      REAL e = LOG_ZERO;
+      for (int j = 0; j < Lp; j++) {
+        int c = lab[(long)s * Lp + j];
+        if (c == -1) continue;
+        if (c == k) e = LogAPlusB(e, AddAB(a[j], b[j]));
+      }
+      REAL ly2 = yr[k] == (REAL)0 ? LOG_ZERO : (REAL)2 * r_log(yr[k]);
+      REAL val = ExpA(SubAB(e, AddAB(pzx[s], ly2)));
+      err[k] = (REAL)-1 * val;
+      err[k] = err[k] * yr[k]; /* MulElements :160 */
+      rowsum += err[k];        /* AddColSumMat :162 */
+    }
+    for (int k = 0; k < K; k++) diff[r * K + k] = err[k] - yr[k] * rowsum; /* :164-168 */
+  }
+  if (alpha_out) memcpy(alpha_out, alpha, sizeof(REAL) * (size_t)N * Lp);
+  if (beta_out) memcpy(beta_out, beta, sizeof(REAL) * (size_t)N * Lp);
+  free(err); free(alpha); free(beta); free(lg); free(lab); free(Ls);
+}
+
+void oracle_sgd_update(long n, REAL *w, REAL *corr, REAL lr, REAL max_grad) {
+  for (long i = 0; i < n; i++) {
+    if (max_grad > (REAL)0) {
+      if (corr[i] < -max_grad) corr[i] = -max_grad; /* ApplyFloor */
+      if (corr[i] > max_grad) corr[i] = max_grad;   /* ApplyCeiling */
+    }
+    w[i] += -lr * corr[i]; /* AddMat(-lr, corr) */
+  }
+}
+
+void oracle_row_argmax(int N, int K, const REAL *y, int *idx) {
+  for (long r = 0; r < N; r++) {
+    REAL mx = (REAL)-1e21;
+    int id = -1;
+    for (int k = 0; k < K; k++)
+      if (mx < y[r * K + k]) { mx = y[r * K + k]; id = k; }
+    idx[r] = id;
+  }
+}
