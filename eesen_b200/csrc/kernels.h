@@ -1,0 +1,78 @@
+// eesen_b200/csrc/kernels.h -- internal (C++) launch interface of the sm_100a kernels.
+// The public boundary is the C ABI in include/eesen_b200.h; these are what it dispatches to.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace eb {
+
+// gemm.cu
+cudaError_t gemm(cudaStream_t st, int num_sms, int transA, int transB, int M, int N, int K, float alpha,
+                 const float *A, int lda, long strideA, const float *B, int ldb, long strideB, float beta,
+                 float *C, int ldc, long strideC, const float *bias, long strideBias, int batch,
+                 int precision, float *ws, size_t ws_bytes);
+size_t gemm_workspace_bytes(int M, int N, int K, int batch, int num_sms);
+
+// lstm.cu -- persistent recurrent kernels (both directions in one cooperative launch)
+struct LstmDirParams {
+  const float *wm;  // [4C x C] recurrent weights, row blocks g,i,f,o
+  const float *pi, *pf, *po;  // [C] peepholes
+};
+struct LstmFwdArgs {
+  int T, S, C;
+  const int *len;        // [S] valid frames per utterance (device)
+  float *G; int ldg;     // [T*S x 8C]: in = x*Wx^T + b (dir block d at col d*4C), out = post-activation g,i,f,o
+  float *cell; int ldc;  // [T*S x 2C] cell state c (dir d at col d*C)
+  float *out; int ldo;   // [T*S x 2C] m = o*tanh(c): the layer output (dir d at col d*C)
+  LstmDirParams p[2];
+  unsigned *flags;       // [2 * groups] step counters, zeroed before launch
+  int precision;         // 0 = 3xTF32, 1 = TF32
+};
+struct LstmBwdArgs {
+  int T, S, C;
+  const float *G; int ldg;      // saved post-activation gates
+  const float *cell; int ldc;   // saved cell states
+  const float *dout; int ldd;   // [T*S x 2C] gradient wrt the layer output
+  float *DG; int lddg;          // [T*S x 8C] out: d(pre-activations) g,i,f,o per direction
+  LstmDirParams p[2];
+  float *pbuf;                  // [2 parity][2 dir][groups][slices][8*NUT][C] partial d_m exchange
+  float *gsum;                  // [2 dir][groups][7][C] per-group sums: db_g,db_i,db_f,db_o,dpi,dpf,dpo
+  unsigned *flags;
+  int precision;
+};
+struct LstmPlan {
+  int nut, nct, ksplit;  // utterance tiles / cell tiles per CTA, K-split warps (fwd)
+  int groups, slices;    // grid = (slices, groups, 2)
+  int threads;
+  size_t smem_fwd, smem_bwd;
+  size_t pbuf_floats, gsum_floats;
+  int valid;
+};
+LstmPlan lstm_plan(int S, int C, int num_sms, size_t max_smem);
+cudaError_t lstm_forward(cudaStream_t st, const LstmPlan &plan, const LstmFwdArgs &a);
+cudaError_t lstm_backward(cudaStream_t st, const LstmPlan &plan, const LstmBwdArgs &a);
+// bias/peephole gradient from the per-group sums: dst[7 blocks] = sum_groups gsum
+cudaError_t lstm_reduce_gsum(cudaStream_t st, const LstmPlan &plan, int C, const float *gsum,
+                             float *db /*[4C]*/, float *dpi, float *dpf, float *dpo, int dir);
+
+// ctc.cu
+cudaError_t softmax_rows(cudaStream_t st, int N, int K, const float *logits, int ld, float *probs, int ldp,
+                         int *argmax);
+cudaError_t row_argmax(cudaStream_t st, int N, int K, const float *x, int ld, int *argmax);
+size_t ctc_workspace_floats(int T, int S, int max_lab);
+cudaError_t ctc_eval(cudaStream_t st, int T, int S, int K, int max_lab, const int *len, const int *labels,
+                     const int *lab_len, const float *probs, int ldp, float *pzx, float *diff, int ldd,
+                     float *ws);
+
+// optim.cu
+struct SgdSegment {
+  long offset, count;
+  float lr;        // learn_rate * learn_rate_coef
+  float max_grad;  // <= 0: no clipping
+};
+cudaError_t sgd_momentum_clip(cudaStream_t st, int num_sms, float *w, float *corr, const float *grad,
+                              float momentum, const SgdSegment *d_segs, int nseg, long total);
+cudaError_t col_sum(cudaStream_t st, int num_sms, int N, int K, const float *x, int ld, float *out, float *ws);
+size_t col_sum_ws_floats(int K, int num_sms);
+
+}  // namespace eb

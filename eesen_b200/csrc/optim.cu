@@ -1,0 +1,106 @@
+// eesen_b200/csrc/optim.cu -- fused momentum + clip + SGD over the contiguous parameter arena,
+// and the column-sum used for the affine bias gradient.
+//
+// Replaces, per parameter tensor and step (12 tensors per BiLSTM layer + 2 for the affine layer):
+//   AddMatMat/AddRowSumMat/AddDiagMatMat(..., beta = momentum)   bilstm-parallel-layer.h:504-510,595-601
+//   ApplyFloor(-max_grad) + ApplyCeiling(max_grad) in place       bilstm-layer.h:848-862, affine-trans-layer.h:186-189
+//   AddMat(-lr*coef, corr)                                        bilstm-layer.h:865-883, affine-trans-layer.h:191-195
+// (36+ launches per layer in the reference) with ONE launch over the whole arena.  The raw
+// gradient `grad` is kept separate from the momentum-carrying `corr` so that the data-parallel
+// all-reduce acts on the raw sum (SURVEY.md section 8e ordering constraint):
+//   corr = grad + momentum * corr ; corr = clamp(corr, +-max_grad) ; w -= lr * corr
+#include "common.cuh"
+#include "kernels.h"
+
+namespace eb {
+
+namespace {
+
+__global__ void sgd_kernel(float *__restrict__ w, float *__restrict__ corr, const float *__restrict__ grad,
+                           float momentum, const SgdSegment *__restrict__ segs, int nseg, long total) {
+  long stride = (long)gridDim.x * blockDim.x * 4;
+  for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < total; i += stride) {
+    // locate the segment of element i (segments are sorted, few dozen entries)
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (segs[mid].offset <= i) lo = mid; else hi = mid - 1;
+    }
+    SgdSegment sg = segs[lo];
+    long seg_end = sg.offset + sg.count;
+    if (i + 4 <= seg_end && i + 4 <= total) {
+      float4 g4 = *reinterpret_cast<const float4 *>(grad + i);
+      float4 c4 = *reinterpret_cast<float4 *>(corr + i);
+      float4 w4 = *reinterpret_cast<float4 *>(w + i);
+      float c[4] = {g4.x + momentum * c4.x, g4.y + momentum * c4.y, g4.z + momentum * c4.z, g4.w + momentum * c4.w};
+      if (sg.max_grad > 0.f) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) c[q] = fminf(fmaxf(c[q], -sg.max_grad), sg.max_grad);
+      }
+      *reinterpret_cast<float4 *>(corr + i) = make_float4(c[0], c[1], c[2], c[3]);
+      *reinterpret_cast<float4 *>(w + i) =
+          make_float4(w4.x - sg.lr * c[0], w4.y - sg.lr * c[1], w4.z - sg.lr * c[2], w4.w - sg.lr * c[3]);
+    } else {
+      for (long k = i; k < i + 4 && k < total; k++) {
+        while (lo + 1 < nseg && segs[lo + 1].offset <= k) lo++;
+        SgdSegment s2 = segs[lo];
+        float c = grad[k] + momentum * corr[k];
+        if (s2.max_grad > 0.f) c = fminf(fmaxf(c, -s2.max_grad), s2.max_grad);
+        corr[k] = c;
+        w[k] -= s2.lr * c;
+      }
+    }
+  }
+}
+
+// partial column sums: block b sums rows b, b+gridDim.x*8, ... ; ws[b][K]
+__global__ void col_sum_partial_kernel(int N, int K, const float *__restrict__ x, int ld, float *__restrict__ ws) {
+  __shared__ float red[8][33];
+  int col = blockIdx.y * 32 + threadIdx.x;
+  float s = 0.f;
+  if (col < K)
+    for (long r = (long)blockIdx.x * 8 + threadIdx.y; r < N; r += (long)gridDim.x * 8) s += x[r * ld + col];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < K) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; q++) t += red[q][threadIdx.x];
+    ws[(size_t)blockIdx.x * K + col] = t;
+  }
+}
+__global__ void col_sum_final_kernel(int K, int nblocks, const float *__restrict__ ws, float *__restrict__ out) {
+  int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= K) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; b++) s += ws[(size_t)b * K + col];
+  out[col] = s;
+}
+
+}  // namespace
+
+cudaError_t sgd_momentum_clip(cudaStream_t st, int num_sms, float *w, float *corr, const float *grad,
+                              float momentum, const SgdSegment *d_segs, int nseg, long total) {
+  if (total <= 0) return cudaSuccess;
+  long vec = (total + 3) / 4;
+  int blocks = (int)((vec + 255) / 256);
+  if (blocks > 8 * num_sms) blocks = 8 * num_sms;
+  sgd_kernel<<<blocks, 256, 0, st>>>(w, corr, grad, momentum, d_segs, nseg, total);
+  return cudaGetLastError();
+}
+
+size_t col_sum_ws_floats(int K, int num_sms) { return (size_t)2 * num_sms * K; }
+
+cudaError_t col_sum(cudaStream_t st, int num_sms, int N, int K, const float *x, int ld, float *out, float *ws) {
+  int nb = 2 * num_sms;
+  if (nb > (N + 7) / 8) nb = (N + 7) / 8;
+  if (nb < 1) nb = 1;
+  dim3 grid(nb, (K + 31) / 32), block(32, 8);
+  col_sum_partial_kernel<<<grid, block, 0, st>>>(N, K, x, ld, ws);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  col_sum_final_kernel<<<(K + 127) / 128, 128, 0, st>>>(K, nb, ws, out);
+  return cudaGetLastError();
+}
+
+}  // namespace eb

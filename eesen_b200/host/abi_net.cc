@@ -1,0 +1,198 @@
+// eesen_b200/host/abi_net.cc -- level-2 C ABI: the Net/Ctc host mirror behind opaque handles
+// (include/eesen_b200.h).  C++ exceptions (KALDI_ERR) are translated to error codes here.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <vector>
+
+#include "../../include/eesen_b200.h"
+#include "context.h"
+#include "net.h"
+
+using namespace eesen;
+
+struct eesen_b200_net {
+  eesen_b200_ctx *ctx;
+  Net net;
+  Ctc ctc;
+  CuMatrix<BaseFloat> feats, net_out, obj_diff, in_diff;
+  float *h_pinned = nullptr;  // pinned staging for the packed features
+  size_t h_cap = 0;
+  std::vector<int> frames;
+  std::vector<std::vector<int32> > labels;
+  int S = 0;
+  bool want_in_diff = false;
+  explicit eesen_b200_net(eesen_b200_ctx *c) : ctx(c), net(c), ctc(c) {}
+  ~eesen_b200_net() { if (h_pinned) cudaFreeHost(h_pinned); }
+};
+
+#define GUARD(ctxp, body)                                      \
+  try {                                                        \
+    body;                                                      \
+    return 0;                                                  \
+  } catch (const std::exception &e) {                          \
+    if (ctxp) (ctxp)->err = e.what();                          \
+    return EESEN_B200_EIO;                                     \
+  }
+
+static void unpack_labels(eesen_b200_net *n, int S, const int *frames, const int *labels, const int *lab_len) {
+  n->S = S;
+  n->frames.assign(frames, frames + S);
+  n->labels.resize(S);
+  size_t off = 0;
+  for (int s = 0; s < S; s++) {
+    n->labels[s].assign(labels + off, labels + off + lab_len[s]);
+    off += lab_len[s];
+  }
+}
+
+static void run_step(eesen_b200_net *n, const CuMatrixBase<BaseFloat> &in, int train) {
+  n->net.SetSeqLengths(n->frames);                                      // train-ctc-parallel.cc:195
+  n->net.Propagate(in, &n->net_out);                                    // :198
+  n->ctc.EvalParallelAsync(n->frames, n->net_out, n->labels, &n->obj_diff);   // :199
+  n->ctc.ErrorRateMSeqAsync(n->frames, n->net_out, n->labels);          // :202
+  if (train) n->net.Backpropagate(n->obj_diff, n->want_in_diff ? &n->in_diff : NULL);   // :207
+}
+
+extern "C" {
+
+int eesen_b200_net_read(eesen_b200_ctx *ctx, const char *model_path, eesen_b200_net **out) {
+  if (!ctx || !model_path || !out) return EESEN_B200_EINVAL;
+  *out = nullptr;
+  eesen_b200_net *n = nullptr;
+  try {
+    n = new eesen_b200_net(ctx);
+    n->net.Read(model_path);
+    *out = n;
+    return 0;
+  } catch (const std::exception &e) {
+    ctx->err = e.what();
+    delete n;
+    return EESEN_B200_EIO;
+  }
+}
+
+int eesen_b200_net_write(eesen_b200_net *n, const char *path, int binary) {
+  if (!n || !path) return EESEN_B200_EINVAL;
+  GUARD(n->ctx, n->net.Write(path, binary != 0));
+}
+
+void eesen_b200_net_free(eesen_b200_net *n) { delete n; }
+
+int eesen_b200_net_set_train_options(eesen_b200_net *n, float learn_rate, float momentum) {
+  if (!n) return EESEN_B200_EINVAL;
+  NetTrainOptions o;
+  o.learn_rate = learn_rate;
+  o.momentum = momentum;
+  GUARD(n->ctx, { n->net.SetTrainOptions(o); n->net.SetUpdateAlgorithm("SGD"); n->net.SetTrainMode(); });
+}
+
+int eesen_b200_net_dims(const eesen_b200_net *n, int *in_dim, int *out_dim, int *num_layers, int64_t *num_params) {
+  if (!n) return EESEN_B200_EINVAL;
+  if (in_dim) *in_dim = n->net.InputDim();
+  if (out_dim) *out_dim = n->net.OutputDim();
+  if (num_layers) *num_layers = n->net.NumLayers();
+  if (num_params) *num_params = n->net.NumParams();
+  return 0;
+}
+
+int eesen_b200_net_train_step(eesen_b200_net *n, const float *feats, int T, int S, const int *frames,
+                              const int *labels, const int *lab_len, int train, double stats[4]) {
+  if (!n || !feats || !frames || !labels || !lab_len || T <= 0 || S <= 0) return EESEN_B200_EINVAL;
+  try {
+    unpack_labels(n, S, frames, labels, lab_len);
+    const int I = n->net.InputDim();
+    size_t elems = (size_t)T * S * I;
+    if (elems > n->h_cap) {
+      if (n->h_pinned) cudaFreeHost(n->h_pinned);
+      if (cudaMallocHost((void **)&n->h_pinned, sizeof(float) * elems) != cudaSuccess) KALDI_ERR << "cudaMallocHost failed";
+      n->h_cap = elems;
+    }
+    memcpy(n->h_pinned, feats, sizeof(float) * elems);   // into pinned staging, then one async H2D
+    n->feats.Resize(T * S, I, kUndefined);
+    n->feats.CopyFromHost(n->h_pinned, I);
+    run_step(n, n->feats, train);
+    double st[4];
+    n->ctc.Finish(st);
+    if (stats) memcpy(stats, st, sizeof(st));
+    return 0;
+  } catch (const std::exception &e) {
+    n->ctx->err = e.what();
+    return EESEN_B200_EIO;
+  }
+}
+
+int eesen_b200_net_train_step_device(eesen_b200_net *n, const float *d_feats, int T, int S, const int *frames,
+                                     const int *labels, const int *lab_len, int train) {
+  if (!n || !d_feats || !frames || !labels || !lab_len || T <= 0 || S <= 0) return EESEN_B200_EINVAL;
+  try {
+    unpack_labels(n, S, frames, labels, lab_len);
+    const int I = n->net.InputDim();
+    CuSubMatrix<BaseFloat> in(const_cast<float *>(d_feats), T * S, I, I);
+    run_step(n, in, train);
+    return 0;
+  } catch (const std::exception &e) {
+    n->ctx->err = e.what();
+    return EESEN_B200_EIO;
+  }
+}
+
+int eesen_b200_net_read_stats(eesen_b200_net *n, double stats[4]) {
+  if (!n || !stats) return EESEN_B200_EINVAL;
+  GUARD(n->ctx, n->ctc.Finish(stats));
+}
+
+static int copy_out(const CuMatrixBase<BaseFloat> &m, float *data, int64_t cap, int *rows, int *cols) {
+  if (rows) *rows = m.NumRows();
+  if (cols) *cols = m.NumCols();
+  if (!data) return 0;
+  if ((int64_t)m.NumRows() * m.NumCols() > cap) return EESEN_B200_EINVAL;
+  m.CopyToHost(data, m.NumCols());
+  return 0;
+}
+
+int eesen_b200_net_get(eesen_b200_net *n, int which, float *data, int64_t capacity, int *rows, int *cols) {
+  if (!n) return EESEN_B200_EINVAL;
+  try {
+    const int L = n->net.NumLayers();
+    if (which >= 0 && which <= L) return copy_out(n->net.PropagateBuffer()[which], data, capacity, rows, cols);
+    if (which == 100) return copy_out(n->obj_diff, data, capacity, rows, cols);
+    if (which == 101) {
+      n->ctc.Finish(NULL);
+      const std::vector<float> &p = n->ctc.LastPzx();
+      if (rows) *rows = 1;
+      if (cols) *cols = (int)p.size();
+      if (data) {
+        if ((int64_t)p.size() > capacity) return EESEN_B200_EINVAL;
+        memcpy(data, p.data(), sizeof(float) * p.size());
+      }
+      return 0;
+    }
+    if (which == 102) {
+      n->want_in_diff = true;  // takes effect from the next step
+      return copy_out(n->in_diff, data, capacity, rows, cols);
+    }
+    if (which >= 200 && which <= 202) {
+      if (rows) *rows = 1;
+      if (cols) *cols = (int)n->net.NumParams();
+      if (data) {
+        if (n->net.NumParams() > capacity) return EESEN_B200_EINVAL;
+        std::vector<float> h;
+        n->net.GetArena(which == 200 ? n->net.Params() : which == 201 ? n->net.Corr() : n->net.Grads(), &h);
+        memcpy(data, h.data(), sizeof(float) * h.size());
+      }
+      return 0;
+    }
+    return EESEN_B200_EINVAL;
+  } catch (const std::exception &e) {
+    n->ctx->err = e.what();
+    return EESEN_B200_EIO;
+  }
+}
+
+int eesen_b200_net_set_params(eesen_b200_net *n, const float *flat, int64_t cnt) {
+  if (!n || !flat) return EESEN_B200_EINVAL;
+  GUARD(n->ctx, n->net.SetParams(flat, cnt));
+}
+
+}  // extern "C"

@@ -1,0 +1,360 @@
+// eesen_b200/host/abi_ops.cc -- level-1 C ABI: context + device operators (include/eesen_b200.h).
+#include <dlfcn.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/eesen_b200.h"
+#include "context.h"
+
+static std::string g_create_error;
+
+#define CTX_CHECK(call, what)                 \
+  do {                                        \
+    int rc__ = ctx->check((call), what);      \
+    if (rc__) return rc__;                    \
+  } while (0)
+
+extern "C" {
+
+int eesen_b200_create(eesen_b200_ctx **out, int device) {
+  if (!out) return EESEN_B200_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                     "); eesen_b200 has no CPU fallback";
+    return EESEN_B200_ENOGPU;
+  }
+  if (device < 0) {
+    const char *lr = getenv("LOCAL_RANK");
+    device = lr ? atoi(lr) % ndev : 0;
+  }
+  if (device >= ndev) {
+    g_create_error = "device index out of range";
+    return EESEN_B200_EINVAL;
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return (int)e; }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return (int)e; }
+  if (prop.major != 10) {
+    g_create_error = "eesen_b200 kernels are built for sm_100a only; found sm_" + std::to_string(prop.major) +
+                     std::to_string(prop.minor);
+    return EESEN_B200_ENOGPU;
+  }
+  eesen_b200_ctx *ctx = new eesen_b200_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->max_smem = prop.sharedMemPerBlockOptin;
+  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return (int)e; }
+  *out = ctx;
+  return 0;
+}
+
+void eesen_b200_destroy(eesen_b200_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  eesen_b200_ctx::Buf *bufs[] = {&ctx->gemm_ws, &ctx->lstm_pbuf, &ctx->lstm_gsum, &ctx->lstm_flags,
+                                 &ctx->ctc_ws, &ctx->colsum_ws, &ctx->seg_buf};
+  for (auto *b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (ctx->nccl_comm && ctx->nccl_lib) {
+    typedef int (*destroy_t)(void *);
+    destroy_t f = (destroy_t)dlsym(ctx->nccl_lib, "ncclCommDestroy");
+    if (f) f(ctx->nccl_comm);
+  }
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *eesen_b200_last_error(const eesen_b200_ctx *ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int eesen_b200_set_precision(eesen_b200_ctx *ctx, int gemm_precision, int recurrent_precision) {
+  if (!ctx || gemm_precision < 0 || gemm_precision > 2 || recurrent_precision < 0 || recurrent_precision > 1)
+    return EESEN_B200_EINVAL;
+  ctx->gemm_prec = gemm_precision;
+  ctx->rec_prec = recurrent_precision;
+  return 0;
+}
+
+int eesen_b200_synchronize(eesen_b200_ctx *ctx) {
+  CTX_CHECK(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+  return 0;
+}
+void *eesen_b200_stream(eesen_b200_ctx *ctx) { return (void *)ctx->stream; }
+int eesen_b200_sm_count(const eesen_b200_ctx *ctx) { return ctx->num_sms; }
+long eesen_b200_launch_count(const eesen_b200_ctx *ctx) { return ctx->launches; }
+
+static int do_gemm(eesen_b200_ctx *ctx, int ta, int tb, int M, int N, int K, float alpha, const float *A, int lda,
+                   long sA, const float *B, int ldb, long sB, float beta, float *C, int ldc, long sC,
+                   const float *bias, long sBias, int batch) {
+  void *ws = nullptr;
+  size_t need = eb::gemm_workspace_bytes(M, N, K, batch, ctx->num_sms);
+  if (K >= 4096) {
+    int rc = ctx->reserve(ctx->gemm_ws, need, &ws);
+    if (rc) return rc;
+  }
+  cudaError_t e = eb::gemm(ctx->stream, ctx->num_sms, ta, tb, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc,
+                           sC, bias, sBias, batch, ctx->gemm_prec, (float *)ws, ws ? ctx->gemm_ws.bytes : 0);
+  ctx->launches += 1;
+  return ctx->check(e, "gemm");
+}
+
+int eesen_b200_gemm(eesen_b200_ctx *ctx, int transA, int transB, int M, int N, int K, float alpha, const float *A,
+                    int lda, const float *B, int ldb, float beta, float *C, int ldc) {
+  if (!ctx || !A || !B || !C) return EESEN_B200_EINVAL;
+  return do_gemm(ctx, transA, transB, M, N, K, alpha, A, lda, 0, B, ldb, 0, beta, C, ldc, 0, nullptr, 0, 1);
+}
+
+static int lstm_prepare(eesen_b200_ctx *ctx, int S, int C, eb::LstmPlan *plan, float **pbuf, float **gsum,
+                        unsigned **flags) {
+  *plan = eb::lstm_plan(S, C, ctx->num_sms, ctx->max_smem);
+  if (!plan->valid)
+    return ctx->fail(EESEN_B200_ESHAPE, "no resident-weight LSTM configuration fits S=" + std::to_string(S) +
+                                            " C=" + std::to_string(C) + " (C must be a multiple of 8)");
+  int rc;
+  if ((rc = ctx->reserve(ctx->lstm_pbuf, plan->pbuf_floats * sizeof(float), (void **)pbuf))) return rc;
+  if ((rc = ctx->reserve(ctx->lstm_gsum, plan->gsum_floats * sizeof(float), (void **)gsum))) return rc;
+  if ((rc = ctx->reserve(ctx->lstm_flags, sizeof(unsigned) * 2 * plan->groups, (void **)flags))) return rc;
+  return 0;
+}
+
+int eesen_b200_bilstm_forward(eesen_b200_ctx *ctx, int T, int S, int I, int C, const int *d_len, const float *x,
+                              int ldx, const eesen_b200_bilstm_params *p, float *gates, float *cell, float *out,
+                              int ldo) {
+  if (!ctx || !p || !x || !gates || !cell || !out || T <= 0 || S <= 0) return EESEN_B200_EINVAL;
+  eb::LstmPlan plan;
+  float *pbuf, *gsum;
+  unsigned *flags;
+  int rc = lstm_prepare(ctx, S, C, &plan, &pbuf, &gsum, &flags);
+  if (rc) return rc;
+  // input-side gate pre-activations for both directions: G[:, d*4C..] = x * Wx_d^T + b_d
+  // (bilstm-parallel-layer.h:109-110,163-164).  Batched over the direction when the two weight
+  // blocks are equally strided (they are in the Net arena), else two launches.
+  long sW = p->wx[1] - p->wx[0], sB = p->bias[1] - p->bias[0];
+  const int N = T * S;
+  if (sW > 0 && (sW & 3) == 0 && sB > 0) {
+    rc = do_gemm(ctx, 0, 1, N, 4 * C, I, 1.f, x, ldx, 0, p->wx[0], I, sW, 0.f, gates, 8 * C, 4 * C, p->bias[0], sB, 2);
+    if (rc) return rc;
+  } else {
+    for (int d = 0; d < 2; d++) {
+      rc = do_gemm(ctx, 0, 1, N, 4 * C, I, 1.f, x, ldx, 0, p->wx[d], I, 0, 0.f, gates + (size_t)d * 4 * C, 8 * C, 0,
+                   p->bias[d], 0, 1);
+      if (rc) return rc;
+    }
+  }
+  eb::LstmFwdArgs a;
+  a.T = T; a.S = S; a.C = C; a.len = d_len;
+  a.G = gates; a.ldg = 8 * C;
+  a.cell = cell; a.ldc = 2 * C;
+  a.out = out; a.ldo = ldo;
+  for (int d = 0; d < 2; d++) { a.p[d].wm = p->wm[d]; a.p[d].pi = p->pi[d]; a.p[d].pf = p->pf[d]; a.p[d].po = p->po[d]; }
+  a.flags = flags;
+  a.precision = ctx->rec_prec;
+  ctx->launches += 1;
+  return ctx->check(eb::lstm_forward(ctx->stream, plan, a), "lstm_forward");
+}
+
+int eesen_b200_bilstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, const float *x, int ldx,
+                               const eesen_b200_bilstm_params *p, const float *gates, const float *cell,
+                               const float *out, int ldo, const float *dout, int ldd, float *dgates, float *dx,
+                               int lddx, const eesen_b200_bilstm_grads *gr) {
+  if (!ctx || !p || !gr || !x || !gates || !cell || !out || !dout || !dgates || T <= 0 || S <= 0) return EESEN_B200_EINVAL;
+  eb::LstmPlan plan;
+  float *pbuf, *gsum;
+  unsigned *flags;
+  int rc = lstm_prepare(ctx, S, C, &plan, &pbuf, &gsum, &flags);
+  if (rc) return rc;
+  eb::LstmBwdArgs a;
+  a.T = T; a.S = S; a.C = C;
+  a.G = gates; a.ldg = 8 * C;
+  a.cell = cell; a.ldc = 2 * C;
+  a.dout = dout; a.ldd = ldd;
+  a.DG = dgates; a.lddg = 8 * C;
+  for (int d = 0; d < 2; d++) { a.p[d].wm = p->wm[d]; a.p[d].pi = p->pi[d]; a.p[d].pf = p->pf[d]; a.p[d].po = p->po[d]; }
+  a.pbuf = pbuf; a.gsum = gsum; a.flags = flags;
+  a.precision = ctx->rec_prec;
+  ctx->launches += 1;
+  if ((rc = ctx->check(eb::lstm_backward(ctx->stream, plan, a), "lstm_backward"))) return rc;
+  const int N = T * S;
+  for (int d = 0; d < 2; d++) {
+    ctx->launches += 1;
+    if ((rc = ctx->check(eb::lstm_reduce_gsum(ctx->stream, plan, C, gsum, gr->bias[d], gr->pi[d], gr->pf[d],
+                                              gr->po[d], d), "lstm_reduce_gsum")))
+      return rc;
+  }
+  // dx = DG_fw * Wx_fw + DG_bw * Wx_bw   (:502 beta=0, :593 beta=1)
+  if (dx) {
+    for (int d = 0; d < 2; d++) {
+      rc = do_gemm(ctx, 0, 0, N, I, 4 * C, 1.f, dgates + (size_t)d * 4 * C, 8 * C, 0, p->wx[d], I, 0,
+                   d == 0 ? 0.f : 1.f, dx, lddx, 0, nullptr, 0, 1);
+      if (rc) return rc;
+    }
+  }
+  long sGW = gr->wx[1] - gr->wx[0], sGM = gr->wm[1] - gr->wm[0];
+  bool batched = sGW > 0 && (sGW & 3) == 0 && sGM > 0 && (sGM & 3) == 0;
+  // Wx grad = DG^T * x   (:505 / :596), both directions batched
+  if (batched) {
+    rc = do_gemm(ctx, 1, 0, 4 * C, I, N, 1.f, dgates, 8 * C, 4 * C, x, ldx, 0, 0.f, gr->wx[0], I, sGW, nullptr, 0, 2);
+    if (rc) return rc;
+  } else {
+    for (int d = 0; d < 2; d++) {
+      rc = do_gemm(ctx, 1, 0, 4 * C, I, N, 1.f, dgates + (size_t)d * 4 * C, 8 * C, 0, x, ldx, 0, 0.f, gr->wx[d], I, 0,
+                   nullptr, 0, 1);
+      if (rc) return rc;
+    }
+  }
+  // Wm grad = DG^T * m_prev: fw pairs DG rows [S, N) with out rows [0, N-S) (:506);
+  //                          bw pairs DG rows [0, N-S) with out rows [S, N) (:597)
+  if (T > 1) {
+    const int Nm = N - S;
+    rc = do_gemm(ctx, 1, 0, 4 * C, C, Nm, 1.f, dgates + (size_t)S * 8 * C, 8 * C, 0, out, ldo, 0, 0.f, gr->wm[0], C, 0,
+                 nullptr, 0, 1);
+    if (rc) return rc;
+    rc = do_gemm(ctx, 1, 0, 4 * C, C, Nm, 1.f, dgates + 4 * C, 8 * C, 0, out + (size_t)S * ldo + C, ldo, 0, 0.f,
+                 gr->wm[1], C, 0, nullptr, 0, 1);
+    if (rc) return rc;
+  } else {
+    CTX_CHECK(cudaMemsetAsync(gr->wm[0], 0, sizeof(float) * 4 * C * C, ctx->stream), "memset");
+    CTX_CHECK(cudaMemsetAsync(gr->wm[1], 0, sizeof(float) * 4 * C * C, ctx->stream), "memset");
+  }
+  return 0;
+}
+
+int eesen_b200_affine_forward(eesen_b200_ctx *ctx, int N, int D, int K, const float *x, int ldx, const float *W,
+                              const float *b, float *y, int ldy) {
+  if (!ctx || !x || !W || !b || !y) return EESEN_B200_EINVAL;
+  return do_gemm(ctx, 0, 1, N, K, D, 1.f, x, ldx, 0, W, D, 0, 0.f, y, ldy, 0, b, 0, 1);
+}
+
+int eesen_b200_affine_backward(eesen_b200_ctx *ctx, int N, int D, int K, const float *x, int ldx, const float *diff,
+                               int lddiff, const float *W, float *dx, int lddx, float *dW, float *db) {
+  if (!ctx || !x || !diff || !W) return EESEN_B200_EINVAL;
+  int rc;
+  if (dx && (rc = do_gemm(ctx, 0, 0, N, D, K, 1.f, diff, lddiff, 0, W, D, 0, 0.f, dx, lddx, 0, nullptr, 0, 1))) return rc;
+  if (dW && (rc = do_gemm(ctx, 1, 0, K, D, N, 1.f, diff, lddiff, 0, x, ldx, 0, 0.f, dW, D, 0, nullptr, 0, 1))) return rc;
+  if (db) {
+    void *ws = nullptr;
+    if ((rc = ctx->reserve(ctx->colsum_ws, eb::col_sum_ws_floats(K, ctx->num_sms) * sizeof(float), &ws))) return rc;
+    ctx->launches += 2;
+    if ((rc = ctx->check(eb::col_sum(ctx->stream, ctx->num_sms, N, K, diff, lddiff, db, (float *)ws), "col_sum"))) return rc;
+  }
+  return 0;
+}
+
+int eesen_b200_softmax(eesen_b200_ctx *ctx, int N, int K, const float *logits, int ld, float *probs, int ldp,
+                       int *d_argmax) {
+  if (!ctx || !logits || !probs) return EESEN_B200_EINVAL;
+  ctx->launches += 1;
+  return ctx->check(eb::softmax_rows(ctx->stream, N, K, logits, ld, probs, ldp, d_argmax), "softmax_rows");
+}
+
+int eesen_b200_row_argmax(eesen_b200_ctx *ctx, int N, int K, const float *x, int ld, int *d_argmax) {
+  if (!ctx || !x || !d_argmax) return EESEN_B200_EINVAL;
+  ctx->launches += 1;
+  return ctx->check(eb::row_argmax(ctx->stream, N, K, x, ld, d_argmax), "row_argmax");
+}
+
+int eesen_b200_ctc_eval(eesen_b200_ctx *ctx, int T, int S, int K, int max_lab, const int *d_len, const int *d_labels,
+                        const int *d_lab_len, const float *probs, int ldp, float *pzx, float *diff, int ldd) {
+  if (!ctx || !d_len || !d_labels || !d_lab_len || !probs || !pzx || !diff || max_lab < 1) return EESEN_B200_EINVAL;
+  if (2 * max_lab + 1 > 1024) return ctx->fail(EESEN_B200_ESHAPE, "more than 511 labels per utterance");
+  void *ws = nullptr;
+  int rc = ctx->reserve(ctx->ctc_ws, eb::ctc_workspace_floats(T, S, max_lab) * sizeof(float), &ws);
+  if (rc) return rc;
+  ctx->launches += 1;
+  return ctx->check(eb::ctc_eval(ctx->stream, T, S, K, max_lab, d_len, d_labels, d_lab_len, probs, ldp, pzx, diff, ldd,
+                                 (float *)ws), "ctc_eval");
+}
+
+int eesen_b200_sgd_update(eesen_b200_ctx *ctx, float *w, float *corr, const float *grad, int64_t n, float momentum,
+                          const eesen_b200_sgd_segment *segments, int nseg) {
+  if (!ctx || !w || !corr || !grad || !segments || nseg < 1) return EESEN_B200_EINVAL;
+  std::vector<eb::SgdSegment> h(nseg);
+  for (int i = 0; i < nseg; i++) {
+    h[i].offset = segments[i].offset; h[i].count = segments[i].count;
+    h[i].lr = segments[i].lr; h[i].max_grad = segments[i].max_grad;
+  }
+  void *d;
+  int rc = ctx->reserve(ctx->seg_buf, sizeof(eb::SgdSegment) * nseg, &d);
+  if (rc) return rc;
+  // synchronous small copy: the host vector dies at return
+  CTX_CHECK(cudaMemcpyAsync(d, h.data(), sizeof(eb::SgdSegment) * nseg, cudaMemcpyHostToDevice, ctx->stream), "memcpy(segments)");
+  CTX_CHECK(cudaStreamSynchronize(ctx->stream), "sync(segments)");
+  ctx->launches += 1;
+  return ctx->check(eb::sgd_momentum_clip(ctx->stream, ctx->num_sms, w, corr, grad, momentum, (eb::SgdSegment *)d, nseg,
+                                          (long)n), "sgd_momentum_clip");
+}
+
+// ------------------------------------------------------------------------------------ NCCL (dlopen)
+typedef struct { char internal[128]; } nccl_uid;
+static void *nccl_open() {
+  static void *lib = nullptr;
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  return lib;
+}
+
+int eesen_b200_nccl_unique_id(char id[128]) {
+  void *lib = nccl_open();
+  if (!lib) return EESEN_B200_ENCCL;
+  typedef int (*fn_t)(nccl_uid *);
+  fn_t f = (fn_t)dlsym(lib, "ncclGetUniqueId");
+  if (!f) return EESEN_B200_ENCCL;
+  nccl_uid u;
+  int r = f(&u);
+  if (r != 0) return EESEN_B200_ENCCL;
+  memcpy(id, u.internal, 128);
+  return 0;
+}
+
+int eesen_b200_nccl_init(eesen_b200_ctx *ctx, int rank, int nranks, const char id[128]) {
+  if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return EESEN_B200_EINVAL;
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  if (nranks == 1) return 0;
+  void *lib = nccl_open();
+  if (!lib) return ctx->fail(EESEN_B200_ENCCL, std::string("cannot load libnccl: ") + dlerror());
+  ctx->nccl_lib = lib;
+  typedef int (*init_t)(void **, int, nccl_uid, int);
+  init_t f = (init_t)dlsym(lib, "ncclCommInitRank");
+  if (!f) return ctx->fail(EESEN_B200_ENCCL, "ncclCommInitRank not found");
+  nccl_uid u;
+  memcpy(u.internal, id, 128);
+  cudaSetDevice(ctx->device);
+  int r = f(&ctx->nccl_comm, nranks, u, rank);
+  if (r != 0) return ctx->fail(EESEN_B200_ENCCL, "ncclCommInitRank failed with code " + std::to_string(r));
+  return 0;
+}
+
+int eesen_b200_allreduce_sum(eesen_b200_ctx *ctx, float *buf, int64_t n) {
+  if (!ctx || !buf) return EESEN_B200_EINVAL;
+  if (ctx->nranks == 1) return 0;
+  if (!ctx->nccl_comm) return ctx->fail(EESEN_B200_ENCCL, "NCCL communicator not initialised");
+  // ncclAllReduce(sendbuff, recvbuff, count, ncclFloat32 = 7, ncclSum = 0, comm, stream)
+  typedef int (*ar_t)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+  static ar_t f = nullptr;
+  if (!f) f = (ar_t)dlsym(ctx->nccl_lib, "ncclAllReduce");
+  if (!f) return ctx->fail(EESEN_B200_ENCCL, "ncclAllReduce not found");
+  int r = f(buf, buf, (size_t)n, 7, 0, ctx->nccl_comm, ctx->stream);
+  if (r != 0) return ctx->fail(EESEN_B200_ENCCL, "ncclAllReduce failed with code " + std::to_string(r));
+  return 0;
+}
+
+int eesen_b200_world(const eesen_b200_ctx *ctx, int *rank, int *nranks) {
+  if (!ctx) return EESEN_B200_EINVAL;
+  if (rank) *rank = ctx->rank;
+  if (nranks) *nranks = ctx->nranks;
+  return 0;
+}
+
+}  // extern "C"

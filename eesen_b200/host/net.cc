@@ -1,0 +1,787 @@
+// eesen_b200/host/net.cc -- see net.h.
+#include "net.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+
+#include "context.h"
+
+namespace eesen {
+
+static eesen_b200_ctx *g_ctx = nullptr;  // the process-wide device context (reference: CuDevice singleton)
+static cudaStream_t Stream() { return g_ctx ? g_ctx->stream : (cudaStream_t)0; }
+
+#define CU_CHECK(call)                                                                  \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess) KALDI_ERR << "CUDA error: " << cudaGetErrorString(e__) << " in " #call; \
+  } while (0)
+
+void CheckAbi(eesen_b200_ctx *ctx, int rc, const char *what) {
+  if (rc != 0) KALDI_ERR << what << " failed (code " << rc << "): " << eesen_b200_last_error(ctx);
+}
+
+// ------------------------------------------------------------------------------------ CuMatrix
+template <typename Real>
+void CuMatrixBase<Real>::SetZero() {
+  if (num_rows_ == 0) return;
+  CU_CHECK(cudaMemsetAsync(data_, 0, sizeof(Real) * (size_t)num_rows_ * stride_, Stream()));
+}
+template <typename Real>
+void CuMatrixBase<Real>::CopyFromMat(const CuMatrixBase<Real> &src) {
+  KALDI_ASSERT(src.NumRows() == num_rows_ && src.NumCols() == num_cols_);
+  if (num_rows_ == 0) return;
+  CU_CHECK(cudaMemcpy2DAsync(data_, sizeof(Real) * stride_, src.Data(), sizeof(Real) * src.Stride(),
+                             sizeof(Real) * num_cols_, num_rows_, cudaMemcpyDeviceToDevice, Stream()));
+}
+template <typename Real>
+void CuMatrixBase<Real>::CopyFromHost(const Real *src, int32 ld) {
+  if (num_rows_ == 0) return;
+  CU_CHECK(cudaMemcpy2DAsync(data_, sizeof(Real) * stride_, src, sizeof(Real) * ld, sizeof(Real) * num_cols_,
+                             num_rows_, cudaMemcpyHostToDevice, Stream()));
+}
+template <typename Real>
+void CuMatrixBase<Real>::CopyToHost(Real *dst, int32 ld) const {
+  if (num_rows_ == 0) return;
+  CU_CHECK(cudaMemcpy2DAsync(dst, sizeof(Real) * ld, data_, sizeof(Real) * stride_, sizeof(Real) * num_cols_,
+                             num_rows_, cudaMemcpyDeviceToHost, Stream()));
+  CU_CHECK(cudaStreamSynchronize(Stream()));
+}
+
+template <typename Real>
+void CuMatrix<Real>::Resize(int32 rows, int32 cols, MatrixResizeType t) {
+  int32 stride = (cols + 3) & ~3;
+  size_t need = (size_t)rows * stride;
+  if (need > capacity_) {
+    if (this->data_) {
+      CU_CHECK(cudaStreamSynchronize(Stream()));
+      CU_CHECK(cudaFree(this->data_));
+      this->data_ = nullptr;
+    }
+    CU_CHECK(cudaMalloc((void **)&this->data_, sizeof(Real) * need));
+    capacity_ = need;
+  }
+  this->num_rows_ = rows; this->num_cols_ = cols; this->stride_ = stride;
+  if (t == kSetZero) this->SetZero();
+}
+template <typename Real>
+CuMatrix<Real>::CuMatrix(const HostMatrix &m) {
+  Resize(m.rows, m.cols, kUndefined);
+  this->CopyFromHost(m.data.data(), m.cols);
+}
+template <typename Real>
+CuMatrix<Real>::CuMatrix(const CuMatrix<Real> &o) : CuMatrixBase<Real>() {
+  Resize(o.NumRows(), o.NumCols(), kUndefined);
+  this->CopyFromMat(o);
+}
+template <typename Real>
+CuMatrix<Real> &CuMatrix<Real>::operator=(const CuMatrixBase<Real> &o) {
+  if (&o == this) return *this;
+  Resize(o.NumRows(), o.NumCols(), kUndefined);
+  this->CopyFromMat(o);
+  return *this;
+}
+template <typename Real>
+CuMatrix<Real> &CuMatrix<Real>::operator=(const CuMatrix<Real> &o) {
+  return *this = static_cast<const CuMatrixBase<Real> &>(o);
+}
+template <typename Real>
+CuMatrix<Real>::~CuMatrix() {
+  if (this->data_) cudaFree(this->data_);
+}
+template class CuMatrixBase<float>;
+template class CuMatrix<float>;
+
+// ------------------------------------------------------------------------------------ Layer
+const char *Layer::TypeToMarker(LayerType t) {
+  switch (t) {
+    case l_BiLstm_Parallel: return "<BiLstmParallel>";
+    case l_Affine_Transform: return "<AffineTransform>";
+    case l_Softmax: return "<Softmax>";
+    default: return "<Unknown>";
+  }
+}
+Layer::LayerType Layer::MarkerToType(const std::string &s) {
+  if (s == "<BiLstmParallel>") return l_BiLstm_Parallel;
+  if (s == "<AffineTransform>") return l_Affine_Transform;
+  if (s == "<Softmax>") return l_Softmax;
+  KALDI_ERR << "Unknown or unsupported layer marker on the B200 CTC path: " << s
+            << " (supported: <BiLstmParallel> <AffineTransform> <Softmax>)";
+  return l_Unknown;
+}
+
+void Layer::Propagate(const CuMatrixBase<BaseFloat> &in, CuMatrix<BaseFloat> *out) {
+  if (input_dim_ != in.NumCols())
+    KALDI_ERR << "Non-matching dims! " << TypeToMarker(GetType()) << " input-dim : " << input_dim_
+              << " data : " << in.NumCols();
+  out->Resize(in.NumRows(), output_dim_, kUndefined);  // every kernel overwrites its full output
+  PropagateFnc(in, out);
+}
+
+void Layer::Backpropagate(const CuMatrixBase<BaseFloat> &in, const CuMatrixBase<BaseFloat> &out,
+                          const CuMatrixBase<BaseFloat> &out_diff, CuMatrix<BaseFloat> *in_diff) {
+  if (output_dim_ != out_diff.NumCols())
+    KALDI_ERR << "Non-matching output dims, component:" << output_dim_ << " data:" << out_diff.NumCols();
+  in_diff->Resize(out_diff.NumRows(), input_dim_, kUndefined);
+  KALDI_ASSERT(in.NumRows() == out.NumRows() && in.NumRows() == out_diff.NumRows());
+  BackpropagateFnc(in, out, out_diff, in_diff);
+}
+
+Layer *Layer::Read(std::istream &is, bool binary) {
+  int32 dim_out, dim_in;
+  std::string token;
+  int first_char = Peek(is, binary);
+  if (first_char == EOF) return NULL;
+  ReadToken(is, binary, &token);
+  if (token == "</Nnet>") return NULL;
+  if (token == "<Nnet>") ReadToken(is, binary, &token);
+  LayerType type = MarkerToType(token);
+  ExpectToken(is, binary, "<InputDim>");
+  ReadBasicType(is, binary, &dim_in);
+  ExpectToken(is, binary, type == l_BiLstm_Parallel ? "<CellDim>" : "<OutputDim>");
+  ReadBasicType(is, binary, &dim_out);
+  Layer *layer = NULL;
+  switch (type) {
+    case l_BiLstm_Parallel: layer = new BiLstmParallel(dim_in, dim_out); break;
+    case l_Affine_Transform: layer = new AffineTransform(dim_in, dim_out); break;
+    case l_Softmax: layer = new Softmax(dim_in, dim_out); break;
+    default: KALDI_ERR << "Missing type: " << token;
+  }
+  layer->ReadData(is, binary);
+  return layer;
+}
+
+void Layer::Write(std::ostream &os, bool binary) const {
+  WriteToken(os, binary, TypeToMarker(GetType()));
+  WriteToken(os, binary, "<InputDim>");
+  WriteBasicType(os, binary, InputDim());
+  WriteToken(os, binary, GetType() == l_BiLstm_Parallel ? "<CellDim>" : "<OutputDim>");
+  WriteBasicType(os, binary, OutputDim());
+  if (!binary) os << "\n";
+  WriteData(os, binary);
+}
+
+// ------------------------------------------------------------------------------------ BiLstmParallel
+static const char *kBiLstmFlagTokens[7] = {"<ForwardTimeStepDropout>", "<ForwardSequenceDropout>",
+                                           "<RecurrentTimeStepDropout>", "<RecurrentSequenceDropout>",
+                                           "<RNNDrop>", "<NoMemLossDropout>", "<TwiddleForward>"};
+
+int64 BiLstmParallel::NumParams() const {
+  int64 C = cell_dim_, I = input_dim_;
+  return 2 * (4 * C * I + 4 * C * C + 4 * C + 3 * C);
+}
+
+BiLstmParallel::~BiLstmParallel() {
+  if (d_len_) cudaFree(d_len_);
+}
+
+void BiLstmParallel::ReadData(std::istream &is, bool binary) {
+  // optional tokens, in the order of bilstm-layer.h:317-375
+  while ('<' == Peek(is, binary)) {
+    std::string tok;
+    ReadToken(is, binary, &tok);
+    if (tok == "<LearnRateCoef>") ReadBasicType(is, binary, &learn_rate_coef_);
+    else if (tok == "<MaxGrad>") ReadBasicType(is, binary, &max_grad_);
+    else if (tok == "<ForwardDropoutFactor>") ReadBasicType(is, binary, &forward_dropout_);
+    else if (tok == "<RecurrentDropoutFactor>") ReadBasicType(is, binary, &recurrent_dropout_);
+    else if (tok == "<BiLstmAccus>")
+      KALDI_ERR << "Adagrad/RMSProp accumulators are not supported on the B200 CTC path (SGD only)";
+    else {
+      int f = -1;
+      for (int i = 0; i < 7; i++)
+        if (tok == kBiLstmFlagTokens[i]) f = i;
+      if (f < 0) KALDI_ERR << "Unknown token " << tok << " in <BiLstmParallel>";
+      ReadBasicType(is, binary, &flags_[f]);
+    }
+  }
+  if (forward_dropout_ != 0.f || recurrent_dropout_ != 0.f || flags_[4] || flags_[5])
+    KALDI_WARN << "dropout variants of BiLstmParallel are not on the B200 path; training runs the vanilla passes";
+  const int64 C = cell_dim_, I = input_dim_;
+  if (C % 8 != 0 || I % 4 != 0)
+    KALDI_ERR << "BiLstmParallel on B200 needs cells/direction % 8 == 0 and input dim % 4 == 0, got C=" << C
+              << " I=" << I;
+  host_params_.clear();
+  host_params_.reserve(NumParams());
+  for (int d = 0; d < 2; d++) {   // bilstm-layer.h:395-424: wx, wm, bias, phole i/f/o for fw then bw
+    HostMatrix wx, wm;
+    HostVector b, pi, pf, po;
+    wx.Read(is, binary); wm.Read(is, binary);
+    b.Read(is, binary); pi.Read(is, binary); pf.Read(is, binary); po.Read(is, binary);
+    KALDI_ASSERT(wx.rows == 4 * C && wx.cols == I && wm.rows == 4 * C && wm.cols == C);
+    KALDI_ASSERT((int64)b.data.size() == 4 * C && (int64)pi.data.size() == C && (int64)pf.data.size() == C &&
+                 (int64)po.data.size() == C);
+    host_params_.insert(host_params_.end(), wx.data.begin(), wx.data.end());
+    host_params_.insert(host_params_.end(), wm.data.begin(), wm.data.end());
+    host_params_.insert(host_params_.end(), b.data.begin(), b.data.end());
+    host_params_.insert(host_params_.end(), pi.data.begin(), pi.data.end());
+    host_params_.insert(host_params_.end(), pf.data.begin(), pf.data.end());
+    host_params_.insert(host_params_.end(), po.data.begin(), po.data.end());
+  }
+}
+
+void BiLstmParallel::WriteData(std::ostream &os, bool binary) const {
+  // bilstm-layer.h:429-493
+  WriteToken(os, binary, "<LearnRateCoef>"); WriteBasicType(os, binary, learn_rate_coef_);
+  WriteToken(os, binary, "<MaxGrad>"); WriteBasicType(os, binary, max_grad_);
+  WriteToken(os, binary, "<ForwardDropoutFactor>"); WriteBasicType(os, binary, forward_dropout_);
+  for (int i = 0; i < 6; i++) { WriteToken(os, binary, kBiLstmFlagTokens[i]); WriteBasicType(os, binary, flags_[i]); }
+  WriteToken(os, binary, "<RecurrentDropoutFactor>"); WriteBasicType(os, binary, recurrent_dropout_);
+  WriteToken(os, binary, kBiLstmFlagTokens[6]); WriteBasicType(os, binary, flags_[6]);
+  const int64 C = cell_dim_, I = input_dim_;
+  const float *p = host_params_.data();
+  for (int d = 0; d < 2; d++) {
+    HostMatrix wx, wm;
+    wx.rows = 4 * C; wx.cols = I; wx.data.assign(p, p + 4 * C * I); p += 4 * C * I;
+    wm.rows = 4 * C; wm.cols = C; wm.data.assign(p, p + 4 * C * C); p += 4 * C * C;
+    HostVector b, pi, pf, po;
+    b.data.assign(p, p + 4 * C); p += 4 * C;
+    pi.data.assign(p, p + C); p += C;
+    pf.data.assign(p, p + C); p += C;
+    po.data.assign(p, p + C); p += C;
+    wx.Write(os, binary); wm.Write(os, binary);
+    b.Write(os, binary); pi.Write(os, binary); pf.Write(os, binary); po.Write(os, binary);
+  }
+}
+
+void BiLstmParallel::Params(eesen_b200_bilstm_params *p, eesen_b200_bilstm_grads *g) const {
+  const int64 C = cell_dim_, I = input_dim_;
+  const int64 dir_stride = 4 * C * I + 4 * C * C + 4 * C + 3 * C;
+  for (int d = 0; d < 2; d++) {
+    int64 o = d * dir_stride;
+    if (p) {
+      p->wx[d] = w_ + o; p->wm[d] = w_ + o + 4 * C * I; p->bias[d] = w_ + o + 4 * C * I + 4 * C * C;
+      p->pi[d] = p->bias[d] + 4 * C; p->pf[d] = p->pi[d] + C; p->po[d] = p->pf[d] + C;
+    }
+    if (g) {
+      g->wx[d] = g_ + o; g->wm[d] = g_ + o + 4 * C * I; g->bias[d] = g_ + o + 4 * C * I + 4 * C * C;
+      g->pi[d] = g->bias[d] + 4 * C; g->pf[d] = g->pi[d] + C; g->po[d] = g->pf[d] + C;
+    }
+  }
+}
+
+void BiLstmParallel::SetSeqLengths(std::vector<int> &sequence_lengths) {
+  sequence_lengths_ = sequence_lengths;
+  int32 S = sequence_lengths.size();
+  if (S > d_len_cap_) {
+    if (d_len_) { CU_CHECK(cudaStreamSynchronize(Stream())); CU_CHECK(cudaFree(d_len_)); }
+    CU_CHECK(cudaMalloc((void **)&d_len_, sizeof(int) * S));
+    d_len_cap_ = S;
+  }
+  CU_CHECK(cudaMemcpyAsync(d_len_, sequence_lengths_.data(), sizeof(int) * S, cudaMemcpyHostToDevice, Stream()));
+}
+
+void BiLstmParallel::PropagateFnc(const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseFloat> *out) {
+  int32 S = sequence_lengths_.size();
+  KALDI_ASSERT(S > 0 && in.NumRows() % S == 0);
+  int32 T = in.NumRows() / S, C = cell_dim_;
+  gates_.Resize(in.NumRows(), 8 * C, kUndefined);
+  cell_.Resize(in.NumRows(), 2 * C, kUndefined);
+  eesen_b200_bilstm_params p;
+  Params(&p, NULL);
+  CheckAbi(ctx_, eesen_b200_bilstm_forward(ctx_, T, S, input_dim_, C, d_len_, in.Data(), in.Stride(), &p,
+                                           gates_.Data(), cell_.Data(), out->Data(), out->Stride()),
+           "eesen_b200_bilstm_forward");
+}
+
+void BiLstmParallel::BackpropagateFnc(const CuMatrixBase<BaseFloat> &in, const CuMatrixBase<BaseFloat> &out,
+                                      const CuMatrixBase<BaseFloat> &out_diff, CuMatrixBase<BaseFloat> *in_diff) {
+  int32 S = sequence_lengths_.size();
+  KALDI_ASSERT(S > 0 && in.NumRows() % S == 0);
+  int32 T = in.NumRows() / S, C = cell_dim_;
+  dgates_.Resize(in.NumRows(), 8 * C, kUndefined);
+  eesen_b200_bilstm_params p;
+  eesen_b200_bilstm_grads g;
+  Params(&p, &g);
+  CheckAbi(ctx_, eesen_b200_bilstm_backward(ctx_, T, S, input_dim_, C, in.Data(), in.Stride(), &p, gates_.Data(),
+                                            cell_.Data(), out.Data(), out.Stride(), out_diff.Data(),
+                                            out_diff.Stride(), dgates_.Data(),
+                                            need_in_diff_ ? in_diff->Data() : NULL, in_diff->Stride(), &g),
+           "eesen_b200_bilstm_backward");
+}
+
+std::string BiLstmParallel::Info() const {
+  std::ostringstream os;
+  os << "<BiLstmParallel> input " << input_dim_ << " cells/direction " << cell_dim_;
+  return os.str();
+}
+
+// ------------------------------------------------------------------------------------ Affine / Softmax
+void AffineTransform::ReadData(std::istream &is, bool binary) {
+  while ('<' == Peek(is, binary)) {
+    std::string tok;
+    ReadToken(is, binary, &tok);
+    if (tok == "<LearnRateCoef>") ReadBasicType(is, binary, &learn_rate_coef_);
+    else if (tok == "<MaxGrad>") ReadBasicType(is, binary, &max_grad_);
+    else if (tok == "<AffineAccus>")
+      KALDI_ERR << "Adagrad/RMSProp accumulators are not supported on the B200 CTC path (SGD only)";
+    else KALDI_ERR << "Unknown token " << tok << " in <AffineTransform>";
+  }
+  if (input_dim_ % 4 != 0) KALDI_ERR << "AffineTransform on B200 needs input dim % 4 == 0, got " << input_dim_;
+  HostMatrix w;
+  HostVector b;
+  w.Read(is, binary);
+  b.Read(is, binary);
+  KALDI_ASSERT(w.rows == output_dim_ && w.cols == input_dim_ && (int32)b.data.size() == output_dim_);
+  host_params_ = w.data;
+  host_params_.insert(host_params_.end(), b.data.begin(), b.data.end());
+}
+
+void AffineTransform::WriteData(std::ostream &os, bool binary) const {
+  WriteToken(os, binary, "<LearnRateCoef>"); WriteBasicType(os, binary, learn_rate_coef_);
+  WriteToken(os, binary, "<MaxGrad>"); WriteBasicType(os, binary, max_grad_);
+  HostMatrix w;
+  w.rows = output_dim_; w.cols = input_dim_;
+  w.data.assign(host_params_.begin(), host_params_.begin() + (size_t)output_dim_ * input_dim_);
+  HostVector b;
+  b.data.assign(host_params_.begin() + (size_t)output_dim_ * input_dim_, host_params_.end());
+  w.Write(os, binary);
+  b.Write(os, binary);
+}
+
+void AffineTransform::PropagateFnc(const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseFloat> *out) {
+  CheckAbi(ctx_, eesen_b200_affine_forward(ctx_, in.NumRows(), input_dim_, output_dim_, in.Data(), in.Stride(), w_,
+                                           w_ + (size_t)output_dim_ * input_dim_, out->Data(), out->Stride()),
+           "eesen_b200_affine_forward");
+}
+
+void AffineTransform::BackpropagateFnc(const CuMatrixBase<BaseFloat> &in, const CuMatrixBase<BaseFloat> &,
+                                       const CuMatrixBase<BaseFloat> &out_diff, CuMatrixBase<BaseFloat> *in_diff) {
+  // in_diff = out_diff * W (affine-trans-layer.h:171) and the gradient part of Update (:182-183)
+  CheckAbi(ctx_, eesen_b200_affine_backward(ctx_, in.NumRows(), input_dim_, output_dim_, in.Data(), in.Stride(),
+                                            out_diff.Data(), out_diff.Stride(), w_,
+                                            need_in_diff_ ? in_diff->Data() : NULL, in_diff->Stride(), g_,
+                                            g_ + (size_t)output_dim_ * input_dim_),
+           "eesen_b200_affine_backward");
+}
+
+void Softmax::PropagateFnc(const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseFloat> *out) {
+  CheckAbi(ctx_, eesen_b200_softmax(ctx_, in.NumRows(), input_dim_, in.Data(), in.Stride(), out->Data(),
+                                    out->Stride(), NULL), "eesen_b200_softmax");
+}
+void Softmax::BackpropagateFnc(const CuMatrixBase<BaseFloat> &, const CuMatrixBase<BaseFloat> &,
+                               const CuMatrixBase<BaseFloat> &out_diff, CuMatrixBase<BaseFloat> *in_diff) {
+  in_diff->CopyFromMat(out_diff);  // softmax-layer.h:49-57: the CTC diff is already wrt the activations
+}
+
+// ------------------------------------------------------------------------------------ Net
+Net::~Net() {
+  for (size_t i = 0; i < layers_.size(); i++) delete layers_[i];
+  if (w_) cudaFree(w_);
+  if (g_) cudaFree(g_);
+  if (corr_) cudaFree(corr_);
+  if (d_segs_) cudaFree(d_segs_);
+}
+
+void Net::Read(const std::string &file) {
+  g_ctx = ctx_;
+  std::ifstream is(file.c_str(), std::ios::in | std::ios::binary);
+  if (!is.is_open()) KALDI_ERR << "Failed to open model file " << file;
+  bool binary;
+  if (!InitKaldiInputStream(is, &binary)) KALDI_ERR << "Bad header in " << file;
+  Read(is, binary);
+  if (NumLayers() == 0) KALDI_WARN << "The network '" << file << "' is empty.";
+}
+
+void Net::Read(std::istream &is, bool binary) {
+  g_ctx = ctx_;
+  Layer *layer;
+  while (NULL != (layer = Layer::Read(is, binary))) {
+    if (NumLayers() > 0 && layers_.back()->OutputDim() != layer->InputDim())
+      KALDI_ERR << "Dimensionality mismatch! Previous layer output:" << layers_.back()->OutputDim()
+                << " Current layer input:" << layer->InputDim();
+    layer->ctx_ = ctx_;
+    layers_.push_back(layer);
+  }
+  propagate_buf_.resize(NumLayers() + 1);
+  backpropagate_buf_.resize(NumLayers() + 1);
+  opts_.learn_rate = 0.0;  // net.cc:274,294
+  BindArena();
+}
+
+// Lay all trainable layers out in three contiguous arenas (params / raw grads / momentum), each
+// layer block starting on a 16-byte boundary.
+void Net::BindArena() {
+  int64 total = 0;
+  num_params_ = 0;
+  std::vector<int64> offs;
+  for (size_t i = 0; i < layers_.size(); i++) {
+    if (!layers_[i]->IsTrainable()) { offs.push_back(-1); continue; }
+    TrainableLayer *tl = dynamic_cast<TrainableLayer *>(layers_[i]);
+    total = (total + 3) & ~(int64)3;
+    offs.push_back(total);
+    total += tl->NumParams();
+    num_params_ += tl->NumParams();
+  }
+  arena_size_ = (total + 3) & ~(int64)3;
+  if (arena_size_ == 0) return;
+  CU_CHECK(cudaMalloc((void **)&w_, sizeof(float) * arena_size_));
+  CU_CHECK(cudaMalloc((void **)&g_, sizeof(float) * arena_size_));
+  CU_CHECK(cudaMalloc((void **)&corr_, sizeof(float) * arena_size_));
+  CU_CHECK(cudaMemsetAsync(w_, 0, sizeof(float) * arena_size_, Stream()));
+  CU_CHECK(cudaMemsetAsync(g_, 0, sizeof(float) * arena_size_, Stream()));
+  CU_CHECK(cudaMemsetAsync(corr_, 0, sizeof(float) * arena_size_, Stream()));   // *_corr_.SetZero() bilstm-layer.h:401-406
+  layer_offset_ = offs;
+  for (size_t i = 0; i < layers_.size(); i++) {
+    if (offs[i] < 0) continue;
+    TrainableLayer *tl = dynamic_cast<TrainableLayer *>(layers_[i]);
+    KALDI_ASSERT((int64)tl->host_params_.size() == tl->NumParams());
+    CU_CHECK(cudaMemcpyAsync(w_ + offs[i], tl->host_params_.data(), sizeof(float) * tl->NumParams(),
+                             cudaMemcpyHostToDevice, Stream()));
+    tl->Bind(w_ + offs[i], g_ + offs[i]);
+  }
+  CU_CHECK(cudaStreamSynchronize(Stream()));
+  segs_dirty_ = true;
+}
+
+void Net::GetParams(std::vector<float> *host) const { GetArena(w_, host); }
+
+void Net::GetArena(const float *arena, std::vector<float> *host) const {
+  host->resize(num_params_);
+  int64 o = 0;
+  CU_CHECK(cudaStreamSynchronize(Stream()));
+  for (size_t i = 0; i < layers_.size(); i++) {
+    if (layer_offset_[i] < 0) continue;
+    TrainableLayer *tl = dynamic_cast<TrainableLayer *>(layers_[i]);
+    CU_CHECK(cudaMemcpy(host->data() + o, arena + layer_offset_[i], sizeof(float) * tl->NumParams(),
+                        cudaMemcpyDeviceToHost));
+    o += tl->NumParams();
+  }
+}
+
+void Net::SetParams(const float *host, int64 n) {
+  KALDI_ASSERT(n == num_params_);
+  int64 o = 0;
+  CU_CHECK(cudaStreamSynchronize(Stream()));
+  for (size_t i = 0; i < layers_.size(); i++) {
+    if (layer_offset_[i] < 0) continue;
+    TrainableLayer *tl = dynamic_cast<TrainableLayer *>(layers_[i]);
+    CU_CHECK(cudaMemcpy(w_ + layer_offset_[i], host + o, sizeof(float) * tl->NumParams(), cudaMemcpyHostToDevice));
+    o += tl->NumParams();
+  }
+}
+
+void Net::Write(const std::string &file, bool binary) {
+  std::ofstream os(file.c_str(), std::ios::out | std::ios::binary);
+  if (!os.is_open()) KALDI_ERR << "Failed to open " << file << " for writing";
+  if (binary) { os.put('\0'); os.put('B'); }
+  Write(os, binary);
+  os.close();
+  if (os.fail()) KALDI_ERR << "Failed to write " << file;
+}
+
+void Net::Write(std::ostream &os, bool binary) {
+  // refresh the host copies from the device arena
+  CU_CHECK(cudaStreamSynchronize(Stream()));
+  for (size_t i = 0; i < layers_.size(); i++) {
+    if (layer_offset_[i] < 0) continue;
+    TrainableLayer *tl = dynamic_cast<TrainableLayer *>(layers_[i]);
+    tl->host_params_.resize(tl->NumParams());
+    CU_CHECK(cudaMemcpy(tl->host_params_.data(), w_ + layer_offset_[i], sizeof(float) * tl->NumParams(),
+                        cudaMemcpyDeviceToHost));
+  }
+  WriteToken(os, binary, "<Nnet>");
+  if (!binary) os << std::endl;
+  for (int32 i = 0; i < NumLayers(); i++) layers_[i]->Write(os, binary);
+  WriteToken(os, binary, "</Nnet>");
+  if (!binary) os << std::endl;
+}
+
+int32 Net::InputDim() const { return layers_.empty() ? 0 : layers_.front()->InputDim(); }
+int32 Net::OutputDim() const { return layers_.empty() ? 0 : layers_.back()->OutputDim(); }
+
+void Net::SetSeqLengths(std::vector<int> &sequence_lengths) {
+  for (size_t i = 0; i < layers_.size(); i++) layers_[i]->SetSeqLengths(sequence_lengths);
+}
+
+void Net::SetTrainOptions(const NetTrainOptions &opts) {
+  opts_ = opts;
+  segs_dirty_ = true;
+}
+
+void Net::SetUpdateAlgorithm(const std::string &opt) {
+  if (opt != "SGD") KALDI_ERR << "Only --opt-algorithm=SGD is implemented on the B200 CTC path, got " << opt;
+}
+
+void Net::UploadSegments() {
+  std::vector<eb::SgdSegment> segs;
+  for (size_t i = 0; i < layers_.size(); i++) {
+    if (layer_offset_[i] < 0) continue;
+    TrainableLayer *tl = dynamic_cast<TrainableLayer *>(layers_[i]);
+    eb::SgdSegment s;
+    s.offset = layer_offset_[i];
+    s.count = 0;  // fixed below: up to the next segment start
+    s.lr = opts_.learn_rate * tl->learn_rate_coef_;
+    s.max_grad = tl->max_grad_;
+    segs.push_back(s);
+  }
+  for (size_t k = 0; k < segs.size(); k++)
+    segs[k].count = (k + 1 < segs.size() ? segs[k + 1].offset : arena_size_) - segs[k].offset;
+  nseg_ = segs.size();
+  if (!d_segs_) CU_CHECK(cudaMalloc(&d_segs_, sizeof(eb::SgdSegment) * std::max<size_t>(1, layers_.size())));
+  CU_CHECK(cudaMemcpy(d_segs_, segs.data(), sizeof(eb::SgdSegment) * nseg_, cudaMemcpyHostToDevice));
+  segs_dirty_ = false;
+}
+
+void Net::Propagate(const CuMatrixBase<BaseFloat> &in, CuMatrix<BaseFloat> *out) {
+  KALDI_ASSERT(NULL != out);
+  g_ctx = ctx_;
+  if (NumLayers() == 0) { (*out) = in; return; }
+  propagate_buf_[0].Resize(in.NumRows(), in.NumCols(), kUndefined);
+  propagate_buf_[0].CopyFromMat(in);
+  for (int32 i = 0; i < NumLayers(); i++) layers_[i]->Propagate(propagate_buf_[i], &propagate_buf_[i + 1]);
+  (*out) = propagate_buf_[NumLayers()];
+}
+
+void Net::Backpropagate(const CuMatrixBase<BaseFloat> &out_diff, CuMatrix<BaseFloat> *in_diff) {
+  g_ctx = ctx_;
+  if (NumLayers() == 0) { if (in_diff) (*in_diff) = out_diff; return; }
+  if (!in_train_) KALDI_ERR << "Can't backpropagate in test mode";
+  const CuMatrixBase<BaseFloat> *diff = &out_diff;
+  for (int32 i = NumLayers() - 1; i >= 0; i--) {
+    layers_[i]->need_in_diff_ = (i > 0) || (in_diff != NULL);
+    layers_[i]->Backpropagate(propagate_buf_[i], propagate_buf_[i + 1], *diff, &backpropagate_buf_[i]);
+    diff = &backpropagate_buf_[i];
+  }
+  // data-parallel: one all-reduce of the raw gradient arena, then the identical update on every rank
+  int rank, nranks;
+  eesen_b200_world(ctx_, &rank, &nranks);
+  if (nranks > 1) CheckAbi(ctx_, eesen_b200_allreduce_sum(ctx_, g_, arena_size_), "eesen_b200_allreduce_sum");
+  if (segs_dirty_) UploadSegments();
+  if (nseg_ > 0) {
+    cudaError_t e = eb::sgd_momentum_clip(ctx_->stream, ctx_->num_sms, w_, corr_, g_, opts_.momentum,
+                                          (const eb::SgdSegment *)d_segs_, nseg_, arena_size_);
+    ctx_->launches += 1;
+    if (e != cudaSuccess) KALDI_ERR << "sgd_momentum_clip: " << cudaGetErrorString(e);
+  }
+  if (NULL != in_diff) (*in_diff) = backpropagate_buf_[0];
+}
+
+static std::string Moments(const std::vector<float> &v, int64 b, int64 n) {
+  double s = 0, s2 = 0, mn = 1e30, mx = -1e30;
+  for (int64 i = b; i < b + n; i++) { s += v[i]; s2 += (double)v[i] * v[i]; mn = std::min<double>(mn, v[i]); mx = std::max<double>(mx, v[i]); }
+  double mean = s / n, var = s2 / n - mean * mean;
+  std::ostringstream os;
+  os << " ( min " << mn << ", max " << mx << ", mean " << mean << ", variance " << var << " ) ";
+  return os.str();
+}
+
+std::string Net::Info() const {
+  std::ostringstream os;
+  os << "num-layers " << NumLayers() << "\ninput-dim " << InputDim() << "\noutput-dim " << OutputDim()
+     << "\nnumber-of-parameters " << num_params_ / 1e6 << " millions\n";
+  std::vector<float> p;
+  GetArena(w_, &p);
+  int64 o = 0;
+  for (size_t i = 0; i < layers_.size(); i++) {
+    os << "layer " << i + 1 << " : " << Layer::TypeToMarker(layers_[i]->GetType()) << ", input-dim "
+       << layers_[i]->InputDim() << ", output-dim " << layers_[i]->OutputDim();
+    if (layer_offset_[i] >= 0) {
+      TrainableLayer *tl = dynamic_cast<TrainableLayer *>(layers_[i]);
+      os << ", params" << Moments(p, o, tl->NumParams());
+      o += tl->NumParams();
+    }
+    os << "\n";
+  }
+  return os.str();
+}
+
+std::string Net::InfoGradient() const {
+  std::ostringstream os;
+  std::vector<float> c;
+  GetArena(corr_, &c);
+  int64 o = 0;
+  os << "### Gradient stats :\n";
+  for (size_t i = 0; i < layers_.size(); i++) {
+    if (layer_offset_[i] < 0) continue;
+    TrainableLayer *tl = dynamic_cast<TrainableLayer *>(layers_[i]);
+    os << "Layer " << i + 1 << " : " << Layer::TypeToMarker(layers_[i]->GetType()) << ", corr_"
+       << Moments(c, o, tl->NumParams()) << "\n";
+    o += tl->NumParams();
+  }
+  return os.str();
+}
+
+// ------------------------------------------------------------------------------------ Ctc
+template <typename Tp>
+static void GrowDevice(Tp **p, size_t *cap, size_t need) {
+  if (need <= *cap) return;
+  if (*p) { CU_CHECK(cudaStreamSynchronize(Stream())); CU_CHECK(cudaFree(*p)); }
+  size_t want = need + need / 4 + 16;
+  CU_CHECK(cudaMalloc((void **)p, sizeof(Tp) * want));
+  *cap = want;
+}
+template <typename Tp>
+static void GrowPinned(Tp **p, size_t *cap, size_t need) {
+  if (need <= *cap) return;
+  if (*p) { CU_CHECK(cudaStreamSynchronize(Stream())); CU_CHECK(cudaFreeHost(*p)); }
+  size_t want = need + need / 4 + 16;
+  CU_CHECK(cudaMallocHost((void **)p, sizeof(Tp) * want));
+  *cap = want;
+}
+
+Ctc::Ctc(eesen_b200_ctx *ctx) : ctx_(ctx) { g_ctx = ctx; }
+
+Ctc::~Ctc() {
+  if (d_len_) cudaFree(d_len_);
+  if (d_argmax_) cudaFree(d_argmax_);
+  if (h_argmax_) cudaFreeHost(h_argmax_);
+  if (h_pzx_) cudaFreeHost(h_pzx_);
+}
+
+// label staging: [S x max_lab] padded matrix + lengths (the reference uploads the expanded
+// S x (2*max+1) matrix on every one of its 2T kernel launches, cuda-matrix.cc:882-883,948-950)
+void Ctc::Upload(const std::vector<int32> &frame_num_utt, std::vector<std::vector<int32> > &label) {
+  int32 S = frame_num_utt.size();
+  KALDI_ASSERT((int32)label.size() >= S);
+  max_lab_ = 1;
+  for (int32 s = 0; s < S; s++) max_lab_ = std::max<int32>(max_lab_, label[s].size());
+  // one buffer: [len S][lablen S][pzx S as float][labels S*max_lab]
+  size_t ints = (size_t)3 * S + (size_t)S * max_lab_;
+  GrowDevice(&d_len_, &cap_len_, ints);
+  std::vector<int32> h(ints, 0);
+  for (int32 s = 0; s < S; s++) {
+    h[s] = frame_num_utt[s];
+    h[S + s] = label[s].size();
+    for (size_t l = 0; l < label[s].size(); l++) h[3 * S + (size_t)s * max_lab_ + l] = label[s][l];
+  }
+  CU_CHECK(cudaMemcpyAsync(d_len_, h.data(), sizeof(int32) * ints, cudaMemcpyHostToDevice, Stream()));
+  d_lablen_ = d_len_ + S;
+  d_pzx_ = reinterpret_cast<float *>(d_len_ + 2 * S);
+  d_lab_ = nullptr;  // labels live inside the same buffer
+}
+
+void Ctc::EvalParallelAsync(const std::vector<int32> &frame_num_utt, const CuMatrixBase<BaseFloat> &net_out,
+                            std::vector<std::vector<int32> > &label, CuMatrix<BaseFloat> *diff) {
+  g_ctx = ctx_;
+  if (pending_eval_) Finish(NULL);
+  diff->Resize(net_out.NumRows(), net_out.NumCols(), kUndefined);
+  int32 S = frame_num_utt.size();
+  int32 num_frames = net_out.NumRows();
+  KALDI_ASSERT(S > 0 && num_frames % S == 0);
+  int32 T = num_frames / S;
+  Upload(frame_num_utt, label);
+  CheckAbi(ctx_, eesen_b200_ctc_eval(ctx_, T, S, net_out.NumCols(), max_lab_, d_len_, d_len_ + 3 * S, d_lablen_,
+                                     net_out.Data(), net_out.Stride(), d_pzx_, diff->Data(), diff->Stride()),
+           "eesen_b200_ctc_eval");
+  GrowPinned(&h_pzx_, &cap_hpzx_, (size_t)S);
+  CU_CHECK(cudaMemcpyAsync(h_pzx_, d_pzx_, sizeof(float) * S, cudaMemcpyDeviceToHost, Stream()));
+  p_frames_ = frame_num_utt;
+  p_S_ = S;
+  pending_eval_ = true;
+}
+
+void Ctc::ErrorRateMSeqAsync(const std::vector<int> &frame_num_utt, const CuMatrixBase<BaseFloat> &net_out,
+                             std::vector<std::vector<int> > &label) {
+  g_ctx = ctx_;
+  if (pending_err_) Finish(NULL);
+  int32 rows = net_out.NumRows();
+  GrowDevice(&d_argmax_, &cap_arg_, (size_t)rows);
+  GrowPinned(&h_argmax_, &cap_harg_, (size_t)rows);
+  CheckAbi(ctx_, eesen_b200_row_argmax(ctx_, rows, net_out.NumCols(), net_out.Data(), net_out.Stride(), d_argmax_),
+           "eesen_b200_row_argmax");
+  CU_CHECK(cudaMemcpyAsync(h_argmax_, d_argmax_, sizeof(int) * rows, cudaMemcpyDeviceToHost, Stream()));
+  p_frames_ = frame_num_utt;
+  p_labels_ = label;
+  p_S_ = frame_num_utt.size();
+  p_rows_ = rows;
+  pending_err_ = true;
+}
+
+// util/edit-distance-inl.h:28-75
+static int32 LevenshteinEditDistance(const std::vector<int32> &a, const std::vector<int32> &b) {
+  std::vector<int32> prev(b.size() + 1), cur(b.size() + 1);
+  for (size_t j = 0; j <= b.size(); j++) prev[j] = j;
+  for (size_t i = 1; i <= a.size(); i++) {
+    cur[0] = i;
+    for (size_t j = 1; j <= b.size(); j++)
+      cur[j] = std::min(std::min(prev[j] + 1, cur[j - 1] + 1), prev[j - 1] + (a[i - 1] != b[j - 1] ? 1 : 0));
+    prev.swap(cur);
+  }
+  return prev[b.size()];
+}
+
+void Ctc::Finish(double stats[4]) {
+  if (!pending_eval_ && !pending_err_) { if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0; return; }
+  CU_CHECK(cudaStreamSynchronize(Stream()));
+  double obj = 0, err_batch = 0, ref_batch = 0, frames_batch = 0;
+  if (pending_eval_) {
+    pzx_host_.assign(h_pzx_, h_pzx_ + p_S_);
+    for (int32 s = 0; s < p_S_; s++) obj += pzx_host_[s];
+    obj_progress_ += obj;                      // ctc-loss.cc:171-177
+    sequences_progress_ += p_S_;
+    sequences_num_ += p_S_;
+    for (int32 s = 0; s < p_S_; s++) { frames_progress_ += p_frames_[s]; frames_ += p_frames_[s]; frames_batch += p_frames_[s]; }
+  }
+  if (pending_err_) {
+    // ctc-loss.cc:250-282: per sequence, collapse repeats, drop blanks, edit distance
+    int32 S = p_S_;
+    for (int32 s = 0; s < S; s++) {
+      int32 nf = p_frames_[s];
+      std::vector<int32> hyp;
+      int32 prev = -1;
+      for (int32 f = 0; f < nf; f++) {
+        int32 c = h_argmax_[(size_t)f * S + s];
+        if (c != prev && c != 0) hyp.push_back(c);
+        prev = c;
+      }
+      int32 e = LevenshteinEditDistance(p_labels_[s], hyp);
+      err_batch += e;
+      ref_batch += p_labels_[s].size();
+    }
+    error_num_ += err_batch; ref_num_ += ref_batch;
+    error_num_progress_ += err_batch; ref_num_progress_ += ref_batch;
+  }
+  if (pending_eval_ && sequences_progress_ >= report_step_) {   // ctc-loss.cc:180-192
+    KALDI_VLOG(1) << "After " << sequences_num_ << " sequences (" << frames_ / (100.0 * 3600) << "Hr): "
+                  << "Obj(log[Pzx]) = " << obj_progress_ / sequences_progress_
+                  << "   TokenAcc = " << 100.0 * (1.0 - error_num_progress_ / ref_num_progress_) << "%";
+    sequences_progress_ = 0; frames_progress_ = 0; obj_progress_ = 0.0;
+    error_num_progress_ = 0; ref_num_progress_ = 0;
+  }
+  pending_eval_ = pending_err_ = false;
+  if (stats) { stats[0] = obj; stats[1] = err_batch; stats[2] = ref_batch; stats[3] = frames_batch; }
+}
+
+void Ctc::EvalParallel(const std::vector<int32> &frame_num_utt, const CuMatrixBase<BaseFloat> &net_out,
+                       std::vector<std::vector<int32> > &label, CuMatrix<BaseFloat> *diff) {
+  EvalParallelAsync(frame_num_utt, net_out, label, diff);
+  // statistics are folded lazily (Finish) so that ErrorRateMSeq can share the single host sync;
+  // a caller that never calls ErrorRateMSeq/Report still gets them at the next Eval/Report.
+}
+
+void Ctc::ErrorRateMSeq(const std::vector<int> &frame_num_utt, const CuMatrixBase<BaseFloat> &net_out,
+                        std::vector<std::vector<int> > &label, std::string &out) {
+  ErrorRateMSeqAsync(frame_num_utt, net_out, label);
+  if (out.length()) {
+    Finish(NULL);
+    // ctc-loss.cc:283-291: hypothesis with frame index and probability, appended to `out`
+    std::ofstream output(out.c_str(), std::ofstream::out | std::ofstream::app);
+    std::vector<float> host((size_t)net_out.NumRows() * net_out.NumCols());
+    net_out.CopyToHost(host.data(), net_out.NumCols());
+    int32 S = frame_num_utt.size();
+    for (int32 s = 0; s < S; s++) {
+      output << "utt";
+      int32 prev = -1;
+      for (int32 f = 0; f < frame_num_utt[s]; f++) {
+        int32 c = h_argmax_[(size_t)f * S + s];
+        if (c != prev && c != 0)
+          output << " | " << c << " " << f << " " << host[((size_t)f * S + s) * net_out.NumCols() + c];
+        prev = c;
+      }
+      output << "\n";
+    }
+  }
+}
+
+std::string Ctc::Report() {
+  Finish(NULL);
+  std::ostringstream oss;
+  oss << "\nTOKEN_ACCURACY >> " << 100.0 * (1.0 - error_num_ / ref_num_) << "% <<";
+  return oss.str();
+}
+
+}  // namespace eesen

@@ -1,0 +1,216 @@
+// eesen_b200/host/train-ctc-parallel.cc -- the training driver, host logic as in the reference
+// (src/netbin/train-ctc-parallel.cc:30-264): same usage line, options, batching/padding rule,
+// per-batch call sequence on Net/Ctc and log lines (the recipes grep "TOKEN_ACCURACY" and the fps
+// line, asr_egs/wsj/steps/train_ctc_parallel.sh:146,158).  What changes (north_star):
+//   * no CuDevice::SelectGpuId / per-call sync: one eesen_b200 context per process;
+//   * --num-jobs/--job-id select NCCL ranks: every step all-reduces the gradient over NVLink
+//     instead of averaging model files every --utts-per-avg utterances
+//     (src/net/communicator.h:39-119).  The NCCL unique id is exchanged through the file
+//     <model-out>.ncclid written by job 1 (the same shared-filesystem rendezvous the reference uses).
+#include <unistd.h>
+
+#include <chrono>
+#include <cstring>
+#include <fstream>
+
+#include "net.h"
+
+using namespace eesen;
+
+struct Options {
+  std::map<std::string, std::string> kv;
+  std::vector<std::string> args;
+  bool Has(const std::string &k) const { return kv.count(k) > 0; }
+  std::string Str(const std::string &k, const std::string &d) const { return Has(k) ? kv.at(k) : d; }
+  double Num(const std::string &k, double d) const { return Has(k) ? atof(kv.at(k).c_str()) : d; }
+  bool Bool(const std::string &k, bool d) const {
+    if (!Has(k)) return d;
+    const std::string &v = kv.at(k);
+    return v == "" || v == "true" || v == "1" || v == "yes";
+  }
+};
+
+static const char *kUsage =
+    "Perform one iteration of CTC training by SGD.\n"
+    "The updates are done per-utterance and by processing multiple utterances in parallel.\n"
+    "\n"
+    "Usage: train-ctc-parallel [options] <feature-rspecifier> <labels-rspecifier> <model-in> [<model-out>]\n"
+    "e.g.: \n"
+    "train-ctc-parallel scp:feature.scp ark:labels.ark nnet.init nnet.iter1\n"
+    "Options: --learn-rate --momentum --binary --cross-validate --num-sequence --frame-limit --report-step\n"
+    "         --num-jobs --job-id --opt-algorithm=SGD --sequence-out-file --verbose\n"
+    "         --gemm-precision=fp32x3|tf32|bf16 --recurrent-precision=fp32x3|tf32\n";
+
+static int PrecFromString(const std::string &s) {
+  if (s == "fp32x3" || s == "0") return 0;
+  if (s == "tf32" || s == "1") return 1;
+  if (s == "bf16" || s == "2") return 2;
+  KALDI_ERR << "unknown precision " << s;
+  return 0;
+}
+
+int main(int argc, char *argv[]) {
+  try {
+    Options po;
+    for (int i = 1; i < argc; i++) {
+      std::string a = argv[i];
+      if (a.size() > 2 && a[0] == '-' && a[1] == '-') {
+        size_t eq = a.find('=');
+        if (eq == std::string::npos) po.kv[a.substr(2)] = "";
+        else po.kv[a.substr(2, eq - 2)] = a.substr(eq + 1);
+      } else {
+        po.args.push_back(a);
+      }
+    }
+    if (po.Has("config")) {
+      std::ifstream cf(po.kv["config"].c_str());
+      std::string line;
+      while (std::getline(cf, line)) {
+        size_t h = line.find('#');
+        if (h != std::string::npos) line.resize(h);
+        size_t b = line.find("--");
+        if (b == std::string::npos) continue;
+        line = line.substr(b + 2);
+        while (!line.empty() && isspace(line[line.size() - 1])) line.resize(line.size() - 1);
+        size_t eq = line.find('=');
+        std::string k = eq == std::string::npos ? line : line.substr(0, eq);
+        if (!po.kv.count(k)) po.kv[k] = eq == std::string::npos ? "" : line.substr(eq + 1);
+      }
+    }
+    g_verbose_level = (int)po.Num("verbose", 0);
+
+    NetTrainOptions trn_opts;
+    trn_opts.learn_rate = po.Num("learn-rate", trn_opts.learn_rate);
+    trn_opts.momentum = po.Num("momentum", trn_opts.momentum);
+    bool binary = po.Bool("binary", true), crossvalidate = po.Bool("cross-validate", false);
+    std::string sequence_out_file = po.Str("sequence-out-file", "");
+    int32 num_sequence = (int32)po.Num("num-sequence", 5);
+    double frame_limit = po.Num("frame-limit", 100000);
+    int32 report_step = (int32)po.Num("report-step", 100);
+    int32 num_jobs = (int32)po.Num("num-jobs", 1), job_id = (int32)po.Num("job-id", 1);
+    std::string opt = po.Str("opt-algorithm", "SGD");
+
+    if ((int)po.args.size() != 4 - (crossvalidate ? 1 : 0)) {
+      std::cerr << kUsage;
+      return 1;
+    }
+    std::string feature_rspecifier = po.args[0], targets_rspecifier = po.args[1], model_filename = po.args[2];
+    std::string target_model_filename = crossvalidate ? "" : po.args[3];
+
+    eesen_b200_ctx *ctx = NULL;
+    int rc = eesen_b200_create(&ctx, num_jobs > 1 ? job_id - 1 : -1);
+    if (rc) KALDI_ERR << "eesen_b200_create failed: " << eesen_b200_last_error(NULL);
+    CheckAbi(ctx, eesen_b200_set_precision(ctx, PrecFromString(po.Str("gemm-precision", "fp32x3")),
+                                           PrecFromString(po.Str("recurrent-precision", "fp32x3"))),
+             "eesen_b200_set_precision");
+    if (num_jobs > 1) {
+      std::string idfile = (crossvalidate ? model_filename + ".cv" : target_model_filename) + ".ncclid";
+      char id[128];
+      if (job_id == 1) {
+        if (eesen_b200_nccl_unique_id(id)) KALDI_ERR << "ncclGetUniqueId failed";
+        std::string tmp = idfile + ".tmp";
+        { std::ofstream f(tmp.c_str(), std::ios::binary); f.write(id, 128); }
+        std::rename(tmp.c_str(), idfile.c_str());
+      } else {
+        for (int tries = 0;; tries++) {
+          std::ifstream f(idfile.c_str(), std::ios::binary);
+          if (f.is_open() && f.read(id, 128)) break;
+          if (tries > 200000) KALDI_ERR << "timed out waiting for " << idfile;
+          usleep(300);
+        }
+      }
+      CheckAbi(ctx, eesen_b200_nccl_init(ctx, job_id - 1, num_jobs, id), "eesen_b200_nccl_init");
+      if (job_id == 1) { usleep(200000); }
+    }
+
+    {
+      Net net(ctx);
+      net.Read(model_filename);
+      net.SetTrainOptions(trn_opts);
+      net.SetUpdateAlgorithm(opt);
+      if (crossvalidate) net.SetTestMode(); else net.SetTrainMode();
+
+      int64 total_frames = 0;
+      SequentialBaseFloatMatrixReader feature_reader(feature_rspecifier);
+      RandomAccessInt32VectorReader targets_reader(targets_rspecifier);
+
+      Ctc ctc(ctx);
+      ctc.SetReportStep(report_step);
+      CuMatrix<BaseFloat> net_out, obj_diff;
+
+      auto t_start = std::chrono::steady_clock::now();
+      KALDI_LOG << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << " STARTED";
+      if (sequence_out_file.length()) std::remove(sequence_out_file.c_str());
+
+      std::vector<HostMatrix> feats_utt(num_sequence);
+      std::vector<std::vector<int> > labels_utt(num_sequence);
+      int32 feat_dim = net.InputDim();
+      int32 num_done = 0, num_no_tgt_mat = 0, num_other_error = 0;
+      HostMatrix feat_mat_host;
+
+      while (1) {
+        // ---- gather up to num_sequence utterances under the frame limit (train-ctc-parallel.cc:146-184)
+        std::vector<int> frame_num_utt;
+        int32 sequence_index = 0, max_frame_num = 0;
+        for (; !feature_reader.Done(); feature_reader.Next()) {
+          std::string utt = feature_reader.Key();
+          if (!targets_reader.HasKey(utt)) {
+            KALDI_WARN << utt << ", missing targets";
+            num_no_tgt_mat++;
+            continue;
+          }
+          const HostMatrix &mat = feature_reader.Value();
+          if (mat.rows > frame_limit) {
+            KALDI_WARN << utt << ", has too many frames; ignoring: " << mat.rows << " > " << frame_limit;
+            continue;
+          }
+          if (mat.cols != feat_dim) KALDI_ERR << utt << ": feature dim " << mat.cols << " != net input " << feat_dim;
+          int new_max = std::max<int>(max_frame_num, mat.rows);
+          if (new_max * (double)(frame_num_utt.size() + 1) > frame_limit) break;  // does not fit in this batch
+          max_frame_num = new_max;
+          feats_utt[sequence_index] = mat;
+          labels_utt[sequence_index] = targets_reader.Value(utt);
+          frame_num_utt.push_back(mat.rows);
+          sequence_index++;
+          if ((int32)frame_num_utt.size() == num_sequence) { feature_reader.Next(); break; }
+        }
+        int32 cur_sequence_num = frame_num_utt.size();
+        if (cur_sequence_num == 0) break;
+
+        // ---- pad + interleave: row t*S+s (:186-193)
+        feat_mat_host.Resize(cur_sequence_num * max_frame_num, feat_dim);
+        for (int s = 0; s < cur_sequence_num; s++)
+          for (int r = 0; r < frame_num_utt[s]; r++)
+            memcpy(feat_mat_host.Row(r * cur_sequence_num + s), feats_utt[s].Row(r), sizeof(float) * feat_dim);
+
+        net.SetSeqLengths(frame_num_utt);                                          // :195
+        net.Propagate(CuMatrix<BaseFloat>(feat_mat_host), &net_out);               // :198
+        std::vector<std::vector<int> > labels_cur(labels_utt.begin(), labels_utt.begin() + cur_sequence_num);
+        ctc.EvalParallel(frame_num_utt, net_out, labels_cur, &obj_diff);           // :199
+        ctc.ErrorRateMSeq(frame_num_utt, net_out, labels_cur, sequence_out_file);  // :202
+        if (!crossvalidate) net.Backpropagate(obj_diff, NULL);                     // :207 (+ NCCL all-reduce inside)
+
+        num_done += cur_sequence_num;
+        total_frames += feat_mat_host.rows;
+        if (feature_reader.Done()) break;
+      }
+
+      std::string report = ctc.Report();  // also drains the stream
+      if (!crossvalidate) {
+        KALDI_LOG << net.Info();
+        KALDI_LOG << net.InfoGradient();
+        if (num_jobs == 1 || job_id == 1) net.Write(target_model_filename, binary);
+      }
+      double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+      KALDI_LOG << "Done " << num_done << " files, " << num_no_tgt_mat << " with no targets, " << num_other_error
+                << " with other errors. [" << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << ", "
+                << elapsed / 60 << " min, fps" << total_frames / elapsed << "]";
+      KALDI_LOG << report;
+    }
+    eesen_b200_destroy(ctx);
+    return 0;
+  } catch (const std::exception &e) {
+    std::cerr << e.what();
+    return -1;
+  }
+}

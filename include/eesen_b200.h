@@ -1,0 +1,170 @@
+/* include/eesen_b200.h -- C ABI of the B200-native Eesen CTC-training hot path.
+ *
+ * The drop-in boundary.  Plain pointers and sizes only; no C++ or
+ * torch types.  Every entry point returns 0 on success or a non-zero code (the CUDA/NCCL
+ * error value, or EESEN_B200_E*); eesen_b200_last_error() returns the message.  The C++
+ * host mirror (eesen_b200/host, namespace eesen: Net / Layer / BiLstmParallel / Ctc, same
+ * method names and argument meaning as the reference) turns a non-zero code into a
+ * std::runtime_error, matching the reference convention that any CUDA failure throws
+ * (reference src/gpucompute/cuda-common.h:37-44 CU_SAFE_CALL -> KALDI_ERR).
+ *
+ * There is NO CPU fallback: without a CUDA device eesen_b200_create() fails.
+ *
+ * Conventions at the seam (reference src/netbin/train-ctc-parallel.cc:186-193):
+ *   packed minibatch, time-major interleaved: row r = t*S + s (frame t of utterance s),
+ *   zero padded to T frames; fp32 row-major; leading dimensions (ld*) are in floats and
+ *   must be multiples of 4 (16-byte rows) -- the reference's cudaMallocPitch strides satisfy
+ *   this; blank = class 0, labels are 1-based, padded label cells are ignored.
+ *   All device pointers must be 16-byte aligned.  Calls are stream-ordered on the context's
+ *   stream and asynchronous unless stated; one context per process/GPU, not thread-safe
+ *   (same contract as the reference's singleton CuDevice, src/gpucompute/cuda-device.h:47,128).
+ */
+#ifndef EESEN_B200_H_
+#define EESEN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EESEN_B200_EINVAL 100001   /* bad argument */
+#define EESEN_B200_ENOGPU 100002   /* no CUDA device / kernel image unusable on this device */
+#define EESEN_B200_ENCCL 100003    /* NCCL unavailable or failed */
+#define EESEN_B200_EIO 100004      /* model / archive I/O error */
+#define EESEN_B200_ESHAPE 100005   /* shape not supported by the resident-weight recurrent kernels */
+
+/* Arithmetic of the tensor-core contractions (storage is always fp32):
+ *   0 = 3xTF32 split (fp32-faithful, default)   1 = TF32   2 = BF16 (dense GEMMs only) */
+#define EESEN_B200_PREC_FP32X3 0
+#define EESEN_B200_PREC_TF32 1
+#define EESEN_B200_PREC_BF16 2
+
+typedef struct eesen_b200_ctx eesen_b200_ctx;
+typedef struct eesen_b200_net eesen_b200_net;
+
+/* ---------------------------------------------------------------- context (replaces CuDevice,
+ * reference src/gpucompute/cuda-device.{h,cc}: SelectGpuId :64-168, allocator :473-816) */
+int eesen_b200_create(eesen_b200_ctx **ctx, int device /* -1: LOCAL_RANK or 0 */);
+void eesen_b200_destroy(eesen_b200_ctx *ctx);
+const char *eesen_b200_last_error(const eesen_b200_ctx *ctx /* may be NULL: last create() error */);
+int eesen_b200_set_precision(eesen_b200_ctx *ctx, int gemm_precision, int recurrent_precision);
+int eesen_b200_synchronize(eesen_b200_ctx *ctx);
+void *eesen_b200_stream(eesen_b200_ctx *ctx); /* cudaStream_t */
+int eesen_b200_sm_count(const eesen_b200_ctx *ctx);
+/* number of kernels this library launched on the context so far (bench.py "gpu_launches") */
+long eesen_b200_launch_count(const eesen_b200_ctx *ctx);
+
+/* ---------------------------------------------------------------- level 1: device operators */
+
+/* C = alpha*op(A)*op(B) + beta*C.  Replaces CuMatrixBase::AddMatMat -> cublasSgemm
+ * (reference src/gpucompute/cuda-matrix.cc:603-639).  transA/transB: 0 = as stored, 1 = transposed;
+ * (1,1) is not provided (unused by the path). */
+int eesen_b200_gemm(eesen_b200_ctx *ctx, int transA, int transB, int M, int N, int K, float alpha,
+                    const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc);
+
+/* Parameters of one BiLSTM layer, both directions ([0] = forward cells, [1] = backward cells), in
+ * the reference's shapes (src/net/bilstm-layer.h:187-210): wx[4C x I], wm[4C x C], bias[4C],
+ * peepholes pi/pf/po[C]; gate row blocks in the order g, i, f, o. */
+typedef struct {
+  const float *wx[2], *wm[2], *bias[2], *pi[2], *pf[2], *po[2];
+} eesen_b200_bilstm_params;
+typedef struct {
+  float *wx[2], *wm[2], *bias[2], *pi[2], *pf[2], *po[2];
+} eesen_b200_bilstm_grads;
+
+/* BiLstmParallel::PropagateFnc (reference src/net/bilstm-parallel-layer.h:379-420).
+ *   x     [T*S x I] (ldx)          in
+ *   gates [T*S x 8C] (ld = 8C)     out: post-activation g,i,f,o; forward cells cols [0,4C), backward [4C,8C)
+ *   cell  [T*S x 2C] (ld = 2C)     out: cell state c (fw | bw)
+ *   out   [T*S x 2C] (ldo)         out: m = o*tanh(c) (fw | bw) -- the layer output
+ * gates/cell are what the reference keeps in propagate_buf_{fw,bw}_ (h = tanh(c) is recomputed). */
+int eesen_b200_bilstm_forward(eesen_b200_ctx *ctx, int T, int S, int I, int C, const int *d_len,
+                              const float *x, int ldx, const eesen_b200_bilstm_params *p, float *gates,
+                              float *cell, float *out, int ldo);
+
+/* BiLstmParallel::BackpropagateFnc (reference :881-913, :422-602).  dgates [T*S x 8C] is scratch/out
+ * (the DGIFO blocks of backpropagate_buf_); dx may be NULL (first layer).  grads receives the RAW
+ * gradient sums over all rows (no momentum: corr = grad + momentum*corr is applied by
+ * eesen_b200_sgd_update after the data-parallel all-reduce). */
+int eesen_b200_bilstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, const float *x, int ldx,
+                               const eesen_b200_bilstm_params *p, const float *gates, const float *cell,
+                               const float *out, int ldo, const float *dout, int ldd, float *dgates,
+                               float *dx, int lddx, const eesen_b200_bilstm_grads *grads);
+
+/* AffineTransform::PropagateFnc / BackpropagateFnc / gradient part of Update
+ * (reference src/net/affine-trans-layer.h:161-166, 168-172, 182-183).  W[K x D], b[K]. */
+int eesen_b200_affine_forward(eesen_b200_ctx *ctx, int N, int D, int K, const float *x, int ldx,
+                              const float *W, const float *b, float *y, int ldy);
+int eesen_b200_affine_backward(eesen_b200_ctx *ctx, int N, int D, int K, const float *x, int ldx,
+                               const float *diff, int lddiff, const float *W, float *dx, int lddx,
+                               float *dW, float *db);
+
+/* Softmax::PropagateFnc (reference src/net/softmax-layer.h:44-47); argmax may be NULL, else
+ * receives FindRowMaxId (src/gpucompute/cuda-matrix.cc:1038-1095) of each row.  Columns
+ * [K, ldp) of probs are zeroed. */
+int eesen_b200_softmax(eesen_b200_ctx *ctx, int N, int K, const float *logits, int ld, float *probs,
+                       int ldp, int *d_argmax);
+int eesen_b200_row_argmax(eesen_b200_ctx *ctx, int N, int K, const float *x, int ld, int *d_argmax);
+
+/* Ctc::EvalParallel compute (reference src/net/ctc-loss.cc:101-168).
+ *   probs    [T*S x K] (ldp) softmax outputs           d_len[S] valid frames
+ *   d_labels [S x max_lab] int32, row s holds d_lab_len[s] labels (1-based), rest ignored
+ *   pzx[S]   out: log p(z|x) per utterance             diff [T*S x K] (ldd) out: d(-log p)/d(logits) */
+int eesen_b200_ctc_eval(eesen_b200_ctx *ctx, int T, int S, int K, int max_lab, const int *d_len,
+                        const int *d_labels, const int *d_lab_len, const float *probs, int ldp,
+                        float *pzx, float *diff, int ldd);
+
+/* Momentum + clip + SGD over a contiguous arena (reference src/net/bilstm-layer.h:846-883,
+ * affine-trans-layer.h:182-195):  corr = grad + momentum*corr; clamp(corr, +-max_grad); w -= lr*corr.
+ * segments (host memory) partition [0, n): lr = learn_rate*learn_rate_coef, max_grad <= 0 disables clipping. */
+typedef struct {
+  int64_t offset, count;
+  float lr, max_grad;
+} eesen_b200_sgd_segment;
+int eesen_b200_sgd_update(eesen_b200_ctx *ctx, float *w, float *corr, const float *grad, int64_t n,
+                          float momentum, const eesen_b200_sgd_segment *segments, int nseg);
+
+/* ---------------------------------------------------------------- data parallelism (new; replaces the
+ * file-system model averaging of reference src/net/communicator.h:39-119 with one gradient all-reduce) */
+int eesen_b200_nccl_unique_id(char id[128]);
+int eesen_b200_nccl_init(eesen_b200_ctx *ctx, int rank, int nranks, const char id[128]);
+int eesen_b200_allreduce_sum(eesen_b200_ctx *ctx, float *buf, int64_t n);
+int eesen_b200_world(const eesen_b200_ctx *ctx, int *rank, int *nranks);
+
+/* ---------------------------------------------------------------- level 2: the Net/Ctc host mirror
+ * (what src/netbin/train-ctc-parallel.cc:112-119,195-207,244 calls) */
+int eesen_b200_net_read(eesen_b200_ctx *ctx, const char *model_path, eesen_b200_net **net); /* Net::Read */
+int eesen_b200_net_write(eesen_b200_net *net, const char *path, int binary);               /* Net::Write */
+void eesen_b200_net_free(eesen_b200_net *net);
+int eesen_b200_net_set_train_options(eesen_b200_net *net, float learn_rate, float momentum); /* SetTrainOptions */
+int eesen_b200_net_dims(const eesen_b200_net *net, int *in_dim, int *out_dim, int *num_layers, int64_t *num_params);
+
+/* One minibatch exactly as the reference driver does it (train-ctc-parallel.cc:195-207):
+ * SetSeqLengths, Propagate (H2D copy of the packed features included), Ctc::EvalParallel,
+ * Ctc::ErrorRateMSeq, and -- if train != 0 -- Backpropagate with the gradient all-reduce (when NCCL
+ * is initialised) and the parameter update.  HOST inputs; blocks until the statistics are back.
+ *   feats [T*S x I] packed, frames[S], labels: concatenated, lab_len[S]
+ *   stats out: [0] sum_s log p(z|x)  [1] token errors  [2] reference tokens  [3] valid frames */
+int eesen_b200_net_train_step(eesen_b200_net *net, const float *feats, int T, int S, const int *frames,
+                              const int *labels, const int *lab_len, int train, double stats[4]);
+/* Same step with inputs ALREADY RESIDENT on the device (d_feats [T*S x I], ld = I); asynchronous:
+ * statistics stay on the device until eesen_b200_net_read_stats. */
+int eesen_b200_net_train_step_device(eesen_b200_net *net, const float *d_feats, int T, int S,
+                                     const int *frames, const int *labels, const int *lab_len, int train);
+int eesen_b200_net_read_stats(eesen_b200_net *net, double stats[4]);
+
+/* Introspection for the parity tests (host copies, synchronous).  which:
+ *   0..L    Net::propagate_buf_[which]     (layer inputs/outputs, L = num_layers)
+ *   100     obj_diff (CTC gradient wrt logits)      101  per-utterance pzx [S]
+ *   102     in_diff  (gradient wrt the network input)
+ *   200     parameters   201 momentum buffers (corr)   202 raw gradients of the last step (after all-reduce)
+ * rows/cols describe the logical matrix; data may be NULL to query the shape only. */
+int eesen_b200_net_get(eesen_b200_net *net, int which, float *data, int64_t capacity, int *rows, int *cols);
+int eesen_b200_net_set_params(eesen_b200_net *net, const float *flat, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EESEN_B200_H_ */

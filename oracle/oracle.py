@@ -1,0 +1,245 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes front-end to the CPU restatement (oracle/cpu_ref.c -> oracle/_ref/liboracle_f{32,64}.so)
+plus a runner for the UNMODIFIED reference binaries (oracle/_ref/ref_dump_{cpu,gpu}).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+import this module; the product (eesen_b200/) never does.
+
+`train_step` strings the restated ops together exactly as train-ctc-parallel.cc:195-207 +
+Net::Propagate/Backpropagate (net.cc:67-108) do.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import subprocess
+import tempfile
+from typing import Dict, List, Optional
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFDIR = os.path.join(HERE, "_ref")
+
+
+def build(quiet: bool = True) -> None:
+    """Compile the restatement (always) and the reference binaries (when /root/reference exists)."""
+    cmd = ["make", "-C", HERE, "-j8", "all"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+
+
+class _Lib:
+    def __init__(self, dtype):
+        self.dtype = np.dtype(dtype)
+        name = "liboracle_f32.so" if self.dtype == np.float32 else "liboracle_f64.so"
+        path = os.path.join(REFDIR, name)
+        if not os.path.exists(path):
+            build()
+        self.lib = C.CDLL(path)
+        assert self.lib.oracle_real_size() == self.dtype.itemsize
+        self.real = C.c_float if self.dtype == np.float32 else C.c_double
+
+    def arr(self, a):
+        a = np.ascontiguousarray(a, self.dtype)
+        return a
+
+    @staticmethod
+    def p(a):
+        return a.ctypes.data_as(C.c_void_p)
+
+    def pp(self, arrs):
+        t = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        return t
+
+
+_LIBS: Dict[str, _Lib] = {}
+
+
+def lib(dtype=np.float32) -> _Lib:
+    k = np.dtype(dtype).name
+    if k not in _LIBS:
+        _LIBS[k] = _Lib(dtype)
+    return _LIBS[k]
+
+
+def ctc_eval(y: np.ndarray, frames, labels: List[np.ndarray], S: int, dtype=np.float32, want_ab=False):
+    L = lib(dtype)
+    y = L.arr(y)
+    N, K = y.shape
+    T = N // S
+    frames = np.ascontiguousarray(frames, np.int32)
+    lab_len = np.array([len(l) for l in labels], np.int32)
+    flat = np.concatenate([np.asarray(l, np.int32) for l in labels]) if lab_len.sum() else np.zeros(1, np.int32)
+    flat = np.ascontiguousarray(flat, np.int32)
+    pzx = np.zeros(S, L.dtype)
+    diff = np.zeros((N, K), L.dtype)
+    Lp = 2 * int(lab_len.max()) + 1
+    alpha = np.zeros((N, Lp), L.dtype) if want_ab else None
+    beta = np.zeros((N, Lp), L.dtype) if want_ab else None
+    L.lib.oracle_ctc_eval_parallel(T, S, K, L.p(frames), L.p(flat), L.p(lab_len), L.p(y), L.p(pzx), L.p(diff),
+                                   L.p(alpha) if want_ab else None, L.p(beta) if want_ab else None)
+    return pzx, diff, alpha, beta
+
+
+def softmax(x: np.ndarray, dtype=np.float32) -> np.ndarray:
+    L = lib(dtype)
+    x = L.arr(x)
+    y = np.empty_like(x)
+    L.lib.oracle_softmax(x.shape[0], x.shape[1], L.p(x), L.p(y))
+    return y
+
+
+class OracleNet:
+    """Holds parameters + momentum buffers in the oracle's precision and runs train steps."""
+
+    def __init__(self, net, dtype=np.float32):
+        self.L = lib(dtype)
+        self.spec = net
+        self.params = [{n: self.L.arr(l.params[n]).copy() for n in l.param_names()} for l in net.layers]
+        self.corr = [{n: np.zeros_like(v) for n, v in p.items()} for p in self.params]
+
+    def forward(self, feats, frames):
+        L = self.L
+        S = len(frames)
+        frames = np.ascontiguousarray(frames, np.int32)
+        x = L.arr(feats)
+        N = x.shape[0]
+        T = N // S
+        acts = [x]
+        self.bufs = []
+        for li, l in enumerate(self.spec.layers):
+            p = self.params[li]
+            if l.kind == "bilstm":
+                Cc = l.cells
+                buf_fw = np.zeros(((T + 2) * S, 7 * Cc), L.dtype)
+                buf_bw = np.zeros(((T + 2) * S, 7 * Cc), L.dtype)
+                out = np.zeros((N, 2 * Cc), L.dtype)
+                plist = [p[n] for n in l.param_names()]
+                L.lib.oracle_bilstm_forward(T, S, l.in_dim, Cc, L.p(frames), L.p(acts[-1]), L.pp(plist),
+                                            L.p(buf_fw), L.p(buf_bw), L.p(out))
+                self.bufs.append((buf_fw, buf_bw))
+                acts.append(out)
+            elif l.kind == "affine":
+                out = np.zeros((N, l.out_dim), L.dtype)
+                L.lib.oracle_affine_forward(N, l.in_dim, l.out_dim, L.p(acts[-1]), L.p(p["w"]), L.p(p["b"]), L.p(out))
+                self.bufs.append(None)
+                acts.append(out)
+            elif l.kind == "softmax":
+                out = np.zeros((N, l.out_dim), L.dtype)
+                L.lib.oracle_softmax(N, l.out_dim, L.p(acts[-1]), L.p(out))
+                self.bufs.append(None)
+                acts.append(out)
+        self.acts = acts
+        return acts[-1]
+
+    def backward_update(self, obj_diff, frames, lr: float, momentum: float):
+        L = self.L
+        S = len(frames)
+        N = obj_diff.shape[0]
+        T = N // S
+        d = L.arr(obj_diff)
+        self.in_diffs = {}
+        for li in range(len(self.spec.layers) - 1, -1, -1):
+            l = self.spec.layers[li]
+            p, c = self.params[li], self.corr[li]
+            x = self.acts[li]
+            if l.kind == "softmax":
+                nd = d.copy()  # softmax-layer.h:49-57: identity
+            elif l.kind == "affine":
+                nd = np.zeros((N, l.in_dim), L.dtype)
+                L.lib.oracle_affine_backward(N, l.in_dim, l.out_dim, L.p(d), L.p(p["w"]), L.p(nd))
+                L.lib.oracle_affine_grad(N, l.in_dim, l.out_dim, L.p(x), L.p(d), L.p(c["w"]), L.p(c["b"]),
+                                         L.real(momentum))
+            else:
+                Cc = l.cells
+                nd = np.zeros((N, l.in_dim), L.dtype)
+                dfw = np.zeros(((T + 2) * S, 7 * Cc), L.dtype)
+                dbw = np.zeros(((T + 2) * S, 7 * Cc), L.dtype)
+                plist = [p[n] for n in l.param_names()]
+                clist = [c[n] for n in l.param_names()]
+                bf, bb = self.bufs[li]
+                L.lib.oracle_bilstm_backward(T, S, l.in_dim, Cc, L.p(x), L.pp(plist), L.p(bf), L.p(bb), L.p(d),
+                                             L.p(dfw), L.p(dbw), L.p(nd), L.pp(clist), L.real(momentum))
+                self.last_dbuf = (dfw, dbw)
+            # TrainableLayer::Update right after the layer's Backpropagate (net.cc:98-105)
+            for n in l.param_names():
+                L.lib.oracle_sgd_update(C.c_long(p[n].size), L.p(p[n]), L.p(c[n]),
+                                        L.real(lr * l.learn_rate_coef), L.real(l.max_grad))
+            self.in_diffs[li] = nd
+            d = nd
+        return d
+
+    def train_step(self, batch, lr: float, momentum: float, diff_override: Optional[np.ndarray] = None):
+        y = self.forward(batch.feats, batch.frames)
+        pzx, diff, _, _ = ctc_eval(y, batch.frames, batch.labels, batch.S, self.L.dtype)
+        if diff_override is not None:
+            diff = self.L.arr(diff_override)
+        in_diff = self.backward_update(diff, batch.frames, lr, momentum)
+        return {"net_out": y, "pzx": pzx, "obj_diff": diff, "in_diff": in_diff}
+
+    def flat_params(self) -> np.ndarray:
+        return np.concatenate([self.params[i][n].ravel() for i, l in enumerate(self.spec.layers) for n in l.param_names()])
+
+    def flat_corr(self) -> np.ndarray:
+        return np.concatenate([self.corr[i][n].ravel() for i, l in enumerate(self.spec.layers) for n in l.param_names()])
+
+
+def greedy_token_errors(y: np.ndarray, frames, labels, S: int):
+    """Ctc::ErrorRateMSeq (ctc-loss.cc:235-298): argmax path -> collapse repeats -> drop blanks ->
+    Levenshtein (util/edit-distance-inl.h:28-75).  Returns (errors, ref_tokens)."""
+    am = np.argmax(y, axis=1)
+    err = 0
+    ref = 0
+    for s in range(S):
+        seq = am[np.arange(int(frames[s])) * S + s]
+        keep = np.concatenate([[True], seq[1:] != seq[:-1]])
+        hyp = [int(v) for v in seq[keep] if v != 0]
+        r = [int(v) for v in labels[s]]
+        # plain DP edit distance
+        prev = list(range(len(hyp) + 1))
+        for i in range(1, len(r) + 1):
+            cur = [i] + [0] * len(hyp)
+            for j in range(1, len(hyp) + 1):
+                cur[j] = min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (r[i - 1] != hyp[j - 1]))
+            prev = cur
+        err += prev[-1]
+        ref += len(r)
+    return err, ref
+
+
+# --------------------------------------------------------------------------- the real reference
+def have_reference(kind: str) -> bool:
+    return os.path.exists(os.path.join(REFDIR, f"ref_dump_{kind}"))
+
+
+def run_reference(kind: str, model_path: str, batch_path: str, outdir: str, lr: float, momentum: float,
+                  steps: int = 1, diff_in: Optional[str] = None, time_only: bool = False,
+                  threads: Optional[int] = None, timeout: int = 3600):
+    """Run oracle/_ref/ref_dump_{cpu,gpu} (the unmodified reference objects) on one batch."""
+    exe = os.path.join(REFDIR, f"ref_dump_{kind}")
+    os.makedirs(outdir, exist_ok=True)
+    cmd = [exe, model_path, batch_path, outdir, "--lr", repr(float(lr)), "--momentum", repr(float(momentum)),
+           "--steps", str(steps)]
+    if diff_in:
+        cmd += ["--diff-in", diff_in]
+    if time_only:
+        cmd += ["--time-only"]
+    env = dict(os.environ)
+    if threads is not None:
+        env["OPENBLAS_NUM_THREADS"] = str(threads)
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError(f"reference run failed ({r.returncode}):\n{r.stdout[-2000:]}\n{r.stderr[-4000:]}")
+    info = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    return info
+
+
+def load_dump(outdir: str) -> Dict[str, np.ndarray]:
+    out = {}
+    for f in os.listdir(outdir):
+        if f.endswith(".npy"):
+            out[f[:-4]] = np.load(os.path.join(outdir, f))
+    return out
