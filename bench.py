@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- CTC training frames/sec of the B200-native Eesen hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--workload c2] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path (Net::Propagate -> Ctc::EvalParallel -> ErrorRateMSeq ->
+Net::Backpropagate incl. the gradient all-reduce and the SGD update) over one packed synthetic
+minibatch of BASELINE.json configs[1]: 4x320 BiLSTM phone-CTC, 40-dim fbank, 64 utterances per GPU,
+T ~ U{400..600}.  Weak scaling: every rank processes its own 64-utterance shard; the only data-path
+collective is the per-step NCCL all-reduce of the 8.3 M-float gradient arena.
+
+Rank 0 prints ONE JSON line:
+  value      valid frames/s, whole job, inputs resident in HBM, CUDA events on the library's stream,
+             max over ranks
+  e2e        same metric through the public C-ABI call with HOST buffers (pinned staging + H2D of
+             the packed features, D2H of the statistics inside the timed region)
+  roofline   dominant kernel category of the step, measured live with CUDA events
+  cpu_baseline  the reference's own cpucompute path (oracle/_ref/ref_dump_cpu = unmodified reference
+             objects) + the restated CTC (the reference has no CPU CTC) on a bounded sample, N=1 only
+--impl reference times that CPU arm as the main line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from eesen_b200 import kaldi_io, synth  # noqa: E402
+
+METRIC = "ctc_train_frames_per_sec"
+UNIT = "frames/s"
+REF_SAMPLE_UTTS = 8  # bounded CPU sample: this many utterances of the same workload per step
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_arm(w, steps: int, warmup: int, tmp: str):
+    """Times the reference's CPU implementation of the path on this box's host cores.
+
+    oracle/_ref/ref_dump_cpu = UNMODIFIED reference objects (Net fwd/bwd/update on cpucompute with
+    OpenBLAS, all host threads).  The reference has no CPU CTC ("not implemented for CPU yet",
+    cuda-matrix.cc:862-864...), so the restated CTC (oracle/cpu_ref.c, fp32, 1 thread) is timed on the
+    same sample and added: "reference-CPU BiLSTM + restated-CPU CTC" (BASELINE.md section 3.4)."""
+    from oracle import oracle  # test/bench-only import: the checker as the CPU baseline
+    cores = os.cpu_count() or 1
+    net = synth.make_model(w, seed=0)
+    b = synth.make_batch(w, seed=1, S=REF_SAMPLE_UTTS)
+    model = os.path.join(tmp, "ref_model")
+    batch = os.path.join(tmp, "ref_batch.bin")
+    kaldi_io.write_model(model, net)
+    kaldi_io.write_batch_file(batch, b)
+    sample = (f"{b.S} utterances of the {w.name} workload per step ({b.valid_frames} valid / "
+              f"{b.feats.shape[0]} padded frames)")
+    # CTC restatement on the sample (fp32 port, single thread)
+    rng = np.random.default_rng(0)
+    y = oracle.softmax(rng.standard_normal((b.feats.shape[0], w.classes)).astype(np.float32), np.float32)
+    t0 = time.perf_counter()
+    oracle.ctc_eval(y, b.frames, b.labels, b.S, np.float32)
+    t_ctc = time.perf_counter() - t0
+    if oracle.have_reference("cpu"):
+        info = oracle.run_reference("cpu", model, batch, os.path.join(tmp, "ref_out"), w.learn_rate, w.momentum,
+                                    steps=steps + warmup, time_only=True, threads=cores)
+        st = info["step_seconds"][warmup:]
+        kind = "reference"
+    else:
+        on = oracle.OracleNet(net, np.float32)
+        st = []
+        for i in range(steps + warmup):
+            t0 = time.perf_counter()
+            on.train_step(b, w.learn_rate, w.momentum)
+            if i >= warmup:
+                st.append(time.perf_counter() - t0 - t_ctc)
+        kind = "port"
+    sec = float(np.mean(st)) + t_ctc
+    return {"value": b.valid_frames / sec, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+            "seconds_per_step": sec, "ctc_restated_seconds": t_ctc,
+            "note": "reference cpucompute BiLSTM/affine/softmax/SGD + restated CPU CTC (reference has none)"}
+
+
+def run_reference_impl(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    with tempfile.TemporaryDirectory() as tmp:
+        cb = cpu_reference_arm(w, args.steps, args.warmup, tmp)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w.name, "utts_per_gpu": w.S, "parallelism": "cpu host cores"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "note")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+def roofline_from_profile(ms, counts, w, batches, peaks, steps, prec):
+    """Dominant kernel category + its roofline.  Algorithmic figures:
+    recurrent forward  : 20*C floats per valid frame per layer  (read pre-acts 8C, write g,i,f,o,c,m 12C)
+    recurrent backward : 22*C floats per valid frame per layer  (read saved 12C + dout 2C, write DGIFO 8C)
+    dense GEMMs        : 48*C*I + 16*C*C per layer + 12*C*K flops per PADDED frame (all rows are multiplied)"""
+    tot = sum(ms.values()) or 1.0
+    top = max(ms, key=lambda k: ms[k])
+    valid = float(np.mean([b.valid_frames for b in batches]))
+    padded = float(np.mean([b.feats.shape[0] for b in batches]))
+    out = {"kernel": top, "share_of_step": ms[top] / tot,
+           "per_category_ms_per_step": {k: v / steps for k, v in ms.items() if v > 0},
+           "launches_per_step": {k: c / steps for k, c in counts.items() if c > 0}}
+    if top in ("lstm_fwd", "lstm_bwd"):
+        fl = (20.0 if top == "lstm_fwd" else 22.0) * w.cells * 4.0 * valid  # bytes per launch (one layer)
+        dur = ms[top] / max(counts[top], 1) * 1e-3
+        ach = fl / dur / 1e9
+        out.update({"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                    "algorithmic_bytes_per_launch": fl, "avg_launch_ms": dur * 1e3})
+    else:
+        d = w.in_dim
+        fl = 0.0
+        for _ in range(w.layers):
+            fl += 48.0 * w.cells * d + 16.0 * w.cells * w.cells
+            d = 2 * w.cells
+        fl += 12.0 * w.cells * w.classes
+        flops = fl * padded  # per step, all GEMM launches together
+        dur = ms["gemm"] / steps * 1e-3
+        ach = flops / dur / 1e12
+        # the contraction runs on the tensor pipe in TF32 (x3 split = 3 MMAs per product in fp32x3 mode);
+        # the roofline denominator is the measured dense bf16 peak (sustained: timed inside a long step)
+        out.update({"kernel": "gemm", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
+                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                    "peak_source": peaks["source"], "algorithmic_flops_per_step": flops,
+                    "note": f"all GEMM launches of a step together; arithmetic mode {prec}"})
+    return out
+
+
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+    from eesen_b200 import binding
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- eesen_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = binding.Context(local, args.gemm_precision, args.recurrent_precision)
+    if world > 1:
+        obj = [ctx.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        ctx.nccl_init(rank, world, obj[0])
+
+    tmp = tempfile.mkdtemp(prefix="eesen_b200_bench_")
+    model_path = os.path.join(tmp, f"model_{rank}")
+    kaldi_io.write_model(model_path, synth.make_model(w, seed=0))  # identical weights on every rank
+    net = binding.Net(ctx, model_path)
+    net.set_train_options(w.learn_rate, w.momentum)
+
+    # a small pool of distinct batches per rank (weak scaling: per-GPU work fixed)
+    pool = [synth.make_batch(w, seed=1000 * rank + 1 + i) for i in range(args.pool)]
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    dev = []
+    for b in pool:
+        flat, lab_len = binding.Net._labels(b.labels)
+        dev.append((torch.from_numpy(b.feats).cuda(), b.T, b.S, np.ascontiguousarray(b.frames, np.int32), flat, lab_len))
+    torch.cuda.synchronize()
+
+    def step_dev(i):
+        d = dev[i % len(dev)]
+        net.train_step_device(d[0], d[1], d[2], d[3], d[4], d[5], True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_dev(i)
+    net.read_stats()
+    barrier()
+
+    # ---- timed region 1: device-resident inputs, CUDA events on the library's stream
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches
+    ctx.profile(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        step_dev(i)
+    e1.record(stream)
+    stats = net.read_stats()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    prof_ms, prof_cnt = ctx.profile(0)
+    launches = ctx.launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    frames_dev = sum(pool[i % len(pool)].valid_frames for i in range(args.steps))
+    padded_dev = sum(pool[i % len(pool)].feats.shape[0] for i in range(args.steps))
+
+    # ---- timed region 2: end to end through the public call with HOST buffers
+    for i in range(min(2, args.warmup)):
+        b = pool[i % len(pool)]
+        net.train_step(b.feats, b.frames, b.labels, True)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        b = pool[i % len(pool)]
+        net.train_step(b.feats, b.frames, b.labels, True)   # blocks until the statistics are back
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+
+    t = torch.tensor([ms_dev, t_e2e * 1e3, float(frames_dev), float(padded_dev)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_dev, ms_e2e = mx[0].item(), mx[1].item()
+        frames_all, padded_all = sm[2].item(), sm[3].item()
+    else:
+        ms_e2e = t_e2e * 1e3
+        frames_all, padded_all = float(frames_dev), float(padded_dev)
+
+    if rank == 0:
+        peaks = load_peaks()
+        value = frames_all / (ms_dev * 1e-3)
+        h2d = int(np.mean([b.feats.nbytes + b.frames.nbytes * 5 + sum(l.nbytes for l in b.labels) + 8 * b.S for b in pool]))
+        d2h = int(np.mean([4 * b.S + 4 * b.feats.shape[0] for b in pool]))   # pzx[S] + argmax[T*S]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w.name, "layers": w.layers, "cells_per_direction": w.cells, "input_dim": w.in_dim,
+                       "classes": w.classes, "utts_per_gpu": w.S, "frames_per_utt": [w.t_lo, w.t_hi],
+                       "global_utts": w.S * world, "parallelism": f"dp{world}",
+                       "gemm_arithmetic": args.gemm_precision, "recurrent_arithmetic": args.recurrent_precision,
+                       "storage": "fp32", "learn_rate": w.learn_rate, "momentum": w.momentum,
+                       "l2": "inputs larger than L2: ~2 GB of activations are streamed per step, no flush needed",
+                       "frames_counted": "valid (unpadded) frames"},
+            "padded_frames_per_sec": padded_all / (ms_dev * 1e-3),
+            "e2e": {"value": frames_all / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline_from_profile(prof_ms, prof_cnt, w, pool, peaks, args.steps,
+                                              args.gemm_precision),
+            "last_step_stats": stats,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_reference_arm(w, 1, 0, tmp)
+            except Exception as e:  # the checker is optional for the measurement itself
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                        "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    net.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(synth.WORKLOADS))
+    ap.add_argument("--gemm-precision", default="fp32x3", choices=["fp32x3", "tf32", "bf16"])
+    ap.add_argument("--recurrent-precision", default="fp32x3", choices=["fp32x3", "tf32"])
+    ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches per rank")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w = synth.WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference_impl(args, w)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: relaunch under torchrun (the driver launches torchrun itself)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_ours(args, w)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

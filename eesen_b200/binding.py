@@ -109,6 +109,16 @@ class Context:
     def sm_count(self) -> int:
         return int(self.lib.eesen_b200_sm_count(self.h))
 
+    PROFILE_CATEGORIES = ("gemm", "lstm_fwd", "lstm_bwd", "softmax", "ctc", "sgd", "allreduce", "misc")
+
+    def profile(self, enable: int = -1):
+        """Returns ({category: ms}, {category: launches}) since the last reset; enable=1/0 switches+resets."""
+        ms = (C.c_double * 8)()
+        cnt = (C.c_long * 8)()
+        self.check(self.lib.eesen_b200_profile(self.h, int(enable), ms, cnt), "profile")
+        return ({k: ms[i] for i, k in enumerate(self.PROFILE_CATEGORIES)},
+                {k: cnt[i] for i, k in enumerate(self.PROFILE_CATEGORIES)})
+
     # ---- level 1 (torch CUDA tensors carry the device memory)
     def gemm(self, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc):
         self.check(self.lib.eesen_b200_gemm(self.h, ta, tb, M, N, K, C.c_float(alpha), _p(A), lda, _p(B), ldb,

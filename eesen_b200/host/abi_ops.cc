@@ -103,8 +103,10 @@ static int do_gemm(eesen_b200_ctx *ctx, int ta, int tb, int M, int N, int K, flo
     int rc = ctx->reserve(ctx->gemm_ws, need, &ws);
     if (rc) return rc;
   }
+  int pe = ctx->prof_begin(eesen_b200_ctx::kGemm);
   cudaError_t e = eb::gemm(ctx->stream, ctx->num_sms, ta, tb, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc,
                            sC, bias, sBias, batch, ctx->gemm_prec, (float *)ws, ws ? ctx->gemm_ws.bytes : 0);
+  ctx->prof_end(pe);
   ctx->launches += 1;
   return ctx->check(e, "gemm");
 }
@@ -161,7 +163,10 @@ int eesen_b200_bilstm_forward(eesen_b200_ctx *ctx, int T, int S, int I, int C, c
   a.flags = flags;
   a.precision = ctx->rec_prec;
   ctx->launches += 1;
-  return ctx->check(eb::lstm_forward(ctx->stream, plan, a), "lstm_forward");
+  int pe = ctx->prof_begin(eesen_b200_ctx::kLstmFwd);
+  cudaError_t le = eb::lstm_forward(ctx->stream, plan, a);
+  ctx->prof_end(pe);
+  return ctx->check(le, "lstm_forward");
 }
 
 int eesen_b200_bilstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, const float *x, int ldx,
@@ -184,13 +189,19 @@ int eesen_b200_bilstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, 
   a.pbuf = pbuf; a.gsum = gsum; a.flags = flags;
   a.precision = ctx->rec_prec;
   ctx->launches += 1;
-  if ((rc = ctx->check(eb::lstm_backward(ctx->stream, plan, a), "lstm_backward"))) return rc;
+  {
+    int pe = ctx->prof_begin(eesen_b200_ctx::kLstmBwd);
+    cudaError_t le = eb::lstm_backward(ctx->stream, plan, a);
+    ctx->prof_end(pe);
+    if ((rc = ctx->check(le, "lstm_backward"))) return rc;
+  }
   const int N = T * S;
   for (int d = 0; d < 2; d++) {
     ctx->launches += 1;
-    if ((rc = ctx->check(eb::lstm_reduce_gsum(ctx->stream, plan, C, gsum, gr->bias[d], gr->pi[d], gr->pf[d],
-                                              gr->po[d], d), "lstm_reduce_gsum")))
-      return rc;
+    int pe = ctx->prof_begin(eesen_b200_ctx::kMisc);
+    cudaError_t le = eb::lstm_reduce_gsum(ctx->stream, plan, C, gsum, gr->bias[d], gr->pi[d], gr->pf[d], gr->po[d], d);
+    ctx->prof_end(pe);
+    if ((rc = ctx->check(le, "lstm_reduce_gsum"))) return rc;
   }
   // dx = DG_fw * Wx_fw + DG_bw * Wx_bw   (:502 beta=0, :593 beta=1)
   if (dx) {
@@ -246,7 +257,10 @@ int eesen_b200_affine_backward(eesen_b200_ctx *ctx, int N, int D, int K, const f
     void *ws = nullptr;
     if ((rc = ctx->reserve(ctx->colsum_ws, eb::col_sum_ws_floats(K, ctx->num_sms) * sizeof(float), &ws))) return rc;
     ctx->launches += 2;
-    if ((rc = ctx->check(eb::col_sum(ctx->stream, ctx->num_sms, N, K, diff, lddiff, db, (float *)ws), "col_sum"))) return rc;
+    int pe = ctx->prof_begin(eesen_b200_ctx::kMisc);
+    cudaError_t ce = eb::col_sum(ctx->stream, ctx->num_sms, N, K, diff, lddiff, db, (float *)ws);
+    ctx->prof_end(pe);
+    if ((rc = ctx->check(ce, "col_sum"))) return rc;
   }
   return 0;
 }
@@ -255,13 +269,19 @@ int eesen_b200_softmax(eesen_b200_ctx *ctx, int N, int K, const float *logits, i
                        int *d_argmax) {
   if (!ctx || !logits || !probs) return EESEN_B200_EINVAL;
   ctx->launches += 1;
-  return ctx->check(eb::softmax_rows(ctx->stream, N, K, logits, ld, probs, ldp, d_argmax), "softmax_rows");
+  int pe = ctx->prof_begin(eesen_b200_ctx::kSoftmax);
+  cudaError_t e = eb::softmax_rows(ctx->stream, N, K, logits, ld, probs, ldp, d_argmax);
+  ctx->prof_end(pe);
+  return ctx->check(e, "softmax_rows");
 }
 
 int eesen_b200_row_argmax(eesen_b200_ctx *ctx, int N, int K, const float *x, int ld, int *d_argmax) {
   if (!ctx || !x || !d_argmax) return EESEN_B200_EINVAL;
   ctx->launches += 1;
-  return ctx->check(eb::row_argmax(ctx->stream, N, K, x, ld, d_argmax), "row_argmax");
+  int pe = ctx->prof_begin(eesen_b200_ctx::kSoftmax);
+  cudaError_t e = eb::row_argmax(ctx->stream, N, K, x, ld, d_argmax);
+  ctx->prof_end(pe);
+  return ctx->check(e, "row_argmax");
 }
 
 int eesen_b200_ctc_eval(eesen_b200_ctx *ctx, int T, int S, int K, int max_lab, const int *d_len, const int *d_labels,
@@ -272,8 +292,11 @@ int eesen_b200_ctc_eval(eesen_b200_ctx *ctx, int T, int S, int K, int max_lab, c
   int rc = ctx->reserve(ctx->ctc_ws, eb::ctc_workspace_floats(T, S, max_lab) * sizeof(float), &ws);
   if (rc) return rc;
   ctx->launches += 1;
-  return ctx->check(eb::ctc_eval(ctx->stream, T, S, K, max_lab, d_len, d_labels, d_lab_len, probs, ldp, pzx, diff, ldd,
-                                 (float *)ws), "ctc_eval");
+  int pe = ctx->prof_begin(eesen_b200_ctx::kCtc);
+  cudaError_t e = eb::ctc_eval(ctx->stream, T, S, K, max_lab, d_len, d_labels, d_lab_len, probs, ldp, pzx, diff, ldd,
+                               (float *)ws);
+  ctx->prof_end(pe);
+  return ctx->check(e, "ctc_eval");
 }
 
 int eesen_b200_sgd_update(eesen_b200_ctx *ctx, float *w, float *corr, const float *grad, int64_t n, float momentum,
@@ -345,8 +368,24 @@ int eesen_b200_allreduce_sum(eesen_b200_ctx *ctx, float *buf, int64_t n) {
   static ar_t f = nullptr;
   if (!f) f = (ar_t)dlsym(ctx->nccl_lib, "ncclAllReduce");
   if (!f) return ctx->fail(EESEN_B200_ENCCL, "ncclAllReduce not found");
+  int pe = ctx->prof_begin(eesen_b200_ctx::kAllReduce);
   int r = f(buf, buf, (size_t)n, 7, 0, ctx->nccl_comm, ctx->stream);
+  ctx->prof_end(pe);
   if (r != 0) return ctx->fail(EESEN_B200_ENCCL, "ncclAllReduce failed with code " + std::to_string(r));
+  return 0;
+}
+
+int eesen_b200_profile(eesen_b200_ctx *ctx, int enable, double *ms, long *counts) {
+  if (!ctx) return EESEN_B200_EINVAL;
+  ctx->prof_collect();
+  if (ms)
+    for (int i = 0; i < eesen_b200_ctx::kNumCat; i++) ms[i] = ctx->prof_ms[i];
+  if (counts)
+    for (int i = 0; i < eesen_b200_ctx::kNumCat; i++) counts[i] = ctx->prof_count[i];
+  if (enable >= 0) {
+    ctx->prof_on = enable != 0;
+    for (int i = 0; i < eesen_b200_ctx::kNumCat; i++) { ctx->prof_ms[i] = 0; ctx->prof_count[i] = 0; }
+  }
   return 0;
 }
 

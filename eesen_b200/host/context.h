@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <vector>
 
 #include "../csrc/kernels.h"
 
@@ -25,6 +26,37 @@ struct eesen_b200_ctx {
     size_t bytes = 0;
   };
   Buf gemm_ws, lstm_pbuf, lstm_gsum, lstm_flags, ctc_ws, colsum_ws, seg_buf;
+
+  // optional per-category kernel timing with CUDA events on `stream` (bench.py roofline)
+  enum { kGemm = 0, kLstmFwd, kLstmBwd, kSoftmax, kCtc, kSgd, kAllReduce, kMisc, kNumCat };
+  struct ProfEv { cudaEvent_t a, b; int cat; };
+  bool prof_on = false;
+  std::vector<ProfEv> prof_events;
+  std::vector<ProfEv> prof_pool;
+  double prof_ms[kNumCat] = {0};
+  long prof_count[kNumCat] = {0};
+  int prof_begin(int cat) {
+    if (!prof_on) return -1;
+    ProfEv e;
+    if (!prof_pool.empty()) { e = prof_pool.back(); prof_pool.pop_back(); }
+    else { cudaEventCreate(&e.a); cudaEventCreate(&e.b); }
+    e.cat = cat;
+    cudaEventRecord(e.a, stream);
+    prof_events.push_back(e);
+    return (int)prof_events.size() - 1;
+  }
+  void prof_end(int idx) {
+    if (idx >= 0) cudaEventRecord(prof_events[idx].b, stream);
+  }
+  void prof_collect() {
+    cudaStreamSynchronize(stream);
+    for (auto &e : prof_events) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) { prof_ms[e.cat] += ms; prof_count[e.cat] += 1; }
+      prof_pool.push_back(e);
+    }
+    prof_events.clear();
+  }
 
   // NCCL (dlopen'ed on demand)
   void *nccl_lib = nullptr;

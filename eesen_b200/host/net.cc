@@ -552,8 +552,10 @@ void Net::Backpropagate(const CuMatrixBase<BaseFloat> &out_diff, CuMatrix<BaseFl
   if (nranks > 1) CheckAbi(ctx_, eesen_b200_allreduce_sum(ctx_, g_, arena_size_), "eesen_b200_allreduce_sum");
   if (segs_dirty_) UploadSegments();
   if (nseg_ > 0) {
+    int pe = ctx_->prof_begin(eesen_b200_ctx::kSgd);
     cudaError_t e = eb::sgd_momentum_clip(ctx_->stream, ctx_->num_sms, w_, corr_, g_, opts_.momentum,
                                           (const eb::SgdSegment *)d_segs_, nseg_, arena_size_);
+    ctx_->prof_end(pe);
     ctx_->launches += 1;
     if (e != cudaSuccess) KALDI_ERR << "sgd_momentum_clip: " << cudaGetErrorString(e);
   }

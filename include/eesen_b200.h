@@ -56,6 +56,13 @@ int eesen_b200_sm_count(const eesen_b200_ctx *ctx);
 /* number of kernels this library launched on the context so far (bench.py "gpu_launches") */
 long eesen_b200_launch_count(const eesen_b200_ctx *ctx);
 
+/* Per-category device timing with CUDA events on the context's stream (for bench.py's roofline).
+ * Categories: 0 gemm, 1 lstm_forward, 2 lstm_backward, 3 softmax/argmax, 4 ctc, 5 sgd, 6 all-reduce, 7 misc.
+ * Synchronises, returns the milliseconds / launch counts accumulated since the last reset in
+ * ms[8] / counts[8] (either may be NULL); enable = 1/0 switches recording and resets, -1 only reads. */
+#define EESEN_B200_NUM_PROFILE_CATEGORIES 8
+int eesen_b200_profile(eesen_b200_ctx *ctx, int enable, double *ms, long *counts);
+
 /* ---------------------------------------------------------------- level 1: device operators */
 
 /* C = alpha*op(A)*op(B) + beta*C.  Replaces CuMatrixBase::AddMatMat -> cublasSgemm

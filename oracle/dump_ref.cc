@@ -187,7 +187,7 @@ int main(int argc, char **argv) {
     std::string no_out_file = "";
 
     Timer timer;
-    double step_seconds = 0.0;
+    std::vector<double> step_seconds;
     for (int step = 0; step < steps; step++) {
       Timer st;
       net.SetSeqLengths(b.frames);
@@ -227,15 +227,18 @@ int main(int argc, char **argv) {
         }
       }
       net.Backpropagate(obj_diff, &in_diff);
-      step_seconds += st.Elapsed();
+      step_seconds.push_back(st.Elapsed());
     }
     double elapsed = timer.Elapsed();
     long valid = 0;
     for (int s = 0; s < b.S; s++) valid += b.frames[s];
     fprintf(stdout, "{\"steps\": %d, \"seconds\": %.6f, \"valid_frames_per_step\": %ld, "
-                    "\"padded_frames_per_step\": %d, \"valid_fps\": %.3f, \"token_err\": %.1f, \"ref_tokens\": %d}\n",
+                    "\"padded_frames_per_step\": %d, \"valid_fps\": %.3f, \"token_err\": %.1f, \"ref_tokens\": %d, "
+                    "\"step_seconds\": [",
             steps, elapsed, valid, b.T * b.S, valid * steps / elapsed,
             ctc.NumErrorTokens(), ctc.NumRefTokens());
+    for (size_t i = 0; i < step_seconds.size(); i++) fprintf(stdout, "%s%.6f", i ? ", " : "", step_seconds[i]);
+    fprintf(stdout, "]}\n");
     if (time_only) return 0;
 
     dump_mat(outdir + "/in_diff.npy", in_diff);

@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Generates the committed golden vectors from the UNMODIFIED reference (oracle/_ref binaries).
+
+    python tests/golden/make_golden.py cpu     # here (no GPU): reference cpucompute build
+    python tests/golden/make_golden.py gpu     # on the B200 box: reference gpucompute build (sm_100a)
+
+The reference ships no tests / golden vectors for this path, so the pins are
+minted from runs of the reference itself on seeded synthetic inputs:
+
+* ``<wl>_refcpu.npz``  Net::Propagate / Backpropagate / Update of the reference's CPU path.  CTC is a
+  no-op on CPU in the reference (cuda-matrix.cc:862-864 ...), so ``obj_diff`` is supplied by the fp32
+  restatement and stored in the fixture; everything else (layer outputs, in_diff, momentum buffers
+  after clipping, updated parameters) is the reference's own output.
+* ``<wl>_refgpu.npz``  the same plus the reference's own CUDA CTC (alpha, beta, pzx, obj_diff):
+  the only place the reference computes CTC at all.
+
+Inputs are regenerated from (workload, seeds) by eesen_b200.synth, so only outputs are stored.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from eesen_b200 import kaldi_io, synth  # noqa: E402
+from oracle import oracle  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = [("tiny", 3, 5, 1e-3, 0.9), ("small", 3, 5, 1e-3, 0.9)]  # workload, model seed, batch seed, lr, momentum
+
+
+def run(kind: str, outdir: str = HERE):
+    for wl, mseed, bseed, lr, mom in CASES:
+        w = synth.WORKLOADS[wl]
+        net = synth.make_model(w, seed=mseed)
+        b = synth.make_batch(w, seed=bseed)
+        d = tempfile.mkdtemp()
+        kaldi_io.write_model(d + "/model", net)
+        kaldi_io.write_batch_file(d + "/batch.bin", b)
+        diff_in = None
+        if kind == "cpu":
+            on = oracle.OracleNet(net, np.float32)
+            r = on.train_step(b, lr, mom)
+            np.save(d + "/diff.npy", r["obj_diff"].astype(np.float32))
+            diff_in = d + "/diff.npy"
+        oracle.run_reference(kind, d + "/model", d + "/batch.bin", d + "/out", lr, mom, steps=2, diff_in=diff_in)
+        dump = oracle.load_dump(d + "/out")
+        m2 = kaldi_io.read_model(d + "/out/model_out")
+        keep = {k: v for k, v in dump.items() if not k.startswith("out_l0")}
+        keep["params_out"] = m2.flat_params()
+        keep["meta"] = np.array([mseed, bseed, 2], np.int64)      # seeds, number of steps run
+        keep["hyper"] = np.array([lr, mom], np.float64)
+        if diff_in:
+            keep["diff_in"] = np.load(diff_in)
+        path = os.path.join(outdir, f"{wl}_ref{kind}.npz")
+        np.savez_compressed(path, **keep)
+        print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    kind = sys.argv[1] if len(sys.argv) > 1 else "cpu"
+    run(kind, sys.argv[2] if len(sys.argv) > 2 else HERE)
