@@ -36,20 +36,21 @@ __device__ __forceinline__ uint32_t cvt_tf32(float x) {
   return r;
 }
 
-__device__ __forceinline__ void wait_flag(const unsigned *flag, unsigned target, int lane) {
-  if (lane == 0) {
-    while (ld_acquire(flag) < target) {
-    }
+// Step-counter protocol between the CTAs of one (direction, utterance group):
+//   producer warp : data stores ; __syncwarp ; lane 0: red.release.gpu(flag += 1)
+//   consumer CTA  : thread 0 spins on ld.relaxed.gpu(flag) >= target, then fence.acq_rel.gpu ;
+//                   __syncthreads ; everybody reads the data with L2 (.cg) loads.
+// One poller per CTA and relaxed polls keep the L2 slice that owns the flag free for the
+// producers' reductions (a polling ld.acquire costs an L1 invalidate, CCTL.IVALL, per iteration).
+__device__ __forceinline__ void poll_flag(const unsigned *flag, unsigned target) {
+  while (ld_relaxed(flag) < target) {
   }
-  __syncwarp();
+  fence_acq_rel_gpu();
 }
 
 __device__ __forceinline__ void signal_flag(unsigned *flag, int lane) {
   __syncwarp();
-  if (lane == 0) {
-    __threadfence();
-    red_release_add(flag, 1u);
-  }
+  if (lane == 0) red_release_add(flag, 1u);
 }
 
 // One k-step of the (gate-rows x utterances) product for one 16-row fragment A (fp32 in smem,
@@ -147,7 +148,8 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
 
     if (step > 0) {
       const int tp = dir == 0 ? t - 1 : t + 1;
-      wait_flag(flag, (unsigned)step * expected_per_step, lane);
+      if (tid == 0) poll_flag(flag, (unsigned)step * expected_per_step);
+      __syncthreads();
       // stage m_{t-1} of the whole group (L2 -> smem), 128-bit loads that bypass L1
       const int c4n = C / 4;
       for (int v = tid; v < 8 * NUT * c4n; v += NTHREADS) {
@@ -202,9 +204,11 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
 
     if (fin) {
       // acc[0] = {g(u0), g(u1), i(u0), i(u1)}, acc[1] = {f(u0), f(u1), o(u0), o(u1)} for cell `cell`
+      float sg[2], si[2], sf[2], so[2], sc[2];
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int u = uidx[e];
+        sg[e] = si[e] = sf[e] = so[e] = sc[e] = 0.f;
         if (cell_ok && u < S) {
           float yg = pre[0][e] + acc[0][e];
           float yi = pre[1][e] + acc[0][2 + e] + cprev[e] * ppi;   // :127
@@ -218,16 +222,24 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
             gg = gi = gf = go = c = m = 0.f;
           }
           cprev[e] = c;
-          float *grow = a.G + ((size_t)t * S + u) * a.ldg + (size_t)dir * 4 * C + cell;
-          grow[0] = gg; grow[(size_t)C] = gi; grow[(size_t)2 * C] = gf; grow[(size_t)3 * C] = go;
-          a.cell[((size_t)t * S + u) * a.ldc + (size_t)dir * C + cell] = c;
+          sg[e] = gg; si[e] = gi; sf[e] = gf; so[e] = go; sc[e] = c;
+          // only m is on the inter-CTA critical path: publish it first ...
           __stcg(a.out + ((size_t)t * S + u) * a.ldo + (size_t)dir * C + cell, m);
         }
       }
-      if (step + 1 < T) {
-        signal_flag(flag, lane);
-        load_pre(dir == 0 ? t + 1 : t - 1);
+      if (step + 1 < T) signal_flag(flag, lane);
+      // ... the saved state for the backward pass is written behind the release
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int u = uidx[e];
+        if (cell_ok && u < S) {
+          float *grow = a.G + ((size_t)t * S + u) * a.ldg + (size_t)dir * 4 * C + cell;
+          __stcs(grow, sg[e]); __stcs(grow + (size_t)C, si[e]);
+          __stcs(grow + (size_t)2 * C, sf[e]); __stcs(grow + (size_t)3 * C, so[e]);
+          __stcs(a.cell + ((size_t)t * S + u) * a.ldc + (size_t)dir * C + cell, sc[e]);
+        }
       }
+      if (step + 1 < T) load_pre(dir == 0 ? t + 1 : t - 1);
     }
   }
 }
@@ -292,14 +304,18 @@ lstm_bwd_kernel(LstmBwdArgs a, int groups, int slices, unsigned expected_per_ste
   const size_t pstride_slice = (size_t)8 * NUT * CP;
   for (int step = 0; step < T; step++) {
     const int t = dir == 0 ? T - 1 - step : step;
+    if (step > 0) {
+      if (tid == 0) poll_flag(flag, (unsigned)step * expected_per_step);
+      __syncthreads();
+    }
     if (is_item) {
       float dm = vd;
       if (step > 0) {
-        wait_flag(flag, (unsigned)step * expected_per_step, lane);
         if (ok) {
           const float *pb = a.pbuf + ((((size_t)((step - 1) & 1) * 2 + dir) * groups + group) * slices) * pstride_slice +
                             (size_t)ul * CP + cell;
           float s_ = 0.f;
+#pragma unroll 8
           for (int sl = 0; sl < slices; sl++) s_ += __ldcg(pb + (size_t)sl * pstride_slice);  // fixed order
           dm += s_;                                                       // :470 / :561
         }

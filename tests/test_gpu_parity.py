@@ -1,0 +1,395 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(include/eesen_b200.h) via eesen_b200.binding; the checker is the oracle (oracle/), the committed
+golden vectors minted from the reference, and -- live on the box -- the reference's own gpucompute
+build (oracle/_ref/ref_dump_gpu, compiled from the unmodified sources for sm_100a).
+
+Stated tolerances (fp32 storage everywhere):
+  default arithmetic "fp32x3" (3xTF32 split, fp32 accumulate): fp32-faithful
+      log p(z|x)          rel 2e-5      (north_star bound: 1e-4)
+      per-frame gradient  abs 1e-4      (the reference's fp32 CTC itself is ~4e-5 from fp64, test_oracle.py)
+      layer outputs       abs 2e-5
+      momentum buffers    abs 2e-3 + rel 2e-3 (sums over thousands of rows, order-dependent)
+  "tf32" arithmetic: log p(z|x) rel 1e-4 (still inside the north_star bound), gradients abs 5e-3.
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from util import GOLDEN, assert_close, case, golden_arrays, model_file
+from eesen_b200 import binding, kaldi_io, synth
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def torch_():
+    import torch
+    return torch
+
+
+# ------------------------------------------------------------------------------------ level 1
+@pytest.mark.parametrize("ta,tb,M,N,K", [(0, 1, 300, 96, 40), (0, 1, 130, 46, 64), (0, 0, 257, 40, 128),
+                                         (0, 0, 64, 640, 46), (1, 0, 128, 40, 700), (1, 0, 46, 64, 5000),
+                                         (1, 0, 1280, 320, 9000)])
+@pytest.mark.parametrize("prec,tol", [("fp32x3", 2e-6), ("tf32", 2e-3), ("bf16", 1.5e-2)])
+def test_gemm(ctx, ta, tb, M, N, K, prec, tol):
+    torch = torch_()
+    rng = np.random.default_rng(M + N + K)
+    ld = lambda c: (c + 3) // 4 * 4
+    Ash = (K, M) if ta else (M, K)
+    Bsh = (N, K) if tb else (K, N)
+    A = np.zeros((Ash[0], ld(Ash[1])), np.float32); A[:, :Ash[1]] = rng.standard_normal(Ash)
+    B = np.zeros((Bsh[0], ld(Bsh[1])), np.float32); B[:, :Bsh[1]] = rng.standard_normal(Bsh)
+    A[:, Ash[1]:] = np.nan  # padding columns must never be read
+    B[:, Bsh[1]:] = np.nan
+    C0 = rng.standard_normal((M, ld(N))).astype(np.float32)
+    dA, dB, dC = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), torch.from_numpy(C0).cuda()
+    torch.cuda.synchronize()
+    ctx.set_precision(prec, "fp32x3")
+    ctx.gemm(ta, tb, M, N, K, 0.5, dA, A.shape[1], dB, B.shape[1], 0.25, dC, C0.shape[1])
+    ctx.synchronize()
+    ctx.set_precision("fp32x3", "fp32x3")
+    a = A[:, :Ash[1]].astype(np.float64); b = B[:, :Bsh[1]].astype(np.float64)
+    ref = 0.5 * ((a.T if ta else a) @ (b.T if tb else b)) + 0.25 * C0[:, :N]
+    got = dC.cpu().numpy()
+    scale = np.sqrt(K)
+    assert_close("gemm", got[:, :N] / scale, ref / scale, atol=tol)
+    assert np.array_equal(got[:, N:], C0[:, N:])   # padding columns of C untouched
+
+
+@pytest.mark.parametrize("N,K", [(7, 5), (1000, 46), (333, 300)])
+def test_softmax_and_argmax(ctx, N, K):
+    torch = torch_()
+    rng = np.random.default_rng(N)
+    ldp = (K + 3) // 4 * 4
+    x = np.zeros((N, ldp), np.float32); x[:, :K] = rng.standard_normal((N, K)) * 3
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.full((N, ldp), 7.0, dtype=torch.float32, device="cuda")
+    da = torch.zeros(N, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.softmax(N, K, dx, ldp, dy, ldp, da)
+    ctx.synchronize()
+    ref = oracle.softmax(x[:, :K], np.float64)
+    got = dy.cpu().numpy()
+    assert_close("softmax", got[:, :K], ref, atol=2e-7)
+    assert np.all(got[:, K:] == 0)
+    assert np.array_equal(da.cpu().numpy(), np.argmax(x[:, :K], 1))
+
+
+def _ctc_case(seed, S, T, K, maxlab, ragged=True):
+    rng = np.random.default_rng(seed)
+    frames = np.full(S, T, np.int32)
+    if ragged:
+        frames = np.sort(rng.integers(max(2 * maxlab + 1, T // 2), T + 1, size=S))[::-1].astype(np.int32)
+        frames[0] = T
+    labels = []
+    for s in range(S):
+        n = int(rng.integers(1, maxlab + 1))
+        lab = rng.integers(1, K, size=n)
+        if n >= 2 and s % 2 == 0:
+            lab[1] = lab[0]
+        labels.append(lab.astype(np.int32))
+    labels[0] = rng.integers(1, K, size=maxlab).astype(np.int32)   # one utterance at the maximum label length
+    logits = (rng.standard_normal((T * S, K)) * 2).astype(np.float32)
+    return frames, labels, logits
+
+
+@pytest.mark.parametrize("seed,S,T,K,maxlab", [(0, 3, 12, 5, 4), (1, 8, 40, 12, 10), (2, 1, 9, 4, 1), (3, 5, 64, 46, 15),
+                                               (4, 64, 120, 46, 31), (5, 4, 300, 32, 60), (6, 2, 700, 32, 130),
+                                               (7, 3, 1100, 8, 255)])
+def test_ctc_eval_vs_oracle(ctx, seed, S, T, K, maxlab):
+    torch = torch_()
+    frames, labels, logits = _ctc_case(seed, S, T, K, maxlab)
+    ldp = (K + 3) // 4 * 4
+    y = oracle.softmax(logits, np.float32)
+    yp = np.zeros((T * S, ldp), np.float32); yp[:, :K] = y
+    lab = np.zeros((S, maxlab), np.int32)
+    for s, l in enumerate(labels):
+        lab[s, :len(l)] = l
+    d_y = torch.from_numpy(yp).cuda()
+    d_len = torch.from_numpy(frames).cuda()
+    d_lab = torch.from_numpy(lab).cuda()
+    d_ll = torch.tensor([len(l) for l in labels], dtype=torch.int32, device="cuda")
+    d_pzx = torch.zeros(S, dtype=torch.float32, device="cuda")
+    d_diff = torch.full((T * S, ldp), 3.0, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.ctc_eval(T, S, K, maxlab, d_len, d_lab, d_ll, d_y, ldp, d_pzx, d_diff, ldp)
+    ctx.synchronize()
+    pzx64, diff64, _, _ = oracle.ctc_eval(y.astype(np.float64), frames, labels, S, np.float64)
+    got_p, got_d = d_pzx.cpu().numpy(), d_diff.cpu().numpy()
+    assert_close("pzx", got_p, pzx64, atol=0, rtol=2e-5)
+    assert_close("diff", got_d[:, :K], diff64, atol=1e-4)
+    for s in range(S):   # rows past the utterance end are exactly zero
+        rows = np.arange(frames[s], T) * S + s
+        assert np.all(got_d[rows, :K] == 0)
+
+
+@pytest.mark.parametrize("S,T,I,C", [(4, 9, 8, 16), (2, 30, 40, 128), (20, 17, 40, 64), (16, 40, 40, 320), (3, 5, 64, 24)])
+@pytest.mark.parametrize("rec", ["fp32x3", "tf32"])
+def test_bilstm_layer_vs_oracle(ctx, S, T, I, C, rec):
+    """Level-1 BiLSTM forward/backward of one layer against the fp64 oracle, ragged lengths."""
+    torch = torch_()
+    rng = np.random.default_rng(S * 1000 + T)
+    frames = np.sort(rng.integers(max(1, T // 2), T + 1, size=S))[::-1].astype(np.int32)
+    frames[0] = T
+    x = rng.standard_normal((T * S, I)).astype(np.float32)
+    for s in range(S):
+        x[np.arange(frames[s], T) * S + s] = 0
+    l = kaldi_io.LayerSpec("bilstm", I, 2 * C)
+    params = [rng.uniform(-0.3, 0.3, size=l.param_shapes()[n]).astype(np.float32) for n in l.param_names()]
+    dout = rng.standard_normal((T * S, 2 * C)).astype(np.float32)
+    for s in range(S):
+        dout[np.arange(frames[s], T) * S + s] = 0   # upper layers hand back zero gradient on padded rows
+    # oracle (fp64)
+    L = oracle.lib(np.float64)
+    p64 = [L.arr(p) for p in params]
+    bf = np.zeros(((T + 2) * S, 7 * C)); bb = np.zeros_like(bf); out64 = np.zeros((T * S, 2 * C))
+    L.lib.oracle_bilstm_forward(T, S, I, C, L.p(frames), L.p(L.arr(x)), L.pp(p64), L.p(bf), L.p(bb), L.p(out64))
+    corr = [np.zeros_like(p) for p in p64]
+    dbf = np.zeros_like(bf); dbb = np.zeros_like(bf); dx64 = np.zeros((T * S, I))
+    L.lib.oracle_bilstm_backward(T, S, I, C, L.p(L.arr(x)), L.pp(p64), L.p(bf), L.p(bb), L.p(L.arr(dout)), L.p(dbf),
+                                 L.p(dbb), L.p(dx64), L.pp(corr), L.real(0.0))
+    # device
+    dp = [torch.from_numpy(p).cuda() for p in params]
+    dg = [torch.full_like(p, 9.0) for p in dp]
+    d_x = torch.from_numpy(x).cuda(); d_len = torch.from_numpy(frames).cuda()
+    gates = torch.empty((T * S, 8 * C), device="cuda"); cell = torch.empty((T * S, 2 * C), device="cuda")
+    out = torch.empty((T * S, 2 * C), device="cuda"); dgates = torch.empty((T * S, 8 * C), device="cuda")
+    d_dout = torch.from_numpy(dout).cuda(); dx = torch.empty((T * S, I), device="cuda")
+    torch.cuda.synchronize()
+    ctx.set_precision("fp32x3", rec)
+    ctx.bilstm_forward(T, S, I, C, d_len, d_x, I, dp, gates, cell, out, 2 * C)
+    ctx.bilstm_backward(T, S, I, C, d_x, I, dp, gates, cell, out, 2 * C, d_dout, 2 * C, dgates, dx, I, dg)
+    ctx.synchronize()
+    ctx.set_precision("fp32x3", "fp32x3")
+    tol = 1.0 if rec == "fp32x3" else 300.0
+    assert_close("out", out.cpu().numpy(), out64, atol=2e-6 * tol)
+    # saved state: cols of the reference's 7-block buffers (g,i,f,o | c)
+    g_fw = gates.cpu().numpy()[:, :4 * C]; g_bw = gates.cpu().numpy()[:, 4 * C:]
+    assert_close("gates_fw", g_fw, bf[S:(T + 1) * S, :4 * C], atol=3e-6 * tol)
+    assert_close("gates_bw", g_bw, bb[S:(T + 1) * S, :4 * C], atol=3e-6 * tol)
+    assert_close("cell_fw", cell.cpu().numpy()[:, :C], bf[S:(T + 1) * S, 4 * C:5 * C], atol=5e-6 * tol)
+    assert_close("dgates_fw", dgates.cpu().numpy()[:, :4 * C], dbf[S:(T + 1) * S, :4 * C], atol=2e-5 * tol, rtol=1e-4)
+    assert_close("dgates_bw", dgates.cpu().numpy()[:, 4 * C:], dbb[S:(T + 1) * S, :4 * C], atol=2e-5 * tol, rtol=1e-4)
+    assert_close("dx", dx.cpu().numpy(), dx64, atol=5e-5 * tol, rtol=1e-4)
+    for k, n in enumerate(l.param_names()):
+        scale = max(1.0, np.abs(corr[k]).max())
+        assert_close(f"grad_{n}", dg[k].cpu().numpy() / scale, corr[k] / scale, atol=2e-5 * tol)
+    # padding semantics (bilstm-parallel-layer.h:201-204): backward cells are zero past the end, forward are not
+    for s in range(S):
+        rows = np.arange(frames[s], T) * S + s
+        if len(rows):
+            assert np.all(out.cpu().numpy()[rows, C:] == 0)
+            assert np.all(dgates.cpu().numpy()[rows] == 0)
+
+
+def test_sgd_update_segments(ctx):
+    torch = torch_()
+    rng = np.random.default_rng(0)
+    n = 1003
+    w = rng.standard_normal(n).astype(np.float32); c = rng.standard_normal(n).astype(np.float32) * 3
+    g = rng.standard_normal(n).astype(np.float32) * 3
+    segs = [(0, 501, 0.1, 2.0), (501, 502, 0.05, 0.0)]
+    dw, dc, dg = (torch.from_numpy(a.copy()).cuda() for a in (w, c, g))
+    torch.cuda.synchronize()
+    ctx.sgd_update(dw, dc, dg, n, 0.9, segs)
+    ctx.synchronize()
+    cref = g + np.float32(0.9) * c
+    cref[:501] = np.clip(cref[:501], -2.0, 2.0)
+    wref = w.copy(); wref[:501] -= np.float32(0.1) * cref[:501]; wref[501:] -= np.float32(0.05) * cref[501:]
+    assert_close("corr", dc.cpu().numpy(), cref, atol=1e-6)
+    assert_close("w", dw.cpu().numpy(), wref, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------ level 2
+def _gpu_steps(ctx, net, b, lr, mom, steps, want_in_diff=True):
+    n = binding.Net(ctx, model_file(net))
+    n.set_train_options(lr, mom)
+    if want_in_diff:
+        n.get(102)
+    st = None
+    for _ in range(steps):
+        st = n.train_step(b.feats, b.frames, b.labels, True)
+    return n, st
+
+
+@pytest.mark.parametrize("wl", ["tiny", "small", "mid"])
+def test_train_step_vs_oracle(ctx, wl):
+    w, net, b = case(wl)
+    lr, mom = 1e-3, 0.9
+    n, st = _gpu_steps(ctx, net, b, lr, mom, 1)
+    on = oracle.OracleNet(net, np.float64)
+    ro = on.train_step(b, lr, mom)
+    for i in range(1, len(net.layers) + 1):
+        assert_close(f"out_l{i}", n.get(i), on.acts[i], atol=2e-5)
+    assert_close("pzx", n.get(101).ravel(), ro["pzx"], atol=0, rtol=2e-5)
+    assert abs(st["obj"] - ro["pzx"].sum()) <= 2e-5 * abs(ro["pzx"].sum())
+    assert_close("obj_diff", n.get(100), ro["obj_diff"], atol=1e-4)
+    assert_close("in_diff", n.get(102), ro["in_diff"], atol=2e-5, rtol=1e-3)
+    assert_close("corr", n.corr(), on.flat_corr(), atol=2e-3, rtol=2e-3)
+    assert_close("params", n.params(), on.flat_params(), atol=2e-6)
+    err, ref = oracle.greedy_token_errors(ro["net_out"], b.frames, b.labels, b.S)
+    assert (st["token_err"], st["ref_tokens"], st["frames"]) == (err, ref, b.valid_frames)
+    # second step exercises the momentum carry
+    st2 = n.train_step(b.feats, b.frames, b.labels, True)
+    ro2 = on.train_step(b, lr, mom)
+    assert abs(st2["obj"] - ro2["pzx"].sum()) <= 5e-5 * abs(ro2["pzx"].sum())
+    assert_close("params2", n.params(), on.flat_params(), atol=5e-6)
+    n.close()
+
+
+@pytest.mark.parametrize("wl", ["tiny", "small"])
+@pytest.mark.parametrize("kind", ["cpu", "gpu"])
+def test_train_step_vs_reference_golden(ctx, wl, kind):
+    """Against the committed outputs of the UNMODIFIED reference (tests/golden/make_golden.py)."""
+    path = os.path.join(GOLDEN, f"{wl}_ref{kind}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated")
+    g = np.load(path)
+    mseed, bseed, steps = [int(v) for v in g["meta"]]
+    lr, mom = [float(v) for v in g["hyper"]]
+    w, net, b = case(wl, mseed, bseed)
+    n, st = _gpu_steps(ctx, net, b, lr, mom, steps)
+    if kind == "gpu":   # the reference's own CUDA CTC drove both steps, as ours did
+        assert_close("pzx", n.get(101).ravel(), g["pzx"], atol=0, rtol=2e-5)
+        assert_close("obj_diff", n.get(100), g["obj_diff"], atol=1e-4)
+        assert_close("params", n.params(), g["params_out"], atol=5e-6)
+        assert_close("corr", n.corr(), golden_arrays(g, net), atol=2e-3, rtol=2e-3)
+        for i in range(1, len(net.layers) + 1):
+            assert_close(f"out_l{i}", n.get(i), g[f"out_l{i}"], atol=2e-5)
+    else:
+        # CPU reference has no CTC: its backward was driven by a stored diff, so only the forward of
+        # step 1 is comparable end to end; compare the first-step forward
+        n1, _ = _gpu_steps(ctx, net, b, lr, mom, 0)
+        n1.train_step(b.feats, b.frames, b.labels, False)
+        g1 = oracle.OracleNet(net, np.float32)
+        g1.forward(b.feats, b.frames)
+        for i in range(1, len(net.layers) + 1):
+            assert_close(f"out_l{i}", n1.get(i), g1.acts[i], atol=2e-5)
+        n1.close()
+    n.close()
+
+
+@pytest.mark.skipif(not oracle.have_reference("gpu"), reason="oracle/_ref/ref_dump_gpu not built")
+@pytest.mark.parametrize("wl,steps", [("small", 2), ("mid", 1)])
+def test_train_step_vs_reference_gpucompute_live(ctx, wl, steps):
+    """Same inputs through the reference's own gpucompute kernels (compiled for sm_100a) on this GPU."""
+    w, net, b = case(wl, 21, 22)
+    lr, mom = 1e-3, 0.9
+    d = tempfile.mkdtemp()
+    kaldi_io.write_model(d + "/model", net)
+    kaldi_io.write_batch_file(d + "/batch.bin", b)
+    oracle.run_reference("gpu", d + "/model", d + "/batch.bin", d + "/out", lr, mom, steps=steps)
+    ref = oracle.load_dump(d + "/out")
+    n, st = _gpu_steps(ctx, net, b, lr, mom, steps)
+    assert_close("pzx", n.get(101).ravel(), ref["pzx"], atol=0, rtol=2e-5)      # north_star: 1e-4 relative
+    assert_close("net_out", n.get(len(net.layers)), ref["net_out"], atol=2e-5)
+    assert_close("obj_diff", n.get(100), ref["obj_diff"], atol=1e-4)
+    assert_close("in_diff", n.get(102), ref["in_diff"], atol=2e-5, rtol=1e-3)
+    assert_close("corr", n.corr(), golden_arrays(ref, net), atol=2e-3, rtol=2e-3)
+    m2 = kaldi_io.read_model(d + "/out/model_out")
+    assert_close("params", n.params(), m2.flat_params(), atol=5e-6)
+    n.close()
+
+
+def test_model_write_is_byte_compatible(ctx):
+    w, net, b = case("tiny")
+    p = model_file(net)
+    n = binding.Net(ctx, p)
+    out = p + ".out"
+    n.write(out, True)
+    assert open(out, "rb").read() == open(p, "rb").read()        # Net::Write(Net::Read(x)) == x
+    txt = p + ".txt"
+    n.write(txt, False)
+    n2 = binding.Net(ctx, txt)                                     # text mode round trip
+    assert_close("text", n2.params(), n.params(), atol=1e-6)
+    n.close(); n2.close()
+
+
+def test_tf32_mode_within_north_star_tolerance(ctx):
+    w, net, b = case("mid")
+    ctx.set_precision("tf32", "tf32")
+    try:
+        n, st = _gpu_steps(ctx, net, b, 1e-3, 0.9, 1)
+    finally:
+        ctx.set_precision("fp32x3", "fp32x3")
+    on = oracle.OracleNet(net, np.float64)
+    ro = on.train_step(b, 1e-3, 0.9)
+    assert_close("pzx", n.get(101).ravel(), ro["pzx"], atol=0, rtol=1e-4)
+    assert_close("obj_diff", n.get(100), ro["obj_diff"], atol=5e-3)
+    n.close()
+
+
+# ------------------------------------------------------------------------------------ full size (C2)
+@pytest.fixture(scope="module")
+def c2_run(ctx):
+    w = synth.WORKLOADS["c2"]
+    net = synth.make_model(w, seed=0)
+    b = synth.make_batch(w, seed=1)
+    n = binding.Net(ctx, model_file(net))
+    n.set_train_options(w.learn_rate, w.momentum)
+    st = n.train_step(b.feats, b.frames, b.labels, True)
+    yield w, net, b, n, st
+    n.close()
+
+
+def test_c2_full_size_properties(ctx, c2_run):
+    """BASELINE configs[1] at full size: size-independent properties of the result."""
+    w, net, b, n, st = c2_run
+    diff = n.get(100)
+    y = n.get(len(net.layers))
+    pzx = n.get(101).ravel()
+    assert st["frames"] == b.valid_frames and np.isfinite(st["obj"]) and np.all(pzx < 0)
+    T, S = b.T, b.S
+    valid = np.zeros(T * S, bool)
+    for s in range(S):
+        valid[np.arange(b.frames[s]) * S + s] = True
+    assert np.abs(y.sum(1) - 1).max() < 1e-5                      # softmax rows
+    assert np.abs(diff[valid].sum(1)).max() < 2e-5                # CTC gradient rows sum to zero
+    assert np.all(diff[~valid] == 0)                              # padded rows exactly zero
+    # the CTC of the full-size posteriors against the fp64 oracle (CTC alone is cheap on the CPU)
+    p64, d64, _, _ = oracle.ctc_eval(y.astype(np.float64), b.frames, b.labels, S, np.float64)
+    assert_close("pzx", pzx, p64, atol=0, rtol=2e-5)
+    assert_close("diff", diff, d64, atol=1e-4)
+    # backward cells of the last BiLSTM layer are zero on padded rows; forward cells are not masked
+    top = n.get(len(net.layers) - 2)
+    assert np.all(top[~valid][:, w.cells:] == 0) and np.abs(top[~valid][:, :w.cells]).max() > 0
+    assert np.all(np.isfinite(n.params()))
+
+
+def test_c2_full_size_deterministic(ctx, c2_run):
+    """Two independent runs of the same step are bit-identical (fixed reduction orders, no atomics
+    on the data path)."""
+    w, net, b, n, st = c2_run
+    n2 = binding.Net(ctx, model_file(net))
+    n2.set_train_options(w.learn_rate, w.momentum)
+    st2 = n2.train_step(b.feats, b.frames, b.labels, True)
+    assert st2["obj"] == st["obj"]
+    assert np.array_equal(n2.params(), n.params())
+    n2.close()
+
+
+@pytest.mark.skipif(not oracle.have_reference("gpu"), reason="oracle/_ref/ref_dump_gpu not built")
+def test_c2_full_size_vs_reference_gpucompute(ctx):
+    """BASELINE configs[1] at full size against the reference's own gpucompute run on the same inputs:
+    CTC log-prob within 1e-4 relative (north_star) and per-frame gradients within the stated tolerance."""
+    w = synth.WORKLOADS["c2"]
+    net = synth.make_model(w, seed=0)
+    b = synth.make_batch(w, seed=1)
+    d = tempfile.mkdtemp()
+    kaldi_io.write_model(d + "/model", net)
+    kaldi_io.write_batch_file(d + "/batch.bin", b)
+    info = oracle.run_reference("gpu", d + "/model", d + "/batch.bin", d + "/out", w.learn_rate, w.momentum, steps=1)
+    ref = oracle.load_dump(d + "/out")
+    n, st = _gpu_steps(ctx, net, b, w.learn_rate, w.momentum, 1, want_in_diff=False)
+    pzx = n.get(101).ravel()
+    rel = np.abs(pzx - ref["pzx"]) / np.abs(ref["pzx"])
+    assert rel.max() < 2e-5, rel.max()
+    assert_close("net_out", n.get(len(net.layers)), ref["net_out"], atol=5e-5)
+    assert_close("obj_diff", n.get(100), ref["obj_diff"], atol=2e-4)
+    m2 = kaldi_io.read_model(d + "/out/model_out")
+    assert_close("params", n.params(), m2.flat_params(), atol=5e-6)
+    print(f"reference gpucompute on this GPU: {info['valid_fps']:.0f} valid frames/s (one cold step)")
+    n.close()
