@@ -12,7 +12,7 @@ OBJDIR  := build
 LIBDIR  := eesen_b200/lib
 BINDIR  := eesen_b200/bin
 
-CU_SRCS := gemm lstm ctc optim
+CU_SRCS := gemm gemm_tc lstm ctc optim
 CC_SRCS := base net abi_ops abi_net
 CU_OBJS := $(patsubst %,$(OBJDIR)/%.cu.o,$(CU_SRCS))
 CC_OBJS := $(patsubst %,$(OBJDIR)/%.cc.o,$(CC_SRCS))

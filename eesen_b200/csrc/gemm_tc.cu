@@ -1,0 +1,443 @@
+// eesen_b200/csrc/gemm_tc.cu -- tcgen05 / TMEM / TMA GEMM for the dense input-side contractions.
+//
+//   C[M x N] = alpha * op(A) * op(B) + beta * C (+ bias row)      fp32 storage, row-major
+//
+// Same call sites as gemm.cu (reference CuMatrixBase::AddMatMat -> cublasSgemm,
+// gpucompute/cuda-matrix.cc:603-639), but on the 5th-generation tensor cores:
+//   * operands are fetched by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) straight from the
+//     row-major fp32 matrices -- K-major when k is the contiguous index (A of NT/NN, B of NT),
+//     MN-major when m/n is contiguous (A and B of TN, B of NN): no transposed copies;
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=64|128, K=8) with
+//     the accumulator in TMEM; tcgen05.commit releases smem stages / publishes the accumulator;
+//   * fp32 fidelity ("3xTF32"): the four otherwise idle epilogue warps split every landed tile in
+//     place into hi = x & 0xffffe000 and a second tile lo = x - hi, and the issuing thread runs
+//     three MMAs per k-slice: lo*hi + hi*lo + hi*hi (fp32 accumulation in TMEM).  The TF32 mode
+//     skips the split and issues one MMA;
+//   * epilogue: tcgen05.ld 32x32b -> registers -> alpha/beta/bias -> 128-bit global stores, or a
+//     split-K partial into a workspace that splitk_reduce sums in fixed order (deterministic).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = operand splitters during the main loop, then the epilogue (TMEM lane quadrant = warp%4).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace eb {
+
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;          // 32 fp32 = 128 bytes = one swizzle row
+constexpr int TC_THREADS = 192;
+
+struct TcArgs {
+  int M, N, K;
+  float *C; int ldc;
+  const float *bias;
+  float alpha, beta;
+  int splits, kblocks_per_split;
+  float *ws;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout).
+//   K-major operand : LayoutType::SWIZZLE_128B (2): rows of 128 B, 8-row atoms, SBO = 1024 B between atoms
+//   MN-major tf32   : LayoutType::SWIZZLE_128B_BASE32B (1) -- the only MN-major layout for 32-bit operands
+//                     (cutlass sm100_common.inl:92): rows of 128 B = 32 elements along M/N, 4-k-row atoms
+//                     (Swizzle<2,5,2>), SBO = 512 B between k atoms, LBO between 32-wide M/N groups
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);             // start address  [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;   // leading byte offset [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;   // stride byte offset  [32,46)
+  d |= (uint64_t)1 << 46;                              // descriptor version 1 (Blackwell)
+  d |= (uint64_t)layout << 61;                         // LayoutType
+  return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// TA: 0 = A stored [M x K] (K-major operand), 1 = A stored [K x M] (MN-major operand)
+// TB: 1 = B stored [N x K] (K-major operand), 0 = B stored [K x N] (MN-major operand)
+template <int BN, int TA, int TB, int NTERMS, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs p) {
+  constexpr int A_BYTES = TC_BM * TC_BK * 4;
+  constexpr int B_BYTES = BN * TC_BK * 4;
+  constexpr int STAGE_BYTES = NTERMS == 3 ? 2 * (A_BYTES + B_BYTES) : (A_BYTES + B_BYTES);
+  // stage layout: [A hi][B hi]([A lo][B lo])
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[STAGES], conv_bar[STAGES], empty_bar[STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_sm;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int split = blockIdx.z;
+  const int kb_total = (p.K + TC_BK - 1) / TC_BK;
+  const int kb_beg = split * p.kblocks_per_split;
+  const int kb_end = min(kb_total, kb_beg + p.kblocks_per_split);
+  const int nkb = kb_end - kb_beg;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&conv_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    // allocate BN (power of two >= 32) TMEM columns for the fp32 accumulator
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_sm)),
+                 "n"(BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = tmem_base_sm;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % STAGES;
+        if (i >= STAGES) mbar_wait(&empty_bar[s], ((i / STAGES) - 1) & 1);
+        uint8_t *sa = smem + (size_t)s * STAGE_BYTES;
+        uint8_t *sb = sa + A_BYTES;
+        mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+        const int k0 = (kb_beg + i) * TC_BK;
+        if (TA == 0) {
+          tma_load_2d(sa, &mapA, k0, m0, &full_bar[s]);              // box {32 k, 128 m}
+        } else {
+#pragma unroll
+          for (int g = 0; g < TC_BM / 32; g++)                        // box {32 m, 32 k} per 32-wide M group
+            tma_load_2d(sa + g * (TC_BK * 128), &mapA, m0 + g * 32, k0, &full_bar[s]);
+        }
+        if (TB == 1) {
+          tma_load_2d(sb, &mapB, k0, n0, &full_bar[s]);              // box {32 k, BN n}
+        } else {
+#pragma unroll
+          for (int g = 0; g < BN / 32; g++)
+            tma_load_2d(sb + g * (TC_BK * 128), &mapB, n0 + g * 32, k0, &full_bar[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // instruction descriptor: D=F32, A=B=TF32, majors, N>>3, M>>4 (cute::UMMA::InstrDescriptor)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TA ? 1 : 0) << 15) |
+                             ((uint32_t)(TB ? 0 : 1) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % STAGES;
+        if (NTERMS == 3) mbar_wait(&conv_bar[s], (i / STAGES) & 1);
+        else mbar_wait(&full_bar[s], (i / STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; k++) {
+          // K-major : 8-row groups 1024 B apart (SBO), a k-slice of 8 tf32 = +32 bytes inside the swizzle row
+          // MN-major: 32-wide m/n groups BK*128 B apart (LBO), 4-k-row atoms 512 B apart (SBO), k-slice of 8 = +1024 bytes
+          const uint32_t a_off = TA == 0 ? k * 32 : k * 1024;
+          const uint32_t b_off = TB == 1 ? k * 32 : k * 1024;
+          const uint32_t a_lbo = TA == 0 ? 16 : TC_BK * 128, b_lbo = TB == 1 ? 16 : TC_BK * 128;
+          const uint32_t a_sbo = TA == 0 ? 1024 : 512, b_sbo = TB == 1 ? 1024 : 512;
+          const uint32_t a_lay = TA == 0 ? 2 : 1, b_lay = TB == 1 ? 2 : 1;
+          const uint64_t ah = umma_desc(sa + a_off, a_lbo, a_sbo, a_lay);
+          const uint64_t bh = umma_desc(sb + b_off, b_lbo, b_sbo, b_lay);
+          if (NTERMS == 3) {
+            const uint64_t al = umma_desc(sa + A_BYTES + B_BYTES + a_off, a_lbo, a_sbo, a_lay);
+            const uint64_t bl = umma_desc(sb + A_BYTES + B_BYTES + b_off, b_lbo, b_sbo, b_lay);
+            umma_tf32(tmem_base, al, bh, idesc, (i | k) != 0);   // small terms first
+            umma_tf32(tmem_base, ah, bl, idesc, 1);
+            umma_tf32(tmem_base, ah, bh, idesc, 1);
+          } else {
+            umma_tf32(tmem_base, ah, bh, idesc, (i | k) != 0);
+          }
+        }
+        umma_commit(&empty_bar[s]);     // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(&accum_bar);          // accumulator complete
+    }
+  } else {
+    // ===== operand splitters (3xTF32), then epilogue =====
+    const int et = threadIdx.x - 64;   // 0..127
+    if (NTERMS == 3) {
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % STAGES;
+        mbar_wait(&full_bar[s], (i / STAGES) & 1);
+        float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * STAGE_BYTES);
+        float4 *lo = reinterpret_cast<float4 *>(smem + (size_t)s * STAGE_BYTES + A_BYTES + B_BYTES);
+        constexpr int NV = (A_BYTES + B_BYTES) / 16;
+#pragma unroll 4
+        for (int v = et; v < NV; v += 128) {
+          float4 x = hi[v];
+          float4 h, l;
+          h.x = u2f(f2u(x.x) & 0xffffe000u); l.x = x.x - h.x;
+          h.y = u2f(f2u(x.y) & 0xffffe000u); l.y = x.y - h.y;
+          h.z = u2f(f2u(x.z) & 0xffffe000u); l.z = x.z - h.z;
+          h.w = u2f(f2u(x.w) & 0xffffe000u); l.w = x.w - h.w;
+          hi[v] = h;
+          lo[v] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
+        mbar_arrive(&conv_bar[s]);
+      }
+    }
+    mbar_wait(&accum_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    // Epilogue: TMEM (lane = output row) -> registers -> this warp's private 32 x BN staging tile in
+    // shared memory (the operand stages are free: every MMA has completed) -> row-wise, fully
+    // coalesced global traffic (512-byte row segments) for the alpha/beta/bias update.
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    constexpr int EST = BN + 4;                // staging row stride (floats): conflict-free v4 stores
+    float *stg = reinterpret_cast<float *>(smem) + (size_t)quad * 32 * EST;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      float4 *dst = reinterpret_cast<float4 *>(stg + (size_t)lane * EST + c0);
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        dst[j] = make_float4(u2f(r[4 * j]), u2f(r[4 * j + 1]), u2f(r[4 * j + 2]), u2f(r[4 * j + 3]));
+    }
+    __syncwarp();
+    const bool vec_ok = (p.ldc & 3) == 0 && (p.N & 3) == 0 && p.splits == 1 && ((uintptr_t)p.C & 15) == 0 &&
+                        ((uintptr_t)p.bias & 15) == 0;
+    for (int rr = 0; rr < 32; rr++) {
+      const int row = m0 + quad * 32 + rr;
+      if (row >= p.M) break;
+      const float *srow = stg + (size_t)rr * EST;
+      if (p.splits > 1) {
+        float *wrow = p.ws + ((size_t)split * p.M + row) * p.N + n0;
+        for (int c = lane; c < BN && n0 + c < p.N; c += 32) wrow[c] = srow[c];
+      } else if (vec_ok) {
+        float *crow = p.C + (size_t)row * p.ldc + n0;
+        for (int c = lane * 4; c < BN && n0 + c < p.N; c += 128) {
+          float4 v = *reinterpret_cast<const float4 *>(srow + c);
+          v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
+          if (p.bias) {
+            const float4 b = *reinterpret_cast<const float4 *>(p.bias + n0 + c);
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+          }
+          if (p.beta != 0.f) {
+            const float4 o = *reinterpret_cast<const float4 *>(crow + c);
+            v.x += p.beta * o.x; v.y += p.beta * o.y; v.z += p.beta * o.z; v.w += p.beta * o.w;
+          }
+          *reinterpret_cast<float4 *>(crow + c) = v;
+        }
+      } else {
+        float *crow = p.C + (size_t)row * p.ldc + n0;
+        for (int c = lane; c < BN && n0 + c < p.N; c += 32) {
+          float v = p.alpha * srow[c];
+          if (p.bias) v += p.bias[n0 + c];
+          if (p.beta != 0.f) v += p.beta * crow[c];
+          crow[c] = v;
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+
+__global__ void tc_splitk_reduce_kernel(TcArgs p) {
+  size_t n = (size_t)p.M * p.N;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < p.splits; k++) s += p.ws[k * n + i];
+    int r = (int)(i / p.N), c = (int)(i % p.N);
+    float v = p.alpha * s;
+    if (p.bias) v += p.bias[c];
+    float *dst = p.C + (size_t)r * p.ldc + c;
+    if (p.beta != 0.f) v += p.beta * (*dst);
+    *dst = v;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map over a row-major matrix [rows x cols] with leading dimension ld (floats);
+// box = {box_cols (inner, 32 floats = 128 B), box_rows}; out-of-bounds elements read as zero.
+bool make_map(CUtensorMap *map, const float *base, long rows, long cols, long ld, int box_cols, int box_rows,
+              CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BN, int TA, int TB, int NTERMS>
+cudaError_t launch_tc(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const TcArgs &p) {
+  constexpr int STAGES = NTERMS == 3 ? (BN == 128 ? 3 : 4) : (BN == 128 ? 6 : 8);
+  constexpr int STAGE_BYTES = (NTERMS == 3 ? 2 : 1) * (TC_BM * TC_BK * 4 + BN * TC_BK * 4);
+  constexpr int SMEM = STAGES * STAGE_BYTES + 1024;
+  auto kern = gemm_tc_kernel<BN, TA, TB, NTERMS, STAGES>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  dim3 grid((p.N + BN - 1) / BN, (p.M + TC_BM - 1) / TC_BM, p.splits);
+  kern<<<grid, TC_THREADS, SMEM, st>>>(ma, mb, p);
+  return cudaGetLastError();
+}
+
+template <int TA, int TB>
+cudaError_t launch_tc_layout(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const TcArgs &p, int nterms) {
+  if (p.N > 64) {
+    return nterms == 3 ? launch_tc<128, TA, TB, 3>(st, ma, mb, p) : launch_tc<128, TA, TB, 1>(st, ma, mb, p);
+  }
+  return nterms == 3 ? launch_tc<64, TA, TB, 3>(st, ma, mb, p) : launch_tc<64, TA, TB, 1>(st, ma, mb, p);
+}
+
+}  // namespace
+
+bool gemm_tc_supported(int transA, int transB, int M, int N, int K, const float *A, int lda, const float *B, int ldb,
+                       int precision) {
+  if (precision != 0 && precision != 1) return false;
+  if (transA && transB) return false;
+  if (M <= 0 || N <= 0 || K <= 0) return false;
+  if ((lda & 3) || (ldb & 3) || (((uintptr_t)A) & 15) || (((uintptr_t)B) & 15)) return false;
+  return get_encode() != nullptr;
+}
+
+size_t gemm_tc_workspace_bytes(int M, int N, int K, int num_sms) {
+  int bn = N > 64 ? 128 : 64;
+  long tiles = (long)((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn);
+  if (tiles >= num_sms || K < 4096) return 0;
+  int splits = (int)((2L * num_sms + tiles - 1) / tiles);
+  if (splits > 64) splits = 64;
+  return (size_t)splits * M * N * sizeof(float);
+}
+
+cudaError_t gemm_tc(cudaStream_t st, int num_sms, int transA, int transB, int M, int N, int K, float alpha,
+                    const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc,
+                    const float *bias, int precision, float *ws, size_t ws_bytes) {
+  const int bn = N > 64 ? 128 : 64;
+  CUtensorMap ma, mb;
+  bool ok;
+  // A: stored [M x K] (transA=0) -> K-major box {32 k, 128 m}; stored [K x M] (transA=1) -> MN-major box {32 m, 32 k}
+  const CUtensorMapSwizzle kK = CU_TENSOR_MAP_SWIZZLE_128B, kMN = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  ok = transA == 0 ? make_map(&ma, A, M, K, lda, TC_BK, TC_BM, kK) : make_map(&ma, A, K, M, lda, 32, TC_BK, kMN);
+  // B: stored [N x K] (transB=1) -> K-major box {32 k, bn n}; stored [K x N] (transB=0) -> MN-major box {32 n, 32 k}
+  ok = ok && (transB == 1 ? make_map(&mb, B, N, K, ldb, TC_BK, bn, kK) : make_map(&mb, B, K, N, ldb, 32, TC_BK, kMN));
+  if (!ok) return cudaErrorInvalidValue;
+  TcArgs p;
+  p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.alpha = alpha; p.beta = beta; p.ws = ws;
+  const int kb = (K + TC_BK - 1) / TC_BK;
+  p.splits = 1;
+  p.kblocks_per_split = kb;
+  long tiles = (long)((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn);
+  if (tiles < num_sms && K >= 4096 && ws) {
+    int splits = (int)((2L * num_sms + tiles - 1) / tiles);
+    if (splits > kb / 16) splits = kb / 16;
+    if (splits > 64) splits = 64;
+    while (splits > 1 && (size_t)splits * M * N * sizeof(float) > ws_bytes) splits--;
+    if (splits > 1) {
+      int per = (kb + splits - 1) / splits;
+      p.kblocks_per_split = per;
+      p.splits = (kb + per - 1) / per;
+    }
+  }
+  const int nterms = precision == 0 ? 3 : 1;
+  cudaError_t e;
+  if (transA == 0 && transB == 1) e = launch_tc_layout<0, 1>(st, ma, mb, p, nterms);
+  else if (transA == 0 && transB == 0) e = launch_tc_layout<0, 0>(st, ma, mb, p, nterms);
+  else if (transA == 1 && transB == 0) e = launch_tc_layout<1, 0>(st, ma, mb, p, nterms);
+  else return cudaErrorInvalidValue;
+  if (e != cudaSuccess) return e;
+  if (p.splits > 1) {
+    size_t n = (size_t)M * N;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 4 * num_sms) blocks = 4 * num_sms;
+    tc_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+}  // namespace eb

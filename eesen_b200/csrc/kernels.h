@@ -13,6 +13,14 @@ cudaError_t gemm(cudaStream_t st, int num_sms, int transA, int transB, int M, in
                  int precision, float *ws, size_t ws_bytes);
 size_t gemm_workspace_bytes(int M, int N, int K, int batch, int num_sms);
 
+// gemm_tc.cu -- tcgen05 / TMEM / TMA path (fp32x3 and tf32 arithmetic); one matrix per call
+bool gemm_tc_supported(int transA, int transB, int M, int N, int K, const float *A, int lda, const float *B, int ldb,
+                       int precision);
+size_t gemm_tc_workspace_bytes(int M, int N, int K, int num_sms);
+cudaError_t gemm_tc(cudaStream_t st, int num_sms, int transA, int transB, int M, int N, int K, float alpha,
+                    const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc,
+                    const float *bias, int precision, float *ws, size_t ws_bytes);
+
 // lstm.cu -- persistent recurrent kernels (both directions in one cooperative launch)
 struct LstmDirParams {
   const float *wm;  // [4C x C] recurrent weights, row blocks g,i,f,o

@@ -51,6 +51,10 @@ int eesen_b200_create(eesen_b200_ctx **out, int device) {
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
   ctx->max_smem = prop.sharedMemPerBlockOptin;
+  {
+    const char *eng = getenv("EESEN_B200_GEMM_ENGINE");
+    ctx->gemm_engine = (eng && std::string(eng) == "legacy") ? 1 : 0;
+  }
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return (int)e; }
   *out = ctx;
@@ -98,6 +102,27 @@ static int do_gemm(eesen_b200_ctx *ctx, int ta, int tb, int M, int N, int K, flo
                    long sA, const float *B, int ldb, long sB, float beta, float *C, int ldc, long sC,
                    const float *bias, long sBias, int batch) {
   void *ws = nullptr;
+  // tensor-core engine: tcgen05/TMEM/TMA (gemm_tc.cu) for fp32x3 / tf32; the warp-level mma.sync
+  // kernel (gemm.cu) serves the bf16 mode and EESEN_B200_GEMM_ENGINE=legacy (A/B measurements)
+  if (ctx->gemm_engine == 0 && eb::gemm_tc_supported(ta, tb, M, N, K, A, lda, B, ldb, ctx->gemm_prec) &&
+      (batch == 1 || ((sA & 3) == 0 && (sB & 3) == 0))) {
+    size_t need_tc = eb::gemm_tc_workspace_bytes(M, N, K, ctx->num_sms);
+    if (need_tc) {
+      int rc = ctx->reserve(ctx->gemm_ws, need_tc, &ws);
+      if (rc) return rc;
+    }
+    for (int b = 0; b < batch; b++) {
+      int pe = ctx->prof_begin(eesen_b200_ctx::kGemm);
+      cudaError_t e = eb::gemm_tc(ctx->stream, ctx->num_sms, ta, tb, M, N, K, alpha, A + b * sA, lda, B + b * sB, ldb,
+                                  beta, C + b * sC, ldc, bias ? bias + b * sBias : nullptr, ctx->gemm_prec,
+                                  (float *)ws, ws ? ctx->gemm_ws.bytes : 0);
+      ctx->prof_end(pe);
+      ctx->launches += 1;
+      int rc = ctx->check(e, "gemm_tc");
+      if (rc) return rc;
+    }
+    return 0;
+  }
   size_t need = eb::gemm_workspace_bytes(M, N, K, batch, ctx->num_sms);
   if (K >= 4096) {
     int rc = ctx->reserve(ctx->gemm_ws, need, &ws);

@@ -18,6 +18,7 @@ struct eesen_b200_ctx {
   int num_sms = 0;
   size_t max_smem = 0;
   int gemm_prec = 0, rec_prec = 0;
+  int gemm_engine = 0;  // 0 = tcgen05 (gemm_tc.cu), 1 = warp-level mma.sync (gemm.cu)
   std::string err;
   long launches = 0;
 
