@@ -6,7 +6,7 @@ CUDA    ?= /usr/local/cuda
 NVCC    := $(CUDA)/bin/nvcc
 CXX     := g++
 ARCH    := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall
+NVFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall $(if $(TIMING),-DEB_LSTM_TIMING,)
 CXXFLAGS:= -O2 -std=c++17 -fPIC -Wall -I$(CUDA)/include
 OBJDIR  := build
 LIBDIR  := eesen_b200/lib

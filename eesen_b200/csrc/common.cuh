@@ -43,13 +43,24 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// Activations.  The reference evaluates 1/(1+exp(-x)) and (e^{2x}-1)/(e^{2x}+1) with
-// double-literal promotion (cuda-kernels.cu:693,718-723); these fp32 forms agree to ~1e-7.
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// Activations on the SFU: one MUFU.EX2 + one MUFU.RCP each (no IEEE-division slow path on the
+// serial per-timestep critical path).  The reference evaluates 1/(1+exp(-x)) and
+// (e^{2x}-1)/(e^{2x}+1) with double-literal promotion (cuda-kernels.cu:693,718-723); these agree
+// to ~2e-7 absolute (ex2.approx 2 ulp, rcp.approx 1 ulp), exact limits at +-inf.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanhf_(float x) {
-  // 1 - 2/(e^{2x}+1): exact limits at +-inf, no cancellation blow-up beyond 1 ulp of 1.
-  float e = __expf(2.0f * x);
-  return 1.0f - 2.0f / (e + 1.0f);
+  // 1 - 2/(e^{2x}+1)
+  return fmaf(-2.0f, rcp_approx(ex2_approx(2.8853900817779268f * x) + 1.0f), 1.0f);
 }
 
 // release/acquire flag primitives for the inter-CTA step flags of the recurrent kernels
@@ -66,6 +77,23 @@ __device__ __forceinline__ unsigned ld_relaxed(const unsigned *p) {
   unsigned v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+// "LL" exchange words: a 32-bit payload and a 32-bit step tag travel in ONE 8-byte store, so a
+// consumer that sees the expected tag has the payload -- no fence, no separate flag (the idea of
+// NCCL's LL protocol).  Loads/stores are relaxed at gpu scope (served by L2, never by a stale L1 line).
+__device__ __forceinline__ void st_tagged(uint2 *p, float v, unsigned tag) {
+  asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};\n" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint4 ld_tagged2(const uint4 *p) {
+  uint4 q;
+  asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(p) : "memory");
+  return q;
+}
+__device__ __forceinline__ uint2 ld_tagged(const uint2 *p) {
+  uint2 q;
+  asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];\n" : "=r"(q.x), "=r"(q.y) : "l"(p) : "memory");
+  return q;
 }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;\n" ::: "memory"); }
 

@@ -33,7 +33,7 @@ struct LstmFwdArgs {
   float *cell; int ldc;  // [T*S x 2C] cell state c (dir d at col d*C)
   float *out; int ldo;   // [T*S x 2C] m = o*tanh(c): the layer output (dir d at col d*C)
   LstmDirParams p[2];
-  unsigned *flags;       // [2 * groups] step counters, zeroed before launch
+  void *xbuf;            // [2 parity][2 dir][groups][8*NUT][C] tagged 8-byte exchange words (zeroed per launch)
   int precision;         // 0 = 3xTF32, 1 = TF32
 };
 struct LstmBwdArgs {
@@ -43,9 +43,8 @@ struct LstmBwdArgs {
   const float *dout; int ldd;   // [T*S x 2C] gradient wrt the layer output
   float *DG; int lddg;          // [T*S x 8C] out: d(pre-activations) g,i,f,o per direction
   LstmDirParams p[2];
-  float *pbuf;                  // [2 parity][2 dir][groups][slices][8*NUT][C] partial d_m exchange
+  float *pbuf;                  // [2 parity][2 dir][groups][slices][8*NUT][C] tagged partial d_m words
   float *gsum;                  // [2 dir][groups][7][C] per-group sums: db_g,db_i,db_f,db_o,dpi,dpf,dpo
-  unsigned *flags;
   int precision;
 };
 struct LstmPlan {
@@ -53,7 +52,7 @@ struct LstmPlan {
   int groups, slices;    // grid = (slices, groups, 2)
   int threads;
   size_t smem_fwd, smem_bwd;
-  size_t pbuf_floats, gsum_floats;
+  size_t pbuf_floats, gsum_floats, xbuf_bytes;
   int valid;
 };
 LstmPlan lstm_plan(int S, int C, int num_sms, size_t max_smem);
@@ -62,6 +61,8 @@ cudaError_t lstm_backward(cudaStream_t st, const LstmPlan &plan, const LstmBwdAr
 // bias/peephole gradient from the per-group sums: dst[7 blocks] = sum_groups gsum
 cudaError_t lstm_reduce_gsum(cudaStream_t st, const LstmPlan &plan, int C, const float *gsum,
                              float *db /*[4C]*/, float *dpi, float *dpf, float *dpo, int dir);
+
+int lstm_debug_timing(long long *out32, int reset);  // 1 if built with -DEB_LSTM_TIMING
 
 // ctc.cu
 cudaError_t softmax_rows(cudaStream_t st, int N, int K, const float *logits, int ld, float *probs, int ldp,

@@ -28,6 +28,23 @@
 
 namespace eb {
 
+#ifdef EB_LSTM_TIMING
+// debug build only (make TIMING=1): per-phase clock64 deltas of thread 0 of CTA (0,0,0)
+__device__ long long g_lstm_timing[2][16];
+#define EB_T0() long long tk_ = clock64()
+#define EB_TICK(kernel, i)                                                          \
+  do {                                                                              \
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {        \
+      long long n_ = clock64();                                                     \
+      g_lstm_timing[kernel][i] += n_ - tk_;                                         \
+      tk_ = n_;                                                                     \
+    }                                                                               \
+  } while (0)
+#else
+#define EB_T0()
+#define EB_TICK(kernel, i)
+#endif
+
 namespace {
 
 __device__ __forceinline__ uint32_t cvt_tf32(float x) {
@@ -36,22 +53,13 @@ __device__ __forceinline__ uint32_t cvt_tf32(float x) {
   return r;
 }
 
-// Step-counter protocol between the CTAs of one (direction, utterance group):
-//   producer warp : data stores ; __syncwarp ; lane 0: red.release.gpu(flag += 1)
-//   consumer CTA  : thread 0 spins on ld.relaxed.gpu(flag) >= target, then fence.acq_rel.gpu ;
-//                   __syncthreads ; everybody reads the data with L2 (.cg) loads.
-// One poller per CTA and relaxed polls keep the L2 slice that owns the flag free for the
-// producers' reductions (a polling ld.acquire costs an L1 invalidate, CCTL.IVALL, per iteration).
-__device__ __forceinline__ void poll_flag(const unsigned *flag, unsigned target) {
-  while (ld_relaxed(flag) < target) {
-  }
-  fence_acq_rel_gpu();
-}
-
-__device__ __forceinline__ void signal_flag(unsigned *flag, int lane) {
-  __syncwarp();
-  if (lane == 0) red_release_add(flag, 1u);
-}
+// Inter-CTA exchange between the CTAs of one (direction, utterance group), "LL" style: every
+// exchanged float travels with the step tag in one 8-byte relaxed store (common.cuh:st_tagged);
+// consumers spin on the data words themselves until the tag of the step they need shows up.
+// No release fence on the producer, no flag round trip, no poll barrier on the consumer.  Two
+// parity buffers suffice: a CTA can only publish step n+2 after it has consumed every word of
+// step n+1, which in turn were produced by CTAs that had consumed all of step n.
+// Buffers are zeroed before each launch (tags of a launch are step+1 >= 1).
 
 // One k-step of the (gate-rows x utterances) product for one 16-row fragment A (fp32 in smem,
 // fragment order) against B (2 regs): acc += A*B.
@@ -92,7 +100,7 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
   const int ut = task / NCT, ct = task % NCT;
   const int slice = blockIdx.x, group = blockIdx.y, dir = blockIdx.z;
   const LstmDirParams P = a.p[dir];
-  unsigned *flag = a.flags + dir * groups + group;
+  uint2 *xbuf = reinterpret_cast<uint2 *>(a.xbuf);   // [2 parity][2 dir][groups][8*NUT][C] tagged words
 
   // ---- resident recurrent weights, fragment order
   for (int idx = tid; idx < NCT * KS * 256; idx += NTHREADS) {
@@ -146,20 +154,30 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
 #pragma unroll
       for (int c = 0; c < 4; c++) acc[i][c] = 0.f;
 
+    EB_T0();
     if (step > 0) {
       const int tp = dir == 0 ? t - 1 : t + 1;
-      if (tid == 0) poll_flag(flag, (unsigned)step * expected_per_step);
-      __syncthreads();
-      // stage m_{t-1} of the whole group (L2 -> smem), 128-bit loads that bypass L1
-      const int c4n = C / 4;
-      for (int v = tid; v < 8 * NUT * c4n; v += NTHREADS) {
-        int u = v / c4n, c4 = v % c4n;
+      EB_TICK(0, 0);
+      EB_TICK(0, 1);
+      // stage m_{t-1} of the whole group (L2 -> smem): spin on the tagged words of step-1
+      (void)tp;
+      const int c2n = C / 2;
+      const uint4 *xr = reinterpret_cast<const uint4 *>(xbuf + ((size_t)((step - 1) & 1) * 2 * groups + (size_t)dir * groups + group) * (8 * NUT) * C);
+      const unsigned want = (unsigned)step;   // tag of the data produced at step-1
+      for (int v = tid; v < 8 * NUT * c2n; v += NTHREADS) {
+        int u = v / c2n, c2 = v % c2n;
         int s = group * NUT * 8 + u;
-        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (s < S) val = __ldcg(reinterpret_cast<const float4 *>(a.out + ((size_t)tp * S + s) * a.ldo + (size_t)dir * C) + c4);
-        *reinterpret_cast<float4 *>(stg + (size_t)u * SST + c4 * 4) = val;
+        float2 val = make_float2(0.f, 0.f);
+        if (s < S) {
+          uint4 q;
+          do { q = ld_tagged2(xr + v); } while (q.y != want || q.w != want);
+          val = make_float2(__uint_as_float(q.x), __uint_as_float(q.z));
+        }
+        *reinterpret_cast<float2 *>(stg + (size_t)u * SST + c2 * 2) = val;
       }
+      EB_TICK(0, 2);
       __syncthreads();
+      EB_TICK(0, 3);
       if ((slice * NCT + ct) * 8 < C) {
         float accc[2][4];
 #pragma unroll
@@ -183,6 +201,7 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
             for (int c = 0; c < 4; c++) acc[i][c] += accc[i][c];
         }
       }
+      EB_TICK(0, 4);
       if (KSPLIT > 1) {
         if (!fin) {
           float4 *dst = reinterpret_cast<float4 *>(scr) + ((size_t)(task * (KSPLIT - 1) + ksid - 1) * 32 + lane) * 2;
@@ -190,6 +209,7 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
           dst[1] = make_float4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]);
         }
         __syncthreads();
+        EB_TICK(0, 5);
         if (fin) {
 #pragma unroll
           for (int k = 0; k < KSPLIT - 1; k++) {
@@ -223,11 +243,15 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
           }
           cprev[e] = c;
           sg[e] = gg; si[e] = gi; sf[e] = gf; so[e] = go; sc[e] = c;
-          // only m is on the inter-CTA critical path: publish it first ...
-          __stcg(a.out + ((size_t)t * S + u) * a.ldo + (size_t)dir * C + cell, m);
+          // only m is on the inter-CTA critical path: publish it first (tagged word, no fence) ...
+          if (step + 1 < T)
+            st_tagged(xbuf + (((size_t)(step & 1) * 2 * groups + (size_t)dir * groups + group) * (8 * NUT) + (ut * 8 + 2 * tg + e)) * C + cell,
+                      m, (unsigned)step + 1u);
+          __stcs(a.out + ((size_t)t * S + u) * a.ldo + (size_t)dir * C + cell, m);
         }
       }
-      if (step + 1 < T) signal_flag(flag, lane);
+      EB_TICK(0, 6);
+      EB_TICK(0, 7);
       // ... the saved state for the backward pass is written behind the release
 #pragma unroll
       for (int e = 0; e < 2; e++) {
@@ -240,6 +264,7 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
         }
       }
       if (step + 1 < T) load_pre(dir == 0 ? t + 1 : t - 1);
+      EB_TICK(0, 8);
     }
   }
 }
@@ -264,7 +289,7 @@ lstm_bwd_kernel(LstmBwdArgs a, int groups, int slices, unsigned expected_per_ste
   const int g = lane >> 2, tg = lane & 3;
   const int slice = blockIdx.x, group = blockIdx.y, dir = blockIdx.z;
   const LstmDirParams P = a.p[dir];
-  unsigned *flag = a.flags + dir * groups + group;
+  uint2 *pbuf = reinterpret_cast<uint2 *>(a.pbuf);   // tagged partial d_m words
 
   for (int idx = tid; idx < MT * KSB * 128; idx += NTHREADS) {
     int e = idx & 3, ln = (idx >> 2) & 31, rest = idx >> 7;
@@ -304,19 +329,34 @@ lstm_bwd_kernel(LstmBwdArgs a, int groups, int slices, unsigned expected_per_ste
   const size_t pstride_slice = (size_t)8 * NUT * CP;
   for (int step = 0; step < T; step++) {
     const int t = dir == 0 ? T - 1 - step : step;
-    if (step > 0) {
-      if (tid == 0) poll_flag(flag, (unsigned)step * expected_per_step);
-      __syncthreads();
-    }
+    EB_T0();
+    EB_TICK(1, 0);
+    EB_TICK(1, 1);
     if (is_item) {
       float dm = vd;
       if (step > 0) {
         if (ok) {
-          const float *pb = a.pbuf + ((((size_t)((step - 1) & 1) * 2 + dir) * groups + group) * slices) * pstride_slice +
+          const uint2 *pb = pbuf + ((((size_t)((step - 1) & 1) * 2 + dir) * groups + group) * slices) * pstride_slice +
                             (size_t)ul * CP + cell;
+          const unsigned want = (unsigned)step;
           float s_ = 0.f;
-#pragma unroll 8
-          for (int sl = 0; sl < slices; sl++) s_ += __ldcg(pb + (size_t)sl * pstride_slice);  // fixed order
+          for (int sl0 = 0; sl0 < slices; sl0 += 8) {
+            uint2 q[8];
+            bool all;
+            do {   // issue the (up to) 8 loads together, retry until every tag has arrived
+              all = true;
+#pragma unroll
+              for (int i = 0; i < 8; i++) {
+                if (sl0 + i < slices) {
+                  q[i] = ld_tagged(pb + (size_t)(sl0 + i) * pstride_slice);
+                  all = all && (q[i].y == want);
+                }
+              }
+            } while (!all);
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+              if (sl0 + i < slices) s_ += __uint_as_float(q[i].x);      // fixed order: deterministic
+          }
           dm += s_;                                                       // :470 / :561
         }
       }
@@ -340,7 +380,9 @@ lstm_bwd_kernel(LstmBwdArgs a, int groups, int slices, unsigned expected_per_ste
       if (step + 1 < T) prefetch(t + tstep);
     }
     if (step + 1 == T) break;  // the last step's recurrent contribution is never consumed
+    EB_TICK(1, 2);
     __syncthreads();
+    EB_TICK(1, 3);
     // partial d_m for ALL cells from this CTA's gate rows: P[j, utt] = sum_r Wm[r, j] * D[utt, r]
     for (int wt = warp; wt < MT * NUT; wt += NWARPS) {
       const int mt = wt % MT, ut = wt / MT;
@@ -356,14 +398,16 @@ lstm_bwd_kernel(LstmBwdArgs a, int groups, int slices, unsigned expected_per_ste
 #pragma unroll
         for (int c = 0; c < 4; c++) acc[c] += accc[c];
       }
-      float *pb = a.pbuf + (((((size_t)(step & 1) * 2 + dir) * groups + group) * slices + slice) * 8 * NUT + ut * 8) * CP;
+      uint2 *pb = pbuf + (((((size_t)(step & 1) * 2 + dir) * groups + group) * slices + slice) * 8 * NUT + ut * 8) * CP;
       const int j = mt * 16 + g;
-      __stcg(pb + (size_t)(2 * tg) * CP + j, acc[0]);
-      __stcg(pb + (size_t)(2 * tg + 1) * CP + j, acc[1]);
-      __stcg(pb + (size_t)(2 * tg) * CP + j + 8, acc[2]);
-      __stcg(pb + (size_t)(2 * tg + 1) * CP + j + 8, acc[3]);
+      const unsigned tagw = (unsigned)step + 1u;
+      st_tagged(pb + (size_t)(2 * tg) * CP + j, acc[0], tagw);
+      st_tagged(pb + (size_t)(2 * tg + 1) * CP + j, acc[1], tagw);
+      st_tagged(pb + (size_t)(2 * tg) * CP + j + 8, acc[2], tagw);
+      st_tagged(pb + (size_t)(2 * tg + 1) * CP + j + 8, acc[3], tagw);
     }
-    signal_flag(flag, lane);
+    EB_TICK(1, 4);
+    EB_TICK(1, 5);
   }
 
   // ---- bias / peephole gradient partial sums of this (dir, group): reduce over the CTA's utterances
@@ -444,6 +488,20 @@ cudaError_t launch_bwd(cudaStream_t st, const LstmPlan &pl, const LstmBwdArgs &a
 
 }  // namespace
 
+int lstm_debug_timing(long long *out32, int reset) {
+#ifdef EB_LSTM_TIMING
+  if (out32) cudaMemcpyFromSymbol(out32, g_lstm_timing, sizeof(long long) * 32);
+  if (reset) {
+    long long z[32] = {0};
+    cudaMemcpyToSymbol(g_lstm_timing, z, sizeof(z));
+  }
+  return 1;
+#else
+  (void)out32; (void)reset;
+  return 0;
+#endif
+}
+
 LstmPlan lstm_plan(int S, int C, int num_sms, size_t max_smem) {
   LstmPlan best;
   best.valid = 0;
@@ -463,7 +521,8 @@ LstmPlan lstm_plan(int S, int C, int num_sms, size_t max_smem) {
       best.threads = 32 * c.nut * c.nct * c.ksplit;
       best.smem_fwd = sf; best.smem_bwd = sb;
       size_t cp = (size_t)((C + 15) / 16) * 16;
-      best.pbuf_floats = (size_t)2 * 2 * groups * slices * 8 * c.nut * cp;
+      best.pbuf_floats = (size_t)2 * 2 * 2 * groups * slices * 8 * c.nut * cp;   // 8-byte tagged words
+      best.xbuf_bytes = (size_t)2 * 2 * groups * 8 * c.nut * C * 8;
       best.gsum_floats = (size_t)2 * groups * 7 * C;
       best.valid = 1;
     }
@@ -488,14 +547,14 @@ LstmPlan lstm_plan(int S, int C, int num_sms, size_t max_smem) {
 
 cudaError_t lstm_forward(cudaStream_t st, const LstmPlan &plan, const LstmFwdArgs &a) {
   if (!plan.valid) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaMemsetAsync(a.flags, 0, sizeof(unsigned) * 2 * plan.groups, st);
+  cudaError_t e = cudaMemsetAsync(a.xbuf, 0, plan.xbuf_bytes, st);
   if (e != cudaSuccess) return e;
   EB_DISPATCH(launch_fwd, st, plan, a);
 }
 
 cudaError_t lstm_backward(cudaStream_t st, const LstmPlan &plan, const LstmBwdArgs &a) {
   if (!plan.valid) return cudaErrorInvalidConfiguration;
-  cudaError_t e = cudaMemsetAsync(a.flags, 0, sizeof(unsigned) * 2 * plan.groups, st);
+  cudaError_t e = cudaMemsetAsync(a.pbuf, 0, plan.pbuf_floats * sizeof(float), st);
   if (e != cudaSuccess) return e;
   EB_DISPATCH(launch_bwd, st, plan, a);
 }

@@ -143,7 +143,7 @@ int eesen_b200_gemm(eesen_b200_ctx *ctx, int transA, int transB, int M, int N, i
 }
 
 static int lstm_prepare(eesen_b200_ctx *ctx, int S, int C, eb::LstmPlan *plan, float **pbuf, float **gsum,
-                        unsigned **flags) {
+                        void **xbuf) {
   *plan = eb::lstm_plan(S, C, ctx->num_sms, ctx->max_smem);
   if (!plan->valid)
     return ctx->fail(EESEN_B200_ESHAPE, "no resident-weight LSTM configuration fits S=" + std::to_string(S) +
@@ -151,7 +151,7 @@ static int lstm_prepare(eesen_b200_ctx *ctx, int S, int C, eb::LstmPlan *plan, f
   int rc;
   if ((rc = ctx->reserve(ctx->lstm_pbuf, plan->pbuf_floats * sizeof(float), (void **)pbuf))) return rc;
   if ((rc = ctx->reserve(ctx->lstm_gsum, plan->gsum_floats * sizeof(float), (void **)gsum))) return rc;
-  if ((rc = ctx->reserve(ctx->lstm_flags, sizeof(unsigned) * 2 * plan->groups, (void **)flags))) return rc;
+  if ((rc = ctx->reserve(ctx->lstm_flags, plan->xbuf_bytes, xbuf))) return rc;
   return 0;
 }
 
@@ -161,8 +161,8 @@ int eesen_b200_bilstm_forward(eesen_b200_ctx *ctx, int T, int S, int I, int C, c
   if (!ctx || !p || !x || !gates || !cell || !out || T <= 0 || S <= 0) return EESEN_B200_EINVAL;
   eb::LstmPlan plan;
   float *pbuf, *gsum;
-  unsigned *flags;
-  int rc = lstm_prepare(ctx, S, C, &plan, &pbuf, &gsum, &flags);
+  void *xbuf;
+  int rc = lstm_prepare(ctx, S, C, &plan, &pbuf, &gsum, &xbuf);
   if (rc) return rc;
   // input-side gate pre-activations for both directions: G[:, d*4C..] = x * Wx_d^T + b_d
   // (bilstm-parallel-layer.h:109-110,163-164).  Batched over the direction when the two weight
@@ -185,7 +185,7 @@ int eesen_b200_bilstm_forward(eesen_b200_ctx *ctx, int T, int S, int I, int C, c
   a.cell = cell; a.ldc = 2 * C;
   a.out = out; a.ldo = ldo;
   for (int d = 0; d < 2; d++) { a.p[d].wm = p->wm[d]; a.p[d].pi = p->pi[d]; a.p[d].pf = p->pf[d]; a.p[d].po = p->po[d]; }
-  a.flags = flags;
+  a.xbuf = xbuf;
   a.precision = ctx->rec_prec;
   ctx->launches += 1;
   int pe = ctx->prof_begin(eesen_b200_ctx::kLstmFwd);
@@ -201,8 +201,8 @@ int eesen_b200_bilstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, 
   if (!ctx || !p || !gr || !x || !gates || !cell || !out || !dout || !dgates || T <= 0 || S <= 0) return EESEN_B200_EINVAL;
   eb::LstmPlan plan;
   float *pbuf, *gsum;
-  unsigned *flags;
-  int rc = lstm_prepare(ctx, S, C, &plan, &pbuf, &gsum, &flags);
+  void *xbuf;
+  int rc = lstm_prepare(ctx, S, C, &plan, &pbuf, &gsum, &xbuf);
   if (rc) return rc;
   eb::LstmBwdArgs a;
   a.T = T; a.S = S; a.C = C;
@@ -211,7 +211,7 @@ int eesen_b200_bilstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, 
   a.dout = dout; a.ldd = ldd;
   a.DG = dgates; a.lddg = 8 * C;
   for (int d = 0; d < 2; d++) { a.p[d].wm = p->wm[d]; a.p[d].pi = p->pi[d]; a.p[d].pf = p->pf[d]; a.p[d].po = p->po[d]; }
-  a.pbuf = pbuf; a.gsum = gsum; a.flags = flags;
+  a.pbuf = pbuf; a.gsum = gsum;
   a.precision = ctx->rec_prec;
   ctx->launches += 1;
   {
@@ -412,6 +412,11 @@ int eesen_b200_profile(eesen_b200_ctx *ctx, int enable, double *ms, long *counts
     for (int i = 0; i < eesen_b200_ctx::kNumCat; i++) { ctx->prof_ms[i] = 0; ctx->prof_count[i] = 0; }
   }
   return 0;
+}
+
+int eesen_b200_debug_lstm_timing(eesen_b200_ctx *ctx, long long *out32, int reset) {
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  return eb::lstm_debug_timing(out32, reset);
 }
 
 int eesen_b200_world(const eesen_b200_ctx *ctx, int *rank, int *nranks) {

@@ -63,6 +63,10 @@ long eesen_b200_launch_count(const eesen_b200_ctx *ctx);
 #define EESEN_B200_NUM_PROFILE_CATEGORIES 8
 int eesen_b200_profile(eesen_b200_ctx *ctx, int enable, double *ms, long *counts);
 
+/* Debug builds only (make TIMING=1): clock64 deltas per phase of the recurrent kernels, [2][16]
+ * (forward, backward); returns 1 when compiled in, else 0. */
+int eesen_b200_debug_lstm_timing(eesen_b200_ctx *ctx, long long *out32, int reset);
+
 /* ---------------------------------------------------------------- level 1: device operators */
 
 /* C = alpha*op(A)*op(B) + beta*C.  Replaces CuMatrixBase::AddMatMat -> cublasSgemm
