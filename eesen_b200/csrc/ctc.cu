@@ -70,15 +70,17 @@ __global__ void row_argmax_kernel(int N, int K, const float *__restrict__ x, int
 }
 
 // log of a softmax output with the reference's log(0) sentinel (ApplyLog ctc-loss.cc:133 + ctc-utils.h:36)
-__device__ __forceinline__ float logprob(float y) { return fmaxf(logf(y), kLogZero); }
+__device__ __forceinline__ float logprob(float y) { return fmaxf(__logf(y), kLogZero); }
 
+// log-sum-exp on the SFU: the sum of exponentials lies in [1, 3], where __logf is accurate to
+// 2^-21 absolute -- far below one fp32 ulp of the log-domain values themselves (|alpha| ~ 10^2..10^3)
 __device__ __forceinline__ float lse2(float a, float b) {
   float m = fmaxf(a, b);
-  return m + logf(expf(a - m) + expf(b - m));
+  return m + __logf(__expf(a - m) + __expf(b - m));
 }
 __device__ __forceinline__ float lse3(float a, float b, float c) {
   float m = fmaxf(a, fmaxf(b, c));
-  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
 }
 
 template <int R>
@@ -219,10 +221,10 @@ ctc_kernel(int T, int S, int K, int max_lab, const int *__restrict__ len, const 
       float ab = arow[j] + brow[j];
       if (j & 1) {
         int c = lab_s[j >> 1];
-        float gam = expf(ab - pzx - logprob(yrow[c]));    // exp(log(a*b) - pzx - 2 log y) * y  (:1624 then MulElements)
+        float gam = __expf(ab - pzx - logprob(yrow[c]));    // exp(log(a*b) - pzx - 2 log y) * y  (:1624 then MulElements)
         atomicAdd(&occ[c], gam);
       } else {
-        blank += expf(ab - pzx - lb);
+        blank += __expf(ab - pzx - lb);
       }
     }
     blank = warp_sum(blank);
