@@ -402,3 +402,34 @@ def test_c2_full_size_vs_reference_gpucompute(ctx):
     assert_close("params", n.params(), m2.flat_params(), atol=5e-6)
     print(f"reference gpucompute on this GPU: {info['valid_fps']:.0f} valid frames/s (one cold step)")
     n.close()
+
+
+def test_train_ctc_parallel_driver_matches_api(ctx, tmp_path):
+    """The C++ driver (host logic of reference src/netbin/train-ctc-parallel.cc) on Kaldi archives gives
+    the same model as the level-2 API fed the same minibatches, and prints the recipe-facing log lines."""
+    import subprocess
+    from util import ROOT
+    w, net, b = case("small")
+    mpath = str(tmp_path / "nnet.in")
+    kaldi_io.write_model(mpath, net)
+    S, T = b.S, b.T
+    utts = [b.feats[np.arange(b.frames[s]) * S + s] for s in range(S)]
+    keys = [f"utt{s:03d}" for s in range(S)]
+    kaldi_io.write_feature_ark(str(tmp_path / "feats.ark"), keys, utts)
+    kaldi_io.write_label_ark(str(tmp_path / "labels.ark"), keys, b.labels)
+    out = str(tmp_path / "nnet.out")
+    exe = os.path.join(ROOT, "eesen_b200", "bin", "train-ctc-parallel")
+    r = subprocess.run([exe, "--learn-rate=0.001", "--momentum=0.9", "--num-sequence=4", "--frame-limit=100000",
+                        "--report-step=4", "--verbose=1", f"ark:{tmp_path}/feats.ark", f"ark,t:{tmp_path}/labels.ark",
+                        mpath, out], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "TOKEN_ACCURACY >>" in r.stderr and "fps" in r.stderr and "TRAINING STARTED" in r.stderr
+    got = kaldi_io.read_model(out).flat_params()
+    # the same two minibatches (utterances 0-3, then 4-7) through the level-2 API
+    n = binding.Net(ctx, mpath)
+    n.set_train_options(1e-3, 0.9)
+    for lo in (0, 4):
+        feats, frames = kaldi_io.pack_utterances(utts[lo:lo + 4])
+        n.train_step(feats, frames, b.labels[lo:lo + 4], True)
+    assert_close("driver_vs_api", got, n.params(), atol=1e-7)
+    n.close()
