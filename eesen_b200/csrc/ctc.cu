@@ -69,18 +69,26 @@ __global__ void row_argmax_kernel(int N, int K, const float *__restrict__ x, int
   if (lane == 0) argmax[row] = mi;
 }
 
-// log of a softmax output with the reference's log(0) sentinel (ApplyLog ctc-loss.cc:133 + ctc-utils.h:36)
-__device__ __forceinline__ float logprob(float y) { return fmaxf(__logf(y), kLogZero); }
+// The lattice is kept in the log2 domain (alpha2 = alpha / ln 2): every log-sum-exp is then bare SFU
+// work -- ex2.approx / lg2.approx, no range reduction, no denormal fix-ups -- and only pzx is
+// converted back to natural log.  Sentinel log(0) = -1e30 (ApplyLog ctc-loss.cc:133 + ctc-utils.h:36)
+// survives unchanged: -1e30 + x == -1e30 in fp32 and ex2(-1e30) == 0.
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float logprob(float y) { return fmaxf(lg2_approx(y), kLogZero); }   // log2 y
 
 // log-sum-exp on the SFU: the sum of exponentials lies in [1, 3], where __logf is accurate to
 // 2^-21 absolute -- far below one fp32 ulp of the log-domain values themselves (|alpha| ~ 10^2..10^3)
-__device__ __forceinline__ float lse2(float a, float b) {
+__device__ __forceinline__ float lse2(float a, float b) {   // log2(2^a + 2^b)
   float m = fmaxf(a, b);
-  return m + __logf(__expf(a - m) + __expf(b - m));
+  return m + lg2_approx(ex2_approx(a - m) + ex2_approx(b - m));
 }
 __device__ __forceinline__ float lse3(float a, float b, float c) {
   float m = fmaxf(a, fmaxf(b, c));
-  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+  return m + lg2_approx(ex2_approx(a - m) + ex2_approx(b - m) + ex2_approx(c - m));
 }
 
 template <int R>
@@ -192,8 +200,8 @@ ctc_kernel(int T, int S, int K, int max_lab, const int *__restrict__ len, const 
       a2 = warp_max(a2);
       if (lane == 0) {
         float p = lse2(a1, a2);
-        pzx_sm = p;
-        pzx_out[s] = p;
+        pzx_sm = p;                                   // log2 domain for the occupancies below
+        pzx_out[s] = p < 0.5f * kLogZero ? kLogZero : p * 0.6931471805599453f;   // natural log at the boundary
       }
     }
   } else if (warp == 0 && lane == 0) {
@@ -221,10 +229,10 @@ ctc_kernel(int T, int S, int K, int max_lab, const int *__restrict__ len, const 
       float ab = arow[j] + brow[j];
       if (j & 1) {
         int c = lab_s[j >> 1];
-        float gam = __expf(ab - pzx - logprob(yrow[c]));    // exp(log(a*b) - pzx - 2 log y) * y  (:1624 then MulElements)
+        float gam = ex2_approx(ab - pzx - logprob(yrow[c]));    // exp(log(a*b) - pzx - 2 log y) * y  (:1624 then MulElements)
         atomicAdd(&occ[c], gam);
       } else {
-        blank += __expf(ab - pzx - lb);
+        blank += ex2_approx(ab - pzx - lb);
       }
     }
     blank = warp_sum(blank);

@@ -2,6 +2,9 @@
 // (include/eesen_b200.h).  C++ exceptions (KALDI_ERR) are translated to error codes here.
 #include <cuda_runtime.h>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -100,6 +103,8 @@ int eesen_b200_net_train_step(eesen_b200_net *n, const float *feats, int T, int 
                               const int *labels, const int *lab_len, int train, double stats[4]) {
   if (!n || !feats || !frames || !labels || !lab_len || T <= 0 || S <= 0) return EESEN_B200_EINVAL;
   try {
+    static const bool trace = getenv("EESEN_B200_TRACE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
     unpack_labels(n, S, frames, labels, lab_len);
     const int I = n->net.InputDim();
     size_t elems = (size_t)T * S * I;
@@ -109,11 +114,21 @@ int eesen_b200_net_train_step(eesen_b200_net *n, const float *feats, int T, int 
       n->h_cap = elems;
     }
     memcpy(n->h_pinned, feats, sizeof(float) * elems);   // into pinned staging, then one async H2D
+    auto t1 = std::chrono::steady_clock::now();
     n->feats.Resize(T * S, I, kUndefined);
     n->feats.CopyFromHost(n->h_pinned, I);
     run_step(n, n->feats, train);
+    auto t2 = std::chrono::steady_clock::now();
     double st[4];
     n->ctc.Finish(st);
+    auto t3 = std::chrono::steady_clock::now();
+    if (trace) {
+      auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count();
+      };
+      fprintf(stderr, "[eesen_b200 trace] stage-to-pinned %ld us, enqueue %ld us, wait+stats %ld us\n", us(t0, t1),
+              us(t1, t2), us(t2, t3));
+    }
     if (stats) memcpy(stats, st, sizeof(st));
     return 0;
   } catch (const std::exception &e) {

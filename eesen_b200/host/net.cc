@@ -35,18 +35,32 @@ template <typename Real>
 void CuMatrixBase<Real>::CopyFromMat(const CuMatrixBase<Real> &src) {
   KALDI_ASSERT(src.NumRows() == num_rows_ && src.NumCols() == num_cols_);
   if (num_rows_ == 0) return;
+  if (stride_ == num_cols_ && src.Stride() == num_cols_) {   // dense on both sides: one flat DMA, not one per row
+    CU_CHECK(cudaMemcpyAsync(data_, src.Data(), sizeof(Real) * (size_t)num_rows_ * num_cols_,
+                             cudaMemcpyDeviceToDevice, Stream()));
+    return;
+  }
   CU_CHECK(cudaMemcpy2DAsync(data_, sizeof(Real) * stride_, src.Data(), sizeof(Real) * src.Stride(),
                              sizeof(Real) * num_cols_, num_rows_, cudaMemcpyDeviceToDevice, Stream()));
 }
 template <typename Real>
 void CuMatrixBase<Real>::CopyFromHost(const Real *src, int32 ld) {
   if (num_rows_ == 0) return;
+  if (stride_ == num_cols_ && ld == num_cols_) {
+    CU_CHECK(cudaMemcpyAsync(data_, src, sizeof(Real) * (size_t)num_rows_ * num_cols_, cudaMemcpyHostToDevice, Stream()));
+    return;
+  }
   CU_CHECK(cudaMemcpy2DAsync(data_, sizeof(Real) * stride_, src, sizeof(Real) * ld, sizeof(Real) * num_cols_,
                              num_rows_, cudaMemcpyHostToDevice, Stream()));
 }
 template <typename Real>
 void CuMatrixBase<Real>::CopyToHost(Real *dst, int32 ld) const {
   if (num_rows_ == 0) return;
+  if (stride_ == num_cols_ && ld == num_cols_) {
+    CU_CHECK(cudaMemcpyAsync(dst, data_, sizeof(Real) * (size_t)num_rows_ * num_cols_, cudaMemcpyDeviceToHost, Stream()));
+    CU_CHECK(cudaStreamSynchronize(Stream()));
+    return;
+  }
   CU_CHECK(cudaMemcpy2DAsync(dst, sizeof(Real) * ld, data_, sizeof(Real) * stride_, sizeof(Real) * num_cols_,
                              num_rows_, cudaMemcpyDeviceToHost, Stream()));
   CU_CHECK(cudaStreamSynchronize(Stream()));
