@@ -35,8 +35,8 @@ template <typename Real>
 void CuMatrixBase<Real>::CopyFromMat(const CuMatrixBase<Real> &src) {
   KALDI_ASSERT(src.NumRows() == num_rows_ && src.NumCols() == num_cols_);
   if (num_rows_ == 0) return;
-  if (stride_ == num_cols_ && src.Stride() == num_cols_) {   // dense on both sides: one flat DMA, not one per row
-    CU_CHECK(cudaMemcpyAsync(data_, src.Data(), sizeof(Real) * (size_t)num_rows_ * num_cols_,
+  if (stride_ == src.Stride()) {   // same pitch on both sides (padding columns included): one flat copy
+    CU_CHECK(cudaMemcpyAsync(data_, src.Data(), sizeof(Real) * (size_t)num_rows_ * stride_,
                              cudaMemcpyDeviceToDevice, Stream()));
     return;
   }
