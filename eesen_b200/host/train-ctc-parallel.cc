@@ -9,10 +9,13 @@
 //     <model-out>.ncclid written by job 1 (the same shared-filesystem rendezvous the reference uses).
 #include <unistd.h>
 
+#include <cuda_runtime.h>
+
 #include <chrono>
 #include <cstring>
 #include <fstream>
 
+#include "minibatch.h"
 #include "net.h"
 
 using namespace eesen;
@@ -130,79 +133,56 @@ int main(int argc, char *argv[]) {
       net.SetUpdateAlgorithm(opt);
       if (crossvalidate) net.SetTestMode(); else net.SetTrainMode();
 
-      int64 total_frames = 0;
-      SequentialBaseFloatMatrixReader feature_reader(feature_rspecifier);
-      RandomAccessInt32VectorReader targets_reader(targets_rspecifier);
-
       Ctc ctc(ctx);
       ctc.SetReportStep(report_step);
-      CuMatrix<BaseFloat> net_out, obj_diff;
+      CuMatrix<BaseFloat> feats_dev, net_out, obj_diff;
 
-      auto t_start = std::chrono::steady_clock::now();
       KALDI_LOG << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << " STARTED";
       if (sequence_out_file.length()) std::remove(sequence_out_file.c_str());
+      const auto t_start = std::chrono::steady_clock::now();
 
-      std::vector<HostMatrix> feats_utt(num_sequence);
-      std::vector<std::vector<int> > labels_utt(num_sequence);
-      int32 feat_dim = net.InputDim();
-      int32 num_done = 0, num_no_tgt_mat = 0, num_other_error = 0;
-      HostMatrix feat_mat_host;
-
-      while (1) {
-        // ---- gather up to num_sequence utterances under the frame limit (train-ctc-parallel.cc:146-184)
-        std::vector<int> frame_num_utt;
-        int32 sequence_index = 0, max_frame_num = 0;
-        for (; !feature_reader.Done(); feature_reader.Next()) {
-          std::string utt = feature_reader.Key();
-          if (!targets_reader.HasKey(utt)) {
-            KALDI_WARN << utt << ", missing targets";
-            num_no_tgt_mat++;
-            continue;
-          }
-          const HostMatrix &mat = feature_reader.Value();
-          if (mat.rows > frame_limit) {
-            KALDI_WARN << utt << ", has too many frames; ignoring: " << mat.rows << " > " << frame_limit;
-            continue;
-          }
-          if (mat.cols != feat_dim) KALDI_ERR << utt << ": feature dim " << mat.cols << " != net input " << feat_dim;
-          int new_max = std::max<int>(max_frame_num, mat.rows);
-          if (new_max * (double)(frame_num_utt.size() + 1) > frame_limit) break;  // does not fit in this batch
-          max_frame_num = new_max;
-          feats_utt[sequence_index] = mat;
-          labels_utt[sequence_index] = targets_reader.Value(utt);
-          frame_num_utt.push_back(mat.rows);
-          sequence_index++;
-          if ((int32)frame_num_utt.size() == num_sequence) { feature_reader.Next(); break; }
-        }
-        int32 cur_sequence_num = frame_num_utt.size();
-        if (cur_sequence_num == 0) break;
-
-        // ---- pad + interleave: row t*S+s (:186-193)
-        feat_mat_host.Resize(cur_sequence_num * max_frame_num, feat_dim);
-        for (int s = 0; s < cur_sequence_num; s++)
-          for (int r = 0; r < frame_num_utt[s]; r++)
-            memcpy(feat_mat_host.Row(r * cur_sequence_num + s), feats_utt[s].Row(r), sizeof(float) * feat_dim);
-
-        net.SetSeqLengths(frame_num_utt);                                          // :195
-        net.Propagate(CuMatrix<BaseFloat>(feat_mat_host), &net_out);               // :198
-        std::vector<std::vector<int> > labels_cur(labels_utt.begin(), labels_utt.begin() + cur_sequence_num);
-        ctc.EvalParallel(frame_num_utt, net_out, labels_cur, &obj_diff);           // :199
-        ctc.ErrorRateMSeq(frame_num_utt, net_out, labels_cur, sequence_out_file);  // :202
-        if (!crossvalidate) net.Backpropagate(obj_diff, NULL);                     // :207 (+ NCCL all-reduce inside)
-
-        num_done += cur_sequence_num;
-        total_frames += feat_mat_host.rows;
-        if (feature_reader.Done()) break;
+      // producer thread: archives -> packed, pinned minibatches (minibatch.h); this loop only feeds the GPU
+      int device_index = 0;
+      cudaGetDevice(&device_index);
+      MinibatchAssembler batches(feature_rspecifier, targets_rspecifier, net.InputDim(), num_sequence, frame_limit,
+                                 device_index);
+      int64 total_frames = 0;
+      int32 num_done = 0;
+      cudaStream_t stream = (cudaStream_t)eesen_b200_stream(ctx);
+      cudaEvent_t h2d_done;
+      cudaEventCreateWithFlags(&h2d_done, cudaEventDisableTiming);
+      bool h2d_pending = false;
+      while (true) {
+        // the pinned slot of the previous minibatch goes back to the producer inside Next():
+        // its (asynchronous) upload must have left the host buffer by then
+        if (h2d_pending) { cudaEventSynchronize(h2d_done); h2d_pending = false; }
+        const Minibatch *mb = batches.Next();
+        if (!mb) break;
+        std::vector<int> frame_num_utt = mb->frames;
+        std::vector<std::vector<int> > labels_utt = mb->labels;
+        feats_dev.Resize(mb->T * mb->S, mb->dim, kUndefined);
+        feats_dev.CopyFromHost(mb->feats, mb->dim);                                   // one async H2D from pinned memory
+        cudaEventRecord(h2d_done, stream);
+        h2d_pending = true;
+        net.SetSeqLengths(frame_num_utt);                                             // reference :195
+        net.Propagate(feats_dev, &net_out);                                           // :198
+        ctc.EvalParallel(frame_num_utt, net_out, labels_utt, &obj_diff);              // :199
+        ctc.ErrorRateMSeq(frame_num_utt, net_out, labels_utt, sequence_out_file);     // :202
+        if (!crossvalidate) net.Backpropagate(obj_diff, NULL);                        // :207, gradient all-reduce inside
+        num_done += mb->S;
+        total_frames += mb->padded_frames();
       }
 
-      std::string report = ctc.Report();  // also drains the stream
+      cudaEventDestroy(h2d_done);
+      const std::string report = ctc.Report();   // drains the stream and folds the last statistics
+      MinibatchAssembler::Counters skipped = batches.counters();
       if (!crossvalidate) {
         KALDI_LOG << net.Info();
         KALDI_LOG << net.InfoGradient();
         if (num_jobs == 1 || job_id == 1) net.Write(target_model_filename, binary);
       }
-      double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
-      KALDI_LOG << "Done " << num_done << " files, " << num_no_tgt_mat << " with no targets, " << num_other_error
+      const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+      KALDI_LOG << "Done " << num_done << " files, " << skipped.no_targets << " with no targets, " << skipped.too_long
                 << " with other errors. [" << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << ", "
                 << elapsed / 60 << " min, fps" << total_frames / elapsed << "]";
       KALDI_LOG << report;

@@ -28,7 +28,7 @@ from eesen_b200 import kaldi_io, synth  # noqa: E402
 from oracle import oracle  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CASES = [("tiny", 3, 5, 1e-3, 0.9), ("small", 3, 5, 1e-3, 0.9)]  # workload, model seed, batch seed, lr, momentum
+CASES = [("tiny", 3, 5, 1e-3, 0.9), ("small", 3, 5, 1e-3, 0.9), ("c1", 0, 0, 4e-5, 0.9)]  # workload, model seed, batch seed, lr, momentum
 
 
 def run(kind: str, outdir: str = HERE):

@@ -249,7 +249,7 @@ def test_train_step_vs_oracle(ctx, wl):
     n.close()
 
 
-@pytest.mark.parametrize("wl", ["tiny", "small"])
+@pytest.mark.parametrize("wl", ["tiny", "small", "c1"])
 @pytest.mark.parametrize("kind", ["cpu", "gpu"])
 def test_train_step_vs_reference_golden(ctx, wl, kind):
     """Against the committed outputs of the UNMODIFIED reference (tests/golden/make_golden.py)."""
@@ -399,7 +399,12 @@ def test_c2_full_size_vs_reference_gpucompute(ctx):
     assert_close("net_out", n.get(len(net.layers)), ref["net_out"], atol=5e-5)
     assert_close("obj_diff", n.get(100), ref["obj_diff"], atol=2 * diff_atol(ref["pzx"]))
     m2 = kaldi_io.read_model(d + "/out/model_out")
-    assert_close("params", n.params(), m2.flat_params(), atol=5e-6)
+    # parameter update = lr * (momentum buffer); the buffers are sums over all T*S rows of per-frame
+    # gradients that individually agree only to diff_atol (fp32 log-domain CTC at |log p| ~ 2000 in BOTH
+    # implementations), so their difference random-walks to ~sqrt(T*S) * diff_atol
+    rows = b.feats.shape[0]
+    assert_close("params", n.params(), m2.flat_params(),
+                 atol=5e-6 + w.learn_rate * np.sqrt(rows) * diff_atol(ref["pzx"]))
     print(f"reference gpucompute on this GPU: {info['valid_fps']:.0f} valid frames/s (one cold step)")
     n.close()
 

@@ -26,7 +26,7 @@ def _oracle_two_steps(net, b, lr, mom, diff_override=None, dtype=np.float32):
     return on, r
 
 
-@pytest.mark.parametrize("wl", ["tiny", "small"])
+@pytest.mark.parametrize("wl", ["tiny", "small", "c1"])
 def test_oracle_matches_reference_cpu_golden(wl):
     g = np.load(os.path.join(GOLDEN, f"{wl}_refcpu.npz"))
     mseed, bseed, steps = [int(v) for v in g["meta"]]
@@ -42,7 +42,7 @@ def test_oracle_matches_reference_cpu_golden(wl):
     assert_close("params", on.flat_params(), g["params_out"], atol=1e-6)
 
 
-@pytest.mark.parametrize("wl", ["tiny", "small"])
+@pytest.mark.parametrize("wl", ["tiny", "small", "c1"])
 def test_oracle_matches_reference_gpu_golden(wl):
     """The reference's own CUDA CTC (and everything else) run on the B200 box."""
     path = os.path.join(GOLDEN, f"{wl}_refgpu.npz")
