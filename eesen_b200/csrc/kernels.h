@@ -28,6 +28,7 @@ struct LstmDirParams {
 };
 struct LstmFwdArgs {
   int T, S, C;
+  int s_begin, s_count;  // utterances [s_begin, s_begin+s_count) are processed by this launch
   const int *len;        // [S] valid frames per utterance (device)
   float *G; int ldg;     // [T*S x 8C]: in = x*Wx^T + b (dir block d at col d*4C), out = post-activation g,i,f,o
   float *cell; int ldc;  // [T*S x 2C] cell state c (dir d at col d*C)
@@ -38,6 +39,7 @@ struct LstmFwdArgs {
 };
 struct LstmBwdArgs {
   int T, S, C;
+  int s_begin, s_count;
   const float *G; int ldg;      // saved post-activation gates
   const float *cell; int ldc;   // saved cell states
   const float *dout; int ldd;   // [T*S x 2C] gradient wrt the layer output
@@ -59,7 +61,7 @@ LstmPlan lstm_plan(int S, int C, int num_sms, size_t max_smem);
 cudaError_t lstm_forward(cudaStream_t st, const LstmPlan &plan, const LstmFwdArgs &a);
 cudaError_t lstm_backward(cudaStream_t st, const LstmPlan &plan, const LstmBwdArgs &a);
 // bias/peephole gradient from the per-group sums: dst[7 blocks] = sum_groups gsum
-cudaError_t lstm_reduce_gsum(cudaStream_t st, const LstmPlan &plan, int C, const float *gsum,
+cudaError_t lstm_reduce_gsum(cudaStream_t st, const LstmPlan &plan, int C, const float *gsum, int nchunks,
                              float *db /*[4C]*/, float *dpi, float *dpf, float *dpo, int dir);
 
 int lstm_debug_timing(long long *out32, int reset);  // 1 if built with -DEB_LSTM_TIMING

@@ -124,7 +124,8 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
   float ppi = 0.f, ppf = 0.f, ppo = 0.f;
   int lenu[2] = {0, 0};
   int uidx[2];
-  uidx[0] = (group * NUT + ut) * 8 + 2 * tg;
+  const int s0 = a.s_begin, s1 = a.s_begin + a.s_count;   // utterance window of this launch (rows still index all S)
+  uidx[0] = s0 + (group * NUT + ut) * 8 + 2 * tg;
   uidx[1] = uidx[0] + 1;
   const bool fin = (ksid == 0);
   if (fin && cell_ok) {
@@ -132,12 +133,12 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
   }
   if (fin) {
 #pragma unroll
-    for (int e = 0; e < 2; e++) lenu[e] = uidx[e] < S ? a.len[uidx[e]] : 0;
+    for (int e = 0; e < 2; e++) lenu[e] = uidx[e] < s1 ? a.len[uidx[e]] : 0;
   }
   auto load_pre = [&](int t) {
 #pragma unroll
     for (int e = 0; e < 2; e++) {
-      bool ok = cell_ok && uidx[e] < S;
+      bool ok = cell_ok && uidx[e] < s1;
       const float *row = a.G + ((size_t)t * S + (ok ? uidx[e] : 0)) * a.ldg + (size_t)dir * 4 * C + (ok ? cell : 0);
 #pragma unroll
       for (int q = 0; q < 4; q++) pre[q][e] = ok ? __ldcs(row + (size_t)q * C) : 0.f;
@@ -166,9 +167,9 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
       const unsigned want = (unsigned)step;   // tag of the data produced at step-1
       for (int v = tid; v < 8 * NUT * c2n; v += NTHREADS) {
         int u = v / c2n, c2 = v % c2n;
-        int s = group * NUT * 8 + u;
+        int s = s0 + group * NUT * 8 + u;
         float2 val = make_float2(0.f, 0.f);
-        if (s < S) {
+        if (s < s1) {
           uint4 q;
           do { q = ld_tagged2(xr + v); } while (q.y != want || q.w != want);
           val = make_float2(__uint_as_float(q.x), __uint_as_float(q.z));
@@ -229,7 +230,7 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
       for (int e = 0; e < 2; e++) {
         const int u = uidx[e];
         sg[e] = si[e] = sf[e] = so[e] = sc[e] = 0.f;
-        if (cell_ok && u < S) {
+        if (cell_ok && u < s1) {
           float yg = pre[0][e] + acc[0][e];
           float yi = pre[1][e] + acc[0][2 + e] + cprev[e] * ppi;   // :127
           float yf = pre[2][e] + acc[1][e] + cprev[e] * ppf;       // :129
@@ -256,7 +257,7 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int u = uidx[e];
-        if (cell_ok && u < S) {
+        if (cell_ok && u < s1) {
           float *grow = a.G + ((size_t)t * S + u) * a.ldg + (size_t)dir * 4 * C + cell;
           __stcs(grow, sg[e]); __stcs(grow + (size_t)C, si[e]);
           __stcs(grow + (size_t)2 * C, sf[e]); __stcs(grow + (size_t)3 * C, so[e]);
@@ -306,8 +307,8 @@ lstm_bwd_kernel(LstmBwdArgs a, int groups, int slices, unsigned expected_per_ste
   const bool is_item = tid < ITEMS;
   const int cl = tid % (8 * NCT), ul = tid / (8 * NCT);
   const int cell = slice * NCT * 8 + cl;
-  const int u = group * NUT * 8 + ul;
-  const bool ok = is_item && cell < C && u < S;
+  const int u = a.s_begin + group * NUT * 8 + ul;
+  const bool ok = is_item && cell < C && u < a.s_begin + a.s_count;
   float ppi = 0.f, ppf = 0.f, ppo = 0.f;
   if (ok) { ppi = P.pi[cell]; ppf = P.pf[cell]; ppo = P.po[cell]; }
   float dc_next = 0.f, f_next = 0.f, di_next = 0.f, df_next = 0.f;
@@ -430,13 +431,14 @@ lstm_bwd_kernel(LstmBwdArgs a, int groups, int slices, unsigned expected_per_ste
   }
 }
 
-__global__ void gsum_reduce_kernel(int C, int groups, const float *gsum, float *db, float *dpi, float *dpf,
-                                   float *dpo, int dir) {
+__global__ void gsum_reduce_kernel(int C, int groups, int nchunks, size_t chunk_stride, const float *gsum, float *db,
+                                   float *dpi, float *dpf, float *dpo, int dir) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 7 * C) return;
   int q = i / C, c = i % C;
   float s = 0.f;
-  for (int gr = 0; gr < groups; gr++) s += gsum[(((size_t)dir * groups + gr) * 7 + q) * C + c];
+  for (int ch = 0; ch < nchunks; ch++)
+    for (int gr = 0; gr < groups; gr++) s += gsum[ch * chunk_stride + (((size_t)dir * groups + gr) * 7 + q) * C + c];
   if (q < 4) db[(size_t)q * C + c] = s;
   else if (q == 4) dpi[c] = s;
   else if (q == 5) dpf[c] = s;
@@ -559,10 +561,10 @@ cudaError_t lstm_backward(cudaStream_t st, const LstmPlan &plan, const LstmBwdAr
   EB_DISPATCH(launch_bwd, st, plan, a);
 }
 
-cudaError_t lstm_reduce_gsum(cudaStream_t st, const LstmPlan &plan, int C, const float *gsum, float *db,
+cudaError_t lstm_reduce_gsum(cudaStream_t st, const LstmPlan &plan, int C, const float *gsum, int nchunks, float *db,
                              float *dpi, float *dpf, float *dpo, int dir) {
   int n = 7 * C;
-  gsum_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(C, plan.groups, gsum, db, dpi, dpf, dpo, dir);
+  gsum_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(C, plan.groups, nchunks, plan.gsum_floats, gsum, db, dpi, dpf, dpo, dir);
   return cudaGetLastError();
 }
 

@@ -1,6 +1,7 @@
 // eesen_b200/host/abi_ops.cc -- level-1 C ABI: context + device operators (include/eesen_b200.h).
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -142,15 +143,25 @@ int eesen_b200_gemm(eesen_b200_ctx *ctx, int transA, int transB, int M, int N, i
   return do_gemm(ctx, transA, transB, M, N, K, alpha, A, lda, 0, B, ldb, 0, beta, C, ldc, 0, nullptr, 0, 1);
 }
 
-static int lstm_prepare(eesen_b200_ctx *ctx, int S, int C, eb::LstmPlan *plan, float **pbuf, float **gsum,
+// Picks the resident-weight plan.  The recurrence is independent per utterance, so a minibatch that
+// does not fit one co-resident grid (e.g. 128 utterances at C=320) is processed in utterance chunks
+// of the largest size that does: chunk = S, else the largest multiple of 8 in {64, 32, 16, 8}.
+static int lstm_prepare(eesen_b200_ctx *ctx, int S, int C, eb::LstmPlan *plan, int *chunk, float **pbuf, float **gsum,
                         void **xbuf) {
-  *plan = eb::lstm_plan(S, C, ctx->num_sms, ctx->max_smem);
+  const int cands[5] = {S, 64, 32, 16, 8};
+  plan->valid = 0;
+  for (int i = 0; i < 5 && !plan->valid; i++) {
+    if (cands[i] > S || cands[i] <= 0) continue;
+    *plan = eb::lstm_plan(cands[i], C, ctx->num_sms, ctx->max_smem);
+    *chunk = cands[i];
+  }
   if (!plan->valid)
-    return ctx->fail(EESEN_B200_ESHAPE, "no resident-weight LSTM configuration fits S=" + std::to_string(S) +
-                                            " C=" + std::to_string(C) + " (C must be a multiple of 8)");
+    return ctx->fail(EESEN_B200_ESHAPE, "no resident-weight LSTM configuration fits C=" + std::to_string(C) +
+                                            " on this device (cells per direction must be a multiple of 8, <= ~640)");
   int rc;
+  const int nchunks = (S + *chunk - 1) / *chunk;
   if ((rc = ctx->reserve(ctx->lstm_pbuf, plan->pbuf_floats * sizeof(float), (void **)pbuf))) return rc;
-  if ((rc = ctx->reserve(ctx->lstm_gsum, plan->gsum_floats * sizeof(float), (void **)gsum))) return rc;
+  if ((rc = ctx->reserve(ctx->lstm_gsum, plan->gsum_floats * sizeof(float) * nchunks, (void **)gsum))) return rc;
   if ((rc = ctx->reserve(ctx->lstm_flags, plan->xbuf_bytes, xbuf))) return rc;
   return 0;
 }
@@ -162,7 +173,8 @@ int eesen_b200_bilstm_forward(eesen_b200_ctx *ctx, int T, int S, int I, int C, c
   eb::LstmPlan plan;
   float *pbuf, *gsum;
   void *xbuf;
-  int rc = lstm_prepare(ctx, S, C, &plan, &pbuf, &gsum, &xbuf);
+  int chunk = S;
+  int rc = lstm_prepare(ctx, S, C, &plan, &chunk, &pbuf, &gsum, &xbuf);
   if (rc) return rc;
   // input-side gate pre-activations for both directions: G[:, d*4C..] = x * Wx_d^T + b_d
   // (bilstm-parallel-layer.h:109-110,163-164).  Batched over the direction when the two weight
@@ -187,11 +199,16 @@ int eesen_b200_bilstm_forward(eesen_b200_ctx *ctx, int T, int S, int I, int C, c
   for (int d = 0; d < 2; d++) { a.p[d].wm = p->wm[d]; a.p[d].pi = p->pi[d]; a.p[d].pf = p->pf[d]; a.p[d].po = p->po[d]; }
   a.xbuf = xbuf;
   a.precision = ctx->rec_prec;
-  ctx->launches += 1;
-  int pe = ctx->prof_begin(eesen_b200_ctx::kLstmFwd);
-  cudaError_t le = eb::lstm_forward(ctx->stream, plan, a);
-  ctx->prof_end(pe);
-  return ctx->check(le, "lstm_forward");
+  for (int s0 = 0; s0 < S; s0 += chunk) {
+    a.s_begin = s0;
+    a.s_count = std::min(chunk, S - s0);
+    ctx->launches += 1;
+    int pe = ctx->prof_begin(eesen_b200_ctx::kLstmFwd);
+    cudaError_t le = eb::lstm_forward(ctx->stream, plan, a);
+    ctx->prof_end(pe);
+    if ((rc = ctx->check(le, "lstm_forward"))) return rc;
+  }
+  return 0;
 }
 
 int eesen_b200_bilstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, const float *x, int ldx,
@@ -202,8 +219,10 @@ int eesen_b200_bilstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, 
   eb::LstmPlan plan;
   float *pbuf, *gsum;
   void *xbuf;
-  int rc = lstm_prepare(ctx, S, C, &plan, &pbuf, &gsum, &xbuf);
+  int chunk = S;
+  int rc = lstm_prepare(ctx, S, C, &plan, &chunk, &pbuf, &gsum, &xbuf);
   if (rc) return rc;
+  const int nchunks = (S + chunk - 1) / chunk;
   eb::LstmBwdArgs a;
   a.T = T; a.S = S; a.C = C;
   a.G = gates; a.ldg = 8 * C;
@@ -213,8 +232,11 @@ int eesen_b200_bilstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, 
   for (int d = 0; d < 2; d++) { a.p[d].wm = p->wm[d]; a.p[d].pi = p->pi[d]; a.p[d].pf = p->pf[d]; a.p[d].po = p->po[d]; }
   a.pbuf = pbuf; a.gsum = gsum;
   a.precision = ctx->rec_prec;
-  ctx->launches += 1;
-  {
+  for (int ci = 0; ci < nchunks; ci++) {
+    a.s_begin = ci * chunk;
+    a.s_count = std::min(chunk, S - a.s_begin);
+    a.gsum = gsum + (size_t)ci * plan.gsum_floats;
+    ctx->launches += 1;
     int pe = ctx->prof_begin(eesen_b200_ctx::kLstmBwd);
     cudaError_t le = eb::lstm_backward(ctx->stream, plan, a);
     ctx->prof_end(pe);
@@ -224,7 +246,7 @@ int eesen_b200_bilstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, 
   for (int d = 0; d < 2; d++) {
     ctx->launches += 1;
     int pe = ctx->prof_begin(eesen_b200_ctx::kMisc);
-    cudaError_t le = eb::lstm_reduce_gsum(ctx->stream, plan, C, gsum, gr->bias[d], gr->pi[d], gr->pf[d], gr->po[d], d);
+    cudaError_t le = eb::lstm_reduce_gsum(ctx->stream, plan, C, gsum, nchunks, gr->bias[d], gr->pi[d], gr->pf[d], gr->po[d], d);
     ctx->prof_end(pe);
     if ((rc = ctx->check(le, "lstm_reduce_gsum"))) return rc;
   }

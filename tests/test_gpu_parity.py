@@ -101,6 +101,8 @@ def _ctc_case(seed, S, T, K, maxlab, ragged=True):
             lab[1] = lab[0]
         labels.append(lab.astype(np.int32))
     labels[0] = rng.integers(1, K, size=maxlab).astype(np.int32)   # one utterance at the maximum label length
+    if S >= 3:
+        labels[2] = np.zeros(0, np.int32)   # empty transcription: only the all-blank path (|l| = 0, L' = 1)
     logits = (rng.standard_normal((T * S, K)) * 2).astype(np.float32)
     return frames, labels, logits
 
@@ -135,7 +137,8 @@ def test_ctc_eval_vs_oracle(ctx, seed, S, T, K, maxlab):
         assert np.all(got_d[rows, :K] == 0)
 
 
-@pytest.mark.parametrize("S,T,I,C", [(4, 9, 8, 16), (2, 30, 40, 128), (20, 17, 40, 64), (16, 40, 40, 320), (3, 5, 64, 24)])
+@pytest.mark.parametrize("S,T,I,C", [(4, 9, 8, 16), (2, 30, 40, 128), (20, 17, 40, 64), (16, 40, 40, 320), (3, 5, 64, 24),
+                                     (100, 7, 40, 320), (1, 1, 40, 64)])   # 100 utts: two utterance chunks (64 + 36)
 @pytest.mark.parametrize("rec", ["fp32x3", "tf32"])
 def test_bilstm_layer_vs_oracle(ctx, S, T, I, C, rec):
     """Level-1 BiLSTM forward/backward of one layer against the fp64 oracle, ragged lengths."""
