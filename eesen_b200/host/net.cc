@@ -433,7 +433,7 @@ void Net::BindArena() {
   arena_size_ = (total + 3) & ~(int64)3;
   if (arena_size_ == 0) return;
   CU_CHECK(cudaMalloc((void **)&w_, sizeof(float) * arena_size_));
-  CU_CHECK(cudaMalloc((void **)&g_, sizeof(float) * arena_size_));
+  CU_CHECK(cudaMalloc((void **)&g_, sizeof(float) * (arena_size_ + 4)));   // +4: vote slot of BackpropagateShared
   CU_CHECK(cudaMalloc((void **)&corr_, sizeof(float) * arena_size_));
   CU_CHECK(cudaMemsetAsync(w_, 0, sizeof(float) * arena_size_, Stream()));
   CU_CHECK(cudaMemsetAsync(g_, 0, sizeof(float) * arena_size_, Stream()));
@@ -550,9 +550,7 @@ void Net::Propagate(const CuMatrixBase<BaseFloat> &in, CuMatrix<BaseFloat> *out)
   (*out) = propagate_buf_[NumLayers()];
 }
 
-void Net::Backpropagate(const CuMatrixBase<BaseFloat> &out_diff, CuMatrix<BaseFloat> *in_diff) {
-  g_ctx = ctx_;
-  if (NumLayers() == 0) { if (in_diff) (*in_diff) = out_diff; return; }
+void Net::BackpropagateLayers(const CuMatrixBase<BaseFloat> &out_diff, CuMatrix<BaseFloat> *in_diff) {
   if (!in_train_) KALDI_ERR << "Can't backpropagate in test mode";
   const CuMatrixBase<BaseFloat> *diff = &out_diff;
   for (int32 i = NumLayers() - 1; i >= 0; i--) {
@@ -560,10 +558,17 @@ void Net::Backpropagate(const CuMatrixBase<BaseFloat> &out_diff, CuMatrix<BaseFl
     layers_[i]->Backpropagate(propagate_buf_[i], propagate_buf_[i + 1], *diff, &backpropagate_buf_[i]);
     diff = &backpropagate_buf_[i];
   }
-  // data-parallel: one all-reduce of the raw gradient arena, then the identical update on every rank
+}
+
+// data-parallel: one all-reduce of the raw gradient arena ...
+void Net::Reduce(int64 reduce_count) {
   int rank, nranks;
   eesen_b200_world(ctx_, &rank, &nranks);
-  if (nranks > 1) CheckAbi(ctx_, eesen_b200_allreduce_sum(ctx_, g_, arena_size_), "eesen_b200_allreduce_sum");
+  if (nranks > 1) CheckAbi(ctx_, eesen_b200_allreduce_sum(ctx_, g_, reduce_count), "eesen_b200_allreduce_sum");
+}
+
+// ... then the identical momentum / clip / SGD update on every rank
+void Net::Update() {
   if (segs_dirty_) UploadSegments();
   if (nseg_ > 0) {
     int pe = ctx_->prof_begin(eesen_b200_ctx::kSgd);
@@ -573,7 +578,32 @@ void Net::Backpropagate(const CuMatrixBase<BaseFloat> &out_diff, CuMatrix<BaseFl
     ctx_->launches += 1;
     if (e != cudaSuccess) KALDI_ERR << "sgd_momentum_clip: " << cudaGetErrorString(e);
   }
+}
+
+void Net::Backpropagate(const CuMatrixBase<BaseFloat> &out_diff, CuMatrix<BaseFloat> *in_diff) {
+  g_ctx = ctx_;
+  if (NumLayers() == 0) { if (in_diff) (*in_diff) = out_diff; return; }
+  BackpropagateLayers(out_diff, in_diff);
+  Reduce(arena_size_);
+  Update();
   if (NULL != in_diff) (*in_diff) = backpropagate_buf_[0];
+}
+
+int32 Net::BackpropagateShared(const CuMatrixBase<BaseFloat> *out_diff) {
+  g_ctx = ctx_;
+  if (NumLayers() == 0 || arena_size_ == 0) return out_diff ? 1 : 0;
+  if (out_diff) BackpropagateLayers(*out_diff, NULL);
+  else CU_CHECK(cudaMemsetAsync(g_, 0, sizeof(float) * arena_size_, Stream()));
+  // the 4 spare floats behind the arena carry the "I had a minibatch" vote through the same all-reduce
+  const float vote[4] = {out_diff ? 1.0f : 0.0f, 0.f, 0.f, 0.f};
+  CU_CHECK(cudaMemcpyAsync(g_ + arena_size_, vote, sizeof(vote), cudaMemcpyHostToDevice, Stream()));
+  Reduce(arena_size_ + 4);
+  float active = 0.f;
+  CU_CHECK(cudaMemcpyAsync(&active, g_ + arena_size_, sizeof(float), cudaMemcpyDeviceToHost, Stream()));
+  CU_CHECK(cudaStreamSynchronize(Stream()));
+  const int32 n_active = (int32)(active + 0.5f);
+  if (n_active > 0) Update();   // a step in which NO rank had data is not a training step: no momentum-only update
+  return n_active;
 }
 
 static std::string Moments(const std::vector<float> &v, int64 b, int64 n) {

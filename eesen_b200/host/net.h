@@ -192,6 +192,11 @@ class Net {
   void Write(std::ostream &os, bool binary);
   void Propagate(const CuMatrixBase<BaseFloat> &in, CuMatrix<BaseFloat> *out);       // net.cc:67-86
   void Backpropagate(const CuMatrixBase<BaseFloat> &out_diff, CuMatrix<BaseFloat> *in_diff);  // net.cc:88-108
+  // Data-parallel step that tolerates ranks running out of data: a rank without a minibatch passes
+  // out_diff == NULL, contributes a zero gradient and still takes part in the all-reduce and the
+  // (identical) update.  Returns how many ranks had a minibatch this step (0: everybody is done).
+  // Replaces the done-file handshake of the reference (src/net/communicator.h:57-71,107-113).
+  int32 BackpropagateShared(const CuMatrixBase<BaseFloat> *out_diff);
   void SetSeqLengths(std::vector<int> &sequence_lengths);                            // net.h:157-161
   void SetTrainOptions(const NetTrainOptions &opts);
   const NetTrainOptions &GetTrainOptions() const { return opts_; }
@@ -219,6 +224,9 @@ class Net {
  private:
   void BindArena();
   void UploadSegments();
+  void BackpropagateLayers(const CuMatrixBase<BaseFloat> &out_diff, CuMatrix<BaseFloat> *in_diff);
+  void Reduce(int64 reduce_count);
+  void Update();
   eesen_b200_ctx *ctx_;
   std::vector<Layer *> layers_;
   std::vector<CuMatrix<BaseFloat> > propagate_buf_, backpropagate_buf_;

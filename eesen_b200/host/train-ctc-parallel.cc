@@ -157,7 +157,12 @@ int main(int argc, char *argv[]) {
         // its (asynchronous) upload must have left the host buffer by then
         if (h2d_pending) { cudaEventSynchronize(h2d_done); h2d_pending = false; }
         const Minibatch *mb = batches.Next();
-        if (!mb) break;
+        if (!mb) {
+          // out of data: in a multi-rank training run keep voting "idle" in the per-step all-reduce
+          // until every rank is done (ranks may hold different numbers of minibatches)
+          if (num_jobs > 1 && !crossvalidate && net.BackpropagateShared(NULL) > 0) continue;
+          break;
+        }
         std::vector<int> frame_num_utt = mb->frames;
         std::vector<std::vector<int> > labels_utt = mb->labels;
         feats_dev.Resize(mb->T * mb->S, mb->dim, kUndefined);
@@ -168,7 +173,10 @@ int main(int argc, char *argv[]) {
         net.Propagate(feats_dev, &net_out);                                           // :198
         ctc.EvalParallel(frame_num_utt, net_out, labels_utt, &obj_diff);              // :199
         ctc.ErrorRateMSeq(frame_num_utt, net_out, labels_utt, sequence_out_file);     // :202
-        if (!crossvalidate) net.Backpropagate(obj_diff, NULL);                        // :207, gradient all-reduce inside
+        if (!crossvalidate) {                                                         // :207, gradient all-reduce inside
+          if (num_jobs > 1) net.BackpropagateShared(&obj_diff);
+          else net.Backpropagate(obj_diff, NULL);
+        }
         num_done += mb->S;
         total_frames += mb->padded_frames();
       }
