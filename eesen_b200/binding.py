@@ -208,6 +208,13 @@ class Net:
         self.ctx.check(self.lib.eesen_b200_net_set_train_options(self.h, C.c_float(learn_rate), C.c_float(momentum)),
                        "net_set_train_options")
 
+    def set_optimizer(self, algorithm: str = "SGD", adagrad_epsilon: float = 1e-6, rmsprop_rho: float = 0.9,
+                      rmsprop_one_minus_rho: float = -1.0):
+        """Net::SetUpdateAlgorithm + the adaptive NetTrainOptions (one_minus_rho < 0: the reference's fixed 0.1)."""
+        self.ctx.check(self.lib.eesen_b200_net_set_optimizer(self.h, algorithm.encode(), C.c_float(adagrad_epsilon),
+                                                             C.c_float(rmsprop_rho), C.c_float(rmsprop_one_minus_rho)),
+                       "net_set_optimizer")
+
     def write(self, path: str, binary: bool = True):
         self.ctx.check(self.lib.eesen_b200_net_write(self.h, path.encode(), int(binary)), "net_write")
 
@@ -259,6 +266,9 @@ class Net:
 
     def corr(self) -> np.ndarray:
         return self.get(201).ravel()
+
+    def accu(self) -> np.ndarray:
+        return self.get(203).ravel()
 
     def grads(self) -> np.ndarray:
         return self.get(202).ravel()

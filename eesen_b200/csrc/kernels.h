@@ -83,6 +83,10 @@ struct SgdSegment {
 };
 cudaError_t sgd_momentum_clip(cudaStream_t st, int num_sms, float *w, float *corr, const float *grad,
                               float momentum, const SgdSegment *d_segs, int nseg, long total);
+// mode 0 SGD, 1 Adagrad, 2 RMSProp (accu: the adaptive accumulator arena, same layout as w)
+cudaError_t optimizer_update(cudaStream_t st, int num_sms, int mode, float *w, float *corr, float *accu,
+                             const float *grad, float momentum, float eps, float rho, float one_minus_rho,
+                             const SgdSegment *d_segs, int nseg, long total);
 cudaError_t col_sum(cudaStream_t st, int num_sms, int N, int K, const float *x, int ld, float *out, float *ws);
 size_t col_sum_ws_floats(int K, int num_sms);
 

@@ -16,6 +16,45 @@ namespace eb {
 
 namespace {
 
+// element update shared by the vector and the scalar path.
+//   MODE 0  SGD      : w -= lr * corr                                   (bilstm-layer.h:865-883)
+//   MODE 1  Adagrad  : accu += corr^2                                   (trainable-layer.h:65-78)
+//   MODE 2  RMSProp  : accu  = rho*accu + one_minus_rho*corr^2          (trainable-layer.h:80-96)
+//           then       w -= lr * corr / sqrt(accu + eps)                (trainable-layer.h:98-114, bilstm-layer.h:885-955)
+// corr = clamp(grad + momentum*corr) in every mode (the adaptive rules act on the momentum buffer too).
+template <int MODE>
+__device__ __forceinline__ void opt_elem(float &w, float &c, float &a, float g, float momentum, float lr, float max_grad,
+                                         float eps, float rho, float omr) {
+  c = g + momentum * c;
+  if (max_grad > 0.f) c = fminf(fmaxf(c, -max_grad), max_grad);
+  if (MODE == 0) {
+    w -= lr * c;
+  } else {
+    a = MODE == 1 ? a + c * c : rho * a + omr * (c * c);
+    w -= lr * (1.f / sqrtf(a + eps)) * c;
+  }
+}
+
+template <int MODE>
+__global__ void opt_kernel(float *__restrict__ w, float *__restrict__ corr, float *__restrict__ accu,
+                           const float *__restrict__ grad, float momentum, float eps, float rho, float omr,
+                           const SgdSegment *__restrict__ segs, int nseg, long total) {
+  long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (segs[mid].offset <= i) lo = mid; else hi = mid - 1;
+    }
+    const SgdSegment sg = segs[lo];
+    float a = MODE ? accu[i] : 0.f, c = corr[i], ww = w[i];
+    opt_elem<MODE>(ww, c, a, grad[i], momentum, sg.lr, sg.max_grad, eps, rho, omr);
+    corr[i] = c;
+    w[i] = ww;
+    if (MODE) accu[i] = a;
+  }
+}
+
 __global__ void sgd_kernel(float *__restrict__ w, float *__restrict__ corr, const float *__restrict__ grad,
                            float momentum, const SgdSegment *__restrict__ segs, int nseg, long total) {
   long stride = (long)gridDim.x * blockDim.x * 4;
@@ -86,6 +125,19 @@ cudaError_t sgd_momentum_clip(cudaStream_t st, int num_sms, float *w, float *cor
   int blocks = (int)((vec + 255) / 256);
   if (blocks > 8 * num_sms) blocks = 8 * num_sms;
   sgd_kernel<<<blocks, 256, 0, st>>>(w, corr, grad, momentum, d_segs, nseg, total);
+  return cudaGetLastError();
+}
+
+cudaError_t optimizer_update(cudaStream_t st, int num_sms, int mode, float *w, float *corr, float *accu,
+                             const float *grad, float momentum, float eps, float rho, float one_minus_rho,
+                             const SgdSegment *d_segs, int nseg, long total) {
+  if (mode == 0) return sgd_momentum_clip(st, num_sms, w, corr, grad, momentum, d_segs, nseg, total);
+  if (total <= 0) return cudaSuccess;
+  if (!accu || (mode != 1 && mode != 2)) return cudaErrorInvalidValue;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 16 * num_sms) blocks = 16 * num_sms;
+  if (mode == 1) opt_kernel<1><<<blocks, 256, 0, st>>>(w, corr, accu, grad, momentum, eps, rho, one_minus_rho, d_segs, nseg, total);
+  else opt_kernel<2><<<blocks, 256, 0, st>>>(w, corr, accu, grad, momentum, eps, rho, one_minus_rho, d_segs, nseg, total);
   return cudaGetLastError();
 }
 

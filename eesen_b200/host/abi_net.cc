@@ -84,10 +84,20 @@ void eesen_b200_net_free(eesen_b200_net *n) { delete n; }
 
 int eesen_b200_net_set_train_options(eesen_b200_net *n, float learn_rate, float momentum) {
   if (!n) return EESEN_B200_EINVAL;
-  NetTrainOptions o;
+  NetTrainOptions o = n->net.GetTrainOptions();
   o.learn_rate = learn_rate;
   o.momentum = momentum;
-  GUARD(n->ctx, { n->net.SetTrainOptions(o); n->net.SetUpdateAlgorithm("SGD"); n->net.SetTrainMode(); });
+  GUARD(n->ctx, { n->net.SetTrainOptions(o); n->net.SetTrainMode(); });
+}
+
+int eesen_b200_net_set_optimizer(eesen_b200_net *n, const char *algorithm, float adagrad_epsilon, float rmsprop_rho,
+                                 float rmsprop_one_minus_rho) {
+  if (!n || !algorithm) return EESEN_B200_EINVAL;
+  NetTrainOptions o = n->net.GetTrainOptions();
+  o.adagrad_epsilon = adagrad_epsilon;
+  o.rmsprop_rho = rmsprop_rho;
+  o.rmsprop_one_minus_rho = rmsprop_one_minus_rho < 0.f ? 0.1f : rmsprop_one_minus_rho;
+  GUARD(n->ctx, { n->net.SetUpdateAlgorithm(algorithm); n->net.SetTrainOptions(o); });
 }
 
 int eesen_b200_net_dims(const eesen_b200_net *n, int *in_dim, int *out_dim, int *num_layers, int64_t *num_params) {
@@ -187,13 +197,23 @@ int eesen_b200_net_get(eesen_b200_net *n, int which, float *data, int64_t capaci
       n->want_in_diff = true;  // takes effect from the next step
       return copy_out(n->in_diff, data, capacity, rows, cols);
     }
-    if (which >= 200 && which <= 202) {
+    if (which == 203 && !n->net.Accu()) {
+      if (rows) *rows = 1;
+      if (cols) *cols = (int)n->net.NumParams();
+      if (data) {
+        if (n->net.NumParams() > capacity) return EESEN_B200_EINVAL;
+        memset(data, 0, sizeof(float) * n->net.NumParams());
+      }
+      return 0;
+    }
+    if (which >= 200 && which <= 203) {
       if (rows) *rows = 1;
       if (cols) *cols = (int)n->net.NumParams();
       if (data) {
         if (n->net.NumParams() > capacity) return EESEN_B200_EINVAL;
         std::vector<float> h;
-        n->net.GetArena(which == 200 ? n->net.Params() : which == 201 ? n->net.Corr() : n->net.Grads(), &h);
+        n->net.GetArena(which == 200 ? n->net.Params() : which == 201 ? n->net.Corr() : which == 202 ? n->net.Grads()
+                                                                                                      : n->net.Accu(), &h);
         memcpy(data, h.data(), sizeof(float) * h.size());
       }
       return 0;

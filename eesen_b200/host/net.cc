@@ -202,9 +202,11 @@ void BiLstmParallel::ReadData(std::istream &is, bool binary) {
     else if (tok == "<MaxGrad>") ReadBasicType(is, binary, &max_grad_);
     else if (tok == "<ForwardDropoutFactor>") ReadBasicType(is, binary, &forward_dropout_);
     else if (tok == "<RecurrentDropoutFactor>") ReadBasicType(is, binary, &recurrent_dropout_);
-    else if (tok == "<BiLstmAccus>")
-      KALDI_ERR << "Adagrad/RMSProp accumulators are not supported on the B200 CTC path (SGD only)";
-    else {
+    else if (tok == "<BiLstmAccus>") {   // bilstm-layer.h:375-395: 12 accumulators, then the weights
+      ReadDirections(is, binary, &host_accu_);
+      has_accu_ = true;
+      break;
+    } else {
       int f = -1;
       for (int i = 0; i < 7; i++)
         if (tok == kBiLstmFlagTokens[i]) f = i;
@@ -218,9 +220,15 @@ void BiLstmParallel::ReadData(std::istream &is, bool binary) {
   if (C % 8 != 0 || I % 4 != 0)
     KALDI_ERR << "BiLstmParallel on B200 needs cells/direction % 8 == 0 and input dim % 4 == 0, got C=" << C
               << " I=" << I;
-  host_params_.clear();
-  host_params_.reserve(NumParams());
-  for (int d = 0; d < 2; d++) {   // bilstm-layer.h:395-424: wx, wm, bias, phole i/f/o for fw then bw
+  ReadDirections(is, binary, &host_params_);
+}
+
+// wx, wm, bias, phole i/f/o for fw then bw (bilstm-layer.h:395-424; the accumulators use the same order :381-393)
+void BiLstmParallel::ReadDirections(std::istream &is, bool binary, std::vector<float> *flat) const {
+  const int64 C = cell_dim_, I = input_dim_;
+  flat->clear();
+  flat->reserve(NumParams());
+  for (int d = 0; d < 2; d++) {
     HostMatrix wx, wm;
     HostVector b, pi, pf, po;
     wx.Read(is, binary); wm.Read(is, binary);
@@ -228,25 +236,18 @@ void BiLstmParallel::ReadData(std::istream &is, bool binary) {
     KALDI_ASSERT(wx.rows == 4 * C && wx.cols == I && wm.rows == 4 * C && wm.cols == C);
     KALDI_ASSERT((int64)b.data.size() == 4 * C && (int64)pi.data.size() == C && (int64)pf.data.size() == C &&
                  (int64)po.data.size() == C);
-    host_params_.insert(host_params_.end(), wx.data.begin(), wx.data.end());
-    host_params_.insert(host_params_.end(), wm.data.begin(), wm.data.end());
-    host_params_.insert(host_params_.end(), b.data.begin(), b.data.end());
-    host_params_.insert(host_params_.end(), pi.data.begin(), pi.data.end());
-    host_params_.insert(host_params_.end(), pf.data.begin(), pf.data.end());
-    host_params_.insert(host_params_.end(), po.data.begin(), po.data.end());
+    flat->insert(flat->end(), wx.data.begin(), wx.data.end());
+    flat->insert(flat->end(), wm.data.begin(), wm.data.end());
+    flat->insert(flat->end(), b.data.begin(), b.data.end());
+    flat->insert(flat->end(), pi.data.begin(), pi.data.end());
+    flat->insert(flat->end(), pf.data.begin(), pf.data.end());
+    flat->insert(flat->end(), po.data.begin(), po.data.end());
   }
 }
 
-void BiLstmParallel::WriteData(std::ostream &os, bool binary) const {
-  // bilstm-layer.h:429-493
-  WriteToken(os, binary, "<LearnRateCoef>"); WriteBasicType(os, binary, learn_rate_coef_);
-  WriteToken(os, binary, "<MaxGrad>"); WriteBasicType(os, binary, max_grad_);
-  WriteToken(os, binary, "<ForwardDropoutFactor>"); WriteBasicType(os, binary, forward_dropout_);
-  for (int i = 0; i < 6; i++) { WriteToken(os, binary, kBiLstmFlagTokens[i]); WriteBasicType(os, binary, flags_[i]); }
-  WriteToken(os, binary, "<RecurrentDropoutFactor>"); WriteBasicType(os, binary, recurrent_dropout_);
-  WriteToken(os, binary, kBiLstmFlagTokens[6]); WriteBasicType(os, binary, flags_[6]);
+void BiLstmParallel::WriteDirections(std::ostream &os, bool binary, const std::vector<float> &flat) const {
   const int64 C = cell_dim_, I = input_dim_;
-  const float *p = host_params_.data();
+  const float *p = flat.data();
   for (int d = 0; d < 2; d++) {
     HostMatrix wx, wm;
     wx.rows = 4 * C; wx.cols = I; wx.data.assign(p, p + 4 * C * I); p += 4 * C * I;
@@ -259,6 +260,21 @@ void BiLstmParallel::WriteData(std::ostream &os, bool binary) const {
     wx.Write(os, binary); wm.Write(os, binary);
     b.Write(os, binary); pi.Write(os, binary); pf.Write(os, binary); po.Write(os, binary);
   }
+}
+
+void BiLstmParallel::WriteData(std::ostream &os, bool binary) const {
+  // bilstm-layer.h:429-493
+  WriteToken(os, binary, "<LearnRateCoef>"); WriteBasicType(os, binary, learn_rate_coef_);
+  WriteToken(os, binary, "<MaxGrad>"); WriteBasicType(os, binary, max_grad_);
+  WriteToken(os, binary, "<ForwardDropoutFactor>"); WriteBasicType(os, binary, forward_dropout_);
+  for (int i = 0; i < 6; i++) { WriteToken(os, binary, kBiLstmFlagTokens[i]); WriteBasicType(os, binary, flags_[i]); }
+  WriteToken(os, binary, "<RecurrentDropoutFactor>"); WriteBasicType(os, binary, recurrent_dropout_);
+  WriteToken(os, binary, kBiLstmFlagTokens[6]); WriteBasicType(os, binary, flags_[6]);
+  if (has_accu_) {   // bilstm-layer.h:458-475
+    WriteToken(os, binary, "<BiLstmAccus>");
+    WriteDirections(os, binary, host_accu_);
+  }
+  WriteDirections(os, binary, host_params_);
 }
 
 void BiLstmParallel::Params(eesen_b200_bilstm_params *p, eesen_b200_bilstm_grads *g) const {
@@ -330,9 +346,17 @@ void AffineTransform::ReadData(std::istream &is, bool binary) {
     ReadToken(is, binary, &tok);
     if (tok == "<LearnRateCoef>") ReadBasicType(is, binary, &learn_rate_coef_);
     else if (tok == "<MaxGrad>") ReadBasicType(is, binary, &max_grad_);
-    else if (tok == "<AffineAccus>")
-      KALDI_ERR << "Adagrad/RMSProp accumulators are not supported on the B200 CTC path (SGD only)";
-    else KALDI_ERR << "Unknown token " << tok << " in <AffineTransform>";
+    else if (tok == "<AffineAccus>") {   // affine-trans-layer.h:98-106
+      HostMatrix aw;
+      HostVector ab;
+      aw.Read(is, binary);
+      ab.Read(is, binary);
+      KALDI_ASSERT(aw.rows == output_dim_ && aw.cols == input_dim_ && (int32)ab.data.size() == output_dim_);
+      host_accu_ = aw.data;
+      host_accu_.insert(host_accu_.end(), ab.data.begin(), ab.data.end());
+      has_accu_ = true;
+      break;
+    } else KALDI_ERR << "Unknown token " << tok << " in <AffineTransform>";
   }
   if (input_dim_ % 4 != 0) KALDI_ERR << "AffineTransform on B200 needs input dim % 4 == 0, got " << input_dim_;
   HostMatrix w;
@@ -347,11 +371,22 @@ void AffineTransform::ReadData(std::istream &is, bool binary) {
 void AffineTransform::WriteData(std::ostream &os, bool binary) const {
   WriteToken(os, binary, "<LearnRateCoef>"); WriteBasicType(os, binary, learn_rate_coef_);
   WriteToken(os, binary, "<MaxGrad>"); WriteBasicType(os, binary, max_grad_);
+  const size_t nw = (size_t)output_dim_ * input_dim_;
+  if (has_accu_) {   // affine-trans-layer.h:123-129
+    WriteToken(os, binary, "<AffineAccus>");
+    HostMatrix aw;
+    aw.rows = output_dim_; aw.cols = input_dim_;
+    aw.data.assign(host_accu_.begin(), host_accu_.begin() + nw);
+    HostVector ab;
+    ab.data.assign(host_accu_.begin() + nw, host_accu_.end());
+    aw.Write(os, binary);
+    ab.Write(os, binary);
+  }
   HostMatrix w;
   w.rows = output_dim_; w.cols = input_dim_;
-  w.data.assign(host_params_.begin(), host_params_.begin() + (size_t)output_dim_ * input_dim_);
+  w.data.assign(host_params_.begin(), host_params_.begin() + nw);
   HostVector b;
-  b.data.assign(host_params_.begin() + (size_t)output_dim_ * input_dim_, host_params_.end());
+  b.data.assign(host_params_.begin() + nw, host_params_.end());
   w.Write(os, binary);
   b.Write(os, binary);
 }
@@ -387,6 +422,7 @@ Net::~Net() {
   if (w_) cudaFree(w_);
   if (g_) cudaFree(g_);
   if (corr_) cudaFree(corr_);
+  if (accu_) cudaFree(accu_);
   if (d_segs_) cudaFree(d_segs_);
 }
 
@@ -449,6 +485,31 @@ void Net::BindArena() {
   }
   CU_CHECK(cudaStreamSynchronize(Stream()));
   segs_dirty_ = true;
+  bool any_accu = false;
+  for (size_t i = 0; i < layers_.size(); i++)
+    if (offs[i] >= 0 && dynamic_cast<TrainableLayer *>(layers_[i])->has_accu_) any_accu = true;
+  if (any_accu) EnsureAccu(false);
+}
+
+// The accumulator arena of the adaptive rules: allocated when a model file carries accumulators or
+// at the first Adagrad/RMSProp update (InitAdaBuffers, bilstm-layer.h:275-315: zero-initialised).
+void Net::EnsureAccu(bool mark_all_layers) {
+  if (!accu_ && arena_size_ > 0) {
+    CU_CHECK(cudaMalloc((void **)&accu_, sizeof(float) * arena_size_));
+    CU_CHECK(cudaMemsetAsync(accu_, 0, sizeof(float) * arena_size_, Stream()));
+    for (size_t i = 0; i < layers_.size(); i++) {
+      if (layer_offset_[i] < 0) continue;
+      TrainableLayer *tl = dynamic_cast<TrainableLayer *>(layers_[i]);
+      if (!tl->has_accu_) continue;
+      KALDI_ASSERT((int64)tl->host_accu_.size() == tl->NumParams());
+      CU_CHECK(cudaMemcpyAsync(accu_ + layer_offset_[i], tl->host_accu_.data(), sizeof(float) * tl->NumParams(),
+                               cudaMemcpyHostToDevice, Stream()));
+    }
+    CU_CHECK(cudaStreamSynchronize(Stream()));
+  }
+  if (mark_all_layers)
+    for (size_t i = 0; i < layers_.size(); i++)
+      if (layer_offset_[i] >= 0) dynamic_cast<TrainableLayer *>(layers_[i])->has_accu_ = true;
 }
 
 void Net::GetParams(std::vector<float> *host) const { GetArena(w_, host); }
@@ -496,6 +557,11 @@ void Net::Write(std::ostream &os, bool binary) {
     tl->host_params_.resize(tl->NumParams());
     CU_CHECK(cudaMemcpy(tl->host_params_.data(), w_ + layer_offset_[i], sizeof(float) * tl->NumParams(),
                         cudaMemcpyDeviceToHost));
+    if (tl->has_accu_ && accu_) {
+      tl->host_accu_.resize(tl->NumParams());
+      CU_CHECK(cudaMemcpy(tl->host_accu_.data(), accu_ + layer_offset_[i], sizeof(float) * tl->NumParams(),
+                          cudaMemcpyDeviceToHost));
+    }
   }
   WriteToken(os, binary, "<Nnet>");
   if (!binary) os << std::endl;
@@ -516,8 +582,12 @@ void Net::SetTrainOptions(const NetTrainOptions &opts) {
   segs_dirty_ = true;
 }
 
-void Net::SetUpdateAlgorithm(const std::string &opt) {
-  if (opt != "SGD") KALDI_ERR << "Only --opt-algorithm=SGD is implemented on the B200 CTC path, got " << opt;
+void Net::SetUpdateAlgorithm(const std::string &opt) {   // net.cc:481-496
+  if (opt == "SGD") update_algorithm_ = 0;
+  else if (opt == "Adagrad") update_algorithm_ = 1;
+  else if (opt == "RMSProp") update_algorithm_ = 2;
+  else KALDI_ERR << "This optimization algorithm is unsupported: " << opt;
+  segs_dirty_ = true;
 }
 
 void Net::UploadSegments() {
@@ -528,7 +598,9 @@ void Net::UploadSegments() {
     eb::SgdSegment s;
     s.offset = layer_offset_[i];
     s.count = 0;  // fixed below: up to the next segment start
-    s.lr = opts_.learn_rate * tl->learn_rate_coef_;
+    // learn_rate_coef_ scales the SGD step only; the adaptive branch uses opts_.learn_rate as is
+    // (bilstm-layer.h:865-869 vs :885-955, affine-trans-layer.h:191-219)
+    s.lr = update_algorithm_ == 0 ? opts_.learn_rate * tl->learn_rate_coef_ : opts_.learn_rate;
     s.max_grad = tl->max_grad_;
     segs.push_back(s);
   }
@@ -572,11 +644,14 @@ void Net::Update() {
   if (segs_dirty_) UploadSegments();
   if (nseg_ > 0) {
     int pe = ctx_->prof_begin(eesen_b200_ctx::kSgd);
-    cudaError_t e = eb::sgd_momentum_clip(ctx_->stream, ctx_->num_sms, w_, corr_, g_, opts_.momentum,
-                                          (const eb::SgdSegment *)d_segs_, nseg_, arena_size_);
+    if (update_algorithm_ != 0) EnsureAccu(true);
+    cudaError_t e = eb::optimizer_update(ctx_->stream, ctx_->num_sms, update_algorithm_, w_, corr_, accu_, g_,
+                                         opts_.momentum, opts_.adagrad_epsilon, opts_.rmsprop_rho,
+                                         opts_.rmsprop_one_minus_rho, (const eb::SgdSegment *)d_segs_, nseg_,
+                                         arena_size_);
     ctx_->prof_end(pe);
     ctx_->launches += 1;
-    if (e != cudaSuccess) KALDI_ERR << "sgd_momentum_clip: " << cudaGetErrorString(e);
+    if (e != cudaSuccess) KALDI_ERR << "optimizer_update: " << cudaGetErrorString(e);
   }
 }
 

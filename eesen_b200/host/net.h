@@ -124,6 +124,10 @@ class TrainableLayer : public Layer {
   friend class Net;
   // host staging of the parameters between ReadData and Net::BindArena / for WriteData
   std::vector<float> host_params_;
+  // Adagrad/RMSProp accumulators (<BiLstmAccus>/<AffineAccus>), same tensor order as host_params_;
+  // has_accu_ mirrors the reference's adaBuffersInitialized (bilstm-layer.h:375-395,458-475)
+  std::vector<float> host_accu_;
+  bool has_accu_ = false;
   float *w_ = nullptr, *g_ = nullptr;  // this layer's block of the Net arenas (device)
   virtual void Bind(float *w, float *g) { w_ = w; g_ = g; }
 };
@@ -144,6 +148,8 @@ class BiLstmParallel : public TrainableLayer {
   void ReadData(std::istream &is, bool binary);
   void WriteData(std::ostream &os, bool binary) const;
   void Params(eesen_b200_bilstm_params *p, eesen_b200_bilstm_grads *g) const;
+  void ReadDirections(std::istream &is, bool binary, std::vector<float> *flat) const;
+  void WriteDirections(std::ostream &os, bool binary, const std::vector<float> &flat) const;
   int32 cell_dim_;
   std::vector<int> sequence_lengths_;
   int *d_len_ = nullptr;
@@ -200,7 +206,8 @@ class Net {
   void SetSeqLengths(std::vector<int> &sequence_lengths);                            // net.h:157-161
   void SetTrainOptions(const NetTrainOptions &opts);
   const NetTrainOptions &GetTrainOptions() const { return opts_; }
-  void SetUpdateAlgorithm(const std::string &opt);       // "SGD" only on this path
+  void SetUpdateAlgorithm(const std::string &opt);       // SGD | Adagrad | RMSProp (net.cc:481-496)
+  int UpdateAlgorithm() const { return update_algorithm_; }
   void SetTrainMode() { in_train_ = true; }
   void SetTestMode() { in_train_ = false; }
   int32 InputDim() const;
@@ -215,6 +222,7 @@ class Net {
   float *Params() { return w_; }
   float *Grads() { return g_; }
   float *Corr() { return corr_; }
+  float *Accu() { return accu_; }   // NULL until an accumulator was read or an adaptive update ran
   void GetParams(std::vector<float> *host) const;
   void GetArena(const float *arena, std::vector<float> *host) const;  // packs one arena in model-file order
   void SetParams(const float *host, int64 n);
@@ -235,6 +243,9 @@ class Net {
   int64 num_params_ = 0, arena_size_ = 0;
   std::vector<int64> layer_offset_;  // arena offset of each layer's block (-1: not trainable)
   float *w_ = nullptr, *g_ = nullptr, *corr_ = nullptr;
+  float *accu_ = nullptr;
+  void EnsureAccu(bool mark_all_layers);
+  int update_algorithm_ = 0;  // 0 sgd_update, 1 adagrad_update, 2 rmsprop_update (trainable-layer.h:34-38)
   void *d_segs_ = nullptr;
   int nseg_ = 0;
   bool segs_dirty_ = true;

@@ -41,7 +41,7 @@ static const char *kUsage =
     "e.g.: \n"
     "train-ctc-parallel scp:feature.scp ark:labels.ark nnet.init nnet.iter1\n"
     "Options: --learn-rate --momentum --binary --cross-validate --num-sequence --frame-limit --report-step\n"
-    "         --num-jobs --job-id --opt-algorithm=SGD --sequence-out-file --verbose\n"
+    "         --num-jobs --job-id --opt-algorithm=SGD|Adagrad|RMSProp --adagrad-epsilon --rms-prop-rho --sequence-out-file --verbose\n"
     "         --gemm-precision=fp32x3|tf32|bf16 --recurrent-precision=fp32x3|tf32\n";
 
 static int PrecFromString(const std::string &s) {
@@ -85,6 +85,10 @@ int main(int argc, char *argv[]) {
     NetTrainOptions trn_opts;
     trn_opts.learn_rate = po.Num("learn-rate", trn_opts.learn_rate);
     trn_opts.momentum = po.Num("momentum", trn_opts.momentum);
+    trn_opts.adagrad_epsilon = po.Num("adagrad-epsilon", trn_opts.adagrad_epsilon);
+    // as in the reference, rmsprop_one_minus_rho keeps its default 0.1: train-opts.h:50 derives it
+    // inside Register(), i.e. before --rms-prop-rho is parsed
+    trn_opts.rmsprop_rho = po.Num("rms-prop-rho", trn_opts.rmsprop_rho);
     bool binary = po.Bool("binary", true), crossvalidate = po.Bool("cross-validate", false);
     std::string sequence_out_file = po.Str("sequence-out-file", "");
     int32 num_sequence = (int32)po.Num("num-sequence", 5);

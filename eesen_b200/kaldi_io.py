@@ -34,6 +34,9 @@ class LayerSpec:
     learn_rate_coef: float = 1.0
     max_grad: float = 0.0
     params: Dict[str, np.ndarray] = field(default_factory=dict)
+    # Adagrad/RMSProp accumulators (<BiLstmAccus>/<AffineAccus>, bilstm-layer.h:375-395,
+    # affine-trans-layer.h:98-106); empty when the model carries none
+    accus: Dict[str, np.ndarray] = field(default_factory=dict)
 
     @property
     def cells(self) -> int:
@@ -75,6 +78,15 @@ class NetSpec:
     def flat_params(self) -> np.ndarray:
         """All parameters concatenated in model-file order (the gradient-arena order)."""
         out = [l.params[n].astype(np.float32).ravel() for l in self.layers for n in l.param_names()]
+        return np.concatenate(out) if out else np.zeros(0, np.float32)
+
+    def flat_accus(self) -> np.ndarray:
+        """Accumulators in the same order; zeros for layers without any."""
+        out = []
+        for l in self.layers:
+            shapes = l.param_shapes()
+            for n in l.param_names():
+                out.append(l.accus[n].astype(np.float32).ravel() if l.accus else np.zeros(int(np.prod(shapes[n])), np.float32))
         return np.concatenate(out) if out else np.zeros(0, np.float32)
 
     def set_flat_params(self, flat: np.ndarray) -> None:
@@ -162,11 +174,18 @@ def write_model(path_or_file, net: NetSpec) -> None:
             _wtok(f, "<NoMemLossDropout>"); _wbool(f, False)
             _wtok(f, "<RecurrentDropoutFactor>"); _wf32(f, 0.0)
             _wtok(f, "<TwiddleForward>"); _wbool(f, False)
+            if l.accus:
+                _wtok(f, "<BiLstmAccus>")
+                for n in l.param_names():
+                    _wmat(f, l.accus[n])
             for n in l.param_names():
                 _wmat(f, l.params[n])
         elif l.kind == "affine":
             _wtok(f, "<LearnRateCoef>"); _wf32(f, l.learn_rate_coef)
             _wtok(f, "<MaxGrad>"); _wf32(f, l.max_grad)
+            if l.accus:
+                _wtok(f, "<AffineAccus>")
+                _wmat(f, l.accus["w"]); _wmat(f, l.accus["b"])
             _wmat(f, l.params["w"]); _wmat(f, l.params["b"])
     _wtok(f, "</Nnet>")
     if isinstance(path_or_file, str):
@@ -252,6 +271,10 @@ def read_model(path: str) -> NetSpec:
                 elif tk == "<MaxGrad>": l.max_grad = r.f32()
                 elif tk in ("<ForwardDropoutFactor>", "<RecurrentDropoutFactor>"): r.f32()
                 elif tk in _BILSTM_FLAGS or tk == "<TwiddleForward>": r.boolean()
+                elif tk == "<BiLstmAccus>":
+                    for n in l.param_names():
+                        l.accus[n] = r.mat()
+                    break
                 else: raise ValueError(f"unsupported token {tk}")
             for n in l.param_names():
                 l.params[n] = r.mat()
@@ -260,6 +283,9 @@ def read_model(path: str) -> NetSpec:
                 tk = r.tok()
                 if tk == "<LearnRateCoef>": l.learn_rate_coef = r.f32()
                 elif tk == "<MaxGrad>": l.max_grad = r.f32()
+                elif tk == "<AffineAccus>":
+                    l.accus["w"] = r.mat(); l.accus["b"] = r.mat()
+                    break
                 else: raise ValueError(f"unsupported token {tk}")
             l.params["w"] = r.mat(); l.params["b"] = r.mat()
         layers.append(l)

@@ -150,6 +150,15 @@ int eesen_b200_net_read(eesen_b200_ctx *ctx, const char *model_path, eesen_b200_
 int eesen_b200_net_write(eesen_b200_net *net, const char *path, int binary);               /* Net::Write */
 void eesen_b200_net_free(eesen_b200_net *net);
 int eesen_b200_net_set_train_options(eesen_b200_net *net, float learn_rate, float momentum); /* SetTrainOptions */
+/* Net::SetUpdateAlgorithm (reference src/net/net.cc:481-496; driver option --opt-algorithm,
+ * src/netbin/train-ctc-parallel.cc:77-78,114) plus the two adaptive options of NetTrainOptions
+ * (src/net/train-opts.h:33-50).  algorithm: "SGD" | "Adagrad" | "RMSProp".  The update rules are
+ * trainable-layer.h:65-114 applied by bilstm-layer.h:885-955 / affine-trans-layer.h:196-219.
+ * NOTE the reference fixes rmsprop_one_minus_rho at 0.1 whatever --rms-prop-rho says (it is computed
+ * inside Register(), before the command line is parsed: train-opts.h:50); pass one_minus_rho < 0 to get
+ * that behaviour, or the value you want. */
+int eesen_b200_net_set_optimizer(eesen_b200_net *net, const char *algorithm, float adagrad_epsilon,
+                                 float rmsprop_rho, float rmsprop_one_minus_rho);
 int eesen_b200_net_dims(const eesen_b200_net *net, int *in_dim, int *out_dim, int *num_layers, int64_t *num_params);
 
 /* One minibatch exactly as the reference driver does it (train-ctc-parallel.cc:195-207):
@@ -171,6 +180,7 @@ int eesen_b200_net_read_stats(eesen_b200_net *net, double stats[4]);
  *   100     obj_diff (CTC gradient wrt logits)      101  per-utterance pzx [S]
  *   102     in_diff  (gradient wrt the network input)
  *   200     parameters   201 momentum buffers (corr)   202 raw gradients of the last step (after all-reduce)
+ *   203     Adagrad/RMSProp accumulators (zeros while none exist)
  * rows/cols describe the logical matrix; data may be NULL to query the shape only. */
 int eesen_b200_net_get(eesen_b200_net *net, int which, float *data, int64_t capacity, int *rows, int *cols);
 int eesen_b200_net_set_params(eesen_b200_net *net, const float *flat, int64_t n);

@@ -399,6 +399,26 @@ void oracle_sgd_update(long n, REAL *w, REAL *corr, REAL lr, REAL max_grad) {
   }
 }
 
+/* Adaptive updates (GPU-only in the reference: the CPU branches exit(-101), cuda-matrix.cc:572-573):
+ * clip as in the SGD branch, then AdagradAccuUpdate / RMSPropAccuUpdate (trainable-layer.h:65-96),
+ * AdagradScaleCompute = 1/sqrt(accu + eps) (:98-114) and w += -lr * scale * corr
+ * (bilstm-layer.h:885-955, affine-trans-layer.h:197-219).  mode 1 = Adagrad, 2 = RMSProp.
+ * one_minus_rho is its own option: the reference leaves it at 0.1 whatever rho is (train-opts.h:50). */
+void oracle_ada_update(long n, REAL *w, REAL *corr, REAL *accu, REAL lr, REAL max_grad, REAL eps, REAL rho,
+                       REAL one_minus_rho, int mode) {
+  for (long i = 0; i < n; i++) {
+    if (max_grad > (REAL)0) {
+      if (corr[i] < -max_grad) corr[i] = -max_grad;
+      if (corr[i] > max_grad) corr[i] = max_grad;
+    }
+    REAL g2 = corr[i] * corr[i];
+    if (mode == 1) accu[i] = accu[i] + g2;
+    else accu[i] = rho * accu[i] + one_minus_rho * g2;
+    REAL scale = (REAL)1 / (sizeof(REAL) == 4 ? (REAL)sqrtf((float)(accu[i] + eps)) : (REAL)sqrt((double)(accu[i] + eps)));
+    w[i] += -lr * scale * corr[i];
+  }
+}
+
 void oracle_row_argmax(int N, int K, const REAL *y, int *idx) {
   for (long r = 0; r < N; r++) {
     REAL mx = (REAL)-1e21;

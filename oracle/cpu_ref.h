@@ -72,6 +72,10 @@ void oracle_ctc_eval_parallel(int T, int S, int K, const int *len, const int *la
  * w -= lr*corr. */
 void oracle_sgd_update(long n, REAL *w, REAL *corr, REAL lr, REAL max_grad);
 
+/* Adagrad (mode 1) / RMSProp (mode 2) update of one tensor; see cpu_ref.c */
+void oracle_ada_update(long n, REAL *w, REAL *corr, REAL *accu, REAL lr, REAL max_grad, REAL eps, REAL rho,
+                       REAL one_minus_rho, int mode);
+
 /* FindRowMaxId (cuda-matrix.cc:1038-1095): first index of the row maximum. */
 void oracle_row_argmax(int N, int K, const REAL *y, int *idx);
 

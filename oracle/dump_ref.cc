@@ -146,13 +146,15 @@ static void read_npy_f32(const char *path, Matrix<BaseFloat> *m, int rows, int c
 int main(int argc, char **argv) {
   if (argc < 4) {
     fprintf(stderr, "usage: %s <model-in> <batch.bin> <outdir> [--lr x] [--momentum m] [--steps n]"
-                    " [--diff-in obj_diff.npy] [--time-only] [--no-dump-layers]\n", argv[0]);
+                    " [--diff-in obj_diff.npy] [--time-only] [--no-dump-layers]"
+                    " [--opt SGD|Adagrad|RMSProp] [--eps e] [--rho r]\n", argv[0]);
     return 1;
   }
   std::string model = argv[1], batch_path = argv[2], outdir = argv[3];
   float lr = 0.0f, momentum = 0.0f;
   int steps = 1;
-  std::string diff_in;
+  std::string diff_in, opt = "SGD";
+  float eps = -1.f, rho = -1.f;
   bool time_only = false, dump_layers = true;
   for (int i = 4; i < argc; i++) {
     std::string a = argv[i];
@@ -160,6 +162,9 @@ int main(int argc, char **argv) {
     else if (a == "--momentum") momentum = atof(argv[++i]);
     else if (a == "--steps") steps = atoi(argv[++i]);
     else if (a == "--diff-in") diff_in = argv[++i];
+    else if (a == "--opt") opt = argv[++i];
+    else if (a == "--eps") eps = atof(argv[++i]);
+    else if (a == "--rho") rho = atof(argv[++i]);
     else if (a == "--time-only") time_only = true;
     else if (a == "--no-dump-layers") dump_layers = false;
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 1; }
@@ -177,8 +182,10 @@ int main(int argc, char **argv) {
     NetTrainOptions opts;
     opts.learn_rate = lr;
     opts.momentum = momentum;
+    if (eps >= 0.f) opts.adagrad_epsilon = eps;
+    if (rho >= 0.f) opts.rmsprop_rho = rho;   // rmsprop_one_minus_rho stays 0.1, as through the driver's option parser
     net.SetTrainOptions(opts);
-    net.SetUpdateAlgorithm("SGD");
+    net.SetUpdateAlgorithm(opt);
     net.SetTrainMode();
 
     Ctc ctc;

@@ -100,6 +100,15 @@ class OracleNet:
         self.spec = net
         self.params = [{n: self.L.arr(l.params[n]).copy() for n in l.param_names()} for l in net.layers]
         self.corr = [{n: np.zeros_like(v) for n, v in p.items()} for p in self.params]
+        # Net::SetUpdateAlgorithm (net.cc:481-496) + NetTrainOptions (train-opts.h:33-50)
+        self.algorithm = "SGD"
+        self.adagrad_epsilon, self.rmsprop_rho, self.rmsprop_one_minus_rho = 1e-6, 0.9, 0.1   # train-opts.h:40-42,50
+        self.accu = [{n: np.zeros_like(v) for n, v in p.items()} for p in self.params]
+
+    def set_optimizer(self, algorithm="SGD", adagrad_epsilon=1e-6, rmsprop_rho=0.9, rmsprop_one_minus_rho=0.1):
+        assert algorithm in ("SGD", "Adagrad", "RMSProp")
+        self.algorithm, self.adagrad_epsilon = algorithm, adagrad_epsilon
+        self.rmsprop_rho, self.rmsprop_one_minus_rho = rmsprop_rho, rmsprop_one_minus_rho
 
     def forward(self, feats, frames):
         L = self.L
@@ -166,8 +175,15 @@ class OracleNet:
                 self.last_dbuf = (dfw, dbw)
             # TrainableLayer::Update right after the layer's Backpropagate (net.cc:98-105)
             for n in l.param_names():
-                L.lib.oracle_sgd_update(C.c_long(p[n].size), L.p(p[n]), L.p(c[n]),
-                                        L.real(lr * l.learn_rate_coef), L.real(l.max_grad))
+                if self.algorithm == "SGD":
+                    L.lib.oracle_sgd_update(C.c_long(p[n].size), L.p(p[n]), L.p(c[n]),
+                                            L.real(lr * l.learn_rate_coef), L.real(l.max_grad))
+                else:   # the adaptive branch ignores learn_rate_coef (bilstm-layer.h:885-955)
+                    a = self.accu[li][n]
+                    L.lib.oracle_ada_update(C.c_long(p[n].size), L.p(p[n]), L.p(c[n]), L.p(a), L.real(lr),
+                                            L.real(l.max_grad), L.real(self.adagrad_epsilon),
+                                            L.real(self.rmsprop_rho), L.real(self.rmsprop_one_minus_rho),
+                                            1 if self.algorithm == "Adagrad" else 2)
             self.in_diffs[li] = nd
             d = nd
         return d
@@ -182,6 +198,9 @@ class OracleNet:
 
     def flat_params(self) -> np.ndarray:
         return np.concatenate([self.params[i][n].ravel() for i, l in enumerate(self.spec.layers) for n in l.param_names()])
+
+    def flat_accu(self) -> np.ndarray:
+        return np.concatenate([self.accu[i][n].ravel() for i, l in enumerate(self.spec.layers) for n in l.param_names()])
 
     def flat_corr(self) -> np.ndarray:
         return np.concatenate([self.corr[i][n].ravel() for i, l in enumerate(self.spec.layers) for n in l.param_names()])
@@ -217,12 +236,14 @@ def have_reference(kind: str) -> bool:
 
 def run_reference(kind: str, model_path: str, batch_path: str, outdir: str, lr: float, momentum: float,
                   steps: int = 1, diff_in: Optional[str] = None, time_only: bool = False,
-                  threads: Optional[int] = None, timeout: int = 3600):
+                  threads: Optional[int] = None, timeout: int = 3600, opt: str = "SGD"):
     """Run oracle/_ref/ref_dump_{cpu,gpu} (the unmodified reference objects) on one batch."""
     exe = os.path.join(REFDIR, f"ref_dump_{kind}")
     os.makedirs(outdir, exist_ok=True)
     cmd = [exe, model_path, batch_path, outdir, "--lr", repr(float(lr)), "--momentum", repr(float(momentum)),
            "--steps", str(steps)]
+    if opt != "SGD":
+        cmd += ["--opt", opt]
     if diff_in:
         cmd += ["--diff-in", diff_in]
     if time_only:

@@ -14,6 +14,11 @@ minted from runs of the reference itself on seeded synthetic inputs:
 * ``<wl>_refgpu.npz``  the same plus the reference's own CUDA CTC (alpha, beta, pzx, obj_diff):
   the only place the reference computes CTC at all.
 
+* ``<wl>_refgpu_{adagrad,rmsprop}.npz``  three steps of the reference's GPU build with
+  --opt-algorithm Adagrad / RMSProp (GPU-only in the reference: the CPU branches of ApplySqrt /
+  AddMatMatElements exit, cuda-matrix.cc:572-573,658-659): updated parameters and the accumulators the
+  reference writes into the model (<BiLstmAccus>/<AffineAccus>).
+
 Inputs are regenerated from (workload, seeds) by eesen_b200.synth, so only outputs are stored.
 """
 import os
@@ -59,6 +64,31 @@ def run(kind: str, outdir: str = HERE):
         print("wrote", path, os.path.getsize(path), "bytes")
 
 
+ADAPTIVE = [("tiny", 3, 5, 1e-3, 0.9, "Adagrad"), ("tiny", 3, 5, 1e-3, 0.9, "RMSProp"),
+            ("small", 3, 5, 2e-3, 0.5, "Adagrad"), ("small", 3, 5, 2e-3, 0.5, "RMSProp")]
+
+
+def run_adaptive(outdir: str = HERE, steps: int = 3):
+    for wl, mseed, bseed, lr, mom, opt in ADAPTIVE:
+        w = synth.WORKLOADS[wl]
+        net = synth.make_model(w, seed=mseed)
+        b = synth.make_batch(w, seed=bseed)
+        d = tempfile.mkdtemp()
+        kaldi_io.write_model(d + "/model", net)
+        kaldi_io.write_batch_file(d + "/batch.bin", b)
+        oracle.run_reference("gpu", d + "/model", d + "/batch.bin", d + "/out", lr, mom, steps=steps, opt=opt)
+        dump = oracle.load_dump(d + "/out")
+        m2 = kaldi_io.read_model(d + "/out/model_out")
+        keep = {"pzx": dump["pzx"], "params_out": m2.flat_params(), "accus_out": m2.flat_accus(),
+                "meta": np.array([mseed, bseed, steps], np.int64), "hyper": np.array([lr, mom], np.float64)}
+        path = os.path.join(outdir, f"{wl}_refgpu_{opt.lower()}.npz")
+        np.savez_compressed(path, **keep)
+        print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "adaptive":
+        run_adaptive(sys.argv[2] if len(sys.argv) > 2 else HERE)
+        sys.exit(0)
     kind = sys.argv[1] if len(sys.argv) > 1 else "cpu"
     run(kind, sys.argv[2] if len(sys.argv) > 2 else HERE)

@@ -82,6 +82,46 @@ def test_model_roundtrip_and_layout():
                                            "wx_bw", "wm_bw", "b_bw", "pi_bw", "pf_bw", "po_bw"]
 
 
+def test_model_accumulators_roundtrip():
+    """<BiLstmAccus>/<AffineAccus> sit between the option tokens and the weights (bilstm-layer.h:375-395,458-475)."""
+    w, net, b = case("tiny")
+    rng = np.random.default_rng(1)
+    for l in net.layers:
+        for n, shp in l.param_shapes().items():
+            l.accus[n] = rng.random(shp).astype(np.float32)
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "m")
+        kaldi_io.write_model(p, net)
+        raw = open(p, "rb").read()
+        assert raw.index(b"<TwiddleForward>") < raw.index(b"<BiLstmAccus>") < raw.index(b"<AffineTransform>")
+        assert raw.count(b"<BiLstmAccus>") == sum(l.kind == "bilstm" for l in net.layers)
+        assert raw.count(b"<AffineAccus>") == 1
+        net2 = kaldi_io.read_model(p)
+    assert np.array_equal(net.flat_params(), net2.flat_params())
+    assert np.array_equal(net.flat_accus(), net2.flat_accus())
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_dump_cpu")),
+                    reason="reference build (oracle/_ref) not present")
+def test_reference_reads_and_rewrites_our_accumulators():
+    """The reference's Net::Read accepts the accumulator blocks we write and its Net::Write puts them back
+    byte for byte (SGD leaves them alone), so the two writers agree on the format."""
+    from oracle import oracle
+    w, net, b = case("tiny")
+    rng = np.random.default_rng(2)
+    for l in net.layers:
+        for n, shp in l.param_shapes().items():
+            l.accus[n] = rng.random(shp).astype(np.float32)
+    with tempfile.TemporaryDirectory() as d:
+        kaldi_io.write_model(d + "/model", net)
+        kaldi_io.write_batch_file(d + "/batch.bin", b)
+        diff = np.zeros((b.feats.shape[0], w.classes), np.float32)
+        np.save(d + "/diff.npy", diff)
+        oracle.run_reference("cpu", d + "/model", d + "/batch.bin", d + "/out", 0.0, 0.0, steps=1,
+                             diff_in=d + "/diff.npy")
+        assert open(d + "/out/model_out", "rb").read() == open(d + "/model", "rb").read()
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_net_initialize")),
                     reason="reference net-initialize not built")
 def test_reads_model_written_by_reference_net_initialize():

@@ -306,6 +306,125 @@ def test_train_step_vs_reference_gpucompute_live(ctx, wl, steps):
     n.close()
 
 
+# ------------------------------------------------------------------------------------ Adagrad / RMSProp
+def _adaptive_steps(ctx, net, b, lr, mom, opt, steps, model_path=None, **kw):
+    n = binding.Net(ctx, model_path or model_file(net))
+    n.set_train_options(lr, mom)
+    n.set_optimizer(opt, **kw)
+    for _ in range(steps):
+        n.train_step(b.feats, b.frames, b.labels, True)
+    return n
+
+
+# the adaptive step lr*c/sqrt(accu+eps) has slope <= lr/sqrt(eps) = 1e3*lr in c: a momentum-buffer
+# difference of 1e-6 (fp32 reduction order) may move a parameter by 1e-3*lr*... -> budget 2% of one step
+def _ada_atol(lr):
+    return 0.02 * lr
+
+
+@pytest.mark.parametrize("opt", ["Adagrad", "RMSProp"])
+@pytest.mark.parametrize("wl", ["tiny", "small"])
+def test_adaptive_update_vs_oracle(ctx, wl, opt):
+    """Net::SetUpdateAlgorithm(Adagrad|RMSProp): three steps against the fp64 restatement."""
+    w, net, b = case(wl)
+    lr, mom = 2e-3, 0.5
+    n = _adaptive_steps(ctx, net, b, lr, mom, opt, 3)
+    on = oracle.OracleNet(net, np.float64)
+    on.set_optimizer(opt)
+    for _ in range(3):
+        on.train_step(b, lr, mom)
+    assert_close("accu", n.accu(), on.flat_accu(), atol=1e-7, rtol=5e-3)
+    assert_close("params", n.params(), on.flat_params(), atol=_ada_atol(lr))
+    moved = np.abs(on.flat_params() - net.flat_params()).max()
+    assert moved > 1.5 * lr          # the rule really is adaptive: ~lr per step whatever the gradient scale
+    n.close()
+
+
+def test_adaptive_options_and_learn_rate_coef(ctx):
+    """eps / rho / one_minus_rho are honoured; learn_rate_coef is ignored by the adaptive branch
+    (bilstm-layer.h:865-869 vs :885-955) while max_grad still clips."""
+    w, net, b = case("tiny")
+    for l in net.layers:
+        if l.kind != "softmax":
+            l.learn_rate_coef, l.max_grad = 0.25, 0.01
+    lr, mom = 1e-3, 0.9
+    n = _adaptive_steps(ctx, net, b, lr, mom, "RMSProp", 2, adagrad_epsilon=1e-4, rmsprop_rho=0.8,
+                        rmsprop_one_minus_rho=0.3)
+    on = oracle.OracleNet(net, np.float64)
+    on.set_optimizer("RMSProp", 1e-4, 0.8, 0.3)
+    for _ in range(2):
+        on.train_step(b, lr, mom)
+    assert_close("accu", n.accu(), on.flat_accu(), atol=1e-9, rtol=5e-3)
+    assert_close("params", n.params(), on.flat_params(), atol=_ada_atol(lr))
+    assert np.abs(n.corr()).max() <= 0.01 + 1e-9
+    n.close()
+
+
+@pytest.mark.parametrize("opt", ["adagrad", "rmsprop"])
+@pytest.mark.parametrize("wl", ["tiny", "small"])
+def test_adaptive_update_vs_reference_golden(ctx, wl, opt):
+    """Against the committed output of the reference's GPU build run with --opt-algorithm (make_golden.py adaptive)."""
+    path = os.path.join(GOLDEN, f"{wl}_refgpu_{opt}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated")
+    g = np.load(path)
+    mseed, bseed, steps = [int(v) for v in g["meta"]]
+    lr, mom = [float(v) for v in g["hyper"]]
+    w, net, b = case(wl, mseed, bseed)
+    n = _adaptive_steps(ctx, net, b, lr, mom, {"adagrad": "Adagrad", "rmsprop": "RMSProp"}[opt], steps)
+    assert_close("pzx", n.get(101).ravel(), g["pzx"], atol=0, rtol=5e-5)
+    assert_close("accu", n.accu(), g["accus_out"], atol=1e-7, rtol=5e-3)
+    assert_close("params", n.params(), g["params_out"], atol=_ada_atol(lr))
+    n.close()
+
+
+@pytest.mark.skipif(not oracle.have_reference("gpu"), reason="oracle/_ref/ref_dump_gpu not built")
+@pytest.mark.parametrize("opt", ["Adagrad", "RMSProp"])
+def test_adaptive_update_vs_reference_gpucompute_live(ctx, opt):
+    w, net, b = case("small", 21, 22)
+    lr, mom = 1e-3, 0.9
+    d = tempfile.mkdtemp()
+    kaldi_io.write_model(d + "/model", net)
+    kaldi_io.write_batch_file(d + "/batch.bin", b)
+    oracle.run_reference("gpu", d + "/model", d + "/batch.bin", d + "/out", lr, mom, steps=3, opt=opt)
+    m2 = kaldi_io.read_model(d + "/out/model_out")
+    n = _adaptive_steps(ctx, net, b, lr, mom, opt, 3)
+    assert_close("accu", n.accu(), m2.flat_accus(), atol=1e-7, rtol=5e-3)
+    assert_close("params", n.params(), m2.flat_params(), atol=_ada_atol(lr))
+    # the model we write carries the accumulators where the reference puts them: the reference's own
+    # writer and ours agree token for token (same length, same tokens; payload compared above)
+    out = d + "/ours_out"
+    n.write(out, True)
+    ours, theirs = open(out, "rb").read(), open(d + "/out/model_out", "rb").read()
+    assert len(ours) == len(theirs) and ours.count(b"<BiLstmAccus>") == theirs.count(b"<BiLstmAccus>") == sum(
+        l.kind == "bilstm" for l in net.layers) and ours.count(b"<AffineAccus>") == theirs.count(b"<AffineAccus>") == 1
+    n.close()
+
+
+def test_adaptive_resume_from_written_model(ctx):
+    """Accumulators survive Net::Write -> Net::Read (the reference resumes Adagrad across epochs this way;
+    momentum buffers are NOT stored, so the check uses momentum 0)."""
+    w, net, b = case("tiny")
+    lr = 1e-3
+    full = _adaptive_steps(ctx, net, b, lr, 0.0, "Adagrad", 4)
+    half = _adaptive_steps(ctx, net, b, lr, 0.0, "Adagrad", 2)
+    p = model_file(net) + ".half"
+    half.write(p, True)
+    m = kaldi_io.read_model(p)
+    assert_close("accus in file", m.flat_accus(), half.accu(), atol=0)
+    rest = _adaptive_steps(ctx, net, b, lr, 0.0, "Adagrad", 2, model_path=p)
+    assert np.array_equal(rest.params(), full.params()) and np.array_equal(rest.accu(), full.accu())
+    # SGD on a model that carries accumulators keeps and re-writes them untouched (adaBuffersInitialized)
+    sgd = binding.Net(ctx, p)
+    sgd.set_train_options(lr, 0.0)
+    sgd.train_step(b.feats, b.frames, b.labels, True)
+    assert np.array_equal(sgd.accu(), half.accu())
+    sgd.write(p + ".sgd", True)
+    assert_close("accus kept", kaldi_io.read_model(p + ".sgd").flat_accus(), half.accu(), atol=0)
+    for x in (full, half, rest, sgd):
+        x.close()
+
+
 def test_model_write_is_byte_compatible(ctx):
     w, net, b = case("tiny")
     p = model_file(net)

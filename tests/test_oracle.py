@@ -69,6 +69,42 @@ def test_oracle_matches_reference_gpu_golden(wl):
     assert np.array_equal(g["alpha"] > -1e29, a > -1e29)
 
 
+@pytest.mark.parametrize("opt", ["Adagrad", "RMSProp"])
+@pytest.mark.parametrize("wl", ["tiny", "small"])
+def test_oracle_adaptive_matches_reference_gpu_golden(wl, opt):
+    """Adagrad/RMSProp exist only in the reference's GPU build: pinned on its output from the B200 box."""
+    path = os.path.join(GOLDEN, f"{wl}_refgpu_{opt.lower()}.npz")
+    if not os.path.exists(path):
+        pytest.skip("GPU-minted golden not generated yet (tests/golden/make_golden.py adaptive)")
+    g = np.load(path)
+    mseed, bseed, steps = [int(v) for v in g["meta"]]
+    lr, mom = [float(v) for v in g["hyper"]]
+    w, net, b = case(wl, mseed, bseed)
+    on = oracle.OracleNet(net, np.float32)
+    on.set_optimizer(opt)
+    for _ in range(steps):
+        r = on.train_step(b, lr, mom)
+    assert_close("pzx", r["pzx"], g["pzx"], atol=0, rtol=5e-5)
+    assert_close("accu", on.flat_accu(), g["accus_out"], atol=1e-7, rtol=5e-3)
+    assert_close("params", on.flat_params(), g["params_out"], atol=0.02 * lr)   # 2% of one adaptive step
+
+
+def test_oracle_adaptive_rules_closed_form():
+    """trainable-layer.h:65-114 on one tensor, against the formulas written out in numpy fp64."""
+    rng = np.random.default_rng(4)
+    L = oracle.lib(np.float64)
+    import ctypes as C
+    for mode, rho, omr in ((1, 0.9, 0.1), (2, 0.9, 0.1), (2, 0.7, 0.1)):
+        w = rng.standard_normal(257); c = rng.standard_normal(257) * 3; a = rng.random(257)
+        w0, c0, a0 = w.copy(), c.copy(), a.copy()
+        L.lib.oracle_ada_update(C.c_long(257), L.p(w), L.p(c), L.p(a), L.real(0.01), L.real(2.0), L.real(1e-6),
+                                L.real(rho), L.real(omr), mode)
+        cc = np.clip(c0, -2.0, 2.0)
+        aa = a0 + cc * cc if mode == 1 else rho * a0 + omr * cc * cc
+        assert np.allclose(c, cc, rtol=0, atol=0) and np.allclose(a, aa, rtol=1e-15)
+        assert np.allclose(w, w0 - 0.01 * cc / np.sqrt(aa + 1e-6), rtol=1e-14)
+
+
 @pytest.mark.skipif(not oracle.have_reference("cpu"), reason="reference build (oracle/_ref) not present")
 def test_oracle_matches_reference_cpu_live():
     w, net, b = case("small", 11, 12)
