@@ -1,6 +1,8 @@
 # Build of the B200-native Eesen CTC hot path (in-tree; artefacts are git-ignored but travel with gpurun).
 #   eesen_b200/lib/libeesen_b200.so   CUDA kernels (sm_100a) + C ABI (include/eesen_b200.h) + C++ host mirror
 #   eesen_b200/bin/train-ctc-parallel the training driver (host logic of reference src/netbin/train-ctc-parallel.cc)
+#   eesen_b200/bin/net-output-extract the forward-only tool (src/netbin/net-output-extract.cc), batched
+#   eesen_b200/bin/format-to-nonparallel  <BiLstmParallel> -> <BiLstm> marker rewrite (src/netbin/format-to-nonparallel.cc)
 # `make oracle` builds the CPU checker (test infrastructure, oracle/).
 CUDA    ?= /usr/local/cuda
 NVCC    := $(CUDA)/bin/nvcc
@@ -17,7 +19,9 @@ CC_SRCS := base net abi_ops abi_net
 CU_OBJS := $(patsubst %,$(OBJDIR)/%.cu.o,$(CU_SRCS))
 CC_OBJS := $(patsubst %,$(OBJDIR)/%.cc.o,$(CC_SRCS))
 
-all: $(LIBDIR)/libeesen_b200.so $(BINDIR)/train-ctc-parallel
+BINS    := train-ctc-parallel net-output-extract format-to-nonparallel
+
+all: $(LIBDIR)/libeesen_b200.so $(patsubst %,$(BINDIR)/%,$(BINS))
 
 $(OBJDIR)/%.cu.o: eesen_b200/csrc/%.cu eesen_b200/csrc/common.cuh eesen_b200/csrc/kernels.h
 	@mkdir -p $(OBJDIR)
@@ -31,7 +35,7 @@ $(LIBDIR)/libeesen_b200.so: $(CU_OBJS) $(CC_OBJS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart shared -ldl
 
-$(BINDIR)/train-ctc-parallel: eesen_b200/host/train-ctc-parallel.cc $(LIBDIR)/libeesen_b200.so
+$(BINDIR)/%: eesen_b200/host/%.cc eesen_b200/host/options.h eesen_b200/host/minibatch.h $(LIBDIR)/libeesen_b200.so
 	@mkdir -p $(BINDIR)
 	$(CXX) $(CXXFLAGS) $< -o $@ -L$(LIBDIR) -leesen_b200 -Wl,-rpath,'$$ORIGIN/../lib' -L$(CUDA)/lib64 -lcudart -Wl,-rpath,$(CUDA)/lib64
 

@@ -180,6 +180,18 @@ class Context:
         self.check(self.lib.eesen_b200_allreduce_sum(self.h, _p(buf), C.c_int64(n)), "allreduce_sum")
 
 
+def class_log_priors(counts, prior_cutoff: float = 1e-10, blank_scale: float = 1.0) -> np.ndarray:
+    """ClassPrior::ClassPrior host arithmetic (class-prior.cc:28-76) through the C ABI."""
+    lib = load_library()
+    c = np.ascontiguousarray(counts, np.float64)
+    out = np.empty(c.size, np.float32)
+    rc = lib.eesen_b200_class_log_priors(c.ctypes.data_as(C.c_void_p), int(c.size), C.c_float(prior_cutoff),
+                                         C.c_float(blank_scale), out.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise EesenB200Error(f"class_log_priors failed ({rc})")
+    return out
+
+
 class Net:
     """Level-2 handle: the Net + Ctc host mirror (reference train-ctc-parallel.cc call sequence)."""
 
@@ -214,6 +226,30 @@ class Net:
         self.ctx.check(self.lib.eesen_b200_net_set_optimizer(self.h, algorithm.encode(), C.c_float(adagrad_epsilon),
                                                              C.c_float(rmsprop_rho), C.c_float(rmsprop_one_minus_rho)),
                        "net_set_optimizer")
+
+    def feedforward(self, feats: np.ndarray, frames, apply_log: bool = False, log_priors: Optional[np.ndarray] = None,
+                    prior_scale: float = 1.0) -> np.ndarray:
+        """Forward-only pass of one packed batch (net-output-extract): returns [T*S, K] host array."""
+        feats = np.ascontiguousarray(feats, np.float32)
+        if frames is None:      # the reference's call pattern: no SetSeqLengths, one sequence
+            S, fptr = 1, None
+        else:
+            frames = np.ascontiguousarray(frames, np.int32)
+            S, fptr = frames.size, frames.ctypes.data_as(C.c_void_p)
+        T = feats.shape[0] // S
+        out = np.empty((T * S, self.out_dim), np.float32)
+        lp = None
+        if log_priors is not None:
+            lp = np.ascontiguousarray(log_priors, np.float32)
+            assert lp.size == self.out_dim
+        self.ctx.check(self.lib.eesen_b200_net_feedforward(
+            self.h, feats.ctypes.data_as(C.c_void_p), T, S, fptr, int(apply_log),
+            lp.ctypes.data_as(C.c_void_p) if lp is not None else None, C.c_float(prior_scale),
+            out.ctypes.data_as(C.c_void_p)), "net_feedforward")
+        return out
+
+    def write_nonparallel(self, path: str, binary: bool = True):
+        self.ctx.check(self.lib.eesen_b200_net_write_nonparallel(self.h, path.encode(), int(binary)), "net_write_nonparallel")
 
     def write(self, path: str, binary: bool = True):
         self.ctx.check(self.lib.eesen_b200_net_write(self.h, path.encode(), int(binary)), "net_write")

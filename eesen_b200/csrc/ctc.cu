@@ -49,6 +49,22 @@ __global__ void softmax_rows_kernel(int N, int K, const float *__restrict__ logi
   if (argmax && lane == 0) argmax[row] = mi;
 }
 
+// the output side of net-output-extract (src/netbin/net-output-extract.cc:100-110) in one pass:
+//   y = log(y) if apply_log (CuMatrixBase::ApplyLog, cuda-kernels.cu:221-227)
+//   y -= prior_scale * log_prior[col]   (ClassPrior::SubtractOnLogpost -> AddVecToRows, class-prior.cc:78-90)
+__global__ void loglik_rows_kernel(long n, int K, float *__restrict__ y, int ld, int apply_log,
+                                   const float *__restrict__ log_prior, float prior_scale) {
+  long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    long r = i / K;
+    int k = (int)(i - r * K);
+    float v = y[r * ld + k];
+    if (apply_log) v = logf(v);
+    if (log_prior) v += -prior_scale * log_prior[k];
+    y[r * ld + k] = v;
+  }
+}
+
 // first index of the row maximum (CPU branch of FindRowMaxId, cuda-matrix.cc:1077-1093)
 __global__ void row_argmax_kernel(int N, int K, const float *__restrict__ x, int ld, int *__restrict__ argmax) {
   int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -255,6 +271,16 @@ cudaError_t softmax_rows(cudaStream_t st, int N, int K, const float *logits, int
   int rows_per_block = 8;
   softmax_rows_kernel<<<(N + rows_per_block - 1) / rows_per_block, rows_per_block * 32, 0, st>>>(
       N, K, logits, ld, probs, ldp, argmax);
+  return cudaGetLastError();
+}
+
+cudaError_t loglik_rows(cudaStream_t st, int num_sms, int N, int K, float *y, int ld, int apply_log,
+                        const float *log_prior, float prior_scale) {
+  long n = (long)N * K;
+  if (n <= 0 || (!apply_log && !log_prior)) return cudaSuccess;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 8 * num_sms) blocks = 8 * num_sms;
+  loglik_rows_kernel<<<blocks, 256, 0, st>>>(n, K, y, ld, apply_log, log_prior, prior_scale);
   return cudaGetLastError();
 }
 

@@ -70,6 +70,9 @@ int lstm_debug_timing(long long *out32, int reset);  // 1 if built with -DEB_LST
 cudaError_t softmax_rows(cudaStream_t st, int N, int K, const float *logits, int ld, float *probs, int ldp,
                          int *argmax);
 cudaError_t row_argmax(cudaStream_t st, int N, int K, const float *x, int ld, int *argmax);
+// in place: y = log(y) (if apply_log) - prior_scale * log_prior[col] (if log_prior)
+cudaError_t loglik_rows(cudaStream_t st, int num_sms, int N, int K, float *y, int ld, int apply_log,
+                        const float *log_prior, float prior_scale);
 size_t ctc_workspace_floats(int T, int S, int max_lab);
 cudaError_t ctc_eval(cudaStream_t st, int T, int S, int K, int max_lab, const int *len, const int *labels,
                      const int *lab_len, const float *probs, int ldp, float *pzx, float *diff, int ldd,

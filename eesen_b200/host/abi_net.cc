@@ -2,6 +2,7 @@
 // (include/eesen_b200.h).  C++ exceptions (KALDI_ERR) are translated to error codes here.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -25,8 +26,13 @@ struct eesen_b200_net {
   std::vector<std::vector<int32> > labels;
   int S = 0;
   bool want_in_diff = false;
+  float *d_prior = nullptr;   // log priors of the forward-only path
+  size_t prior_dim = 0;
   explicit eesen_b200_net(eesen_b200_ctx *c) : ctx(c), net(c), ctc(c) {}
-  ~eesen_b200_net() { if (h_pinned) cudaFreeHost(h_pinned); }
+  ~eesen_b200_net() {
+    if (h_pinned) cudaFreeHost(h_pinned);
+    if (d_prior) cudaFree(d_prior);
+  }
 };
 
 #define GUARD(ctxp, body)                                      \
@@ -98,6 +104,66 @@ int eesen_b200_net_set_optimizer(eesen_b200_net *n, const char *algorithm, float
   o.rmsprop_rho = rmsprop_rho;
   o.rmsprop_one_minus_rho = rmsprop_one_minus_rho < 0.f ? 0.1f : rmsprop_one_minus_rho;
   GUARD(n->ctx, { n->net.SetUpdateAlgorithm(algorithm); n->net.SetTrainOptions(o); });
+}
+
+int eesen_b200_net_write_nonparallel(eesen_b200_net *n, const char *path, int binary) {
+  if (!n || !path) return EESEN_B200_EINVAL;
+  GUARD(n->ctx, n->net.WriteNonParal(path, binary != 0));
+}
+
+int eesen_b200_class_log_priors(const double *counts, int K, float prior_cutoff, float blank_scale, float *log_priors) {
+  if (!counts || !log_priors || K < 1) return EESEN_B200_EINVAL;
+  try {
+    std::vector<double> c(counts, counts + K);
+    std::vector<float> lp;
+    ClassPrior::LogPriors(c, prior_cutoff, blank_scale, &lp);
+    memcpy(log_priors, lp.data(), sizeof(float) * K);
+    return 0;
+  } catch (const std::exception &) {
+    return EESEN_B200_EIO;
+  }
+}
+
+int eesen_b200_net_feedforward(eesen_b200_net *n, const float *feats, int T, int S, const int *frames, int apply_log,
+                               const float *log_priors, float prior_scale, float *out) {
+  if (!n || !feats || !out || T <= 0 || S <= 0 || (!frames && S != 1)) return EESEN_B200_EINVAL;
+  try {
+    const int I = n->net.InputDim(), K = n->net.OutputDim();
+    size_t elems = (size_t)T * S * std::max(I, K);
+    if (elems > n->h_cap) {
+      if (n->h_pinned) cudaFreeHost(n->h_pinned);
+      n->h_pinned = nullptr; n->h_cap = 0;
+      if (cudaMallocHost((void **)&n->h_pinned, sizeof(float) * elems) != cudaSuccess) KALDI_ERR << "cudaMallocHost failed";
+      n->h_cap = elems;
+    }
+    memcpy(n->h_pinned, feats, sizeof(float) * (size_t)T * S * I);
+    if (frames) n->frames.assign(frames, frames + S);
+    else n->frames.clear();   // no SetSeqLengths, the reference tool's own call pattern: <BiLstm> layers only
+    n->feats.Resize(T * S, I, kUndefined);
+    n->feats.CopyFromHost(n->h_pinned, I);
+    n->net.SetSeqLengths(n->frames);
+    n->net.Feedforward(n->feats, &n->net_out);
+    if (log_priors) {
+      if ((int)n->prior_dim != K) {
+        if (n->d_prior) cudaFree(n->d_prior);
+        n->d_prior = nullptr;
+        if (cudaMalloc((void **)&n->d_prior, sizeof(float) * K) != cudaSuccess) KALDI_ERR << "cudaMalloc failed";
+        n->prior_dim = K;
+      }
+      if (cudaMemcpyAsync(n->d_prior, log_priors, sizeof(float) * K, cudaMemcpyHostToDevice, n->ctx->stream) != cudaSuccess)
+        KALDI_ERR << "prior upload failed";
+    }
+    // ApplyLog + SubtractOnLogpost fused into one pass over [T*S x K]
+    CheckAbi(n->ctx, eesen_b200_loglik(n->ctx, T * S, K, n->net_out.Data(), n->net_out.Stride(), apply_log,
+                                       log_priors ? n->d_prior : NULL, prior_scale), "eesen_b200_loglik");
+    n->net_out.CopyToHost(n->h_pinned, K);
+    if (cudaStreamSynchronize(n->ctx->stream) != cudaSuccess) KALDI_ERR << "stream sync failed";
+    memcpy(out, n->h_pinned, sizeof(float) * (size_t)T * S * K);
+    return 0;
+  } catch (const std::exception &e) {
+    n->ctx->err = e.what();
+    return EESEN_B200_EIO;
+  }
 }
 
 int eesen_b200_net_dims(const eesen_b200_net *n, int *in_dim, int *out_dim, int *num_layers, int64_t *num_params) {

@@ -331,6 +331,17 @@ int eesen_b200_row_argmax(eesen_b200_ctx *ctx, int N, int K, const float *x, int
   return ctx->check(e, "row_argmax");
 }
 
+int eesen_b200_loglik(eesen_b200_ctx *ctx, int N, int K, float *y, int ld, int apply_log, const float *d_log_prior,
+                      float prior_scale) {
+  if (!ctx || !y || N < 0 || K < 1 || ld < K) return EESEN_B200_EINVAL;
+  if (!apply_log && !d_log_prior) return 0;
+  ctx->launches += 1;
+  int pe = ctx->prof_begin(eesen_b200_ctx::kSoftmax);
+  cudaError_t e = eb::loglik_rows(ctx->stream, ctx->num_sms, N, K, y, ld, apply_log, d_log_prior, prior_scale);
+  ctx->prof_end(pe);
+  return ctx->check(e, "loglik_rows");
+}
+
 int eesen_b200_ctc_eval(eesen_b200_ctx *ctx, int T, int S, int K, int max_lab, const int *d_len, const int *d_labels,
                         const int *d_lab_len, const float *probs, int ldp, float *pzx, float *diff, int ldd) {
   if (!ctx || !d_len || !d_labels || !d_lab_len || !probs || !pzx || !diff || max_lab < 1) return EESEN_B200_EINVAL;

@@ -317,6 +317,65 @@ void SequentialBaseFloatMatrixReader::ReadOne() {
   }
 }
 
+BaseFloatMatrixWriter::BaseFloatMatrixWriter(const std::string &wspecifier) {
+  size_t colon = wspecifier.find(':');
+  if (colon == std::string::npos) KALDI_ERR << "Invalid wspecifier " << wspecifier;
+  std::string head = wspecifier.substr(0, colon), rest = wspecifier.substr(colon + 1);
+  bool want_scp = false, is_ark = false;
+  std::istringstream hs(head);
+  std::string opt;
+  while (std::getline(hs, opt, ',')) {
+    if (opt == "ark") is_ark = true;
+    else if (opt == "scp") want_scp = true;
+    else if (opt == "t") binary_ = false;
+    else if (opt == "b" || opt == "f" || opt == "nf" || opt == "p") {}
+    else KALDI_ERR << "Unsupported wspecifier option '" << opt << "' in " << wspecifier;
+  }
+  if (!is_ark) KALDI_ERR << "Only archive wspecifiers are supported: " << wspecifier;
+  std::string ark = rest, scp;
+  if (want_scp) {
+    size_t comma = rest.find(',');
+    if (comma == std::string::npos) KALDI_ERR << "ark,scp needs two file names: " << wspecifier;
+    ark = rest.substr(0, comma);
+    scp = rest.substr(comma + 1);
+  }
+  while (!ark.empty() && isspace(ark[0])) ark.erase(0, 1);
+  ark_name_ = ark;
+  if (ark == "-" || ark.empty()) {
+    os_ = &std::cout;
+  } else if (ark[0] == '|') {
+    pipe_ = popen(ark.substr(1).c_str(), "w");
+    if (!pipe_) KALDI_ERR << "Failed to open pipe: " << ark;
+    os_ = new std::ostream(new __gnu_cxx::stdio_filebuf<char>(pipe_, std::ios::out | std::ios::binary));
+    owns_ = true;
+  } else {
+    auto *fs = new std::ofstream(ark.c_str(), std::ios::out | std::ios::binary);
+    if (!fs->is_open()) { delete fs; KALDI_ERR << "Failed to open " << ark << " for writing"; }
+    os_ = fs;
+    owns_ = true;
+  }
+  if (want_scp) {
+    auto *fs = new std::ofstream(scp.c_str());
+    if (!fs->is_open()) { delete fs; KALDI_ERR << "Failed to open " << scp << " for writing"; }
+    scp_ = fs;
+  }
+}
+
+BaseFloatMatrixWriter::~BaseFloatMatrixWriter() {
+  if (os_) os_->flush();
+  if (owns_ && os_) { std::streambuf *b = pipe_ ? os_->rdbuf() : nullptr; delete os_; delete b; }
+  if (pipe_) pclose(pipe_);
+  if (scp_) delete scp_;
+}
+
+void BaseFloatMatrixWriter::Write(const std::string &key, const HostMatrix &value) {
+  *os_ << key << ' ';
+  if (scp_) *scp_ << key << ' ' << ark_name_ << ':' << (long)os_->tellp() << "\n";
+  if (binary_) { os_->put('\0'); os_->put('B'); }
+  value.Write(*os_, binary_);
+  if (os_->fail()) KALDI_ERR << "Write failure for key " << key;
+}
+
 RandomAccessInt32VectorReader::RandomAccessInt32VectorReader(const std::string &rspecifier) {
   std::string kind, opts, rest;
   SplitRspecifier(rspecifier, &kind, &opts, &rest);

@@ -106,6 +106,22 @@ class RandomAccessInt32VectorReader {
   std::map<std::string, std::vector<int32> > items_;
 };
 
+// wspecifiers: ark:file, ark,t:file, ark:- (stdout), "ark:| cmd", ark,scp:file.ark,file.scp
+// (the archive entry format of util/kaldi-holder-inl.h: "<key> " + "\0B" + FM matrix, or text)
+class BaseFloatMatrixWriter {
+ public:
+  explicit BaseFloatMatrixWriter(const std::string &wspecifier);
+  ~BaseFloatMatrixWriter();
+  void Write(const std::string &key, const HostMatrix &value);
+
+ private:
+  bool binary_ = true;
+  FILE *pipe_ = nullptr;
+  std::ostream *os_ = nullptr, *scp_ = nullptr;
+  bool owns_ = false;
+  std::string ark_name_;
+};
+
 std::istream *OpenInput(const std::string &rxfilename, FILE **pipe_out, bool *owns);
 
 }  // namespace eesen

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -107,6 +108,16 @@ template <typename Real>
 CuMatrix<Real>::~CuMatrix() {
   if (this->data_) cudaFree(this->data_);
 }
+template <typename Real>
+void CuMatrixBase<Real>::ApplyLog() {
+  CheckAbi(g_ctx, eesen_b200_loglik(g_ctx, num_rows_, num_cols_, data_, stride_, 1, NULL, 0.f), "eesen_b200_loglik");
+}
+template <typename Real>
+void CuMatrixBase<Real>::AddVecToRows(Real alpha, const Real *d_vec, int32 dim) {
+  KALDI_ASSERT(dim == num_cols_);
+  // y += alpha * vec  ==  y -= (-alpha) * vec
+  CheckAbi(g_ctx, eesen_b200_loglik(g_ctx, num_rows_, num_cols_, data_, stride_, 0, d_vec, -alpha), "eesen_b200_loglik");
+}
 template class CuMatrixBase<float>;
 template class CuMatrix<float>;
 
@@ -114,6 +125,7 @@ template class CuMatrix<float>;
 const char *Layer::TypeToMarker(LayerType t) {
   switch (t) {
     case l_BiLstm_Parallel: return "<BiLstmParallel>";
+    case l_BiLstm: return "<BiLstm>";
     case l_Affine_Transform: return "<AffineTransform>";
     case l_Softmax: return "<Softmax>";
     default: return "<Unknown>";
@@ -121,10 +133,11 @@ const char *Layer::TypeToMarker(LayerType t) {
 }
 Layer::LayerType Layer::MarkerToType(const std::string &s) {
   if (s == "<BiLstmParallel>") return l_BiLstm_Parallel;
+  if (s == "<BiLstm>") return l_BiLstm;
   if (s == "<AffineTransform>") return l_Affine_Transform;
   if (s == "<Softmax>") return l_Softmax;
   KALDI_ERR << "Unknown or unsupported layer marker on the B200 CTC path: " << s
-            << " (supported: <BiLstmParallel> <AffineTransform> <Softmax>)";
+            << " (supported: <BiLstmParallel> <BiLstm> <AffineTransform> <Softmax>)";
   return l_Unknown;
 }
 
@@ -156,11 +169,12 @@ Layer *Layer::Read(std::istream &is, bool binary) {
   LayerType type = MarkerToType(token);
   ExpectToken(is, binary, "<InputDim>");
   ReadBasicType(is, binary, &dim_in);
-  ExpectToken(is, binary, type == l_BiLstm_Parallel ? "<CellDim>" : "<OutputDim>");
+  ExpectToken(is, binary, IsLstmType(type) ? "<CellDim>" : "<OutputDim>");
   ReadBasicType(is, binary, &dim_out);
   Layer *layer = NULL;
   switch (type) {
     case l_BiLstm_Parallel: layer = new BiLstmParallel(dim_in, dim_out); break;
+    case l_BiLstm: layer = new BiLstm(dim_in, dim_out); break;
     case l_Affine_Transform: layer = new AffineTransform(dim_in, dim_out); break;
     case l_Softmax: layer = new Softmax(dim_in, dim_out); break;
     default: KALDI_ERR << "Missing type: " << token;
@@ -169,13 +183,20 @@ Layer *Layer::Read(std::istream &is, bool binary) {
   return layer;
 }
 
-void Layer::Write(std::ostream &os, bool binary) const {
-  WriteToken(os, binary, TypeToMarker(GetType()));
+static void WriteLayerAs(const Layer &l, Layer::LayerType t, std::ostream &os, bool binary) {
+  WriteToken(os, binary, Layer::TypeToMarker(t));
   WriteToken(os, binary, "<InputDim>");
-  WriteBasicType(os, binary, InputDim());
-  WriteToken(os, binary, GetType() == l_BiLstm_Parallel ? "<CellDim>" : "<OutputDim>");
-  WriteBasicType(os, binary, OutputDim());
+  WriteBasicType(os, binary, l.InputDim());
+  WriteToken(os, binary, Layer::IsLstmType(t) ? "<CellDim>" : "<OutputDim>");
+  WriteBasicType(os, binary, l.OutputDim());
   if (!binary) os << "\n";
+}
+void Layer::Write(std::ostream &os, bool binary) const {
+  WriteLayerAs(*this, GetType(), os, binary);
+  WriteData(os, binary);
+}
+void Layer::WriteNonParal(std::ostream &os, bool binary) const {
+  WriteLayerAs(*this, GetTypeNonParal(), os, binary);
   WriteData(os, binary);
 }
 
@@ -296,6 +317,7 @@ void BiLstmParallel::Params(eesen_b200_bilstm_params *p, eesen_b200_bilstm_grads
 void BiLstmParallel::SetSeqLengths(std::vector<int> &sequence_lengths) {
   sequence_lengths_ = sequence_lengths;
   int32 S = sequence_lengths.size();
+  if (S == 0) return;
   if (S > d_len_cap_) {
     if (d_len_) { CU_CHECK(cudaStreamSynchronize(Stream())); CU_CHECK(cudaFree(d_len_)); }
     CU_CHECK(cudaMalloc((void **)&d_len_, sizeof(int) * S));
@@ -315,6 +337,22 @@ void BiLstmParallel::PropagateFnc(const CuMatrixBase<BaseFloat> &in, CuMatrixBas
   CheckAbi(ctx_, eesen_b200_bilstm_forward(ctx_, T, S, input_dim_, C, d_len_, in.Data(), in.Stride(), &p,
                                            gates_.Data(), cell_.Data(), out->Data(), out->Stride()),
            "eesen_b200_bilstm_forward");
+}
+
+void BiLstm::PropagateFnc(const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseFloat> *out) {
+  if (!sequence_lengths_.empty()) { BiLstmParallel::PropagateFnc(in, out); return; }
+  std::vector<int> one(1, in.NumRows());   // bilstm-layer.h:548: T = in.NumRows(), a single sequence
+  SetSeqLengths(one);
+  BiLstmParallel::PropagateFnc(in, out);
+  sequence_lengths_.clear();
+}
+void BiLstm::BackpropagateFnc(const CuMatrixBase<BaseFloat> &in, const CuMatrixBase<BaseFloat> &out,
+                              const CuMatrixBase<BaseFloat> &out_diff, CuMatrixBase<BaseFloat> *in_diff) {
+  if (!sequence_lengths_.empty()) { BiLstmParallel::BackpropagateFnc(in, out, out_diff, in_diff); return; }
+  std::vector<int> one(1, in.NumRows());
+  SetSeqLengths(one);
+  BiLstmParallel::BackpropagateFnc(in, out, out_diff, in_diff);
+  sequence_lengths_.clear();
 }
 
 void BiLstmParallel::BackpropagateFnc(const CuMatrixBase<BaseFloat> &in, const CuMatrixBase<BaseFloat> &out,
@@ -414,6 +452,58 @@ void Softmax::PropagateFnc(const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseF
 void Softmax::BackpropagateFnc(const CuMatrixBase<BaseFloat> &, const CuMatrixBase<BaseFloat> &,
                                const CuMatrixBase<BaseFloat> &out_diff, CuMatrixBase<BaseFloat> *in_diff) {
   in_diff->CopyFromMat(out_diff);  // softmax-layer.h:49-57: the CTC diff is already wrt the activations
+}
+
+// ------------------------------------------------------------------------------------ ClassPrior
+void ClassPrior::LogPriors(const std::vector<double> &counts, BaseFloat prior_cutoff, BaseFloat blank_scale,
+                           std::vector<float> *log_priors) {
+  // class-prior.cc:44-76
+  std::vector<double> p(counts);
+  const size_t n = p.size();
+  std::vector<float> mask(n, 0.f);
+  int32 num_cutoff = 0;
+  for (size_t i = 0; i < n; i++)
+    if (p[i] < prior_cutoff) { p[i] = prior_cutoff; mask[i] = FLT_MAX / 2; num_cutoff++; }
+  if (num_cutoff > 0)
+    KALDI_WARN << num_cutoff << " out of " << n << " classes have counts lower than " << prior_cutoff;
+  if (blank_scale != 1.0f && n > 0) p[0] *= blank_scale;
+  double sum = 0.0;
+  for (size_t i = 0; i < n; i++) sum += p[i];
+  log_priors->resize(n);
+  for (size_t i = 0; i < n; i++) {
+    double lp = std::log(p[i] * (1.0 / sum));
+    (*log_priors)[i] = (float)lp + mask[i];
+  }
+}
+
+ClassPrior::ClassPrior(eesen_b200_ctx *ctx, const ClassPriorOptions &opts) : ctx_(ctx), prior_scale_(opts.prior_scale) {
+  if (opts.class_frame_counts == "") return;
+  KALDI_LOG << "Computing class-priors from : " << opts.class_frame_counts;
+  std::ifstream is(opts.class_frame_counts.c_str());
+  if (!is.is_open()) KALDI_ERR << "Failed to open " << opts.class_frame_counts;
+  std::vector<double> counts;   // text vector "[ c0 c1 ... ]" (Vector<double>::Read, class-prior.cc:37-42)
+  std::string tok;
+  if (!(is >> tok) || tok != "[") KALDI_ERR << "Expected '[' at the start of " << opts.class_frame_counts;
+  while (is >> tok && tok != "]") counts.push_back(atof(tok.c_str()));
+  if (tok != "]") KALDI_ERR << "Missing ']' in " << opts.class_frame_counts;
+  std::vector<float> lp;
+  LogPriors(counts, opts.prior_cutoff, opts.blank_scale, &lp);
+  dim_ = (int32)lp.size();
+  if (dim_ == 0) return;
+  CU_CHECK(cudaMalloc((void **)&d_log_priors_, sizeof(float) * dim_));
+  CU_CHECK(cudaMemcpy(d_log_priors_, lp.data(), sizeof(float) * dim_, cudaMemcpyHostToDevice));
+}
+
+ClassPrior::~ClassPrior() {
+  if (d_log_priors_) cudaFree(d_log_priors_);
+}
+
+void ClassPrior::SubtractOnLogpost(CuMatrixBase<BaseFloat> *llk) {   // class-prior.cc:78-90
+  if (dim_ == 0) KALDI_ERR << "--class-frame-counts is empty: Cannot initialize priors without the counts.";
+  if (dim_ != llk->NumCols())
+    KALDI_ERR << "Dimensionality mismatch, class_frame_counts " << dim_ << " class_output_llk " << llk->NumCols();
+  g_ctx = ctx_;
+  llk->AddVecToRows(-prior_scale_, d_log_priors_, dim_);
 }
 
 // ------------------------------------------------------------------------------------ Net
@@ -549,7 +639,16 @@ void Net::Write(const std::string &file, bool binary) {
 }
 
 void Net::Write(std::ostream &os, bool binary) {
-  // refresh the host copies from the device arena
+  RefreshHostCopies();
+  WriteToken(os, binary, "<Nnet>");
+  if (!binary) os << std::endl;
+  for (int32 i = 0; i < NumLayers(); i++) layers_[i]->Write(os, binary);
+  WriteToken(os, binary, "</Nnet>");
+  if (!binary) os << std::endl;
+}
+
+// refresh the host copies of parameters / accumulators from the device arenas
+void Net::RefreshHostCopies() {
   CU_CHECK(cudaStreamSynchronize(Stream()));
   for (size_t i = 0; i < layers_.size(); i++) {
     if (layer_offset_[i] < 0) continue;
@@ -563,11 +662,34 @@ void Net::Write(std::ostream &os, bool binary) {
                           cudaMemcpyDeviceToHost));
     }
   }
+}
+
+void Net::WriteNonParal(const std::string &file, bool binary) {
+  std::ofstream os(file.c_str(), std::ios::out | std::ios::binary);
+  if (!os.is_open()) KALDI_ERR << "Failed to open " << file << " for writing";
+  if (binary) { os.put('\0'); os.put('B'); }
+  RefreshHostCopies();
   WriteToken(os, binary, "<Nnet>");
   if (!binary) os << std::endl;
-  for (int32 i = 0; i < NumLayers(); i++) layers_[i]->Write(os, binary);
+  for (int32 i = 0; i < NumLayers(); i++) layers_[i]->WriteNonParal(os, binary);
   WriteToken(os, binary, "</Nnet>");
   if (!binary) os << std::endl;
+  os.close();
+  if (os.fail()) KALDI_ERR << "Failed to write " << file;
+}
+
+void Net::Feedforward(const CuMatrixBase<BaseFloat> &in, CuMatrix<BaseFloat> *out) {
+  KALDI_ASSERT(NULL != out);
+  g_ctx = ctx_;
+  if (NumLayers() == 0) { (*out) = in; return; }
+  if (NumLayers() == 1) { layers_[0]->Propagate(in, out); return; }
+  KALDI_ASSERT(propagate_buf_.size() >= 2);
+  int32 L = 0;
+  layers_[L]->Propagate(in, &propagate_buf_[L % 2]);
+  for (L++; L <= NumLayers() - 2; L++) layers_[L]->Propagate(propagate_buf_[(L - 1) % 2], &propagate_buf_[L % 2]);
+  layers_[L]->Propagate(propagate_buf_[(L - 1) % 2], out);
+  // the reference releases the two buffers here (net.cc:134-136); ours stay allocated for the next
+  // utterance batch (stream-ordered reuse, no cudaFree/cudaMalloc per call) but hold no result
 }
 
 int32 Net::InputDim() const { return layers_.empty() ? 0 : layers_.front()->InputDim(); }

@@ -39,6 +39,8 @@ class CuMatrixBase {
   void CopyFromMat(const CuMatrixBase<Real> &src);
   void CopyFromHost(const Real *src, int32 ld);
   void CopyToHost(Real *dst, int32 ld) const;
+  void ApplyLog();                                                   // cuda-matrix.h ApplyLog
+  void AddVecToRows(Real alpha, const Real *d_vec, int32 dim);       // cuda-matrix.h AddVecToRows (device vector)
 
  protected:
   CuMatrixBase() {}
@@ -83,7 +85,7 @@ class Net;
 
 class Layer {
  public:
-  enum LayerType { l_Unknown, l_BiLstm_Parallel, l_Affine_Transform, l_Softmax };
+  enum LayerType { l_Unknown, l_BiLstm_Parallel, l_BiLstm, l_Affine_Transform, l_Softmax };
   Layer(int32 in, int32 out) : input_dim_(in), output_dim_(out) {}
   virtual ~Layer() {}
   virtual LayerType GetType() const = 0;
@@ -97,6 +99,9 @@ class Layer {
                      const CuMatrixBase<BaseFloat> &out_diff, CuMatrix<BaseFloat> *in_diff);
   static Layer *Read(std::istream &is, bool binary);            // layer.cc:138-176
   void Write(std::ostream &os, bool binary) const;              // layer.cc:209-222
+  void WriteNonParal(std::ostream &os, bool binary) const;      // layer.cc:224-237
+  virtual LayerType GetTypeNonParal() const { return GetType(); }
+  static bool IsLstmType(LayerType t) { return t == l_BiLstm_Parallel || t == l_BiLstm; }
   static const char *TypeToMarker(LayerType t);
   static LayerType MarkerToType(const std::string &s);
   virtual std::string Info() const { return ""; }
@@ -137,6 +142,7 @@ class BiLstmParallel : public TrainableLayer {
  public:
   BiLstmParallel(int32 in, int32 out) : TrainableLayer(in, out), cell_dim_(out / 2) {}
   LayerType GetType() const { return l_BiLstm_Parallel; }
+  LayerType GetTypeNonParal() const { return l_BiLstm; }
   void SetSeqLengths(std::vector<int> &sequence_lengths);
   int64 NumParams() const;
   std::string Info() const;
@@ -161,6 +167,21 @@ class BiLstmParallel : public TrainableLayer {
 
  public:
   ~BiLstmParallel();
+};
+
+// <BiLstm> (bilstm-layer.h:547-700): the marker format-to-nonparallel writes for decoding.  Same
+// parameters and arithmetic; without SetSeqLengths the whole input is ONE sequence (what the
+// reference's BiLstm::PropagateFnc does), with SetSeqLengths it runs packed like the parallel layer
+// (valid frames do not depend on the packing, SURVEY.md section 7 hard part 2).
+class BiLstm : public BiLstmParallel {
+ public:
+  BiLstm(int32 in, int32 out) : BiLstmParallel(in, out) {}
+  LayerType GetType() const { return l_BiLstm; }
+
+ protected:
+  void PropagateFnc(const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseFloat> *out);
+  void BackpropagateFnc(const CuMatrixBase<BaseFloat> &in, const CuMatrixBase<BaseFloat> &out,
+                        const CuMatrixBase<BaseFloat> &out_diff, CuMatrixBase<BaseFloat> *in_diff);
 };
 
 class AffineTransform : public TrainableLayer {
@@ -196,6 +217,9 @@ class Net {
   void Read(std::istream &is, bool binary);
   void Write(const std::string &file, bool binary);      // net.cc:319-334
   void Write(std::ostream &os, bool binary);
+  void WriteNonParal(const std::string &file, bool binary);   // net.cc:337-353
+  // forward only, two ping-pong buffers that are released afterwards (net.cc:110-137)
+  void Feedforward(const CuMatrixBase<BaseFloat> &in, CuMatrix<BaseFloat> *out);
   void Propagate(const CuMatrixBase<BaseFloat> &in, CuMatrix<BaseFloat> *out);       // net.cc:67-86
   void Backpropagate(const CuMatrixBase<BaseFloat> &out_diff, CuMatrix<BaseFloat> *in_diff);  // net.cc:88-108
   // Data-parallel step that tolerates ranks running out of data: a rank without a minibatch passes
@@ -231,6 +255,7 @@ class Net {
 
  private:
   void BindArena();
+  void RefreshHostCopies();
   void UploadSegments();
   void BackpropagateLayers(const CuMatrixBase<BaseFloat> &out_diff, CuMatrix<BaseFloat> *in_diff);
   void Reduce(int64 reduce_count);
@@ -249,6 +274,30 @@ class Net {
   void *d_segs_ = nullptr;
   int nseg_ = 0;
   bool segs_dirty_ = true;
+};
+
+// class-prior.h:29-73, class-prior.cc:28-90
+struct ClassPriorOptions {
+  std::string class_frame_counts;
+  BaseFloat prior_scale = 1.0f, prior_cutoff = 1e-10f, blank_scale = 1.0f;
+};
+class ClassPrior {
+ public:
+  ClassPrior(eesen_b200_ctx *ctx, const ClassPriorOptions &opts);
+  ~ClassPrior();
+  void SubtractOnLogpost(CuMatrixBase<BaseFloat> *llk);
+  // the host arithmetic of the constructor: counts -> log priors (+FLT_MAX/2 where count < cutoff)
+  static void LogPriors(const std::vector<double> &counts, BaseFloat prior_cutoff, BaseFloat blank_scale,
+                        std::vector<float> *log_priors);
+  int32 Dim() const { return dim_; }
+  const float *DeviceLogPriors() const { return d_log_priors_; }
+  BaseFloat PriorScale() const { return prior_scale_; }
+
+ private:
+  eesen_b200_ctx *ctx_;
+  BaseFloat prior_scale_;
+  float *d_log_priors_ = nullptr;
+  int32 dim_ = 0;
 };
 
 // ctc-loss.h:29-86

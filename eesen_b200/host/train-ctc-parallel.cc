@@ -17,21 +17,9 @@
 
 #include "minibatch.h"
 #include "net.h"
+#include "options.h"
 
 using namespace eesen;
-
-struct Options {
-  std::map<std::string, std::string> kv;
-  std::vector<std::string> args;
-  bool Has(const std::string &k) const { return kv.count(k) > 0; }
-  std::string Str(const std::string &k, const std::string &d) const { return Has(k) ? kv.at(k) : d; }
-  double Num(const std::string &k, double d) const { return Has(k) ? atof(kv.at(k).c_str()) : d; }
-  bool Bool(const std::string &k, bool d) const {
-    if (!Has(k)) return d;
-    const std::string &v = kv.at(k);
-    return v == "" || v == "true" || v == "1" || v == "yes";
-  }
-};
 
 static const char *kUsage =
     "Perform one iteration of CTC training by SGD.\n"
@@ -55,31 +43,7 @@ static int PrecFromString(const std::string &s) {
 int main(int argc, char *argv[]) {
   try {
     Options po;
-    for (int i = 1; i < argc; i++) {
-      std::string a = argv[i];
-      if (a.size() > 2 && a[0] == '-' && a[1] == '-') {
-        size_t eq = a.find('=');
-        if (eq == std::string::npos) po.kv[a.substr(2)] = "";
-        else po.kv[a.substr(2, eq - 2)] = a.substr(eq + 1);
-      } else {
-        po.args.push_back(a);
-      }
-    }
-    if (po.Has("config")) {
-      std::ifstream cf(po.kv["config"].c_str());
-      std::string line;
-      while (std::getline(cf, line)) {
-        size_t h = line.find('#');
-        if (h != std::string::npos) line.resize(h);
-        size_t b = line.find("--");
-        if (b == std::string::npos) continue;
-        line = line.substr(b + 2);
-        while (!line.empty() && isspace(line[line.size() - 1])) line.resize(line.size() - 1);
-        size_t eq = line.find('=');
-        std::string k = eq == std::string::npos ? line : line.substr(0, eq);
-        if (!po.kv.count(k)) po.kv[k] = eq == std::string::npos ? "" : line.substr(eq + 1);
-      }
-    }
+    po.Parse(argc, argv);
     g_verbose_level = (int)po.Num("verbose", 0);
 
     NetTrainOptions trn_opts;

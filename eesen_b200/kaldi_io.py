@@ -340,6 +340,20 @@ def write_feature_ark(path: str, keys: Sequence[str], utts: Sequence[np.ndarray]
             _wmat(f, u)
 
 
+def read_feature_ark(path: str):
+    """Binary float-matrix archive -> (keys, matrices); the format BaseFloatMatrixWriter produces."""
+    data = open(path, "rb").read()
+    r = _Reader(data)
+    keys, mats = [], []
+    while r.p < len(data):
+        keys.append(r.tok())
+        if data[r.p:r.p + 2] != b"\0B":
+            raise ValueError("only binary archives are supported by this reader")
+        r.p += 2
+        mats.append(r.mat())
+    return keys, mats
+
+
 def write_label_ark(path: str, keys: Sequence[str], labels: Sequence[Sequence[int]]) -> None:
     with open(path, "w") as f:
         for k, l in zip(keys, labels):

@@ -118,6 +118,12 @@ int eesen_b200_affine_backward(eesen_b200_ctx *ctx, int N, int D, int K, const f
 int eesen_b200_softmax(eesen_b200_ctx *ctx, int N, int K, const float *logits, int ld, float *probs,
                        int ldp, int *d_argmax);
 int eesen_b200_row_argmax(eesen_b200_ctx *ctx, int N, int K, const float *x, int ld, int *d_argmax);
+/* Output side of the forward-only path (reference src/netbin/net-output-extract.cc:100-110), in
+ * place on y [N x K] (ld): CuMatrixBase::ApplyLog (src/gpucompute/cuda-matrix.cc ApplyLog ->
+ * cuda-kernels.cu:221-227) if apply_log != 0, then ClassPrior::SubtractOnLogpost
+ * (src/net/class-prior.cc:78-90: y -= prior_scale * log_prior[col]) if d_log_prior != NULL. */
+int eesen_b200_loglik(eesen_b200_ctx *ctx, int N, int K, float *y, int ld, int apply_log,
+                      const float *d_log_prior, float prior_scale);
 
 /* Ctc::EvalParallel compute (reference src/net/ctc-loss.cc:101-168).
  *   probs    [T*S x K] (ldp) softmax outputs           d_len[S] valid frames
@@ -174,6 +180,26 @@ int eesen_b200_net_train_step(eesen_b200_net *net, const float *feats, int T, in
 int eesen_b200_net_train_step_device(eesen_b200_net *net, const float *d_feats, int T, int S,
                                      const int *frames, const int *labels, const int *lab_len, int train);
 int eesen_b200_net_read_stats(eesen_b200_net *net, double stats[4]);
+
+/* ---------------------------------------------------------------- forward-only path
+ * One packed batch through what reference src/netbin/net-output-extract.cc:83-118 does per
+ * utterance: Net::Feedforward (src/net/net.cc:110-137), CuMatrixBase::ApplyLog if apply_log != 0,
+ * ClassPrior::SubtractOnLogpost (src/net/class-prior.cc:78-90) if log_priors != NULL.
+ *   feats [T*S x I] packed time-major (row t*S+s), frames[S]; HOST buffers.  frames == NULL (S must
+ *   be 1): no SetSeqLengths call at all, the reference tool's own call pattern -- accepted by <BiLstm>
+ *   layers (one sequence of T rows, src/net/bilstm-layer.h:548), an error for <BiLstmParallel>
+ *   log_priors [K] host (from eesen_b200_class_log_priors) or NULL, prior_scale = --prior-scale
+ *   out [T*S x K] host, same packing; rows of padding frames hold no meaning
+ * Works for <BiLstmParallel> and <BiLstm> models alike (the reference converts on the fly,
+ * src/net/layer.cc:164-170). */
+int eesen_b200_net_feedforward(eesen_b200_net *net, const float *feats, int T, int S, const int *frames,
+                               int apply_log, const float *log_priors, float prior_scale, float *out);
+/* Host arithmetic of ClassPrior::ClassPrior (src/net/class-prior.cc:28-76): frame counts -> log priors
+ * (classes with count < prior_cutoff get +FLT_MAX/2 so that their likelihood vanishes; class 0 is
+ * scaled by blank_scale before normalisation).  No device work. */
+int eesen_b200_class_log_priors(const double *counts, int K, float prior_cutoff, float blank_scale, float *log_priors);
+/* Net::WriteNonParal (src/net/net.cc:337-353; tool src/netbin/format-to-nonparallel.cc) */
+int eesen_b200_net_write_nonparallel(eesen_b200_net *net, const char *path, int binary);
 
 /* Introspection for the parity tests (host copies, synchronous).  which:
  *   0..L    Net::propagate_buf_[which]     (layer inputs/outputs, L = num_layers)

@@ -206,6 +206,44 @@ class OracleNet:
         return np.concatenate([self.corr[i][n].ravel() for i, l in enumerate(self.spec.layers) for n in l.param_names()])
 
 
+def class_log_priors(counts, prior_cutoff=1e-10, blank_scale=1.0) -> np.ndarray:
+    """ClassPrior::ClassPrior (class-prior.cc:28-76): counts below the cutoff are floored and masked with
+    FLT_MAX/2, class 0 scaled by blank_scale, normalised, log in double, cast to float, mask added."""
+    p = np.asarray(counts, np.float64).copy()
+    cut = np.float64(np.float32(prior_cutoff))
+    mask = np.zeros(p.size, np.float32)
+    low = p < cut
+    p[low] = cut
+    mask[low] = np.finfo(np.float32).max / 2
+    if blank_scale != 1.0:
+        p[0] *= np.float64(np.float32(blank_scale))
+    p = p * (1.0 / p.sum())
+    return (np.log(p).astype(np.float32) + mask).astype(np.float32)
+
+
+def net_output(on: "OracleNet", feats, frames, apply_log=False, log_priors=None, prior_scale=1.0) -> np.ndarray:
+    """net-output-extract.cc:96-110 on a packed batch: Feedforward, ApplyLog, SubtractOnLogpost."""
+    y = on.forward(feats, frames).astype(on.L.dtype).copy()
+    if apply_log:
+        with np.errstate(divide="ignore"):
+            y = np.log(y)
+    if log_priors is not None:
+        y = y + np.asarray(-prior_scale, on.L.dtype) * np.asarray(log_priors, on.L.dtype)[None, :]
+    return y
+
+
+def run_reference_tool(tool: str, args: List[str], timeout: int = 600, threads: Optional[int] = None):
+    """Run one of the reference's own command-line tools built under oracle/_ref (CPU build)."""
+    exe = os.path.join(REFDIR, tool)
+    env = dict(os.environ)
+    if threads is not None:
+        env["OPENBLAS_NUM_THREADS"] = str(threads)
+    r = subprocess.run([exe] + list(args), capture_output=True, text=True, env=env, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError(f"{tool} failed ({r.returncode}):\n{r.stdout[-2000:]}\n{r.stderr[-4000:]}")
+    return r
+
+
 def greedy_token_errors(y: np.ndarray, frames, labels, S: int):
     """Ctc::ErrorRateMSeq (ctc-loss.cc:235-298): argmax path -> collapse repeats -> drop blanks ->
     Levenshtein (util/edit-distance-inl.h:28-75).  Returns (errors, ref_tokens)."""

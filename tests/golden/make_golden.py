@@ -86,7 +86,32 @@ def run_adaptive(outdir: str = HERE, steps: int = 3):
         print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def run_infer(outdir: str = HERE):
+    """small_netout_refcpu.npz: the reference's own net-output-extract (CPU build, utterance by utterance)
+    with --apply-log, class priors, prior scale and blank scale."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_inference_cpu import infer_case
+    w, net, b, utts, counts = infer_case()
+    d = tempfile.mkdtemp()
+    kaldi_io.write_model(d + "/model", net)
+    keys = [f"utt{i:02d}" for i in range(len(utts))]
+    kaldi_io.write_feature_ark(d + "/feats.ark", keys, utts)
+    open(d + "/counts", "w").write("[ " + " ".join(repr(float(c)) for c in counts) + " ]\n")
+    oracle.run_reference_tool("ref_net_output_extract",
+                              ["--apply-log=true", f"--class-frame-counts={d}/counts", "--prior-scale=0.8",
+                               "--blank-scale=0.5", d + "/model", f"ark:{d}/feats.ark", f"ark:{d}/out.ark"], threads=4)
+    rk, rm = kaldi_io.read_feature_ark(d + "/out.ark")
+    keep = {k: m for k, m in zip(rk, rm)}
+    keep.update(counts=counts, prior_scale=np.float64(0.8), blank_scale=np.float64(0.5))
+    path = os.path.join(outdir, "small_netout_refcpu.npz")
+    np.savez_compressed(path, **keep)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "infer":
+        run_infer(sys.argv[2] if len(sys.argv) > 2 else HERE)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "adaptive":
         run_adaptive(sys.argv[2] if len(sys.argv) > 2 else HERE)
         sys.exit(0)
