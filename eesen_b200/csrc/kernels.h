@@ -51,13 +51,14 @@ struct LstmBwdArgs {
 };
 struct LstmPlan {
   int nut, nct, ksplit;  // utterance tiles / cell tiles per CTA, K-split warps (fwd)
-  int groups, slices;    // grid = (slices, groups, 2)
+  int groups, slices;    // grid = (slices, groups, ndir)
+  int ndir;              // 2: BiLstmParallel (fw + bw cells), 1: LstmParallel (fw cells only)
   int threads;
   size_t smem_fwd, smem_bwd;
   size_t pbuf_floats, gsum_floats, xbuf_bytes;
   int valid;
 };
-LstmPlan lstm_plan(int S, int C, int num_sms, size_t max_smem);
+LstmPlan lstm_plan(int S, int C, int num_sms, size_t max_smem, int ndir = 2);
 cudaError_t lstm_forward(cudaStream_t st, const LstmPlan &plan, const LstmFwdArgs &a);
 cudaError_t lstm_backward(cudaStream_t st, const LstmPlan &plan, const LstmBwdArgs &a);
 // bias/peephole gradient from the per-group sums: dst[7 blocks] = sum_groups gsum

@@ -133,7 +133,7 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
   }
   if (fin) {
 #pragma unroll
-    for (int e = 0; e < 2; e++) lenu[e] = uidx[e] < s1 ? a.len[uidx[e]] : 0;
+    for (int e = 0; e < 2; e++) lenu[e] = (a.len && uidx[e] < s1) ? a.len[uidx[e]] : 0;   // NULL: uni-directional (no masking)
   }
   auto load_pre = [&](int t) {
 #pragma unroll
@@ -462,7 +462,7 @@ size_t bwd_smem(const Cfg &c, int C) {
 template <int NUT, int NCT, int KSPLIT>
 cudaError_t launch_fwd(cudaStream_t st, const LstmPlan &pl, const LstmFwdArgs &a) {
   unsigned expected = (unsigned)(pl.slices * NCT * NUT);  // finalising warps per (dir, group) and step
-  dim3 grid(pl.slices, pl.groups, 2), block(pl.threads);
+  dim3 grid(pl.slices, pl.groups, pl.ndir), block(pl.threads);
   int groups = pl.groups;
   LstmFwdArgs args = a;
   void *kargs[] = {&args, &groups, &expected};
@@ -477,7 +477,7 @@ template <int NUT, int NCT, int KSPLIT>
 cudaError_t launch_bwd(cudaStream_t st, const LstmPlan &pl, const LstmBwdArgs &a) {
   constexpr int NWARPS = NUT * NCT * KSPLIT;
   unsigned expected = (unsigned)(NWARPS * pl.slices);
-  dim3 grid(pl.slices, pl.groups, 2), block(pl.threads);
+  dim3 grid(pl.slices, pl.groups, pl.ndir), block(pl.threads);
   int groups = pl.groups, slices = pl.slices;
   LstmBwdArgs args = a;
   void *kargs[] = {&args, &groups, &slices, &expected};
@@ -504,15 +504,16 @@ int lstm_debug_timing(long long *out32, int reset) {
 #endif
 }
 
-LstmPlan lstm_plan(int S, int C, int num_sms, size_t max_smem) {
+LstmPlan lstm_plan(int S, int C, int num_sms, size_t max_smem, int ndir) {
   LstmPlan best;
   best.valid = 0;
+  best.ndir = ndir;
   long best_work = -1;
-  if (C % 8 != 0 || C <= 0 || S <= 0) return best;
+  if (C % 8 != 0 || C <= 0 || S <= 0 || ndir < 1 || ndir > 2) return best;
   for (const Cfg &c : kCfgs) {
     int groups = (S + 8 * c.nut - 1) / (8 * c.nut);
     int slices = (C + 8 * c.nct - 1) / (8 * c.nct);
-    long ctas = 2L * groups * slices;
+    long ctas = (long)ndir * groups * slices;
     size_t sf = fwd_smem(c, C), sb = bwd_smem(c, C);
     if (ctas > num_sms || sf > max_smem || sb > max_smem) continue;
     long work = (long)c.nut * c.nct * 16 + (4 - c.ksplit);  // per-CTA MMA work, then prefer deeper K split

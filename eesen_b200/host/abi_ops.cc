@@ -146,13 +146,13 @@ int eesen_b200_gemm(eesen_b200_ctx *ctx, int transA, int transB, int M, int N, i
 // Picks the resident-weight plan.  The recurrence is independent per utterance, so a minibatch that
 // does not fit one co-resident grid (e.g. 128 utterances at C=320) is processed in utterance chunks
 // of the largest size that does: chunk = S, else the largest multiple of 8 in {64, 32, 16, 8}.
-static int lstm_prepare(eesen_b200_ctx *ctx, int S, int C, eb::LstmPlan *plan, int *chunk, float **pbuf, float **gsum,
-                        void **xbuf) {
+static int lstm_prepare(eesen_b200_ctx *ctx, int ndir, int S, int C, eb::LstmPlan *plan, int *chunk, float **pbuf,
+                        float **gsum, void **xbuf) {
   const int cands[5] = {S, 64, 32, 16, 8};
   plan->valid = 0;
   for (int i = 0; i < 5 && !plan->valid; i++) {
     if (cands[i] > S || cands[i] <= 0) continue;
-    *plan = eb::lstm_plan(cands[i], C, ctx->num_sms, ctx->max_smem);
+    *plan = eb::lstm_plan(cands[i], C, ctx->num_sms, ctx->max_smem, ndir);
     *chunk = cands[i];
   }
   if (!plan->valid)
@@ -166,37 +166,43 @@ static int lstm_prepare(eesen_b200_ctx *ctx, int S, int C, eb::LstmPlan *plan, i
   return 0;
 }
 
-int eesen_b200_bilstm_forward(eesen_b200_ctx *ctx, int T, int S, int I, int C, const int *d_len, const float *x,
-                              int ldx, const eesen_b200_bilstm_params *p, float *gates, float *cell, float *out,
-                              int ldo) {
+// ndir = 2: BiLstmParallel (gates [N x 8C], cell/out [N x 2C]); ndir = 1: LstmParallel, the forward cells
+// alone (gates [N x 4C], cell/out [N x C], index 0 of the parameter arrays) -- lstm-parallel-layer.h:47-113
+// is the forward-cell pass of bilstm-parallel-layer.h:97-150 line for line.
+static int lstm_forward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I, int C, const int *d_len,
+                             const float *x, int ldx, const eesen_b200_bilstm_params *p, float *gates, float *cell,
+                             float *out, int ldo) {
   if (!ctx || !p || !x || !gates || !cell || !out || T <= 0 || S <= 0) return EESEN_B200_EINVAL;
   eb::LstmPlan plan;
   float *pbuf, *gsum;
   void *xbuf;
   int chunk = S;
-  int rc = lstm_prepare(ctx, S, C, &plan, &chunk, &pbuf, &gsum, &xbuf);
+  int rc = lstm_prepare(ctx, ndir, S, C, &plan, &chunk, &pbuf, &gsum, &xbuf);
   if (rc) return rc;
   // input-side gate pre-activations for both directions: G[:, d*4C..] = x * Wx_d^T + b_d
   // (bilstm-parallel-layer.h:109-110,163-164).  Batched over the direction when the two weight
   // blocks are equally strided (they are in the Net arena), else two launches.
-  long sW = p->wx[1] - p->wx[0], sB = p->bias[1] - p->bias[0];
-  const int N = T * S;
-  if (sW > 0 && (sW & 3) == 0 && sB > 0) {
-    rc = do_gemm(ctx, 0, 1, N, 4 * C, I, 1.f, x, ldx, 0, p->wx[0], I, sW, 0.f, gates, 8 * C, 4 * C, p->bias[0], sB, 2);
+  long sW = ndir == 2 ? p->wx[1] - p->wx[0] : 0, sB = ndir == 2 ? p->bias[1] - p->bias[0] : 0;
+  const int N = T * S, ldg = ndir * 4 * C;
+  if (ndir == 2 && sW > 0 && (sW & 3) == 0 && sB > 0) {
+    rc = do_gemm(ctx, 0, 1, N, 4 * C, I, 1.f, x, ldx, 0, p->wx[0], I, sW, 0.f, gates, ldg, 4 * C, p->bias[0], sB, 2);
     if (rc) return rc;
   } else {
-    for (int d = 0; d < 2; d++) {
-      rc = do_gemm(ctx, 0, 1, N, 4 * C, I, 1.f, x, ldx, 0, p->wx[d], I, 0, 0.f, gates + (size_t)d * 4 * C, 8 * C, 0,
+    for (int d = 0; d < ndir; d++) {
+      rc = do_gemm(ctx, 0, 1, N, 4 * C, I, 1.f, x, ldx, 0, p->wx[d], I, 0, 0.f, gates + (size_t)d * 4 * C, ldg, 0,
                    p->bias[d], 0, 1);
       if (rc) return rc;
     }
   }
   eb::LstmFwdArgs a;
   a.T = T; a.S = S; a.C = C; a.len = d_len;
-  a.G = gates; a.ldg = 8 * C;
-  a.cell = cell; a.ldc = 2 * C;
+  a.G = gates; a.ldg = ldg;
+  a.cell = cell; a.ldc = ndir * C;
   a.out = out; a.ldo = ldo;
-  for (int d = 0; d < 2; d++) { a.p[d].wm = p->wm[d]; a.p[d].pi = p->pi[d]; a.p[d].pf = p->pf[d]; a.p[d].po = p->po[d]; }
+  for (int d = 0; d < 2; d++) {
+    const int q = d < ndir ? d : 0;
+    a.p[d].wm = p->wm[q]; a.p[d].pi = p->pi[q]; a.p[d].pf = p->pf[q]; a.p[d].po = p->po[q];
+  }
   a.xbuf = xbuf;
   a.precision = ctx->rec_prec;
   for (int s0 = 0; s0 < S; s0 += chunk) {
@@ -211,25 +217,41 @@ int eesen_b200_bilstm_forward(eesen_b200_ctx *ctx, int T, int S, int I, int C, c
   return 0;
 }
 
-int eesen_b200_bilstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, const float *x, int ldx,
-                               const eesen_b200_bilstm_params *p, const float *gates, const float *cell,
-                               const float *out, int ldo, const float *dout, int ldd, float *dgates, float *dx,
-                               int lddx, const eesen_b200_bilstm_grads *gr) {
+int eesen_b200_bilstm_forward(eesen_b200_ctx *ctx, int T, int S, int I, int C, const int *d_len, const float *x,
+                              int ldx, const eesen_b200_bilstm_params *p, float *gates, float *cell, float *out,
+                              int ldo) {
+  if (!d_len) return EESEN_B200_EINVAL;
+  return lstm_forward_impl(ctx, 2, T, S, I, C, d_len, x, ldx, p, gates, cell, out, ldo);
+}
+
+int eesen_b200_lstm_forward(eesen_b200_ctx *ctx, int T, int S, int I, int C, const float *x, int ldx,
+                            const eesen_b200_bilstm_params *p, float *gates, float *cell, float *out, int ldo) {
+  return lstm_forward_impl(ctx, 1, T, S, I, C, NULL, x, ldx, p, gates, cell, out, ldo);
+}
+
+static int lstm_backward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I, int C, const float *x, int ldx,
+                              const eesen_b200_bilstm_params *p, const float *gates, const float *cell,
+                              const float *out, int ldo, const float *dout, int ldd, float *dgates, float *dx,
+                              int lddx, const eesen_b200_bilstm_grads *gr) {
   if (!ctx || !p || !gr || !x || !gates || !cell || !out || !dout || !dgates || T <= 0 || S <= 0) return EESEN_B200_EINVAL;
   eb::LstmPlan plan;
   float *pbuf, *gsum;
   void *xbuf;
   int chunk = S;
-  int rc = lstm_prepare(ctx, S, C, &plan, &chunk, &pbuf, &gsum, &xbuf);
+  int rc = lstm_prepare(ctx, ndir, S, C, &plan, &chunk, &pbuf, &gsum, &xbuf);
   if (rc) return rc;
   const int nchunks = (S + chunk - 1) / chunk;
+  const int ldg = ndir * 4 * C;
   eb::LstmBwdArgs a;
   a.T = T; a.S = S; a.C = C;
-  a.G = gates; a.ldg = 8 * C;
-  a.cell = cell; a.ldc = 2 * C;
+  a.G = gates; a.ldg = ldg;
+  a.cell = cell; a.ldc = ndir * C;
   a.dout = dout; a.ldd = ldd;
-  a.DG = dgates; a.lddg = 8 * C;
-  for (int d = 0; d < 2; d++) { a.p[d].wm = p->wm[d]; a.p[d].pi = p->pi[d]; a.p[d].pf = p->pf[d]; a.p[d].po = p->po[d]; }
+  a.DG = dgates; a.lddg = ldg;
+  for (int d = 0; d < 2; d++) {
+    const int q = d < ndir ? d : 0;
+    a.p[d].wm = p->wm[q]; a.p[d].pi = p->pi[q]; a.p[d].pf = p->pf[q]; a.p[d].po = p->po[q];
+  }
   a.pbuf = pbuf; a.gsum = gsum;
   a.precision = ctx->rec_prec;
   for (int ci = 0; ci < nchunks; ci++) {
@@ -243,7 +265,7 @@ int eesen_b200_bilstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, 
     if ((rc = ctx->check(le, "lstm_backward"))) return rc;
   }
   const int N = T * S;
-  for (int d = 0; d < 2; d++) {
+  for (int d = 0; d < ndir; d++) {
     ctx->launches += 1;
     int pe = ctx->prof_begin(eesen_b200_ctx::kMisc);
     cudaError_t le = eb::lstm_reduce_gsum(ctx->stream, plan, C, gsum, nchunks, gr->bias[d], gr->pi[d], gr->pf[d], gr->po[d], d);
@@ -252,21 +274,21 @@ int eesen_b200_bilstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, 
   }
   // dx = DG_fw * Wx_fw + DG_bw * Wx_bw   (:502 beta=0, :593 beta=1)
   if (dx) {
-    for (int d = 0; d < 2; d++) {
-      rc = do_gemm(ctx, 0, 0, N, I, 4 * C, 1.f, dgates + (size_t)d * 4 * C, 8 * C, 0, p->wx[d], I, 0,
+    for (int d = 0; d < ndir; d++) {
+      rc = do_gemm(ctx, 0, 0, N, I, 4 * C, 1.f, dgates + (size_t)d * 4 * C, ldg, 0, p->wx[d], I, 0,
                    d == 0 ? 0.f : 1.f, dx, lddx, 0, nullptr, 0, 1);
       if (rc) return rc;
     }
   }
-  long sGW = gr->wx[1] - gr->wx[0], sGM = gr->wm[1] - gr->wm[0];
-  bool batched = sGW > 0 && (sGW & 3) == 0 && sGM > 0 && (sGM & 3) == 0;
+  long sGW = ndir == 2 ? gr->wx[1] - gr->wx[0] : 0, sGM = ndir == 2 ? gr->wm[1] - gr->wm[0] : 0;
+  bool batched = ndir == 2 && sGW > 0 && (sGW & 3) == 0 && sGM > 0 && (sGM & 3) == 0;
   // Wx grad = DG^T * x   (:505 / :596), both directions batched
   if (batched) {
-    rc = do_gemm(ctx, 1, 0, 4 * C, I, N, 1.f, dgates, 8 * C, 4 * C, x, ldx, 0, 0.f, gr->wx[0], I, sGW, nullptr, 0, 2);
+    rc = do_gemm(ctx, 1, 0, 4 * C, I, N, 1.f, dgates, ldg, 4 * C, x, ldx, 0, 0.f, gr->wx[0], I, sGW, nullptr, 0, 2);
     if (rc) return rc;
   } else {
-    for (int d = 0; d < 2; d++) {
-      rc = do_gemm(ctx, 1, 0, 4 * C, I, N, 1.f, dgates + (size_t)d * 4 * C, 8 * C, 0, x, ldx, 0, 0.f, gr->wx[d], I, 0,
+    for (int d = 0; d < ndir; d++) {
+      rc = do_gemm(ctx, 1, 0, 4 * C, I, N, 1.f, dgates + (size_t)d * 4 * C, ldg, 0, x, ldx, 0, 0.f, gr->wx[d], I, 0,
                    nullptr, 0, 1);
       if (rc) return rc;
     }
@@ -275,17 +297,33 @@ int eesen_b200_bilstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, 
   //                          bw pairs DG rows [0, N-S) with out rows [S, N) (:597)
   if (T > 1) {
     const int Nm = N - S;
-    rc = do_gemm(ctx, 1, 0, 4 * C, C, Nm, 1.f, dgates + (size_t)S * 8 * C, 8 * C, 0, out, ldo, 0, 0.f, gr->wm[0], C, 0,
+    rc = do_gemm(ctx, 1, 0, 4 * C, C, Nm, 1.f, dgates + (size_t)S * ldg, ldg, 0, out, ldo, 0, 0.f, gr->wm[0], C, 0,
                  nullptr, 0, 1);
     if (rc) return rc;
-    rc = do_gemm(ctx, 1, 0, 4 * C, C, Nm, 1.f, dgates + 4 * C, 8 * C, 0, out + (size_t)S * ldo + C, ldo, 0, 0.f,
-                 gr->wm[1], C, 0, nullptr, 0, 1);
-    if (rc) return rc;
+    if (ndir == 2) {
+      rc = do_gemm(ctx, 1, 0, 4 * C, C, Nm, 1.f, dgates + 4 * C, ldg, 0, out + (size_t)S * ldo + C, ldo, 0, 0.f,
+                   gr->wm[1], C, 0, nullptr, 0, 1);
+      if (rc) return rc;
+    }
   } else {
-    CTX_CHECK(cudaMemsetAsync(gr->wm[0], 0, sizeof(float) * 4 * C * C, ctx->stream), "memset");
-    CTX_CHECK(cudaMemsetAsync(gr->wm[1], 0, sizeof(float) * 4 * C * C, ctx->stream), "memset");
+    for (int d = 0; d < ndir; d++)
+      CTX_CHECK(cudaMemsetAsync(gr->wm[d], 0, sizeof(float) * 4 * C * C, ctx->stream), "memset");
   }
   return 0;
+}
+
+int eesen_b200_bilstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, const float *x, int ldx,
+                               const eesen_b200_bilstm_params *p, const float *gates, const float *cell,
+                               const float *out, int ldo, const float *dout, int ldd, float *dgates, float *dx,
+                               int lddx, const eesen_b200_bilstm_grads *gr) {
+  return lstm_backward_impl(ctx, 2, T, S, I, C, x, ldx, p, gates, cell, out, ldo, dout, ldd, dgates, dx, lddx, gr);
+}
+
+int eesen_b200_lstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, const float *x, int ldx,
+                             const eesen_b200_bilstm_params *p, const float *gates, const float *cell,
+                             const float *out, int ldo, const float *dout, int ldd, float *dgates, float *dx,
+                             int lddx, const eesen_b200_bilstm_grads *gr) {
+  return lstm_backward_impl(ctx, 1, T, S, I, C, x, ldx, p, gates, cell, out, ldo, dout, ldd, dgates, dx, lddx, gr);
 }
 
 int eesen_b200_affine_forward(eesen_b200_ctx *ctx, int N, int D, int K, const float *x, int ldx, const float *W,

@@ -126,6 +126,8 @@ const char *Layer::TypeToMarker(LayerType t) {
   switch (t) {
     case l_BiLstm_Parallel: return "<BiLstmParallel>";
     case l_BiLstm: return "<BiLstm>";
+    case l_Lstm_Parallel: return "<LstmParallel>";
+    case l_Lstm: return "<Lstm>";
     case l_Affine_Transform: return "<AffineTransform>";
     case l_Softmax: return "<Softmax>";
     default: return "<Unknown>";
@@ -134,10 +136,12 @@ const char *Layer::TypeToMarker(LayerType t) {
 Layer::LayerType Layer::MarkerToType(const std::string &s) {
   if (s == "<BiLstmParallel>") return l_BiLstm_Parallel;
   if (s == "<BiLstm>") return l_BiLstm;
+  if (s == "<LstmParallel>") return l_Lstm_Parallel;
+  if (s == "<Lstm>") return l_Lstm;
   if (s == "<AffineTransform>") return l_Affine_Transform;
   if (s == "<Softmax>") return l_Softmax;
   KALDI_ERR << "Unknown or unsupported layer marker on the B200 CTC path: " << s
-            << " (supported: <BiLstmParallel> <BiLstm> <AffineTransform> <Softmax>)";
+            << " (supported: <BiLstmParallel> <BiLstm> <LstmParallel> <Lstm> <AffineTransform> <Softmax>)";
   return l_Unknown;
 }
 
@@ -175,6 +179,8 @@ Layer *Layer::Read(std::istream &is, bool binary) {
   switch (type) {
     case l_BiLstm_Parallel: layer = new BiLstmParallel(dim_in, dim_out); break;
     case l_BiLstm: layer = new BiLstm(dim_in, dim_out); break;
+    case l_Lstm_Parallel: layer = new LstmParallel(dim_in, dim_out, false); break;
+    case l_Lstm: layer = new LstmParallel(dim_in, dim_out, true); break;
     case l_Affine_Transform: layer = new AffineTransform(dim_in, dim_out); break;
     case l_Softmax: layer = new Softmax(dim_in, dim_out); break;
     default: KALDI_ERR << "Missing type: " << token;
@@ -374,6 +380,128 @@ void BiLstmParallel::BackpropagateFnc(const CuMatrixBase<BaseFloat> &in, const C
 std::string BiLstmParallel::Info() const {
   std::ostringstream os;
   os << "<BiLstmParallel> input " << input_dim_ << " cells/direction " << cell_dim_;
+  return os.str();
+}
+
+// ------------------------------------------------------------------------------------ LstmParallel
+static void ReadLstmTensors(std::istream &is, bool binary, int64 C, int64 I, std::vector<float> *flat) {
+  HostMatrix wx, wm;
+  HostVector b, pi, pf, po;
+  wx.Read(is, binary); wm.Read(is, binary);
+  b.Read(is, binary); pi.Read(is, binary); pf.Read(is, binary); po.Read(is, binary);
+  KALDI_ASSERT(wx.rows == 4 * C && wx.cols == I && wm.rows == 4 * C && wm.cols == C);
+  KALDI_ASSERT((int64)b.data.size() == 4 * C && (int64)pi.data.size() == C && (int64)pf.data.size() == C &&
+               (int64)po.data.size() == C);
+  flat->clear();
+  flat->insert(flat->end(), wx.data.begin(), wx.data.end());
+  flat->insert(flat->end(), wm.data.begin(), wm.data.end());
+  flat->insert(flat->end(), b.data.begin(), b.data.end());
+  flat->insert(flat->end(), pi.data.begin(), pi.data.end());
+  flat->insert(flat->end(), pf.data.begin(), pf.data.end());
+  flat->insert(flat->end(), po.data.begin(), po.data.end());
+}
+static void WriteLstmTensors(std::ostream &os, bool binary, int64 C, int64 I, const std::vector<float> &flat) {
+  const float *p = flat.data();
+  HostMatrix wx, wm;
+  wx.rows = 4 * C; wx.cols = I; wx.data.assign(p, p + 4 * C * I); p += 4 * C * I;
+  wm.rows = 4 * C; wm.cols = C; wm.data.assign(p, p + 4 * C * C); p += 4 * C * C;
+  HostVector b, pi, pf, po;
+  b.data.assign(p, p + 4 * C); p += 4 * C;
+  pi.data.assign(p, p + C); p += C;
+  pf.data.assign(p, p + C); p += C;
+  po.data.assign(p, p + C); p += C;
+  wx.Write(os, binary); wm.Write(os, binary);
+  b.Write(os, binary); pi.Write(os, binary); pf.Write(os, binary); po.Write(os, binary);
+}
+
+void LstmParallel::ReadData(std::istream &is, bool binary) {   // lstm-layer.h:103-145
+  while ('<' == Peek(is, binary)) {
+    std::string tok;
+    ReadToken(is, binary, &tok);
+    if (tok == "<LearnRateCoef>") ReadBasicType(is, binary, &learn_rate_coef_);
+    else if (tok == "<MaxGrad>") ReadBasicType(is, binary, &max_grad_);
+    else if (tok == "<LstmAccus>") {
+      ReadLstmTensors(is, binary, cell_dim_, input_dim_, &host_accu_);
+      has_accu_ = true;
+      break;
+    } else KALDI_ERR << "Unknown token " << tok << " in <LstmParallel>";
+  }
+  if (cell_dim_ % 8 != 0 || input_dim_ % 4 != 0)
+    KALDI_ERR << "LstmParallel on B200 needs cells % 8 == 0 and input dim % 4 == 0, got C=" << cell_dim_
+              << " I=" << input_dim_;
+  ReadLstmTensors(is, binary, cell_dim_, input_dim_, &host_params_);
+}
+
+void LstmParallel::WriteData(std::ostream &os, bool binary) const {   // lstm-layer.h:147-172
+  WriteToken(os, binary, "<LearnRateCoef>"); WriteBasicType(os, binary, learn_rate_coef_);
+  WriteToken(os, binary, "<MaxGrad>"); WriteBasicType(os, binary, max_grad_);
+  if (has_accu_) {
+    // The reference writes the WEIGHTS a second time under <LstmAccus>, not the accumulators
+    // (lstm-layer.h:153-163 writes wei_gifo_x_ ... phole_o_c_ in both blocks).  Mirrored byte for byte:
+    // a model written here must read back in the reference exactly as the reference's own file would.
+    WriteToken(os, binary, "<LstmAccus>");
+    WriteLstmTensors(os, binary, cell_dim_, input_dim_, host_params_);
+  }
+  WriteLstmTensors(os, binary, cell_dim_, input_dim_, host_params_);
+}
+
+void LstmParallel::Params(eesen_b200_bilstm_params *p, eesen_b200_bilstm_grads *g) const {
+  const int64 C = cell_dim_, I = input_dim_;
+  for (int d = 0; d < 2; d++) {   // index 1 mirrors index 0 (unused by the uni-directional entry points)
+    if (p) {
+      const float *b = w_;
+      p->wx[d] = b; b += 4 * C * I;
+      p->wm[d] = b; b += 4 * C * C;
+      p->bias[d] = b; b += 4 * C;
+      p->pi[d] = b; b += C;
+      p->pf[d] = b; b += C;
+      p->po[d] = b;
+    }
+    if (g) {
+      float *b = g_;
+      g->wx[d] = b; b += 4 * C * I;
+      g->wm[d] = b; b += 4 * C * C;
+      g->bias[d] = b; b += 4 * C;
+      g->pi[d] = b; b += C;
+      g->pf[d] = b; b += C;
+      g->po[d] = b;
+    }
+  }
+}
+
+int32 LstmParallel::Streams(int32 rows) const {
+  int32 S = num_streams_;
+  if (S == 0 && nonparallel_) S = 1;   // <Lstm>: the whole input is one sequence
+  KALDI_ASSERT(S > 0 && rows % S == 0);
+  return S;
+}
+
+void LstmParallel::PropagateFnc(const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseFloat> *out) {
+  const int32 S = Streams(in.NumRows()), T = in.NumRows() / S, C = cell_dim_;
+  gates_.Resize(in.NumRows(), 4 * C, kUndefined);
+  cell_.Resize(in.NumRows(), C, kUndefined);
+  eesen_b200_bilstm_params p;
+  Params(&p, NULL);
+  CheckAbi(ctx_, eesen_b200_lstm_forward(ctx_, T, S, input_dim_, C, in.Data(), in.Stride(), &p, gates_.Data(),
+                                         cell_.Data(), out->Data(), out->Stride()), "eesen_b200_lstm_forward");
+}
+
+void LstmParallel::BackpropagateFnc(const CuMatrixBase<BaseFloat> &in, const CuMatrixBase<BaseFloat> &out,
+                                    const CuMatrixBase<BaseFloat> &out_diff, CuMatrixBase<BaseFloat> *in_diff) {
+  const int32 S = Streams(in.NumRows()), T = in.NumRows() / S, C = cell_dim_;
+  dgates_.Resize(in.NumRows(), 4 * C, kUndefined);
+  eesen_b200_bilstm_params p;
+  eesen_b200_bilstm_grads g;
+  Params(&p, &g);
+  CheckAbi(ctx_, eesen_b200_lstm_backward(ctx_, T, S, input_dim_, C, in.Data(), in.Stride(), &p, gates_.Data(),
+                                          cell_.Data(), out.Data(), out.Stride(), out_diff.Data(), out_diff.Stride(),
+                                          dgates_.Data(), need_in_diff_ ? in_diff->Data() : NULL, in_diff->Stride(),
+                                          &g), "eesen_b200_lstm_backward");
+}
+
+std::string LstmParallel::Info() const {
+  std::ostringstream os;
+  os << "<LstmParallel> input " << input_dim_ << " cells " << cell_dim_;
   return os.str();
 }
 

@@ -85,7 +85,7 @@ class Net;
 
 class Layer {
  public:
-  enum LayerType { l_Unknown, l_BiLstm_Parallel, l_BiLstm, l_Affine_Transform, l_Softmax };
+  enum LayerType { l_Unknown, l_BiLstm_Parallel, l_BiLstm, l_Lstm_Parallel, l_Lstm, l_Affine_Transform, l_Softmax };
   Layer(int32 in, int32 out) : input_dim_(in), output_dim_(out) {}
   virtual ~Layer() {}
   virtual LayerType GetType() const = 0;
@@ -101,7 +101,9 @@ class Layer {
   void Write(std::ostream &os, bool binary) const;              // layer.cc:209-222
   void WriteNonParal(std::ostream &os, bool binary) const;      // layer.cc:224-237
   virtual LayerType GetTypeNonParal() const { return GetType(); }
-  static bool IsLstmType(LayerType t) { return t == l_BiLstm_Parallel || t == l_BiLstm; }
+  static bool IsLstmType(LayerType t) {   // layer.h:177-182
+    return t == l_BiLstm_Parallel || t == l_BiLstm || t == l_Lstm_Parallel || t == l_Lstm;
+  }
   static const char *TypeToMarker(LayerType t);
   static LayerType MarkerToType(const std::string &s);
   virtual std::string Info() const { return ""; }
@@ -182,6 +184,33 @@ class BiLstm : public BiLstmParallel {
   void PropagateFnc(const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseFloat> *out);
   void BackpropagateFnc(const CuMatrixBase<BaseFloat> &in, const CuMatrixBase<BaseFloat> &out,
                         const CuMatrixBase<BaseFloat> &out_diff, CuMatrixBase<BaseFloat> *in_diff);
+};
+
+// lstm-layer.h + lstm-parallel-layer.h: the uni-directional layer (<CellDim> = output dim = cells).
+// nonparallel_ = true is the <Lstm> marker; like <BiLstm> it treats the input as ONE sequence when no
+// lengths were set (lstm-layer.h PropagateFnc) -- lengths only give the packing (S), nothing is masked.
+class LstmParallel : public TrainableLayer {
+ public:
+  LstmParallel(int32 in, int32 out, bool nonparallel = false)
+      : TrainableLayer(in, out), cell_dim_(out), nonparallel_(nonparallel) {}
+  LayerType GetType() const { return nonparallel_ ? l_Lstm : l_Lstm_Parallel; }
+  LayerType GetTypeNonParal() const { return l_Lstm; }
+  void SetSeqLengths(std::vector<int> &sequence_lengths) { num_streams_ = (int32)sequence_lengths.size(); }
+  int64 NumParams() const { int64 C = cell_dim_, I = input_dim_; return 4 * C * I + 4 * C * C + 4 * C + 3 * C; }
+  std::string Info() const;
+
+ protected:
+  void PropagateFnc(const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseFloat> *out);
+  void BackpropagateFnc(const CuMatrixBase<BaseFloat> &in, const CuMatrixBase<BaseFloat> &out,
+                        const CuMatrixBase<BaseFloat> &out_diff, CuMatrixBase<BaseFloat> *in_diff);
+  void ReadData(std::istream &is, bool binary);
+  void WriteData(std::ostream &os, bool binary) const;
+  void Params(eesen_b200_bilstm_params *p, eesen_b200_bilstm_grads *g) const;
+  int32 Streams(int32 rows) const;
+  int32 cell_dim_;
+  bool nonparallel_;
+  int32 num_streams_ = 0;
+  CuMatrix<BaseFloat> gates_, cell_, dgates_;
 };
 
 class AffineTransform : public TrainableLayer {

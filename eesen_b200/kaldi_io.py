@@ -28,9 +28,9 @@ BILSTM_TENSORS = ("wx", "wm", "b", "pi", "pf", "po")  # per direction, WriteData
 
 @dataclass
 class LayerSpec:
-    kind: str  # "bilstm" | "affine" | "softmax"
+    kind: str  # "bilstm" | "lstm" (uni-directional) | "affine" | "softmax"
     in_dim: int
-    out_dim: int  # for bilstm this is <CellDim> = 2 * cells-per-direction
+    out_dim: int  # <CellDim>: 2 * cells-per-direction for bilstm, the cell count for lstm
     learn_rate_coef: float = 1.0
     max_grad: float = 0.0
     params: Dict[str, np.ndarray] = field(default_factory=dict)
@@ -40,12 +40,14 @@ class LayerSpec:
 
     @property
     def cells(self) -> int:
-        assert self.kind == "bilstm"
-        return self.out_dim // 2
+        assert self.kind in ("bilstm", "lstm")
+        return self.out_dim // 2 if self.kind == "bilstm" else self.out_dim
 
     def param_names(self) -> List[str]:
         if self.kind == "bilstm":
             return [f"{n}_{d}" for d in ("fw", "bw") for n in BILSTM_TENSORS]
+        if self.kind == "lstm":
+            return list(BILSTM_TENSORS)
         if self.kind == "affine":
             return ["w", "b"]
         return []
@@ -55,6 +57,9 @@ class LayerSpec:
             c, i = self.cells, self.in_dim
             one = {"wx": (4 * c, i), "wm": (4 * c, c), "b": (4 * c,), "pi": (c,), "pf": (c,), "po": (c,)}
             return {f"{n}_{d}": one[n] for d in ("fw", "bw") for n in BILSTM_TENSORS}
+        if self.kind == "lstm":
+            c, i = self.cells, self.in_dim
+            return {"wx": (4 * c, i), "wm": (4 * c, c), "b": (4 * c,), "pi": (c,), "pf": (c,), "po": (c,)}
         if self.kind == "affine":
             return {"w": (self.out_dim, self.in_dim), "b": (self.out_dim,)}
         return {}
@@ -101,7 +106,8 @@ class NetSpec:
 
 
 def make_net(in_dim: int, cells: int, num_layers: int, num_classes: int, seed: int = 0,
-             param_range: float = 0.1, max_grad: float = 50.0, learn_rate_coef: float = 1.0) -> NetSpec:
+             param_range: float = 0.1, max_grad: float = 50.0, learn_rate_coef: float = 1.0,
+             bidirectional: bool = True) -> NetSpec:
     """Random-init BiLSTM stack + affine + softmax, uniform(-range, range) like
     ``InitRandUniform`` (bilstm-layer.h:187-210); proto shape per
     asr_egs/wsj/utils/model_topo.py:80-95."""
@@ -109,11 +115,12 @@ def make_net(in_dim: int, cells: int, num_layers: int, num_classes: int, seed: i
     layers: List[LayerSpec] = []
     d = in_dim
     for _ in range(num_layers):
-        l = LayerSpec("bilstm", d, 2 * cells, learn_rate_coef, max_grad)
+        l = LayerSpec("bilstm", d, 2 * cells, learn_rate_coef, max_grad) if bidirectional else \
+            LayerSpec("lstm", d, cells, learn_rate_coef, max_grad)
         for n, shp in l.param_shapes().items():
             l.params[n] = rng.uniform(-param_range, param_range, size=shp).astype(np.float32)
         layers.append(l)
-        d = 2 * cells
+        d = l.out_dim
     a = LayerSpec("affine", d, num_classes, learn_rate_coef, max_grad)
     for n, shp in a.param_shapes().items():
         a.params[n] = rng.uniform(-param_range, param_range, size=shp).astype(np.float32)
@@ -151,7 +158,7 @@ def _wmat(f: BinaryIO, m: np.ndarray) -> None:
     f.write(m.tobytes())
 
 
-_MARKER = {"bilstm": "<BiLstmParallel>", "affine": "<AffineTransform>", "softmax": "<Softmax>"}
+_MARKER = {"bilstm": "<BiLstmParallel>", "lstm": "<LstmParallel>", "affine": "<AffineTransform>", "softmax": "<Softmax>"}
 _BILSTM_FLAGS = ("<ForwardTimeStepDropout>", "<ForwardSequenceDropout>", "<RecurrentTimeStepDropout>",
                  "<RecurrentSequenceDropout>", "<RNNDrop>", "<NoMemLossDropout>")
 
@@ -163,7 +170,7 @@ def write_model(path_or_file, net: NetSpec) -> None:
     for l in net.layers:
         _wtok(f, _MARKER[l.kind])
         _wtok(f, "<InputDim>"); _wi32(f, l.in_dim)
-        _wtok(f, "<CellDim>" if l.kind == "bilstm" else "<OutputDim>"); _wi32(f, l.out_dim)
+        _wtok(f, "<CellDim>" if l.kind in ("bilstm", "lstm") else "<OutputDim>"); _wi32(f, l.out_dim)
         if l.kind == "bilstm":
             _wtok(f, "<LearnRateCoef>"); _wf32(f, l.learn_rate_coef)
             _wtok(f, "<MaxGrad>"); _wf32(f, l.max_grad)
@@ -176,6 +183,15 @@ def write_model(path_or_file, net: NetSpec) -> None:
             _wtok(f, "<TwiddleForward>"); _wbool(f, False)
             if l.accus:
                 _wtok(f, "<BiLstmAccus>")
+                for n in l.param_names():
+                    _wmat(f, l.accus[n])
+            for n in l.param_names():
+                _wmat(f, l.params[n])
+        elif l.kind == "lstm":   # lstm-layer.h:147-172
+            _wtok(f, "<LearnRateCoef>"); _wf32(f, l.learn_rate_coef)
+            _wtok(f, "<MaxGrad>"); _wf32(f, l.max_grad)
+            if l.accus:
+                _wtok(f, "<LstmAccus>")
                 for n in l.param_names():
                     _wmat(f, l.accus[n])
             for n in l.param_names():
@@ -254,6 +270,7 @@ def read_model(path: str) -> NetSpec:
     layers: List[LayerSpec] = []
     inv = {v: k for k, v in _MARKER.items()}
     inv["<BiLstm>"] = "bilstm"
+    inv["<Lstm>"] = "lstm"
     while r.peek() != -1:
         t = r.tok()
         if t == "</Nnet>":
@@ -262,7 +279,7 @@ def read_model(path: str) -> NetSpec:
             t = r.tok()
         kind = inv[t]
         r.expect("<InputDim>"); i = r.i32()
-        r.expect("<CellDim>" if kind == "bilstm" else "<OutputDim>"); o = r.i32()
+        r.expect("<CellDim>" if kind in ("bilstm", "lstm") else "<OutputDim>"); o = r.i32()
         l = LayerSpec(kind, i, o)
         if kind == "bilstm":
             while r.peek() == ord("<"):
@@ -272,6 +289,18 @@ def read_model(path: str) -> NetSpec:
                 elif tk in ("<ForwardDropoutFactor>", "<RecurrentDropoutFactor>"): r.f32()
                 elif tk in _BILSTM_FLAGS or tk == "<TwiddleForward>": r.boolean()
                 elif tk == "<BiLstmAccus>":
+                    for n in l.param_names():
+                        l.accus[n] = r.mat()
+                    break
+                else: raise ValueError(f"unsupported token {tk}")
+            for n in l.param_names():
+                l.params[n] = r.mat()
+        elif kind == "lstm":
+            while r.peek() == ord("<"):
+                tk = r.tok()
+                if tk == "<LearnRateCoef>": l.learn_rate_coef = r.f32()
+                elif tk == "<MaxGrad>": l.max_grad = r.f32()
+                elif tk == "<LstmAccus>":
                     for n in l.param_names():
                         l.accus[n] = r.mat()
                     break

@@ -62,9 +62,9 @@ def make_batch(w: Workload, seed: int, S: int | None = None) -> Batch:
     return Batch(feats, frames, labels)
 
 
-def make_model(w: Workload, seed: int = 0) -> NetSpec:
+def make_model(w: Workload, seed: int = 0, bidirectional: bool = True) -> NetSpec:
     return make_net(w.in_dim, w.cells, w.layers, w.classes, seed=seed, param_range=0.1,
-                    max_grad=w.max_grad)
+                    max_grad=w.max_grad, bidirectional=bidirectional)
 
 
 def flops_per_frame(w: Workload) -> float:

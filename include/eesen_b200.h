@@ -104,6 +104,17 @@ int eesen_b200_bilstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, 
                                const float *out, int ldo, const float *dout, int ldd, float *dgates,
                                float *dx, int lddx, const eesen_b200_bilstm_grads *grads);
 
+/* LstmParallel::PropagateFnc / BackpropagateFnc (reference src/net/lstm-parallel-layer.h:47-113,
+ * :115-213): the uni-directional layer = the forward cells of the layer above, nothing masked (the
+ * length check is commented out in the reference, :107-110).  Same structs, index [0] only:
+ *   gates [T*S x 4C] (ld 4C), cell [T*S x C] (ld C), out/dout [T*S x C], dgates [T*S x 4C]. */
+int eesen_b200_lstm_forward(eesen_b200_ctx *ctx, int T, int S, int I, int C, const float *x, int ldx,
+                            const eesen_b200_bilstm_params *p, float *gates, float *cell, float *out, int ldo);
+int eesen_b200_lstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, const float *x, int ldx,
+                             const eesen_b200_bilstm_params *p, const float *gates, const float *cell,
+                             const float *out, int ldo, const float *dout, int ldd, float *dgates,
+                             float *dx, int lddx, const eesen_b200_bilstm_grads *grads);
+
 /* AffineTransform::PropagateFnc / BackpropagateFnc / gradient part of Update
  * (reference src/net/affine-trans-layer.h:161-166, 168-172, 182-183).  W[K x D], b[K]. */
 int eesen_b200_affine_forward(eesen_b200_ctx *ctx, int N, int D, int K, const float *x, int ldx,

@@ -146,13 +146,13 @@ void oracle_bilstm_forward(int T, int S, int I, int C, const int *len, const REA
  * dir=-1 (backward cells): :514-602 (t=1..T, next=t-1, prev=t+1) */
 static void lstm_dir_backward(int dir, int T, int S, int I, int C, const REAL *x, const REAL *wx,
                               const REAL *wm, const REAL *pi, const REAL *pf, const REAL *po,
-                              const REAL *buf, const REAL *out_diff, int diff_off, REAL *dbuf,
+                              const REAL *buf, const REAL *out_diff, int diff_ld, int diff_off, REAL *dbuf,
                               REAL *in_diff, REAL in_beta, REAL *const *corr, REAL mmt) {
   const int W = 7 * C;
   memset(dbuf, 0, sizeof(REAL) * (size_t)(T + 2) * S * W); /* :899-900 */
   /* DM rows 1S..(T+1)S <- out_diff half (:448 / :539) */
   for (long r = 0; r < (long)T * S; r++)
-    memcpy(dbuf + (r + S) * W + 6 * C, out_diff + r * 2 * C + diff_off, sizeof(REAL) * C);
+    memcpy(dbuf + (r + S) * W + 6 * C, out_diff + r * diff_ld + diff_off, sizeof(REAL) * C);
   for (int step = 0; step < T; step++) {
     int t = dir > 0 ? T - step : 1 + step;
     int tn = t + dir, tp = t - dir;
@@ -221,10 +221,27 @@ void oracle_bilstm_backward(int T, int S, int I, int C, const REAL *x, const REA
                             const REAL *buf_fw, const REAL *buf_bw, const REAL *out_diff,
                             REAL *dbuf_fw, REAL *dbuf_bw, REAL *in_diff, REAL *const *corr,
                             REAL momentum) {
-  lstm_dir_backward(+1, T, S, I, C, x, p[0], p[1], p[3], p[4], p[5], buf_fw, out_diff, 0, dbuf_fw,
+  lstm_dir_backward(+1, T, S, I, C, x, p[0], p[1], p[3], p[4], p[5], buf_fw, out_diff, 2 * C, 0, dbuf_fw,
                     in_diff, (REAL)0, corr, momentum);
-  lstm_dir_backward(-1, T, S, I, C, x, p[6], p[7], p[9], p[10], p[11], buf_bw, out_diff, C, dbuf_bw,
+  lstm_dir_backward(-1, T, S, I, C, x, p[6], p[7], p[9], p[10], p[11], buf_bw, out_diff, 2 * C, C, dbuf_bw,
                     in_diff, (REAL)1, corr + 6, momentum);
+}
+
+/* LstmParallel (uni-directional): lstm-parallel-layer.h:47-113 is line for line the forward-cell pass of
+ * the bidirectional layer (no masking at all: the length check is commented out, :107-110), the output is
+ * YM rows S..(T+1)S (:112). */
+void oracle_lstm_forward(int T, int S, int I, int C, const REAL *x, const REAL *const *p, REAL *buf, REAL *out) {
+  lstm_dir_forward(+1, T, S, I, C, NULL, x, p[0], p[1], p[2], p[3], p[4], p[5], buf);
+  const int W = 7 * C;
+  for (long r = 0; r < (long)T * S; r++) memcpy(out + r * C, buf + (r + S) * W + 6 * C, sizeof(REAL) * C);
+}
+
+/* LstmParallel::BackpropagateFnc (lstm-parallel-layer.h:115-213): BPTT of the forward cells, in_diff with beta 0,
+ * the six gradient accumulators with beta = momentum (:203-212). */
+void oracle_lstm_backward(int T, int S, int I, int C, const REAL *x, const REAL *const *p, const REAL *buf,
+                          const REAL *out_diff, REAL *dbuf, REAL *in_diff, REAL *const *corr, REAL momentum) {
+  lstm_dir_backward(+1, T, S, I, C, x, p[0], p[1], p[3], p[4], p[5], buf, out_diff, C, 0, dbuf, in_diff, (REAL)0,
+                    corr, momentum);
 }
 
 void oracle_affine_forward(int N, int D, int K, const REAL *in, const REAL *Wt, const REAL *b, REAL *out) {

@@ -50,6 +50,12 @@ void oracle_bilstm_backward(int T, int S, int I, int C, const REAL *x,
                             const REAL *out_diff, REAL *dbuf_fw, REAL *dbuf_bw, REAL *in_diff,
                             REAL *const *corr, REAL momentum);
 
+/* LstmParallel::PropagateFnc / BackpropagateFnc (lstm-parallel-layer.h:47-113, :115-213): 6 params in the
+ * order of Lstm::WriteData (lstm-layer.h:147-172): wx, wm, bias, pi, pf, po.  buf/dbuf: [(T+2)*S x 7C]. */
+void oracle_lstm_forward(int T, int S, int I, int C, const REAL *x, const REAL *const *params, REAL *buf, REAL *out);
+void oracle_lstm_backward(int T, int S, int I, int C, const REAL *x, const REAL *const *params, const REAL *buf,
+                          const REAL *out_diff, REAL *dbuf, REAL *in_diff, REAL *const *corr, REAL momentum);
+
 /* AffineTransform::PropagateFnc (affine-trans-layer.h:161-166): out = in*W^T + b */
 void oracle_affine_forward(int N, int D, int K, const REAL *in, const REAL *W, const REAL *b, REAL *out);
 /* AffineTransform::BackpropagateFnc (:168-172): in_diff = out_diff * W */

@@ -48,6 +48,8 @@
 #include "net/layer.h"
 #include "net/bilstm-layer.h"
 #include "net/bilstm-parallel-layer.h"
+#include "net/lstm-layer.h"
+#include "net/lstm-parallel-layer.h"
 #include "net/affine-trans-layer.h"
 #include "net/ctc-loss.h"
 #undef private
@@ -266,6 +268,14 @@ int main(int argc, char **argv) {
         dump_vec(pre.str() + "pi_bw.npy", bl->phole_i_c_bw_corr_);
         dump_vec(pre.str() + "pf_bw.npy", bl->phole_f_c_bw_corr_);
         dump_vec(pre.str() + "po_bw.npy", bl->phole_o_c_bw_corr_);
+      } else if (ly->GetType() == Layer::l_Lstm_Parallel || ly->GetType() == Layer::l_Lstm) {
+        Lstm *ul = dynamic_cast<Lstm*>(ly);
+        dump_mat(pre.str() + "wx.npy", ul->wei_gifo_x_corr_);
+        dump_mat(pre.str() + "wm.npy", ul->wei_gifo_m_corr_);
+        dump_vec(pre.str() + "b.npy", ul->bias_corr_);
+        dump_vec(pre.str() + "pi.npy", ul->phole_i_c_corr_);
+        dump_vec(pre.str() + "pf.npy", ul->phole_f_c_corr_);
+        dump_vec(pre.str() + "po.npy", ul->phole_o_c_corr_);
       } else if (ly->GetType() == Layer::l_Affine_Transform) {
         AffineTransform *af = dynamic_cast<AffineTransform*>(ly);
         dump_mat(pre.str() + "w.npy", af->linearity_corr_);

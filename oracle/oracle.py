@@ -131,6 +131,14 @@ class OracleNet:
                                             L.p(buf_fw), L.p(buf_bw), L.p(out))
                 self.bufs.append((buf_fw, buf_bw))
                 acts.append(out)
+            elif l.kind == "lstm":
+                Cc = l.cells
+                buf = np.zeros(((T + 2) * S, 7 * Cc), L.dtype)
+                out = np.zeros((N, Cc), L.dtype)
+                plist = [p[n] for n in l.param_names()]
+                L.lib.oracle_lstm_forward(T, S, l.in_dim, Cc, L.p(acts[-1]), L.pp(plist), L.p(buf), L.p(out))
+                self.bufs.append((buf,))
+                acts.append(out)
             elif l.kind == "affine":
                 out = np.zeros((N, l.out_dim), L.dtype)
                 L.lib.oracle_affine_forward(N, l.in_dim, l.out_dim, L.p(acts[-1]), L.p(p["w"]), L.p(p["b"]), L.p(out))
@@ -162,6 +170,14 @@ class OracleNet:
                 L.lib.oracle_affine_backward(N, l.in_dim, l.out_dim, L.p(d), L.p(p["w"]), L.p(nd))
                 L.lib.oracle_affine_grad(N, l.in_dim, l.out_dim, L.p(x), L.p(d), L.p(c["w"]), L.p(c["b"]),
                                          L.real(momentum))
+            elif l.kind == "lstm":
+                Cc = l.cells
+                nd = np.zeros((N, l.in_dim), L.dtype)
+                dbuf = np.zeros(((T + 2) * S, 7 * Cc), L.dtype)
+                plist = [p[n] for n in l.param_names()]
+                clist = [c[n] for n in l.param_names()]
+                L.lib.oracle_lstm_backward(T, S, l.in_dim, Cc, L.p(x), L.pp(plist), L.p(self.bufs[li][0]), L.p(d),
+                                           L.p(dbuf), L.p(nd), L.pp(clist), L.real(momentum))
             else:
                 Cc = l.cells
                 nd = np.zeros((N, l.in_dim), L.dtype)

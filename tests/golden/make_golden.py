@@ -34,12 +34,14 @@ from oracle import oracle  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CASES = [("tiny", 3, 5, 1e-3, 0.9), ("small", 3, 5, 1e-3, 0.9), ("c1", 0, 0, 4e-5, 0.9)]  # workload, model seed, batch seed, lr, momentum
+# the same workloads with <LstmParallel> (uni-directional) layers: "<wl>_uni_ref{cpu,gpu}.npz"
+UNI_CASES = [("tiny", 3, 5, 1e-3, 0.9), ("small", 3, 5, 1e-3, 0.9)]
 
 
-def run(kind: str, outdir: str = HERE):
-    for wl, mseed, bseed, lr, mom in CASES:
+def run(kind: str, outdir: str = HERE, uni: bool = False):
+    for wl, mseed, bseed, lr, mom in (UNI_CASES if uni else CASES):
         w = synth.WORKLOADS[wl]
-        net = synth.make_model(w, seed=mseed)
+        net = synth.make_model(w, seed=mseed, bidirectional=not uni)
         b = synth.make_batch(w, seed=bseed)
         d = tempfile.mkdtemp()
         kaldi_io.write_model(d + "/model", net)
@@ -59,7 +61,7 @@ def run(kind: str, outdir: str = HERE):
         keep["hyper"] = np.array([lr, mom], np.float64)
         if diff_in:
             keep["diff_in"] = np.load(diff_in)
-        path = os.path.join(outdir, f"{wl}_ref{kind}.npz")
+        path = os.path.join(outdir, f"{wl}{'_uni' if uni else ''}_ref{kind}.npz")
         np.savez_compressed(path, **keep)
         print("wrote", path, os.path.getsize(path), "bytes")
 
@@ -116,4 +118,7 @@ if __name__ == "__main__":
         run_adaptive(sys.argv[2] if len(sys.argv) > 2 else HERE)
         sys.exit(0)
     kind = sys.argv[1] if len(sys.argv) > 1 else "cpu"
+    if kind in ("unicpu", "unigpu"):
+        run(kind[3:], sys.argv[2] if len(sys.argv) > 2 else HERE, uni=True)
+        sys.exit(0)
     run(kind, sys.argv[2] if len(sys.argv) > 2 else HERE)

@@ -306,6 +306,88 @@ def test_train_step_vs_reference_gpucompute_live(ctx, wl, steps):
     n.close()
 
 
+# ------------------------------------------------------------------------------------ LstmParallel (uni-directional)
+@pytest.mark.parametrize("wl", ["tiny", "small", "mid"])
+def test_lstm_parallel_train_step_vs_oracle(ctx, wl):
+    """<LstmParallel> stack (lstm-parallel-layer.h): the forward cells alone, nothing masked."""
+    w, net, b = case(wl, bidirectional=False)
+    lr, mom = 1e-3, 0.9
+    n, st = _gpu_steps(ctx, net, b, lr, mom, 1)
+    on = oracle.OracleNet(net, np.float64)
+    ro = on.train_step(b, lr, mom)
+    for i in range(1, len(net.layers) + 1):
+        assert_close(f"out_l{i}", n.get(i), on.acts[i], atol=2e-5)
+    assert_close("pzx", n.get(101).ravel(), ro["pzx"], atol=0, rtol=2e-5)
+    assert_close("obj_diff", n.get(100), ro["obj_diff"], atol=diff_atol(ro["pzx"]))
+    assert_close("in_diff", n.get(102), ro["in_diff"], atol=2e-5, rtol=1e-3)
+    assert_close("corr", n.corr(), on.flat_corr(), atol=2e-3, rtol=2e-3)
+    assert_close("params", n.params(), on.flat_params(), atol=2e-6)
+    n.train_step(b.feats, b.frames, b.labels, True)
+    on.train_step(b, lr, mom)
+    assert_close("params2", n.params(), on.flat_params(), atol=5e-6)
+    n.close()
+
+
+@pytest.mark.parametrize("wl", ["tiny", "small"])
+def test_lstm_parallel_vs_reference_golden(ctx, wl):
+    path = os.path.join(GOLDEN, f"{wl}_uni_refgpu.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated")
+    g = np.load(path)
+    mseed, bseed, steps = [int(v) for v in g["meta"]]
+    lr, mom = [float(v) for v in g["hyper"]]
+    w, net, b = case(wl, mseed, bseed, bidirectional=False)
+    n, st = _gpu_steps(ctx, net, b, lr, mom, steps)
+    assert_close("pzx", n.get(101).ravel(), g["pzx"], atol=0, rtol=2e-5)
+    assert_close("obj_diff", n.get(100), g["obj_diff"], atol=diff_atol(g["pzx"]))
+    assert_close("params", n.params(), g["params_out"], atol=5e-6)
+    assert_close("corr", n.corr(), golden_arrays(g, net), atol=2e-3, rtol=2e-3)
+    for i in range(1, len(net.layers) + 1):
+        assert_close(f"out_l{i}", n.get(i), g[f"out_l{i}"], atol=2e-5)
+    n.close()
+
+
+@pytest.mark.skipif(not oracle.have_reference("gpu"), reason="oracle/_ref/ref_dump_gpu not built")
+def test_lstm_parallel_vs_reference_gpucompute_live_and_model_bytes(ctx):
+    """Live against the reference's GPU build with Adagrad, incl. the model file: the reference stores the
+    WEIGHTS a second time under <LstmAccus> (lstm-layer.h:153-163); our writer produces the same bytes layout."""
+    w, net, b = case("small", 21, 22, bidirectional=False)
+    lr, mom = 1e-3, 0.9
+    d = tempfile.mkdtemp()
+    kaldi_io.write_model(d + "/model", net)
+    kaldi_io.write_batch_file(d + "/batch.bin", b)
+    oracle.run_reference("gpu", d + "/model", d + "/batch.bin", d + "/out", lr, mom, steps=2, opt="Adagrad")
+    m2 = kaldi_io.read_model(d + "/out/model_out")
+    n = _adaptive_steps(ctx, net, b, lr, mom, "Adagrad", 2)
+    assert_close("params", n.params(), m2.flat_params(), atol=_ada_atol(lr))
+    n.write(d + "/ours_out", True)
+    ours = kaldi_io.read_model(d + "/ours_out")
+    for lo, lt in zip(ours.layers, m2.layers):
+        if lo.kind == "lstm":
+            for k in lo.param_names():      # both files: <LstmAccus> block == the weights block
+                assert np.array_equal(lo.accus[k], lo.params[k]) and np.array_equal(lt.accus[k], lt.params[k])
+    assert len(open(d + "/ours_out", "rb").read()) == len(open(d + "/out/model_out", "rb").read())
+    n.close()
+
+
+def test_lstm_nonparallel_marker_and_feedforward(ctx):
+    w, net, b = case("tiny", bidirectional=False)
+    p = model_file(net)
+    n = binding.Net(ctx, p)
+    n.write_nonparallel(p + ".np")
+    assert open(p + ".np", "rb").read() == open(p, "rb").read().replace(b"<LstmParallel>", b"<Lstm>")
+    n2 = binding.Net(ctx, p + ".np")
+    y = n.feedforward(b.feats, b.frames, True)
+    on = oracle.OracleNet(net, np.float64)
+    ref = np.log(on.forward(b.feats, b.frames))
+    s = 1
+    rows = np.arange(b.frames[s]) * b.S + s
+    assert_close("packed", y[rows], ref[rows], atol=2e-5, rtol=1e-5)
+    u = b.feats[rows]
+    assert_close("<Lstm> one sequence", n2.feedforward(u, None, True), y[rows], atol=2e-5, rtol=1e-5)
+    n.close(); n2.close()
+
+
 # ------------------------------------------------------------------------------------ Adagrad / RMSProp
 def _adaptive_steps(ctx, net, b, lr, mom, opt, steps, model_path=None, **kw):
     n = binding.Net(ctx, model_path or model_file(net))

@@ -69,6 +69,38 @@ def test_oracle_matches_reference_gpu_golden(wl):
     assert np.array_equal(g["alpha"] > -1e29, a > -1e29)
 
 
+@pytest.mark.parametrize("wl", ["tiny", "small"])
+def test_oracle_lstm_parallel_matches_reference_cpu_golden(wl):
+    """<LstmParallel> (uni-directional) stack against the reference's CPU build."""
+    g = np.load(os.path.join(GOLDEN, f"{wl}_uni_refcpu.npz"))
+    mseed, bseed, steps = [int(v) for v in g["meta"]]
+    lr, mom = [float(v) for v in g["hyper"]]
+    w, net, b = case(wl, mseed, bseed, bidirectional=False)
+    assert [l.kind for l in net.layers][:w.layers] == ["lstm"] * w.layers
+    on, r = _oracle_two_steps(net, b, lr, mom, diff_override=g["diff_in"])
+    for i in range(1, len(net.layers) + 1):
+        assert_close(f"out_l{i}", on.acts[i], g[f"out_l{i}"], atol=2e-6)
+    assert_close("in_diff", r["in_diff"], g["in_diff"], atol=1e-6, rtol=1e-4)
+    assert_close("corr", on.flat_corr(), golden_arrays(g, net), atol=2e-5, rtol=1e-4)
+    assert_close("params", on.flat_params(), g["params_out"], atol=1e-6)
+
+
+@pytest.mark.parametrize("wl", ["tiny", "small"])
+def test_oracle_lstm_parallel_matches_reference_gpu_golden(wl):
+    path = os.path.join(GOLDEN, f"{wl}_uni_refgpu.npz")
+    if not os.path.exists(path):
+        pytest.skip("GPU-minted golden not generated yet (tests/golden/make_golden.py unigpu)")
+    g = np.load(path)
+    mseed, bseed, steps = [int(v) for v in g["meta"]]
+    lr, mom = [float(v) for v in g["hyper"]]
+    w, net, b = case(wl, mseed, bseed, bidirectional=False)
+    on, r = _oracle_two_steps(net, b, lr, mom)
+    assert_close("pzx", r["pzx"], g["pzx"], atol=0, rtol=1e-5)
+    assert_close("net_out", r["net_out"], g["net_out"], atol=5e-6)
+    assert_close("corr", on.flat_corr(), golden_arrays(g, net), atol=2e-3, rtol=2e-3)
+    assert_close("params", on.flat_params(), g["params_out"], atol=5e-6)
+
+
 @pytest.mark.parametrize("opt", ["Adagrad", "RMSProp"])
 @pytest.mark.parametrize("wl", ["tiny", "small"])
 def test_oracle_adaptive_matches_reference_gpu_golden(wl, opt):

@@ -32,9 +32,9 @@ def model_file(net):
     return p
 
 
-def case(wl, mseed=3, bseed=5):
+def case(wl, mseed=3, bseed=5, bidirectional=True):
     w = synth.WORKLOADS[wl]
-    return w, synth.make_model(w, seed=mseed), synth.make_batch(w, seed=bseed)
+    return w, synth.make_model(w, seed=mseed, bidirectional=bidirectional), synth.make_batch(w, seed=bseed)
 
 
 def golden_arrays(dump, net):
