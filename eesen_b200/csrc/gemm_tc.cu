@@ -263,6 +263,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncwarp();
     const bool vec_ok = (p.ldc & 3) == 0 && (p.N & 3) == 0 && p.splits == 1 && ((uintptr_t)p.C & 15) == 0 &&
                         ((uintptr_t)p.bias & 15) == 0;
+    if (vec_ok && p.beta != 0.f) {
+      // beta != 0: the old C values are fetched 8 rows ahead of their use -- a load -> fma -> store chain per
+      // row would expose one global-memory round trip per row (32 per tile)
+      float4 bv[BN / 128 > 0 ? BN / 128 : 1];
+#pragma unroll
+      for (int q = 0; q < (BN / 128 > 0 ? BN / 128 : 1); q++) {
+        const int c = lane * 4 + q * 128;
+        bv[q] = (p.bias && c < BN && n0 + c < p.N) ? *reinterpret_cast<const float4 *>(p.bias + n0 + c)
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      for (int r0 = 0; r0 < 32; r0 += 8) {
+        float4 old[8][BN / 128 > 0 ? BN / 128 : 1];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int row = m0 + quad * 32 + r0 + j;
+#pragma unroll
+          for (int q = 0; q < (BN / 128 > 0 ? BN / 128 : 1); q++) {
+            const int c = lane * 4 + q * 128;
+            old[j][q] = (row < p.M && c < BN && n0 + c < p.N)
+                            ? *reinterpret_cast<const float4 *>(p.C + (size_t)row * p.ldc + n0 + c)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int row = m0 + quad * 32 + r0 + j;
+          if (row >= p.M) break;
+          const float *srow = stg + (size_t)(r0 + j) * EST;
+#pragma unroll
+          for (int q = 0; q < (BN / 128 > 0 ? BN / 128 : 1); q++) {
+            const int c = lane * 4 + q * 128;
+            if (c < BN && n0 + c < p.N) {
+              float4 v = *reinterpret_cast<const float4 *>(srow + c);
+              v.x = p.alpha * v.x + bv[q].x + p.beta * old[j][q].x;
+              v.y = p.alpha * v.y + bv[q].y + p.beta * old[j][q].y;
+              v.z = p.alpha * v.z + bv[q].z + p.beta * old[j][q].z;
+              v.w = p.alpha * v.w + bv[q].w + p.beta * old[j][q].w;
+              *reinterpret_cast<float4 *>(p.C + (size_t)row * p.ldc + n0 + c) = v;
+            }
+          }
+        }
+      }
+    } else
     for (int rr = 0; rr < 32; rr++) {
       const int row = m0 + quad * 32 + rr;
       if (row >= p.M) break;
@@ -365,7 +408,7 @@ bool hw_hi() {
 
 template <int BN, int TA, int TB, int NTERMS, bool HWHI>
 cudaError_t launch_tc2(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const TcArgs &p) {
-  constexpr int STAGES = NTERMS == 3 ? (BN == 128 ? 3 : 4) : (BN == 128 ? 6 : 8);
+  constexpr int STAGES = NTERMS == 3 ? (BN == 256 ? 2 : BN == 128 ? 3 : 4) : (BN == 256 ? 4 : BN == 128 ? 6 : 8);
   constexpr int STAGE_BYTES = (NTERMS == 3 ? 2 : 1) * (TC_BM * TC_BK * 4 + BN * TC_BK * 4);
   constexpr int SMEM = STAGES * STAGE_BYTES + 1024;
   auto kern = gemm_tc_kernel<BN, TA, TB, NTERMS, STAGES, HWHI>;
@@ -386,9 +429,32 @@ cudaError_t launch_tc(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap 
   return launch_tc2<BN, TA, TB, NTERMS, false>(st, ma, mb, p);
 }
 
+// Tile width.  A 128x256 tile halves the A re-reads per output element: per k-slice the three MMAs of
+// the fp32x3 mode read (128+256)*32 B from shared memory for 2x the flops of a 128x128 tile, which is
+// what the kernel is bound by.  It costs a 2-stage pipeline (96 KB per stage) and up
+// to 255 padded columns, so it is used where N fills the tiles well.  EESEN_B200_GEMM_BN=64|128|256
+// forces a width (A/B measurements, tests/bench_gemm_shapes.py).
+int pick_bn(int M, int N, int K) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char *e = getenv("EESEN_B200_GEMM_BN");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 64 || forced == 128 || forced == 256) return forced;
+  if (N <= 64) return 64;
+  if (N < 256) return 128;
+  const long w128 = ((N + 127) / 128) * 128L, w256 = ((N + 255) / 256) * 256L;
+  // padded work of the wide tile may exceed the narrow one's by at most 10 %
+  return (w256 * 10 <= w128 * 11) ? 256 : 128;
+}
+
 template <int TA, int TB>
-cudaError_t launch_tc_layout(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const TcArgs &p, int nterms) {
-  if (p.N > 64) {
+cudaError_t launch_tc_layout(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const TcArgs &p, int nterms,
+                             int bn) {
+  if (bn == 256) {
+    return nterms == 3 ? launch_tc<256, TA, TB, 3>(st, ma, mb, p) : launch_tc<256, TA, TB, 1>(st, ma, mb, p);
+  }
+  if (bn == 128) {
     return nterms == 3 ? launch_tc<128, TA, TB, 3>(st, ma, mb, p) : launch_tc<128, TA, TB, 1>(st, ma, mb, p);
   }
   return nterms == 3 ? launch_tc<64, TA, TB, 3>(st, ma, mb, p) : launch_tc<64, TA, TB, 1>(st, ma, mb, p);
@@ -405,19 +471,44 @@ bool gemm_tc_supported(int transA, int transB, int M, int N, int K, const float 
   return get_encode() != nullptr;
 }
 
+// Split-K factor for the long-K weight-gradient products (few output tiles, K = T*S rows).  The CTAs of
+// all splits should fill whole waves of the SMs: the smallest factor whose last wave is >= 92 % full
+// (e.g. 50 tiles: 6 splits = 300 CTAs = 2.03 waves ran as 3; 14 splits = 700 CTAs = 4.73 waves run as 5).
+// EESEN_B200_GEMM_SPLITS forces a factor (A/B measurements).
+int pick_splits(long tiles, int kb, int num_sms) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char *e = getenv("EESEN_B200_GEMM_SPLITS");
+    forced = e ? atoi(e) : 0;
+  }
+  int max_splits = kb / 8;
+  if (max_splits > 64) max_splits = 64;
+  if (max_splits < 1) max_splits = 1;
+  if (forced > 0) return forced < max_splits ? forced : max_splits;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= max_splits; s++) {
+    long ctas = tiles * s;
+    long waves = (ctas + num_sms - 1) / num_sms;
+    double eff = (double)ctas / (double)(waves * num_sms);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+    if (eff >= 0.92 && ctas >= 2L * num_sms) return s;
+  }
+  return best;
+}
+
 size_t gemm_tc_workspace_bytes(int M, int N, int K, int num_sms) {
-  int bn = N > 64 ? 128 : 64;
+  int bn = pick_bn(M, N, K);
   long tiles = (long)((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn);
   if (tiles >= num_sms || K < 4096) return 0;
-  int splits = (int)((2L * num_sms + tiles - 1) / tiles);
-  if (splits > 64) splits = 64;
+  int splits = pick_splits(tiles, (K + TC_BK - 1) / TC_BK, num_sms);
   return (size_t)splits * M * N * sizeof(float);
 }
 
 cudaError_t gemm_tc(cudaStream_t st, int num_sms, int transA, int transB, int M, int N, int K, float alpha,
                     const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc,
                     const float *bias, int precision, float *ws, size_t ws_bytes) {
-  const int bn = N > 64 ? 128 : 64;
+  const int bn = pick_bn(M, N, K);
   CUtensorMap ma, mb;
   bool ok;
   // A: stored [M x K] (transA=0) -> K-major box {32 k, 128 m}; stored [K x M] (transA=1) -> MN-major box {32 m, 32 k}
@@ -433,9 +524,7 @@ cudaError_t gemm_tc(cudaStream_t st, int num_sms, int transA, int transB, int M,
   p.kblocks_per_split = kb;
   long tiles = (long)((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn);
   if (tiles < num_sms && K >= 4096 && ws) {
-    int splits = (int)((2L * num_sms + tiles - 1) / tiles);
-    if (splits > kb / 16) splits = kb / 16;
-    if (splits > 64) splits = 64;
+    int splits = pick_splits(tiles, kb, num_sms);
     while (splits > 1 && (size_t)splits * M * N * sizeof(float) > ws_bytes) splits--;
     if (splits > 1) {
       int per = (kb + splits - 1) / splits;
@@ -445,9 +534,9 @@ cudaError_t gemm_tc(cudaStream_t st, int num_sms, int transA, int transB, int M,
   }
   const int nterms = precision == 0 ? 3 : 1;
   cudaError_t e;
-  if (transA == 0 && transB == 1) e = launch_tc_layout<0, 1>(st, ma, mb, p, nterms);
-  else if (transA == 0 && transB == 0) e = launch_tc_layout<0, 0>(st, ma, mb, p, nterms);
-  else if (transA == 1 && transB == 0) e = launch_tc_layout<1, 0>(st, ma, mb, p, nterms);
+  if (transA == 0 && transB == 1) e = launch_tc_layout<0, 1>(st, ma, mb, p, nterms, bn);
+  else if (transA == 0 && transB == 0) e = launch_tc_layout<0, 0>(st, ma, mb, p, nterms, bn);
+  else if (transA == 1 && transB == 0) e = launch_tc_layout<1, 0>(st, ma, mb, p, nterms, bn);
   else return cudaErrorInvalidValue;
   if (e != cudaSuccess) return e;
   if (p.splits > 1) {
