@@ -188,6 +188,9 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
         const float4 *W0 = reinterpret_cast<const float4 *>(Wsm) + ((size_t)(ct * 2 + 0) * KS) * 32 + lane;
         const float4 *W1 = reinterpret_cast<const float4 *>(Wsm) + ((size_t)(ct * 2 + 1) * KS) * 32 + lane;
         const float *brow = stg + (size_t)(ut * 8 + g) * SST + tg;
+        // (an explicit register double buffer for the next k-slice was measured slower here -- 11.3 vs
+        //  10.7 ms per C2 step -- while the same change helps the backward kernel; tests/micro/lstm_inner.cu
+        //  has the isolated loop: shared-memory side 2148 clk, tensor side 2944 clk, this schedule 3879)
 #pragma unroll 2
         for (int ks = kb; ks < ke; ks++) {
           float4 A0 = W0[(size_t)ks * 32], A1 = W1[(size_t)ks * 32];
@@ -221,29 +224,37 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
           }
         }
       }
+      EB_TICK(0, 9);
     }
 
     if (fin) {
       // acc[0] = {g(u0), g(u1), i(u0), i(u1)}, acc[1] = {f(u0), f(u1), o(u0), o(u1)} for cell `cell`
-      float sg[2], si[2], sf[2], so[2], sc[2];
+      // The two utterances of a lane are evaluated branch-free side by side (invalid slots carry zeros):
+      // their exp/rcp chains -- four dependent SFU round trips each -- interleave instead of running
+      // one after the other.
+      float sg[2], si[2], sf[2], so[2], sc[2], sm[2];
+      bool valid[2];
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        valid[e] = cell_ok && uidx[e] < s1;
+        float yg = pre[0][e] + acc[0][e];
+        float yi = pre[1][e] + acc[0][2 + e] + cprev[e] * ppi;   // :127
+        float yf = pre[2][e] + acc[1][e] + cprev[e] * ppf;       // :129
+        float gi = sigmoidf_(yi), gf = sigmoidf_(yf), gg = tanhf_(yg);   // :131-133
+        float c = gg * gi + cprev[e] * gf;                        // :136-137
+        float h = tanhf_(c);                                      // :140
+        float go = sigmoidf_(pre[3][e] + acc[1][2 + e] + c * ppo);  // :143-144
+        float m = h * go;                                         // :147
+        const bool keep = valid[e] && !(dir == 1 && t >= lenu[e]);   // :201-204 (backward cells only)
+        sg[e] = keep ? gg : 0.f; si[e] = keep ? gi : 0.f; sf[e] = keep ? gf : 0.f; so[e] = keep ? go : 0.f;
+        sc[e] = keep ? c : 0.f; sm[e] = keep ? m : 0.f;
+        cprev[e] = sc[e];
+      }
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int u = uidx[e];
-        sg[e] = si[e] = sf[e] = so[e] = sc[e] = 0.f;
-        if (cell_ok && u < s1) {
-          float yg = pre[0][e] + acc[0][e];
-          float yi = pre[1][e] + acc[0][2 + e] + cprev[e] * ppi;   // :127
-          float yf = pre[2][e] + acc[1][e] + cprev[e] * ppf;       // :129
-          float gi = sigmoidf_(yi), gf = sigmoidf_(yf), gg = tanhf_(yg);   // :131-133
-          float c = gg * gi + cprev[e] * gf;                        // :136-137
-          float h = tanhf_(c);                                      // :140
-          float go = sigmoidf_(pre[3][e] + acc[1][2 + e] + c * ppo);  // :143-144
-          float m = h * go;                                         // :147
-          if (dir == 1 && t >= lenu[e]) {                           // :201-204 (backward cells only)
-            gg = gi = gf = go = c = m = 0.f;
-          }
-          cprev[e] = c;
-          sg[e] = gg; si[e] = gi; sf[e] = gf; so[e] = go; sc[e] = c;
+        if (valid[e]) {
+          const float m = sm[e];
           // only m is on the inter-CTA critical path: publish it first (tagged word, no fence) ...
           if (step + 1 < T)
             st_tagged(xbuf + (((size_t)(step & 1) * 2 * groups + (size_t)dir * groups + group) * (8 * NUT) + (ut * 8 + 2 * tg + e)) * C + cell,
@@ -257,7 +268,7 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int u = uidx[e];
-        if (cell_ok && u < s1) {
+        if (valid[e]) {
           float *grow = a.G + ((size_t)t * S + u) * a.ldg + (size_t)dir * 4 * C + cell;
           __stcs(grow, sg[e]); __stcs(grow + (size_t)C, si[e]);
           __stcs(grow + (size_t)2 * C, sf[e]); __stcs(grow + (size_t)3 * C, so[e]);
@@ -335,6 +346,8 @@ lstm_bwd_kernel(LstmBwdArgs a, int groups, int slices, unsigned expected_per_ste
     EB_TICK(1, 1);
     if (is_item) {
       float dm = vd;
+      // (hoisting the d_m-independent factors -- tanh(c) and the gate derivatives -- above the spin-wait was
+      //  measured slower, 11.08 vs 10.78 ms per C2 step: more values live across the wait, a spill)
       if (step > 0) {
         if (ok) {
           const uint2 *pb = pbuf + ((((size_t)((step - 1) & 1) * 2 + dir) * groups + group) * slices) * pstride_slice +
@@ -390,10 +403,18 @@ lstm_bwd_kernel(LstmBwdArgs a, int groups, int slices, unsigned expected_per_ste
       float acc[4] = {0.f, 0.f, 0.f, 0.f}, accc[4] = {0.f, 0.f, 0.f, 0.f};
       const float4 *W = reinterpret_cast<const float4 *>(Wsm) + ((size_t)mt * KSB) * 32 + lane;
       const float *brow = Dsm + (size_t)(ut * 8 + g) * DST + tg;
+      // operands two k-slices ahead of the tensor instructions (see the forward kernel)
+      float4 An[2] = {W[0], W[32]};
+      float bn[2][2] = {{brow[0], brow[4]}, {brow[8], brow[12]}};
 #pragma unroll 4
       for (int ks = 0; ks < KSB; ks++) {
-        float4 A = W[(size_t)ks * 32];
-        mma_step<PREC>(acc, accc, A, brow[ks * 8], brow[ks * 8 + 4]);
+        const float4 A = An[ks & 1];
+        const float b0 = bn[ks & 1][0], b1 = bn[ks & 1][1];
+        if (ks + 2 < KSB) {
+          An[ks & 1] = W[(size_t)(ks + 2) * 32];
+          bn[ks & 1][0] = brow[(ks + 2) * 8]; bn[ks & 1][1] = brow[(ks + 2) * 8 + 4];
+        }
+        mma_step<PREC>(acc, accc, A, b0, b1);
       }
       if (PREC == 0) {
 #pragma unroll

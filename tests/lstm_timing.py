@@ -17,7 +17,7 @@ assert ctx.lib.eesen_b200_debug_lstm_timing(ctx.h, buf, 1) == 1, "not built with
 net.train_step(b.feats, b.frames, b.labels, True)
 ctx.lib.eesen_b200_debug_lstm_timing(ctx.h, buf, 0)
 steps = (b.T - 1) * w.layers
-names_f = ["poll", "barA", "stage_ld", "barB", "mma", "scratch+barD", "reduce+elementwise", "signal", "gate_stores+prefetch"]
+names_f = ["poll", "barA", "stage_ld", "barB", "mma", "scratch+barD", "elementwise+publish", "signal", "gate_stores+prefetch", "scratch reduce"]
 names_b = ["poll", "barA", "partials+elementwise", "barC", "mma+P stores", "signal"]
 print(f"forward ({prec}) cycles/step (thread 0 of CTA 0; {steps} steps):")
 tot = 0
