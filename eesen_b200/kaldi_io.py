@@ -37,6 +37,9 @@ class LayerSpec:
     # Adagrad/RMSProp accumulators (<BiLstmAccus>/<AffineAccus>, bilstm-layer.h:375-395,
     # affine-trans-layer.h:98-106); empty when the model carries none
     accus: Dict[str, np.ndarray] = field(default_factory=dict)
+    # dropout options of <BiLstmParallel> (bilstm-layer.h:62-135): forward (float), fw_step, fw_seq, recurrent (float),
+    # rec_step, rec_seq, rnndrop, nml, twiddle; missing keys = off
+    dropout: Dict[str, float] = field(default_factory=dict)
 
     @property
     def cells(self) -> int:
@@ -174,13 +177,14 @@ def write_model(path_or_file, net: NetSpec) -> None:
         if l.kind == "bilstm":
             _wtok(f, "<LearnRateCoef>"); _wf32(f, l.learn_rate_coef)
             _wtok(f, "<MaxGrad>"); _wf32(f, l.max_grad)
-            _wtok(f, "<ForwardDropoutFactor>"); _wf32(f, 0.0)
-            for t in _BILSTM_FLAGS[:4]:
-                _wtok(f, t); _wbool(f, False)
-            _wtok(f, "<RNNDrop>"); _wbool(f, False)
-            _wtok(f, "<NoMemLossDropout>"); _wbool(f, False)
-            _wtok(f, "<RecurrentDropoutFactor>"); _wf32(f, 0.0)
-            _wtok(f, "<TwiddleForward>"); _wbool(f, False)
+            d = l.dropout
+            _wtok(f, "<ForwardDropoutFactor>"); _wf32(f, float(d.get("forward", 0.0)))
+            for t, key in zip(_BILSTM_FLAGS[:4], ("fw_step", "fw_seq", "rec_step", "rec_seq")):
+                _wtok(f, t); _wbool(f, bool(d.get(key, False)))
+            _wtok(f, "<RNNDrop>"); _wbool(f, bool(d.get("rnndrop", False)))
+            _wtok(f, "<NoMemLossDropout>"); _wbool(f, bool(d.get("nml", False)))
+            _wtok(f, "<RecurrentDropoutFactor>"); _wf32(f, float(d.get("recurrent", 0.0)))
+            _wtok(f, "<TwiddleForward>"); _wbool(f, bool(d.get("twiddle", False)))
             if l.accus:
                 _wtok(f, "<BiLstmAccus>")
                 for n in l.param_names():
@@ -286,8 +290,13 @@ def read_model(path: str) -> NetSpec:
                 tk = r.tok()
                 if tk == "<LearnRateCoef>": l.learn_rate_coef = r.f32()
                 elif tk == "<MaxGrad>": l.max_grad = r.f32()
-                elif tk in ("<ForwardDropoutFactor>", "<RecurrentDropoutFactor>"): r.f32()
-                elif tk in _BILSTM_FLAGS or tk == "<TwiddleForward>": r.boolean()
+                elif tk == "<ForwardDropoutFactor>": l.dropout["forward"] = r.f32()
+                elif tk == "<RecurrentDropoutFactor>": l.dropout["recurrent"] = r.f32()
+                elif tk in _BILSTM_FLAGS or tk == "<TwiddleForward>":
+                    key = {"<ForwardTimeStepDropout>": "fw_step", "<ForwardSequenceDropout>": "fw_seq",
+                           "<RecurrentTimeStepDropout>": "rec_step", "<RecurrentSequenceDropout>": "rec_seq",
+                           "<RNNDrop>": "rnndrop", "<NoMemLossDropout>": "nml", "<TwiddleForward>": "twiddle"}[tk]
+                    l.dropout[key] = r.boolean()
                 elif tk == "<BiLstmAccus>":
                     for n in l.param_names():
                         l.accus[n] = r.mat()

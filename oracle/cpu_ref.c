@@ -87,9 +87,21 @@ static REAL tanh_ref(REAL x) {
 /* One direction of the vanilla forward pass.
  * dir=+1: bilstm-parallel-layer.h:97-150 (t=1..T, prev=t-1, no masking)
  * dir=-1: bilstm-parallel-layer.h:152-206 (t=T..1, prev=t+1, rows with t>len[s] zeroed :201-204) */
+/* drop: 0 vanilla, 1 no-mem-loss dropout, 2 RNNdrop (bilstm-parallel-layer.h:209-377).  rmask: the scaled
+ * recurrent mask of THIS direction, [T*S x C] with row (t-1)*S+s when per_step, else [S x C]; ldr = row stride. */
+static void lstm_dir_forward_drop(int dir, int T, int S, int I, int C, const int *len, const REAL *x,
+                                  const REAL *wx, const REAL *wm, const REAL *bias, const REAL *pi,
+                                  const REAL *pf, const REAL *po, REAL *buf, int drop, const REAL *rmask, int ldr,
+                                  int per_step);
 static void lstm_dir_forward(int dir, int T, int S, int I, int C, const int *len, const REAL *x,
                              const REAL *wx, const REAL *wm, const REAL *bias, const REAL *pi,
                              const REAL *pf, const REAL *po, REAL *buf) {
+  lstm_dir_forward_drop(dir, T, S, I, C, len, x, wx, wm, bias, pi, pf, po, buf, 0, NULL, 0, 0);
+}
+static void lstm_dir_forward_drop(int dir, int T, int S, int I, int C, const int *len, const REAL *x,
+                                  const REAL *wx, const REAL *wm, const REAL *bias, const REAL *pi,
+                                  const REAL *pf, const REAL *po, REAL *buf, int drop, const REAL *rmask, int ldr,
+                                  int per_step) {
   const int W = 7 * C;
   memset(buf, 0, sizeof(REAL) * (size_t)(T + 2) * S * W); /* Resize(kSetZero) :393-394 */
   /* YGIFO[1S..(T+1)S) = in * Wx^T  (:109 / :163), then += bias (:110 / :164) */
@@ -116,8 +128,11 @@ static void lstm_dir_forward(int dir, int T, int S, int I, int C, const int *len
         REAL yi = y[C + j] + cp * pi[j];     /* :127 */
         REAL yf = y[2 * C + j] + cp * pf[j]; /* :129 */
         REAL i_ = sigmoid_ref(yi), f_ = sigmoid_ref(yf), g_ = tanh_ref(y[j]); /* :131-133 */
+        REAL r_ = drop ? rmask[(long)(per_step ? (long)(t - 1) * S + s : s) * ldr + j] : (REAL)1;
         REAL c_ = g_ * i_;                                                    /* :136 */
+        if (drop == 1) c_ = r_ * c_;                                          /* :271-272 no-mem-loss */
         c_ = c_ + cp * f_;                                                    /* :137 */
+        if (drop == 2) c_ = r_ * c_;                                          /* :276-277 RNNdrop */
         REAL h_ = tanh_ref(c_);                                               /* :140 */
         REAL o_ = sigmoid_ref(y[3 * C + j] + c_ * po[j]);                     /* :143-144 */
         y[j] = g_; y[C + j] = i_; y[2 * C + j] = f_; y[3 * C + j] = o_;
@@ -144,10 +159,26 @@ void oracle_bilstm_forward(int T, int S, int I, int C, const int *len, const REA
 /* One direction of BPTT.
  * dir=+1 (forward cells): bilstm-parallel-layer.h:422-512 (t=T..1, next=t+1, prev=t-1)
  * dir=-1 (backward cells): :514-602 (t=1..T, next=t-1, prev=t+1) */
+static void lstm_dir_backward_drop(int dir, int T, int S, int I, int C, const REAL *x, const REAL *wx,
+                                   const REAL *wm, const REAL *pi, const REAL *pf, const REAL *po,
+                                   const REAL *buf, const REAL *out_diff, int diff_ld, int diff_off, REAL *dbuf,
+                                   REAL *in_diff, REAL in_beta, REAL *const *corr, REAL mmt, int drop,
+                                   const REAL *rmask, int ldr, int per_step);
 static void lstm_dir_backward(int dir, int T, int S, int I, int C, const REAL *x, const REAL *wx,
                               const REAL *wm, const REAL *pi, const REAL *pf, const REAL *po,
                               const REAL *buf, const REAL *out_diff, int diff_ld, int diff_off, REAL *dbuf,
                               REAL *in_diff, REAL in_beta, REAL *const *corr, REAL mmt) {
+  lstm_dir_backward_drop(dir, T, S, I, C, x, wx, wm, pi, pf, po, buf, out_diff, diff_ld, diff_off, dbuf, in_diff,
+                         in_beta, corr, mmt, 0, NULL, 0, 0);
+}
+/* with drop != 0: bilstm-parallel-layer.h:604-740 (forward cells) / :742-879 (backward cells).  The masked cell
+ * gradient d_c_m of the reference's side buffer d_c_mask is kept in column block 5 of dbuf (the d_h block, which
+ * nothing reads after its own step). */
+static void lstm_dir_backward_drop(int dir, int T, int S, int I, int C, const REAL *x, const REAL *wx,
+                                   const REAL *wm, const REAL *pi, const REAL *pf, const REAL *po,
+                                   const REAL *buf, const REAL *out_diff, int diff_ld, int diff_off, REAL *dbuf,
+                                   REAL *in_diff, REAL in_beta, REAL *const *corr, REAL mmt, int drop,
+                                   const REAL *rmask, int ldr, int per_step) {
   const int W = 7 * C;
   memset(dbuf, 0, sizeof(REAL) * (size_t)(T + 2) * S * W); /* :899-900 */
   /* DM rows 1S..(T+1)S <- out_diff half (:448 / :539) */
@@ -173,18 +204,25 @@ static void lstm_dir_backward(int dir, int T, int S, int I, int C, const REAL *x
         REAL dO = dm * h;                      /* :477 */
         dO = dO * o * ((REAL)1 - o);           /* :478 DiffSigmoid: e*y*(1-y) */
         REAL dc = dh;                          /* :481 (d_c starts at 0) */
-        dc += ddn[4 * C + j] * yyn[2 * C + j]; /* :482 */
+        if (drop == 0) dc += ddn[4 * C + j] * yyn[2 * C + j]; /* :482 */
         dc += ddn[C + j] * pi[j];              /* :483 */
         dc += ddn[2 * C + j] * pf[j];          /* :484 */
         dc += dO * po[j];                      /* :485 */
-        REAL df = dc * yyp[4 * C + j];         /* :488 */
+        REAL dcm = dc;
+        if (drop) {
+          REAL r_ = rmask[(long)(per_step ? (long)(t - 1) * S + s : s) * ldr + j];
+          if (drop == 2) dc += ddn[5 * C + j] * yyn[2 * C + j];   /* :703-706 RNNdrop: carry the MASKED d_c */
+          if (drop == 1) dc += ddn[4 * C + j] * yyn[2 * C + j];   /* :708-711 no-mem-loss: carry the plain d_c */
+          dcm = dc * r_;
+        }
+        REAL df = (drop == 2 ? dcm : dc) * yyp[4 * C + j];         /* :488 / :715-719 */
         df = df * f * ((REAL)1 - f);           /* :489 */
-        REAL di = dc * g;                      /* :492 */
+        REAL di = dcm * g;                     /* :492 / :723 */
         di = di * i_ * ((REAL)1 - i_);         /* :493 */
-        REAL dg = dc * i_;                     /* :496 */
+        REAL dg = dcm * i_;                    /* :496 / :727 */
         dg = dg * ((REAL)1 - g * g);           /* :497 */
         dd[j] = dg; dd[C + j] = di; dd[2 * C + j] = df; dd[3 * C + j] = dO;
-        dd[4 * C + j] = dc; dd[5 * C + j] = dh;
+        dd[4 * C + j] = dc; dd[5 * C + j] = drop ? dcm : dh;
       }
     }
   }
@@ -225,6 +263,31 @@ void oracle_bilstm_backward(int T, int S, int I, int C, const REAL *x, const REA
                     in_diff, (REAL)0, corr, momentum);
   lstm_dir_backward(-1, T, S, I, C, x, p[6], p[7], p[9], p[10], p[11], buf_bw, out_diff, 2 * C, C, dbuf_bw,
                     in_diff, (REAL)1, corr + 6, momentum);
+}
+
+/* BiLstmParallel with recurrent dropout (bilstm-parallel-layer.h:209-377 forward, :604-879 backward): masks
+ * rmask_fw / rmask_bw are the SCALED masks (0 or 1/(1-p)) the reference draws in InitializeRecurrentMasks
+ * (:63-94), [T*S x C] (row (t-1)*S+s) for step dropout, [S x C] for sequence dropout. */
+void oracle_bilstm_forward_drop(int T, int S, int I, int C, const int *len, const REAL *x, const REAL *const *p,
+                                REAL *buf_fw, REAL *buf_bw, REAL *out, int drop, const REAL *rmask_fw,
+                                const REAL *rmask_bw, int per_step) {
+  lstm_dir_forward_drop(+1, T, S, I, C, len, x, p[0], p[1], p[2], p[3], p[4], p[5], buf_fw, drop, rmask_fw, C, per_step);
+  lstm_dir_forward_drop(-1, T, S, I, C, len, x, p[6], p[7], p[8], p[9], p[10], p[11], buf_bw, drop, rmask_bw, C, per_step);
+  const int W = 7 * C;
+  for (long r = 0; r < (long)T * S; r++) {
+    memcpy(out + r * 2 * C, buf_fw + (r + S) * W + 6 * C, sizeof(REAL) * C);
+    memcpy(out + r * 2 * C + C, buf_bw + (r + S) * W + 6 * C, sizeof(REAL) * C);
+  }
+}
+
+void oracle_bilstm_backward_drop(int T, int S, int I, int C, const REAL *x, const REAL *const *p,
+                                 const REAL *buf_fw, const REAL *buf_bw, const REAL *out_diff, REAL *dbuf_fw,
+                                 REAL *dbuf_bw, REAL *in_diff, REAL *const *corr, REAL momentum, int drop,
+                                 const REAL *rmask_fw, const REAL *rmask_bw, int per_step) {
+  lstm_dir_backward_drop(+1, T, S, I, C, x, p[0], p[1], p[3], p[4], p[5], buf_fw, out_diff, 2 * C, 0, dbuf_fw,
+                         in_diff, (REAL)0, corr, momentum, drop, rmask_fw, C, per_step);
+  lstm_dir_backward_drop(-1, T, S, I, C, x, p[6], p[7], p[9], p[10], p[11], buf_bw, out_diff, 2 * C, C, dbuf_bw,
+                         in_diff, (REAL)1, corr + 6, momentum, drop, rmask_bw, C, per_step);
 }
 
 /* LstmParallel (uni-directional): lstm-parallel-layer.h:47-113 is line for line the forward-cell pass of

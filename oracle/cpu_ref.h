@@ -50,6 +50,18 @@ void oracle_bilstm_backward(int T, int S, int I, int C, const REAL *x,
                             const REAL *out_diff, REAL *dbuf_fw, REAL *dbuf_bw, REAL *in_diff,
                             REAL *const *corr, REAL momentum);
 
+/* The recurrent-dropout passes of BiLstmParallel (bilstm-parallel-layer.h:209-377, :604-879).  drop: 1 =
+ * no-mem-loss dropout (mask on g*i), 2 = RNNdrop (mask on the whole cell).  rmask_*: scaled masks of one
+ * direction, [T*S x C] if per_step (row (t-1)*S+s) else [S x C].  Forward dropout (mask on the layer OUTPUT,
+ * :409-416, and on out_diff, :891-895) is an elementwise product applied by the caller. */
+void oracle_bilstm_forward_drop(int T, int S, int I, int C, const int *len, const REAL *x, const REAL *const *params,
+                                REAL *buf_fw, REAL *buf_bw, REAL *out, int drop, const REAL *rmask_fw,
+                                const REAL *rmask_bw, int per_step);
+void oracle_bilstm_backward_drop(int T, int S, int I, int C, const REAL *x, const REAL *const *params,
+                                 const REAL *buf_fw, const REAL *buf_bw, const REAL *out_diff, REAL *dbuf_fw,
+                                 REAL *dbuf_bw, REAL *in_diff, REAL *const *corr, REAL momentum, int drop,
+                                 const REAL *rmask_fw, const REAL *rmask_bw, int per_step);
+
 /* LstmParallel::PropagateFnc / BackpropagateFnc (lstm-parallel-layer.h:47-113, :115-213): 6 params in the
  * order of Lstm::WriteData (lstm-layer.h:147-172): wx, wm, bias, pi, pf, po.  buf/dbuf: [(T+2)*S x 7C]. */
 void oracle_lstm_forward(int T, int S, int I, int C, const REAL *x, const REAL *const *params, REAL *buf, REAL *out);

@@ -216,6 +216,18 @@ int main(int argc, char **argv) {
             std::ostringstream p; p << outdir << "/out_l" << i << ".npy";
             dump_mat(p.str(), net.propagate_buf_[i]);
           }
+        // dropout masks drawn by this Propagate (scaled 0 | 1/(1-p)); shapes as the reference holds them:
+        // forward [T*S x 2C]; recurrent fw/bw [(T+2)*S x C] (step) or [S x C] (sequence)
+        for (int l = 0; l < net.NumLayers(); l++) {
+          if (net.layers_[l]->GetType() != Layer::l_BiLstm_Parallel) continue;
+          BiLstm *bl = dynamic_cast<BiLstm*>(net.layers_[l]);
+          std::ostringstream pre; pre << outdir << "/mask_" << l << "_";
+          if (bl->forward_drop_mask_.NumRows() > 0) dump_mat(pre.str() + "fwd.npy", bl->forward_drop_mask_);
+          if (bl->recurrent_drop_mask_fw_.NumRows() > 0) {
+            dump_mat(pre.str() + "rec_fw.npy", bl->recurrent_drop_mask_fw_);
+            dump_mat(pre.str() + "rec_bw.npy", bl->recurrent_drop_mask_bw_);
+          }
+        }
         dump_mat(outdir + "/net_out.npy", net_out);
         dump_mat(outdir + "/obj_diff.npy", obj_diff);
         if (ctc.alpha_.NumRows() > 0) {

@@ -110,7 +110,14 @@ class OracleNet:
         self.algorithm, self.adagrad_epsilon = algorithm, adagrad_epsilon
         self.rmsprop_rho, self.rmsprop_one_minus_rho = rmsprop_rho, rmsprop_one_minus_rho
 
-    def forward(self, feats, frames):
+    # ---- dropout (bilstm-parallel-layer.h:46-94, 209-377, 604-879).  masks: one dict per layer (or None):
+    #   "fmask": scaled forward mask [T*S x 2C] applied to the layer OUTPUT and to out_diff (:409-416, :891-895)
+    #   "rmask": scaled recurrent mask [T*S x 2C] (step dropout, row (t-1)*S+s) or [S x 2C] (sequence dropout),
+    #            forward cells in columns [0,C), backward cells in [C,2C) (:85-88)
+    # The reference draws them from a thread-local mt19937 seeded by std::random_device (kaldi-math.h:107-131):
+    # not reproducible by design, so parity is "same masks -> same numbers"; the masks are always inputs here.
+    def forward(self, feats, frames, masks=None):
+        self.masks = masks
         L = self.L
         S = len(frames)
         frames = np.ascontiguousarray(frames, np.int32)
@@ -127,9 +134,22 @@ class OracleNet:
                 buf_bw = np.zeros(((T + 2) * S, 7 * Cc), L.dtype)
                 out = np.zeros((N, 2 * Cc), L.dtype)
                 plist = [p[n] for n in l.param_names()]
-                L.lib.oracle_bilstm_forward(T, S, l.in_dim, Cc, L.p(frames), L.p(acts[-1]), L.pp(plist),
-                                            L.p(buf_fw), L.p(buf_bw), L.p(out))
-                self.bufs.append((buf_fw, buf_bw))
+                mk = masks[li] if masks else None
+                drop = 0
+                if mk is not None and mk.get("rmask") is not None:
+                    drop = 2 if l.dropout.get("rnndrop") else 1
+                    rm = L.arr(mk["rmask"])
+                    rfw, rbw = np.ascontiguousarray(rm[:, :Cc]), np.ascontiguousarray(rm[:, Cc:])
+                    per_step = int(rm.shape[0] == N)
+                    L.lib.oracle_bilstm_forward_drop(T, S, l.in_dim, Cc, L.p(frames), L.p(acts[-1]), L.pp(plist),
+                                                     L.p(buf_fw), L.p(buf_bw), L.p(out), drop, L.p(rfw), L.p(rbw), per_step)
+                    self.bufs.append((buf_fw, buf_bw, drop, rfw, rbw, per_step))
+                else:
+                    L.lib.oracle_bilstm_forward(T, S, l.in_dim, Cc, L.p(frames), L.p(acts[-1]), L.pp(plist),
+                                                L.p(buf_fw), L.p(buf_bw), L.p(out))
+                    self.bufs.append((buf_fw, buf_bw, 0, None, None, 0))
+                if mk is not None and mk.get("fmask") is not None:
+                    out = out * L.arr(mk["fmask"])
                 acts.append(out)
             elif l.kind == "lstm":
                 Cc = l.cells
@@ -185,9 +205,17 @@ class OracleNet:
                 dbw = np.zeros(((T + 2) * S, 7 * Cc), L.dtype)
                 plist = [p[n] for n in l.param_names()]
                 clist = [c[n] for n in l.param_names()]
-                bf, bb = self.bufs[li]
-                L.lib.oracle_bilstm_backward(T, S, l.in_dim, Cc, L.p(x), L.pp(plist), L.p(bf), L.p(bb), L.p(d),
-                                             L.p(dfw), L.p(dbw), L.p(nd), L.pp(clist), L.real(momentum))
+                bf, bb, drop, rfw, rbw, per_step = self.bufs[li]
+                mk = self.masks[li] if getattr(self, "masks", None) else None
+                if mk is not None and mk.get("fmask") is not None:
+                    d = np.ascontiguousarray(d * L.arr(mk["fmask"]))
+                if drop:
+                    L.lib.oracle_bilstm_backward_drop(T, S, l.in_dim, Cc, L.p(x), L.pp(plist), L.p(bf), L.p(bb), L.p(d),
+                                                      L.p(dfw), L.p(dbw), L.p(nd), L.pp(clist), L.real(momentum), drop,
+                                                      L.p(rfw), L.p(rbw), per_step)
+                else:
+                    L.lib.oracle_bilstm_backward(T, S, l.in_dim, Cc, L.p(x), L.pp(plist), L.p(bf), L.p(bb), L.p(d),
+                                                 L.p(dfw), L.p(dbw), L.p(nd), L.pp(clist), L.real(momentum))
                 self.last_dbuf = (dfw, dbw)
             # TrainableLayer::Update right after the layer's Backpropagate (net.cc:98-105)
             for n in l.param_names():
@@ -204,8 +232,8 @@ class OracleNet:
             d = nd
         return d
 
-    def train_step(self, batch, lr: float, momentum: float, diff_override: Optional[np.ndarray] = None):
-        y = self.forward(batch.feats, batch.frames)
+    def train_step(self, batch, lr: float, momentum: float, diff_override: Optional[np.ndarray] = None, masks=None):
+        y = self.forward(batch.feats, batch.frames, masks)
         pzx, diff, _, _ = ctc_eval(y, batch.frames, batch.labels, batch.S, self.L.dtype)
         if diff_override is not None:
             diff = self.L.arr(diff_override)

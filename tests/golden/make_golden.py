@@ -110,7 +110,43 @@ def run_infer(outdir: str = HERE):
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def run_dropout(outdir: str = HERE):
+    """<wl>_drop_<variant>_refcpu.npz: one training step of the reference's CPU build with each dropout variant of
+    BiLstmParallel; the fixture stores the masks the reference drew (they are random_device-seeded), the obj_diff
+    that drove the backward pass and the reference's outputs."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_dropout_cpu import VARIANTS, drop_case, masks_from_dump
+    for wl, variants in (("tiny", sorted(VARIANTS)), ("small", ["fwd+nml", "rnndropstep"])):
+        for variant in variants:
+            w, net, b = drop_case(wl, variant)
+            lr, mom = 1e-3, 0.9
+            d = tempfile.mkdtemp()
+            kaldi_io.write_model(d + "/model", net)
+            kaldi_io.write_batch_file(d + "/batch.bin", b)
+            diff = (np.random.default_rng(1).standard_normal((b.feats.shape[0], w.classes)) * 0.1).astype(np.float32)
+            rows_pad = np.concatenate([np.arange(b.frames[s], b.T) * b.S + s for s in range(b.S)]).astype(np.int64)
+            diff[rows_pad] = 0.0
+            np.save(d + "/diff.npy", diff)
+            oracle.run_reference("cpu", d + "/model", d + "/batch.bin", d + "/out", lr, mom, steps=1, diff_in=d + "/diff.npy")
+            dump = oracle.load_dump(d + "/out")
+            m2 = kaldi_io.read_model(d + "/out/model_out")
+            keep = {k: v for k, v in dump.items() if k.startswith(("grad_", "in_diff")) or k == f"out_l{len(net.layers)}"
+                    or k == f"out_l{w.layers}"}
+            for li, m in enumerate(masks_from_dump(dump, net, b)):
+                if m:
+                    for k, v in m.items():
+                        keep[f"{k}_{li}"] = (v != 0).astype(np.uint8)    # 0/1 pattern; the scale 1/(1-p) is in the model
+            keep.update(params_out=m2.flat_params(), diff_in=diff, hyper=np.array([lr, mom], np.float64),
+                        meta=np.array([3, 5, 1], np.int64))
+            path = os.path.join(outdir, f"{wl}_drop_{variant.replace('+', '_')}_refcpu.npz")
+            np.savez_compressed(path, **keep)
+            print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "dropcpu":
+        run_dropout(sys.argv[2] if len(sys.argv) > 2 else HERE)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "infer":
         run_infer(sys.argv[2] if len(sys.argv) > 2 else HERE)
         sys.exit(0)
