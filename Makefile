@@ -19,7 +19,7 @@ CC_SRCS := base net abi_ops abi_net
 CU_OBJS := $(patsubst %,$(OBJDIR)/%.cu.o,$(CU_SRCS))
 CC_OBJS := $(patsubst %,$(OBJDIR)/%.cc.o,$(CC_SRCS))
 
-BINS    := train-ctc-parallel net-output-extract format-to-nonparallel
+BINS    := train-ctc-parallel net-output-extract format-to-nonparallel net-change-model
 
 all: $(LIBDIR)/libeesen_b200.so $(patsubst %,$(BINDIR)/%,$(BINS))
 

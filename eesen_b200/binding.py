@@ -251,6 +251,25 @@ class Net:
     def write_nonparallel(self, path: str, binary: bool = True):
         self.ctx.check(self.lib.eesen_b200_net_write_nonparallel(self.h, path.encode(), int(binary)), "net_write_nonparallel")
 
+    def change_dropout(self, forward=0.0, fw_step=False, fw_seq=False, rnndrop=False, nml=False, recurrent=0.0,
+                       rec_step=False, rec_seq=False, twiddle=False):
+        """Net::ChangeDropoutParameters (the options net-change-model writes into the model)."""
+        self.ctx.check(self.lib.eesen_b200_net_change_dropout(
+            self.h, C.c_float(forward), int(fw_step), int(fw_seq), int(rnndrop), int(nml), C.c_float(recurrent),
+            int(rec_step), int(rec_seq), int(twiddle)), "net_change_dropout")
+
+    def set_dropout_seed(self, seed: int):
+        self.ctx.check(self.lib.eesen_b200_net_set_dropout_seed(self.h, C.c_ulonglong(seed)), "net_set_dropout_seed")
+
+    def set_dropout_masks(self, layer: int, fmask: Optional[np.ndarray] = None, rmask: Optional[np.ndarray] = None):
+        """Inject explicit scaled masks for one BiLSTM layer (None clears); kept until replaced."""
+        f = np.ascontiguousarray(fmask, np.float32) if fmask is not None else None
+        r = np.ascontiguousarray(rmask, np.float32) if rmask is not None else None
+        self.ctx.check(self.lib.eesen_b200_net_set_dropout_masks(
+            self.h, int(layer), f.ctypes.data_as(C.c_void_p) if f is not None else None, f.shape[0] if f is not None else 0,
+            r.ctypes.data_as(C.c_void_p) if r is not None else None, r.shape[0] if r is not None else 0),
+            "net_set_dropout_masks")
+
     def write(self, path: str, binary: bool = True):
         self.ctx.check(self.lib.eesen_b200_net_write(self.h, path.encode(), int(binary)), "net_write")
 

@@ -36,6 +36,10 @@ struct LstmFwdArgs {
   LstmDirParams p[2];
   void *xbuf;            // [2 parity][2 dir][groups][8*NUT][C] tagged 8-byte exchange words (zeroed per launch)
   int precision;         // 0 = 3xTF32, 1 = TF32
+  // recurrent dropout (bilstm-parallel-layer.h:209-377): 0 none, 1 no-mem-loss (mask on g*i), 2 RNNdrop (mask on c)
+  int drop = 0;
+  const float *rmask = nullptr;  // scaled mask (0 | 1/(1-p)); dir d at col d*C; row t*S+s if per_step else s
+  int ldr = 0, rmask_per_step = 0;
 };
 struct LstmBwdArgs {
   int T, S, C;
@@ -48,6 +52,9 @@ struct LstmBwdArgs {
   float *pbuf;                  // [2 parity][2 dir][groups][slices][8*NUT][C] tagged partial d_m words
   float *gsum;                  // [2 dir][groups][7][C] per-group sums: db_g,db_i,db_f,db_o,dpi,dpf,dpo
   int precision;
+  int drop = 0;                 // as LstmFwdArgs (:604-879)
+  const float *rmask = nullptr;
+  int ldr = 0, rmask_per_step = 0;
 };
 struct LstmPlan {
   int nut, nct, ksplit;  // utterance tiles / cell tiles per CTA, K-split warps (fwd)
@@ -91,6 +98,11 @@ cudaError_t sgd_momentum_clip(cudaStream_t st, int num_sms, float *w, float *cor
 cudaError_t optimizer_update(cudaStream_t st, int num_sms, int mode, float *w, float *corr, float *accu,
                              const float *grad, float momentum, float eps, float rho, float one_minus_rho,
                              const SgdSegment *d_segs, int nseg, long total);
+cudaError_t mul_elements(cudaStream_t st, int num_sms, int N, int cols, const float *a, int lda, const float *b, int ldb,
+                         float *out, int ldo);
+// scaled Bernoulli mask 0 | 1/(1-p) from a counter-based generator (per_col: one draw per column for all rows)
+cudaError_t dropout_mask(cudaStream_t st, int num_sms, int rows, int cols, float *mask, int ld, float p, int per_col,
+                         unsigned long long seed, unsigned long long stream);
 cudaError_t col_sum(cudaStream_t st, int num_sms, int N, int K, const float *x, int ld, float *out, float *ws);
 size_t col_sum_ws_floats(int K, int num_sms);
 

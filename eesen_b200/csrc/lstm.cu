@@ -81,7 +81,7 @@ __device__ __forceinline__ void mma_step(float (&acc)[4], float (&accc)[4], cons
 }
 
 // ------------------------------------------------------------------------------------ forward
-template <int NUT, int NCT, int KSPLIT, int PREC>
+template <int NUT, int NCT, int KSPLIT, int PREC, int DROP>
 __global__ void __launch_bounds__(32 * NUT * NCT * KSPLIT, 1)
 lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
   constexpr int NTASK = NUT * NCT;
@@ -121,6 +121,7 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
   // finalising-warp state
   float cprev[2] = {0.f, 0.f};
   float pre[4][2];
+  float rmk[2] = {1.f, 1.f};   // recurrent dropout mask of this lane's (cell, utterance) pairs at the current step
   float ppi = 0.f, ppf = 0.f, ppo = 0.f;
   int lenu[2] = {0, 0};
   int uidx[2];
@@ -142,6 +143,10 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
       const float *row = a.G + ((size_t)t * S + (ok ? uidx[e] : 0)) * a.ldg + (size_t)dir * 4 * C + (ok ? cell : 0);
 #pragma unroll
       for (int q = 0; q < 4; q++) pre[q][e] = ok ? __ldcs(row + (size_t)q * C) : 0.f;
+      if (DROP != 0)
+        rmk[e] = ok ? __ldg(a.rmask + (size_t)(a.rmask_per_step ? (size_t)t * S + uidx[e] : (size_t)uidx[e]) * a.ldr +
+                            (size_t)dir * C + cell)
+                    : 0.f;
     }
   };
   if (fin) load_pre(dir == 0 ? 0 : T - 1);
@@ -241,7 +246,14 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
         float yi = pre[1][e] + acc[0][2 + e] + cprev[e] * ppi;   // :127
         float yf = pre[2][e] + acc[1][e] + cprev[e] * ppf;       // :129
         float gi = sigmoidf_(yi), gf = sigmoidf_(yf), gg = tanhf_(yg);   // :131-133
-        float c = gg * gi + cprev[e] * gf;                        // :136-137
+        float c;
+        if (DROP == 0) {
+          c = gg * gi + cprev[e] * gf;                            // :136-137
+        } else if (DROP == 1) {
+          c = rmk[e] * (gg * gi) + cprev[e] * gf;                 // :267-274 no-mem-loss: only the new content is dropped
+        } else {
+          c = rmk[e] * (gg * gi + cprev[e] * gf);                 // :276-277 RNNdrop: the whole cell
+        }
         float h = tanhf_(c);                                      // :140
         float go = sigmoidf_(pre[3][e] + acc[1][2 + e] + c * ppo);  // :143-144
         float m = h * go;                                         // :147
@@ -282,7 +294,7 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
 }
 
 // ------------------------------------------------------------------------------------ backward
-template <int NUT, int NCT, int NWARPS, int PREC>
+template <int NUT, int NCT, int NWARPS, int PREC, int DROP>
 __global__ void __launch_bounds__(32 * NWARPS, 1)
 lstm_bwd_kernel(LstmBwdArgs a, int groups, int slices, unsigned expected_per_step) {
   constexpr int NTHREADS = 32 * NWARPS;
@@ -323,6 +335,7 @@ lstm_bwd_kernel(LstmBwdArgs a, int groups, int slices, unsigned expected_per_ste
   float ppi = 0.f, ppf = 0.f, ppo = 0.f;
   if (ok) { ppi = P.pi[cell]; ppf = P.pf[cell]; ppo = P.po[cell]; }
   float dc_next = 0.f, f_next = 0.f, di_next = 0.f, df_next = 0.f;
+  float dcm_next = 0.f, vr = 1.f;   // recurrent dropout: masked cell gradient of the next step, this step's mask
   float sb[4] = {0.f, 0.f, 0.f, 0.f}, spi = 0.f, spf = 0.f, spo = 0.f;
   float vg = 0.f, vi = 0.f, vf = 0.f, vo = 0.f, vc = 0.f, vcp = 0.f, vd = 0.f;
   const int tstep = dir == 0 ? -1 : 1;  // time order of the BPTT sweep
@@ -334,6 +347,8 @@ lstm_bwd_kernel(LstmBwdArgs a, int groups, int slices, unsigned expected_per_ste
     int tp = t + tstep;  // the step the forward pass took before t, i.e. c_{prev}
     vcp = (tp >= 0 && tp < T) ? __ldcs(a.cell + ((size_t)tp * S + u) * a.ldc + (size_t)dir * C + cell) : 0.f;
     vd = __ldcs(a.dout + ((size_t)t * S + u) * a.ldd + (size_t)dir * C + cell);
+    if (DROP != 0)
+      vr = __ldg(a.rmask + (size_t)(a.rmask_per_step ? (size_t)t * S + u : (size_t)u) * a.ldr + (size_t)dir * C + cell);
   };
   prefetch(dir == 0 ? T - 1 : 0);
   __syncthreads();
@@ -379,11 +394,19 @@ lstm_bwd_kernel(LstmBwdArgs a, int groups, int slices, unsigned expected_per_ste
         float h = tanhf_(vc);
         float dh = dm * vo * (1.f - h * h);                               // :473-474
         dO = dm * h * vo * (1.f - vo);                                    // :477-478
-        float dc = dh + dc_next * f_next + di_next * ppi + df_next * ppf + dO * ppo;   // :481-485
-        df = dc * vcp * vf * (1.f - vf);                                  // :488-489
-        di = dc * vg * vi * (1.f - vi);                                   // :492-493
-        dg = dc * vi * (1.f - vg * vg);                                   // :496-497
-        dc_next = dc; f_next = vf; di_next = di; df_next = df;
+        float dc, dcm;
+        if (DROP == 0) {
+          dc = dh + dc_next * f_next + di_next * ppi + df_next * ppf + dO * ppo;   // :481-485
+          dcm = dc;
+        } else {
+          // :697-711: RNNdrop carries the MASKED cell gradient through the forget gate, no-mem-loss the plain one
+          dc = dh + di_next * ppi + df_next * ppf + dO * ppo + (DROP == 2 ? dcm_next : dc_next) * f_next;
+          dcm = dc * vr;
+        }
+        df = (DROP == 2 ? dcm : dc) * vcp * vf * (1.f - vf);              // :488-489 / :715-719
+        di = dcm * vg * vi * (1.f - vi);                                  // :492-493 / :723
+        dg = dcm * vi * (1.f - vg * vg);                                  // :496-497 / :727
+        dc_next = dc; dcm_next = dcm; f_next = vf; di_next = di; df_next = df;
         float *drow = a.DG + ((size_t)t * S + u) * a.lddg + (size_t)dir * 4 * C + cell;
         drow[0] = dg; drow[(size_t)C] = di; drow[(size_t)2 * C] = df; drow[(size_t)3 * C] = dO;
         sb[0] += dg; sb[1] += di; sb[2] += df; sb[3] += dO;               // :507 / :598
@@ -487,8 +510,13 @@ cudaError_t launch_fwd(cudaStream_t st, const LstmPlan &pl, const LstmFwdArgs &a
   int groups = pl.groups;
   LstmFwdArgs args = a;
   void *kargs[] = {&args, &groups, &expected};
-  const void *fn = a.precision == 0 ? (const void *)lstm_fwd_kernel<NUT, NCT, KSPLIT, 0>
-                                    : (const void *)lstm_fwd_kernel<NUT, NCT, KSPLIT, 1>;
+  const void *fn;
+  if (a.drop == 0)
+    fn = a.precision == 0 ? (const void *)lstm_fwd_kernel<NUT, NCT, KSPLIT, 0, 0> : (const void *)lstm_fwd_kernel<NUT, NCT, KSPLIT, 1, 0>;
+  else if (a.drop == 1)
+    fn = a.precision == 0 ? (const void *)lstm_fwd_kernel<NUT, NCT, KSPLIT, 0, 1> : (const void *)lstm_fwd_kernel<NUT, NCT, KSPLIT, 1, 1>;
+  else
+    fn = a.precision == 0 ? (const void *)lstm_fwd_kernel<NUT, NCT, KSPLIT, 0, 2> : (const void *)lstm_fwd_kernel<NUT, NCT, KSPLIT, 1, 2>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_fwd);
   if (e != cudaSuccess) return e;
   return cudaLaunchCooperativeKernel(fn, grid, block, kargs, pl.smem_fwd, st);
@@ -502,8 +530,13 @@ cudaError_t launch_bwd(cudaStream_t st, const LstmPlan &pl, const LstmBwdArgs &a
   int groups = pl.groups, slices = pl.slices;
   LstmBwdArgs args = a;
   void *kargs[] = {&args, &groups, &slices, &expected};
-  const void *fn = a.precision == 0 ? (const void *)lstm_bwd_kernel<NUT, NCT, NWARPS, 0>
-                                    : (const void *)lstm_bwd_kernel<NUT, NCT, NWARPS, 1>;
+  const void *fn;
+  if (a.drop == 0)
+    fn = a.precision == 0 ? (const void *)lstm_bwd_kernel<NUT, NCT, NWARPS, 0, 0> : (const void *)lstm_bwd_kernel<NUT, NCT, NWARPS, 1, 0>;
+  else if (a.drop == 1)
+    fn = a.precision == 0 ? (const void *)lstm_bwd_kernel<NUT, NCT, NWARPS, 0, 1> : (const void *)lstm_bwd_kernel<NUT, NCT, NWARPS, 1, 1>;
+  else
+    fn = a.precision == 0 ? (const void *)lstm_bwd_kernel<NUT, NCT, NWARPS, 0, 2> : (const void *)lstm_bwd_kernel<NUT, NCT, NWARPS, 1, 2>;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bwd);
   if (e != cudaSuccess) return e;
   return cudaLaunchCooperativeKernel(fn, grid, block, kargs, pl.smem_bwd, st);
@@ -571,6 +604,7 @@ LstmPlan lstm_plan(int S, int C, int num_sms, size_t max_smem, int ndir) {
 
 cudaError_t lstm_forward(cudaStream_t st, const LstmPlan &plan, const LstmFwdArgs &a) {
   if (!plan.valid) return cudaErrorInvalidConfiguration;
+  if (a.drop < 0 || a.drop > 2 || (a.drop != 0 && !a.rmask)) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(a.xbuf, 0, plan.xbuf_bytes, st);
   if (e != cudaSuccess) return e;
   EB_DISPATCH(launch_fwd, st, plan, a);
@@ -578,6 +612,7 @@ cudaError_t lstm_forward(cudaStream_t st, const LstmPlan &plan, const LstmFwdArg
 
 cudaError_t lstm_backward(cudaStream_t st, const LstmPlan &plan, const LstmBwdArgs &a) {
   if (!plan.valid) return cudaErrorInvalidConfiguration;
+  if (a.drop < 0 || a.drop > 2 || (a.drop != 0 && !a.rmask)) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(a.pbuf, 0, plan.pbuf_floats * sizeof(float), st);
   if (e != cudaSuccess) return e;
   EB_DISPATCH(launch_bwd, st, plan, a);

@@ -92,6 +92,42 @@ __global__ void sgd_kernel(float *__restrict__ w, float *__restrict__ corr, cons
   }
 }
 
+// out = a (.) b elementwise over [N x cols] (CuMatrixBase::MulElements: the forward-dropout mask on the layer output
+// and on out_diff, bilstm-parallel-layer.h:414, :893)
+__global__ void mul_elements_kernel(long n, int cols, const float *__restrict__ a, int lda, const float *__restrict__ b,
+                                    int ldb, float *__restrict__ out, int ldo) {
+  long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    long r = i / cols;
+    int c = (int)(i - r * cols);
+    out[r * ldo + c] = a[r * lda + c] * b[r * ldb + c];
+  }
+}
+
+// Counter-based uniform: splitmix64 finaliser of (seed, stream, index) -> 24 random bits -> u in (0,1).
+__device__ __forceinline__ float uniform01(unsigned long long seed, unsigned long long stream, unsigned long long idx) {
+  unsigned long long z = seed + 0x9e3779b97f4a7c15ULL * (idx + 1ULL) + 0xbf58476d1ce4e5b9ULL * (stream + 1ULL);
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  z = z ^ (z >> 31);
+  return ((float)(unsigned)(z >> 40) + 0.5f) * (1.0f / 16777216.0f);
+}
+
+// Scaled dropout mask, on the device (the reference draws it on the CPU and copies T*S x 2C floats per layer and
+// step to the GPU, bilstm-parallel-layer.h:46-94): mask = Heaviside(u - p) / (1 - p).  per_col = 1: one draw per
+// column, repeated in every row (MatrixBase::SetRandUniformCol, cpucompute/matrix.cc:952-965).
+__global__ void dropout_mask_kernel(long n, int cols, float *__restrict__ mask, int ld, float p, int per_col,
+                                    unsigned long long seed, unsigned long long stream) {
+  const float scale = 1.0f / (1.0f - p);
+  long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    long r = i / cols;
+    int c = (int)(i - r * cols);
+    float u = uniform01(seed, stream, per_col ? (unsigned long long)c : (unsigned long long)i);
+    mask[r * ld + c] = (u - p > 0.f) ? scale : 0.f;
+  }
+}
+
 // partial column sums: block b sums rows b, b+gridDim.x*8, ... ; ws[b][K]
 __global__ void col_sum_partial_kernel(int N, int K, const float *__restrict__ x, int ld, float *__restrict__ ws) {
   __shared__ float red[8][33];
@@ -138,6 +174,26 @@ cudaError_t optimizer_update(cudaStream_t st, int num_sms, int mode, float *w, f
   if (blocks > 16 * num_sms) blocks = 16 * num_sms;
   if (mode == 1) opt_kernel<1><<<blocks, 256, 0, st>>>(w, corr, accu, grad, momentum, eps, rho, one_minus_rho, d_segs, nseg, total);
   else opt_kernel<2><<<blocks, 256, 0, st>>>(w, corr, accu, grad, momentum, eps, rho, one_minus_rho, d_segs, nseg, total);
+  return cudaGetLastError();
+}
+
+cudaError_t mul_elements(cudaStream_t st, int num_sms, int N, int cols, const float *a, int lda, const float *b, int ldb,
+                         float *out, int ldo) {
+  long n = (long)N * cols;
+  if (n <= 0) return cudaSuccess;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 16 * num_sms) blocks = 16 * num_sms;
+  mul_elements_kernel<<<blocks, 256, 0, st>>>(n, cols, a, lda, b, ldb, out, ldo);
+  return cudaGetLastError();
+}
+
+cudaError_t dropout_mask(cudaStream_t st, int num_sms, int rows, int cols, float *mask, int ld, float p, int per_col,
+                         unsigned long long seed, unsigned long long stream) {
+  long n = (long)rows * cols;
+  if (n <= 0) return cudaSuccess;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 16 * num_sms) blocks = 16 * num_sms;
+  dropout_mask_kernel<<<blocks, 256, 0, st>>>(n, cols, mask, ld, p, per_col, seed, stream);
   return cudaGetLastError();
 }
 

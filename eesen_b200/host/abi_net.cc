@@ -56,6 +56,7 @@ static void unpack_labels(eesen_b200_net *n, int S, const int *frames, const int
 }
 
 static void run_step(eesen_b200_net *n, const CuMatrixBase<BaseFloat> &in, int train) {
+  if (train) n->net.SetTrainMode(); else n->net.SetTestMode();           // train-ctc-parallel.cc:116-120
   n->net.SetSeqLengths(n->frames);                                      // train-ctc-parallel.cc:195
   n->net.Propagate(in, &n->net_out);                                    // :198
   n->ctc.EvalParallelAsync(n->frames, n->net_out, n->labels, &n->obj_diff);   // :199
@@ -166,6 +167,28 @@ int eesen_b200_net_feedforward(eesen_b200_net *n, const float *feats, int T, int
   }
 }
 
+int eesen_b200_net_change_dropout(eesen_b200_net *n, float forward_dropout, int fw_step, int fw_sequence, int rnndrop,
+                                  int no_mem_loss, float recurrent_dropout, int rec_step, int rec_sequence,
+                                  int twiddle_forward) {
+  if (!n) return EESEN_B200_EINVAL;
+  GUARD(n->ctx, n->net.ChangeDropoutParameters(forward_dropout, fw_step != 0, fw_sequence != 0, rnndrop != 0,
+                                               no_mem_loss != 0, recurrent_dropout, rec_step != 0, rec_sequence != 0,
+                                               twiddle_forward != 0));
+}
+
+int eesen_b200_net_set_dropout_seed(eesen_b200_net *n, unsigned long long seed) {
+  if (!n) return EESEN_B200_EINVAL;
+  GUARD(n->ctx, n->net.SetDropoutSeed(seed));
+}
+
+int eesen_b200_net_set_dropout_masks(eesen_b200_net *n, int layer, const float *fmask, int fmask_rows, const float *rmask,
+                                     int rmask_rows) {
+  if (!n || layer < 0 || layer >= n->net.NumLayers()) return EESEN_B200_EINVAL;
+  BiLstmParallel *bl = dynamic_cast<BiLstmParallel *>(n->net.GetLayer(layer));
+  if (!bl) return EESEN_B200_EINVAL;
+  GUARD(n->ctx, bl->InjectDropoutMasks(fmask, fmask_rows, rmask, rmask_rows));
+}
+
 int eesen_b200_net_dims(const eesen_b200_net *n, int *in_dim, int *out_dim, int *num_layers, int64_t *num_params) {
   if (!n) return EESEN_B200_EINVAL;
   if (in_dim) *in_dim = n->net.InputDim();
@@ -262,6 +285,13 @@ int eesen_b200_net_get(eesen_b200_net *n, int which, float *data, int64_t capaci
     if (which == 102) {
       n->want_in_diff = true;  // takes effect from the next step
       return copy_out(n->in_diff, data, capacity, rows, cols);
+    }
+    if (which >= 300 && which < 500) {
+      const int layer = which >= 400 ? which - 400 : which - 300;
+      if (layer >= L) return EESEN_B200_EINVAL;
+      BiLstmParallel *bl = dynamic_cast<BiLstmParallel *>(n->net.GetLayer(layer));
+      if (!bl) return EESEN_B200_EINVAL;
+      return copy_out(which >= 400 ? bl->RecurrentMask() : bl->ForwardMask(), data, capacity, rows, cols);
     }
     if (which == 203 && !n->net.Accu()) {
       if (rows) *rows = 1;

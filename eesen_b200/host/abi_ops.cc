@@ -171,7 +171,9 @@ static int lstm_prepare(eesen_b200_ctx *ctx, int ndir, int S, int C, eb::LstmPla
 // is the forward-cell pass of bilstm-parallel-layer.h:97-150 line for line.
 static int lstm_forward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I, int C, const int *d_len,
                              const float *x, int ldx, const eesen_b200_bilstm_params *p, float *gates, float *cell,
-                             float *out, int ldo) {
+                             float *out, int ldo, int drop = 0, const float *rmask = nullptr, int ldr = 0,
+                             int per_step = 0) {
+  if (drop < 0 || drop > 2 || (drop != 0 && (!rmask || ldr < ndir * C))) return EESEN_B200_EINVAL;
   if (!ctx || !p || !x || !gates || !cell || !out || T <= 0 || S <= 0) return EESEN_B200_EINVAL;
   eb::LstmPlan plan;
   float *pbuf, *gsum;
@@ -205,6 +207,7 @@ static int lstm_forward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I,
   }
   a.xbuf = xbuf;
   a.precision = ctx->rec_prec;
+  a.drop = drop; a.rmask = rmask; a.ldr = ldr; a.rmask_per_step = per_step;
   for (int s0 = 0; s0 < S; s0 += chunk) {
     a.s_begin = s0;
     a.s_count = std::min(chunk, S - s0);
@@ -224,6 +227,39 @@ int eesen_b200_bilstm_forward(eesen_b200_ctx *ctx, int T, int S, int I, int C, c
   return lstm_forward_impl(ctx, 2, T, S, I, C, d_len, x, ldx, p, gates, cell, out, ldo);
 }
 
+int eesen_b200_bilstm_forward_dropout(eesen_b200_ctx *ctx, int T, int S, int I, int C, const int *d_len, const float *x,
+                                      int ldx, const eesen_b200_bilstm_params *p, float *gates, float *cell,
+                                      float *out, int ldo, int drop, const float *rmask, int ldr, int per_step) {
+  if (!d_len) return EESEN_B200_EINVAL;
+  return lstm_forward_impl(ctx, 2, T, S, I, C, d_len, x, ldx, p, gates, cell, out, ldo, drop, rmask, ldr, per_step);
+}
+
+int eesen_b200_bilstm_backward_dropout(eesen_b200_ctx *ctx, int T, int S, int I, int C, const float *x, int ldx,
+                                       const eesen_b200_bilstm_params *p, const float *gates, const float *cell,
+                                       const float *out, int ldo, const float *dout, int ldd, float *dgates, float *dx,
+                                       int lddx, const eesen_b200_bilstm_grads *gr, int drop, const float *rmask,
+                                       int ldr, int per_step);
+
+int eesen_b200_mul_elements(eesen_b200_ctx *ctx, int N, int cols, const float *a, int lda, const float *b, int ldb,
+                            float *out, int ldo) {
+  if (!ctx || !a || !b || !out || N < 0 || cols < 1) return EESEN_B200_EINVAL;
+  ctx->launches += 1;
+  int pe = ctx->prof_begin(eesen_b200_ctx::kMisc);
+  cudaError_t e = eb::mul_elements(ctx->stream, ctx->num_sms, N, cols, a, lda, b, ldb, out, ldo);
+  ctx->prof_end(pe);
+  return ctx->check(e, "mul_elements");
+}
+
+int eesen_b200_dropout_mask(eesen_b200_ctx *ctx, int rows, int cols, float *d_mask, int ld, float p, int per_col,
+                            unsigned long long seed, unsigned long long stream) {
+  if (!ctx || !d_mask || rows < 0 || cols < 1 || ld < cols || !(p >= 0.f && p < 1.f)) return EESEN_B200_EINVAL;
+  ctx->launches += 1;
+  int pe = ctx->prof_begin(eesen_b200_ctx::kMisc);
+  cudaError_t e = eb::dropout_mask(ctx->stream, ctx->num_sms, rows, cols, d_mask, ld, p, per_col, seed, stream);
+  ctx->prof_end(pe);
+  return ctx->check(e, "dropout_mask");
+}
+
 int eesen_b200_lstm_forward(eesen_b200_ctx *ctx, int T, int S, int I, int C, const float *x, int ldx,
                             const eesen_b200_bilstm_params *p, float *gates, float *cell, float *out, int ldo) {
   return lstm_forward_impl(ctx, 1, T, S, I, C, NULL, x, ldx, p, gates, cell, out, ldo);
@@ -232,7 +268,9 @@ int eesen_b200_lstm_forward(eesen_b200_ctx *ctx, int T, int S, int I, int C, con
 static int lstm_backward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I, int C, const float *x, int ldx,
                               const eesen_b200_bilstm_params *p, const float *gates, const float *cell,
                               const float *out, int ldo, const float *dout, int ldd, float *dgates, float *dx,
-                              int lddx, const eesen_b200_bilstm_grads *gr) {
+                              int lddx, const eesen_b200_bilstm_grads *gr, int drop = 0, const float *rmask = nullptr,
+                              int ldr = 0, int per_step = 0) {
+  if (drop < 0 || drop > 2 || (drop != 0 && (!rmask || ldr < ndir * C))) return EESEN_B200_EINVAL;
   if (!ctx || !p || !gr || !x || !gates || !cell || !out || !dout || !dgates || T <= 0 || S <= 0) return EESEN_B200_EINVAL;
   eb::LstmPlan plan;
   float *pbuf, *gsum;
@@ -254,6 +292,7 @@ static int lstm_backward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I
   }
   a.pbuf = pbuf; a.gsum = gsum;
   a.precision = ctx->rec_prec;
+  a.drop = drop; a.rmask = rmask; a.ldr = ldr; a.rmask_per_step = per_step;
   for (int ci = 0; ci < nchunks; ci++) {
     a.s_begin = ci * chunk;
     a.s_count = std::min(chunk, S - a.s_begin);
@@ -317,6 +356,15 @@ int eesen_b200_bilstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, 
                                const float *out, int ldo, const float *dout, int ldd, float *dgates, float *dx,
                                int lddx, const eesen_b200_bilstm_grads *gr) {
   return lstm_backward_impl(ctx, 2, T, S, I, C, x, ldx, p, gates, cell, out, ldo, dout, ldd, dgates, dx, lddx, gr);
+}
+
+int eesen_b200_bilstm_backward_dropout(eesen_b200_ctx *ctx, int T, int S, int I, int C, const float *x, int ldx,
+                                       const eesen_b200_bilstm_params *p, const float *gates, const float *cell,
+                                       const float *out, int ldo, const float *dout, int ldd, float *dgates, float *dx,
+                                       int lddx, const eesen_b200_bilstm_grads *gr, int drop, const float *rmask,
+                                       int ldr, int per_step) {
+  return lstm_backward_impl(ctx, 2, T, S, I, C, x, ldx, p, gates, cell, out, ldo, dout, ldd, dgates, dx, lddx, gr, drop,
+                            rmask, ldr, per_step);
 }
 
 int eesen_b200_lstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, const float *x, int ldx,

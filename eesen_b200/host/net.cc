@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstring>
 #include <fstream>
+#include <random>
 
 #include "context.h"
 
@@ -241,8 +242,7 @@ void BiLstmParallel::ReadData(std::istream &is, bool binary) {
       ReadBasicType(is, binary, &flags_[f]);
     }
   }
-  if (forward_dropout_ != 0.f || recurrent_dropout_ != 0.f || flags_[4] || flags_[5])
-    KALDI_WARN << "dropout variants of BiLstmParallel are not on the B200 path; training runs the vanilla passes";
+  if (flags_[4] && flags_[5]) KALDI_ERR << "Only one of RNNDrop, NoMemLossDropout can be true. Pick one.";
   const int64 C = cell_dim_, I = input_dim_;
   if (C % 8 != 0 || I % 4 != 0)
     KALDI_ERR << "BiLstmParallel on B200 needs cells/direction % 8 == 0 and input dim % 4 == 0, got C=" << C
@@ -332,17 +332,93 @@ void BiLstmParallel::SetSeqLengths(std::vector<int> &sequence_lengths) {
   CU_CHECK(cudaMemcpyAsync(d_len_, sequence_lengths_.data(), sizeof(int) * S, cudaMemcpyHostToDevice, Stream()));
 }
 
+void BiLstmParallel::ChangeDropoutParameters(BaseFloat forward_dropout, bool fw_step, bool fw_sequence, bool rnndrop,
+                                             bool no_mem_loss, BaseFloat recurrent_dropout, bool rec_step,
+                                             bool rec_sequence, bool twiddle_forward) {
+  // bilstm-layer.h:74-112
+  if (forward_dropout > 0.0 && !(fw_sequence || fw_step))
+    KALDI_ERR << "ForwardDropoutFactor > 0 but ForwardTimeStepDropout and ForwardSequenceDropout are both false, One must be true.";
+  if (fw_sequence && fw_step)
+    KALDI_ERR << "Both ForwardTimeStepDropout and ForwardSequenceDropout are true, Only one can be true.";
+  if (forward_dropout == 0.0 && (fw_sequence || fw_step))
+    KALDI_ERR << "ForwardDropoutFactor = 0 but ForwardTimeStepDropout and/or ForwardSequenceDropout is true, both must be false.";
+  if (rec_sequence && rec_step)
+    KALDI_ERR << "RecurrentSequenceDropout and RecurrentTimeStepDropout cannot be true at the same time. Pick one.";
+  if (rnndrop && no_mem_loss) KALDI_ERR << "Only one of RNNDrop, NoMemLossDropout can be true. Pick one.";
+  if (recurrent_dropout == 0.0 && (no_mem_loss || rnndrop))
+    KALDI_ERR << "RecurrentDropoutFactor must be nonzero if RNNDrop or NoMemLossDropout is true";
+  if (!(rec_step || rec_sequence) && (rnndrop || no_mem_loss))
+    KALDI_ERR << " Either RecurrentSequenceDropout or RecurrentTimeStepDropout must be true if RNNDrop or NoMemLossDropout is true";
+  if (forward_dropout >= 1.0 || recurrent_dropout >= 1.0 || forward_dropout < 0.0 || recurrent_dropout < 0.0)
+    KALDI_ERR << "dropout factors must lie in [0, 1)";
+  forward_dropout_ = forward_dropout; flags_[0] = fw_step; flags_[1] = fw_sequence; flags_[6] = twiddle_forward;
+  recurrent_dropout_ = recurrent_dropout; flags_[2] = rec_step; flags_[3] = rec_sequence;
+  flags_[4] = rnndrop; flags_[5] = no_mem_loss;
+}
+
+void BiLstmParallel::InjectDropoutMasks(const float *fmask, int32 frows, const float *rmask, int32 rrows) {
+  const size_t w = (size_t)2 * cell_dim_;
+  if (fmask && frows > 0) { inj_fmask_.assign(fmask, fmask + (size_t)frows * w); inj_frows_ = frows; }
+  else { inj_fmask_.clear(); inj_frows_ = 0; }
+  if (rmask && rrows > 0) { inj_rmask_.assign(rmask, rmask + (size_t)rrows * w); inj_rrows_ = rrows; }
+  else { inj_rmask_.clear(); inj_rrows_ = 0; }
+}
+
+// scaled mask [rows x 2C]: the injected one (tests: the masks the reference drew) or a fresh device draw
+void BiLstmParallel::PrepareMask(CuMatrix<BaseFloat> *mask, int32 rows, BaseFloat p, bool per_col,
+                                 const std::vector<float> &inj, int32 inj_rows) {
+  const int32 w = 2 * cell_dim_;
+  mask->Resize(rows, w, kUndefined);
+  if (!inj.empty()) {
+    if (inj_rows != rows) KALDI_ERR << "injected dropout mask has " << inj_rows << " rows, this minibatch needs " << rows;
+    mask->CopyFromHost(inj.data(), w);
+    CU_CHECK(cudaStreamSynchronize(Stream()));   // inj may be replaced by the caller right after
+    return;
+  }
+  CheckAbi(ctx_, eesen_b200_dropout_mask(ctx_, rows, w, mask->Data(), mask->Stride(), p, per_col ? 1 : 0, drop_seed_,
+                                         (drop_stream_ << 32) + drop_draws_++), "eesen_b200_dropout_mask");
+}
+
 void BiLstmParallel::PropagateFnc(const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseFloat> *out) {
   int32 S = sequence_lengths_.size();
   KALDI_ASSERT(S > 0 && in.NumRows() % S == 0);
   int32 T = in.NumRows() / S, C = cell_dim_;
-  gates_.Resize(in.NumRows(), 8 * C, kUndefined);
-  cell_.Resize(in.NumRows(), 2 * C, kUndefined);
+  const int32 N = in.NumRows();
+  gates_.Resize(N, 8 * C, kUndefined);
+  cell_.Resize(N, 2 * C, kUndefined);
   eesen_b200_bilstm_params p;
   Params(&p, NULL);
-  CheckAbi(ctx_, eesen_b200_bilstm_forward(ctx_, T, S, input_dim_, C, d_len_, in.Data(), in.Stride(), &p,
-                                           gates_.Data(), cell_.Data(), out->Data(), out->Stride()),
-           "eesen_b200_bilstm_forward");
+  // which dropout applies to this pass (bilstm-parallel-layer.h:385-390); TwiddleForward picks one of the two
+  // at random per minibatch
+  const bool has_rec = flags_[4] || flags_[5];
+  bool twiddle_fwd = false;
+  if (flags_[6]) {
+    uint64_t z = drop_seed_ + 0x9e3779b97f4a7c15ULL * (++drop_draws_) + (drop_stream_ << 32);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL; z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL; z ^= z >> 31;
+    twiddle_fwd = (z >> 63) != 0;   // BernoulliDist(0.5)
+  }
+  apply_rec_ = in_train_ && has_rec && recurrent_dropout_ > 0.f && (!flags_[6] || !twiddle_fwd);
+  apply_fwd_ = in_train_ && forward_dropout_ > 0.f && (!flags_[6] || twiddle_fwd);
+  if (GetType() == l_BiLstm && (apply_rec_ || apply_fwd_)) KALDI_ERR << "Dropout not implemented on BiLstm";   // bilstm-layer.h:555-556
+  float *m_dst = out->Data();
+  int32 m_ld = out->Stride();
+  if (apply_fwd_) { m_.Resize(N, 2 * C, kUndefined); m_dst = m_.Data(); m_ld = m_.Stride(); }
+  if (apply_rec_) {
+    PrepareMask(&rmask_, flags_[2] ? N : S, recurrent_dropout_, flags_[3], inj_rmask_, inj_rrows_);
+    CheckAbi(ctx_, eesen_b200_bilstm_forward_dropout(ctx_, T, S, input_dim_, C, d_len_, in.Data(), in.Stride(), &p,
+                                                     gates_.Data(), cell_.Data(), m_dst, m_ld, flags_[4] ? 2 : 1,
+                                                     rmask_.Data(), rmask_.Stride(), flags_[2] ? 1 : 0),
+             "eesen_b200_bilstm_forward_dropout");
+  } else {
+    CheckAbi(ctx_, eesen_b200_bilstm_forward(ctx_, T, S, input_dim_, C, d_len_, in.Data(), in.Stride(), &p,
+                                             gates_.Data(), cell_.Data(), m_dst, m_ld),
+             "eesen_b200_bilstm_forward");
+  }
+  if (apply_fwd_) {   // :409-416: the mask hits the layer OUTPUT only; the recurrence saw the un-masked m
+    PrepareMask(&fmask_, N, forward_dropout_, flags_[1], inj_fmask_, inj_frows_);
+    CheckAbi(ctx_, eesen_b200_mul_elements(ctx_, N, 2 * C, m_.Data(), m_.Stride(), fmask_.Data(), fmask_.Stride(),
+                                           out->Data(), out->Stride()), "eesen_b200_mul_elements");
+  }
 }
 
 void BiLstm::PropagateFnc(const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseFloat> *out) {
@@ -366,15 +442,32 @@ void BiLstmParallel::BackpropagateFnc(const CuMatrixBase<BaseFloat> &in, const C
   int32 S = sequence_lengths_.size();
   KALDI_ASSERT(S > 0 && in.NumRows() % S == 0);
   int32 T = in.NumRows() / S, C = cell_dim_;
-  dgates_.Resize(in.NumRows(), 8 * C, kUndefined);
+  const int32 N = in.NumRows();
+  dgates_.Resize(N, 8 * C, kUndefined);
   eesen_b200_bilstm_params p;
   eesen_b200_bilstm_grads g;
   Params(&p, &g);
-  CheckAbi(ctx_, eesen_b200_bilstm_backward(ctx_, T, S, input_dim_, C, in.Data(), in.Stride(), &p, gates_.Data(),
-                                            cell_.Data(), out.Data(), out.Stride(), out_diff.Data(),
-                                            out_diff.Stride(), dgates_.Data(),
-                                            need_in_diff_ ? in_diff->Data() : NULL, in_diff->Stride(), &g),
-           "eesen_b200_bilstm_backward");
+  const float *dout = out_diff.Data(), *m = out.Data();
+  int32 ldd = out_diff.Stride(), ldm = out.Stride();
+  if (apply_fwd_) {   // :891-895 out_diff_drop = out_diff (.) mask; the Wm gradient pairs DGIFO with the UN-masked m
+    dout_.Resize(N, 2 * C, kUndefined);
+    CheckAbi(ctx_, eesen_b200_mul_elements(ctx_, N, 2 * C, out_diff.Data(), out_diff.Stride(), fmask_.Data(),
+                                           fmask_.Stride(), dout_.Data(), dout_.Stride()), "eesen_b200_mul_elements");
+    dout = dout_.Data(); ldd = dout_.Stride();
+    m = m_.Data(); ldm = m_.Stride();
+  }
+  if (apply_rec_) {
+    CheckAbi(ctx_, eesen_b200_bilstm_backward_dropout(ctx_, T, S, input_dim_, C, in.Data(), in.Stride(), &p, gates_.Data(),
+                                                      cell_.Data(), m, ldm, dout, ldd, dgates_.Data(),
+                                                      need_in_diff_ ? in_diff->Data() : NULL, in_diff->Stride(), &g,
+                                                      flags_[4] ? 2 : 1, rmask_.Data(), rmask_.Stride(), flags_[2] ? 1 : 0),
+             "eesen_b200_bilstm_backward_dropout");
+  } else {
+    CheckAbi(ctx_, eesen_b200_bilstm_backward(ctx_, T, S, input_dim_, C, in.Data(), in.Stride(), &p, gates_.Data(),
+                                              cell_.Data(), m, ldm, dout, ldd, dgates_.Data(),
+                                              need_in_diff_ ? in_diff->Data() : NULL, in_diff->Stride(), &g),
+             "eesen_b200_bilstm_backward");
+  }
 }
 
 std::string BiLstmParallel::Info() const {
@@ -668,6 +761,9 @@ void Net::Read(std::istream &is, bool binary) {
   backpropagate_buf_.resize(NumLayers() + 1);
   opts_.learn_rate = 0.0;  // net.cc:274,294
   BindArena();
+  // the reference's masks come from a std::random_device-seeded generator (kaldi-math.h:107-131): a fresh seed per
+  // process unless the caller fixes one (Net::SetDropoutSeed)
+  SetDropoutSeed(((uint64_t)std::random_device{}() << 32) ^ (uint64_t)std::random_device{}());
 }
 
 // Lay all trainable layers out in three contiguous arenas (params / raw grads / momentum), each
@@ -818,6 +914,32 @@ void Net::Feedforward(const CuMatrixBase<BaseFloat> &in, CuMatrix<BaseFloat> *ou
   layers_[L]->Propagate(propagate_buf_[(L - 1) % 2], out);
   // the reference releases the two buffers here (net.cc:134-136); ours stay allocated for the next
   // utterance batch (stream-ordered reuse, no cudaFree/cudaMalloc per call) but hold no result
+}
+
+void Net::SetTrainMode() {
+  in_train_ = true;
+  for (size_t i = 0; i < layers_.size(); i++) layers_[i]->SetTrainMode();
+}
+void Net::SetTestMode() {
+  in_train_ = false;
+  for (size_t i = 0; i < layers_.size(); i++) layers_[i]->SetTestMode();
+}
+void Net::ChangeDropoutParameters(BaseFloat forward_dropout, bool fw_step, bool fw_sequence, bool rnndrop,
+                                  bool no_mem_loss, BaseFloat recurrent_dropout, bool rec_step, bool rec_sequence,
+                                  bool twiddle_forward) {
+  for (size_t i = 0; i < layers_.size(); i++) {
+    BiLstmParallel *bl = dynamic_cast<BiLstmParallel *>(layers_[i]);
+    if (!bl) continue;
+    KALDI_LOG << "Changing dropout params for layer " << i;
+    bl->ChangeDropoutParameters(forward_dropout, fw_step, fw_sequence, rnndrop, no_mem_loss, recurrent_dropout,
+                                rec_step, rec_sequence, twiddle_forward);
+  }
+}
+void Net::SetDropoutSeed(uint64_t seed) {
+  for (size_t i = 0; i < layers_.size(); i++) {
+    BiLstmParallel *bl = dynamic_cast<BiLstmParallel *>(layers_[i]);
+    if (bl) bl->SetDropoutSeed(seed, (uint64_t)i + 1);
+  }
 }
 
 int32 Net::InputDim() const { return layers_.empty() ? 0 : layers_.front()->InputDim(); }

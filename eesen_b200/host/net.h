@@ -93,6 +93,8 @@ class Layer {
   int32 InputDim() const { return input_dim_; }
   int32 OutputDim() const { return output_dim_; }
   virtual void SetSeqLengths(std::vector<int> &) {}
+  virtual void SetTrainMode() {}   // layer.h:93-94
+  virtual void SetTestMode() {}
   // layer.h:184-217
   void Propagate(const CuMatrixBase<BaseFloat> &in, CuMatrix<BaseFloat> *out);
   void Backpropagate(const CuMatrixBase<BaseFloat> &in, const CuMatrixBase<BaseFloat> &out,
@@ -148,6 +150,17 @@ class BiLstmParallel : public TrainableLayer {
   void SetSeqLengths(std::vector<int> &sequence_lengths);
   int64 NumParams() const;
   std::string Info() const;
+  void SetTrainMode() { in_train_ = true; }    // bilstm-layer.h:49-55: impacts dropout only
+  void SetTestMode() { in_train_ = false; }
+  // bilstm-layer.h:62-135 (same consistency checks, same errors)
+  void ChangeDropoutParameters(BaseFloat forward_dropout, bool fw_step, bool fw_sequence, bool rnndrop, bool no_mem_loss,
+                               BaseFloat recurrent_dropout, bool rec_step, bool rec_sequence, bool twiddle_forward);
+  // Masks.  By default they are drawn on the device from (seed, layer stream, draw counter); tests inject the
+  // masks the reference drew.  Injected masks stay in force until cleared (NULL / empty).
+  void SetDropoutSeed(uint64_t seed, uint64_t stream) { drop_seed_ = seed; drop_stream_ = stream; drop_draws_ = 0; }
+  void InjectDropoutMasks(const float *fmask, int32 frows, const float *rmask, int32 rrows);
+  const CuMatrix<BaseFloat> &ForwardMask() const { return fmask_; }
+  const CuMatrix<BaseFloat> &RecurrentMask() const { return rmask_; }
 
  protected:
   void PropagateFnc(const CuMatrixBase<BaseFloat> &in, CuMatrixBase<BaseFloat> *out);
@@ -163,9 +176,18 @@ class BiLstmParallel : public TrainableLayer {
   int *d_len_ = nullptr;
   int32 d_len_cap_ = 0;
   CuMatrix<BaseFloat> gates_, cell_, dgates_;  // propagate_buf_{fw,bw}_ / backpropagate_buf_{fw,bw}_
-  // options carried through Read/Write unchanged (dropout variants are not on this path)
+  // dropout options (bilstm-layer.h:1040-1056); flags_: ForwardTimeStepDropout, ForwardSequenceDropout,
+  // RecurrentTimeStepDropout, RecurrentSequenceDropout, RNNDrop, NoMemLossDropout, TwiddleForward
   BaseFloat forward_dropout_ = 0.f, recurrent_dropout_ = 0.f;
   bool flags_[7] = {false, false, false, false, false, false, false};
+  bool in_train_ = true;
+  bool apply_fwd_ = false, apply_rec_ = false;       // decided by the last Propagate (:389-390)
+  CuMatrix<BaseFloat> fmask_, rmask_, m_, dout_;    // masks, un-masked output m, masked out_diff
+  std::vector<float> inj_fmask_, inj_rmask_;
+  int32 inj_frows_ = 0, inj_rrows_ = 0;
+  uint64_t drop_seed_ = 0x5eed5eedULL, drop_stream_ = 0, drop_draws_ = 0;
+  void PrepareMask(CuMatrix<BaseFloat> *mask, int32 rows, BaseFloat p, bool per_col, const std::vector<float> &inj,
+                   int32 inj_rows);
 
  public:
   ~BiLstmParallel();
@@ -261,8 +283,12 @@ class Net {
   const NetTrainOptions &GetTrainOptions() const { return opts_; }
   void SetUpdateAlgorithm(const std::string &opt);       // SGD | Adagrad | RMSProp (net.cc:481-496)
   int UpdateAlgorithm() const { return update_algorithm_; }
-  void SetTrainMode() { in_train_ = true; }
-  void SetTestMode() { in_train_ = false; }
+  void SetTrainMode();    // net.cc:396-412: also tells the layers (dropout is a train-mode thing)
+  void SetTestMode();
+  void ChangeDropoutParameters(BaseFloat forward_dropout, bool fw_step, bool fw_sequence, bool rnndrop, bool no_mem_loss,
+                               BaseFloat recurrent_dropout, bool rec_step, bool rec_sequence, bool twiddle_forward);   // net.cc:414-434
+  void SetDropoutSeed(uint64_t seed);
+  Layer *GetLayer(int32 i) { return layers_[i]; }
   int32 InputDim() const;
   int32 OutputDim() const;
   int32 NumLayers() const { return (int32)layers_.size(); }

@@ -29,7 +29,7 @@ static const char *kUsage =
     "e.g.: \n"
     "train-ctc-parallel scp:feature.scp ark:labels.ark nnet.init nnet.iter1\n"
     "Options: --learn-rate --momentum --binary --cross-validate --num-sequence --frame-limit --report-step\n"
-    "         --num-jobs --job-id --opt-algorithm=SGD|Adagrad|RMSProp --adagrad-epsilon --rms-prop-rho --sequence-out-file --verbose\n"
+    "         --num-jobs --job-id --opt-algorithm=SGD|Adagrad|RMSProp --adagrad-epsilon --rms-prop-rho --sequence-out-file --verbose --dropout-seed\n"
     "         --gemm-precision=fp32x3|tf32|bf16 --recurrent-precision=fp32x3|tf32\n";
 
 static int PrecFromString(const std::string &s) {
@@ -99,6 +99,7 @@ int main(int argc, char *argv[]) {
       net.Read(model_filename);
       net.SetTrainOptions(trn_opts);
       net.SetUpdateAlgorithm(opt);
+      if (po.Has("dropout-seed")) net.SetDropoutSeed((uint64_t)po.Num("dropout-seed", 0));   // default: random per run
       if (crossvalidate) net.SetTestMode(); else net.SetTrainMode();
 
       Ctc ctc(ctx);

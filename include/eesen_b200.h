@@ -104,6 +104,31 @@ int eesen_b200_bilstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, 
                                const float *out, int ldo, const float *dout, int ldd, float *dgates,
                                float *dx, int lddx, const eesen_b200_bilstm_grads *grads);
 
+/* The dropout variants of BiLstmParallel (reference src/net/bilstm-parallel-layer.h:46-94 masks, :209-377
+ * forward, :604-879 backward; options src/net/bilstm-layer.h:62-135).
+ *   drop   1 = no-mem-loss dropout (c = r*(g*i) + c_prev*f), 2 = RNNdrop (c = r*(g*i + c_prev*f)); 0 = the plain calls
+ *   rmask  scaled recurrent mask (0 | 1/(1-p)), forward cells in cols [0,C), backward cells in [C,2C), ld = ldr;
+ *          [T*S x 2C] (row t*S+s) when per_step != 0 (RecurrentTimeStepDropout), else [S x 2C]
+ * Forward (non-recurrent) dropout is a product of the layer OUTPUT and of out_diff with a [T*S x 2C] mask
+ * (:409-416, :891-895): eesen_b200_mul_elements; the un-masked m must be kept for the Wm gradient (pass it as
+ * `out` to the backward call).  eesen_b200_dropout_mask draws a mask on the device (the reference draws on the
+ * CPU from a random_device-seeded generator and uploads it; parity is per given mask): one draw per element, or
+ * per column repeated in every row when per_col != 0 (the reference's "sequence" masks, SetRandUniformCol
+ * src/cpucompute/matrix.cc:952-965); deterministic in (seed, stream). */
+int eesen_b200_bilstm_forward_dropout(eesen_b200_ctx *ctx, int T, int S, int I, int C, const int *d_len,
+                                      const float *x, int ldx, const eesen_b200_bilstm_params *p, float *gates,
+                                      float *cell, float *out, int ldo, int drop, const float *rmask, int ldr,
+                                      int per_step);
+int eesen_b200_bilstm_backward_dropout(eesen_b200_ctx *ctx, int T, int S, int I, int C, const float *x, int ldx,
+                                       const eesen_b200_bilstm_params *p, const float *gates, const float *cell,
+                                       const float *out, int ldo, const float *dout, int ldd, float *dgates,
+                                       float *dx, int lddx, const eesen_b200_bilstm_grads *grads, int drop,
+                                       const float *rmask, int ldr, int per_step);
+int eesen_b200_mul_elements(eesen_b200_ctx *ctx, int N, int cols, const float *a, int lda, const float *b, int ldb,
+                            float *out, int ldo);
+int eesen_b200_dropout_mask(eesen_b200_ctx *ctx, int rows, int cols, float *d_mask, int ld, float p, int per_col,
+                            unsigned long long seed, unsigned long long stream);
+
 /* LstmParallel::PropagateFnc / BackpropagateFnc (reference src/net/lstm-parallel-layer.h:47-113,
  * :115-213): the uni-directional layer = the forward cells of the layer above, nothing masked (the
  * length check is commented out in the reference, :107-110).  Same structs, index [0] only:
@@ -176,6 +201,20 @@ int eesen_b200_net_set_train_options(eesen_b200_net *net, float learn_rate, floa
  * that behaviour, or the value you want. */
 int eesen_b200_net_set_optimizer(eesen_b200_net *net, const char *algorithm, float adagrad_epsilon,
                                  float rmsprop_rho, float rmsprop_one_minus_rho);
+/* Dropout of the BiLstmParallel layers.  Net::ChangeDropoutParameters (reference src/net/net.cc:414-434, tool
+ * src/netbin/net-change-model.cc) with the reference's consistency checks (src/net/bilstm-layer.h:74-112); the
+ * options are stored in the model file.  Masks are drawn on the device; eesen_b200_net_set_dropout_seed fixes the
+ * generator (default: a fresh random seed per Net, like the reference's random_device-seeded generator).
+ * eesen_b200_net_set_dropout_masks injects explicit scaled masks (0 | 1/(1-p), HOST pointers) for layer `layer`
+ * (0-based): fmask [T*S x 2C] or NULL, rmask [rmask_rows x 2C] or NULL with rmask_rows = T*S (step) or S
+ * (sequence); they stay in force until called again with NULLs.  This is how the parity tests replay the masks the
+ * reference drew.  Steps run with train == 0 are in test mode: no dropout (reference driver: SetTestMode). */
+int eesen_b200_net_change_dropout(eesen_b200_net *net, float forward_dropout, int fw_step, int fw_sequence, int rnndrop,
+                                  int no_mem_loss, float recurrent_dropout, int rec_step, int rec_sequence,
+                                  int twiddle_forward);
+int eesen_b200_net_set_dropout_seed(eesen_b200_net *net, unsigned long long seed);
+int eesen_b200_net_set_dropout_masks(eesen_b200_net *net, int layer, const float *fmask, int fmask_rows,
+                                     const float *rmask, int rmask_rows);
 int eesen_b200_net_dims(const eesen_b200_net *net, int *in_dim, int *out_dim, int *num_layers, int64_t *num_params);
 
 /* One minibatch exactly as the reference driver does it (train-ctc-parallel.cc:195-207):
@@ -218,6 +257,7 @@ int eesen_b200_net_write_nonparallel(eesen_b200_net *net, const char *path, int 
  *   102     in_diff  (gradient wrt the network input)
  *   200     parameters   201 momentum buffers (corr)   202 raw gradients of the last step (after all-reduce)
  *   203     Adagrad/RMSProp accumulators (zeros while none exist)
+ *   300+l   forward dropout mask used by layer l in the last step   400+l  its recurrent dropout mask
  * rows/cols describe the logical matrix; data may be NULL to query the shape only. */
 int eesen_b200_net_get(eesen_b200_net *net, int which, float *data, int64_t capacity, int *rows, int *cols);
 int eesen_b200_net_set_params(eesen_b200_net *net, const float *flat, int64_t n);

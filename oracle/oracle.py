@@ -250,6 +250,25 @@ class OracleNet:
         return np.concatenate([self.corr[i][n].ravel() for i, l in enumerate(self.spec.layers) for n in l.param_names()])
 
 
+def dropout_mask(rows: int, cols: int, p: float, per_col: bool, seed: int, stream: int) -> np.ndarray:
+    """Replica of the product's device mask generator (eesen_b200/csrc/optim.cu:uniform01 / dropout_mask_kernel):
+    splitmix64 finaliser of (seed, stream, index) -> 24 bits -> u in (0,1); mask = (u - p > 0) / (1 - p), one draw
+    per element or per column.  (The reference's own generator is random_device-seeded; this only checks that OUR
+    generator is the documented function of its seed.)"""
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+    n = cols if per_col else rows * cols
+    idx = np.arange(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed & 0xFFFFFFFFFFFFFFFF) + np.uint64(0x9e3779b97f4a7c15) * (idx + np.uint64(1)) \
+            + np.uint64(0xbf58476d1ce4e5b9) * np.uint64((stream + 1) & 0xFFFFFFFFFFFFFFFF)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xbf58476d1ce4e5b9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94d049bb133111eb)
+        z = z ^ (z >> np.uint64(31))
+    u = ((z >> np.uint64(40)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+    m = np.where(u - np.float32(p) > 0, np.float32(1.0) / (np.float32(1.0) - np.float32(p)), np.float32(0.0)).astype(np.float32)
+    return np.tile(m[None, :], (rows, 1)) if per_col else m.reshape(rows, cols)
+
+
 def class_log_priors(counts, prior_cutoff=1e-10, blank_scale=1.0) -> np.ndarray:
     """ClassPrior::ClassPrior (class-prior.cc:28-76): counts below the cutoff are floored and masked with
     FLT_MAX/2, class 0 scaled by blank_scale, normalised, log in double, cast to float, mask added."""
