@@ -207,15 +207,27 @@ int eesen_b200_net_train_step(eesen_b200_net *n, const float *feats, int T, int 
     unpack_labels(n, S, frames, labels, lab_len);
     const int I = n->net.InputDim();
     size_t elems = (size_t)T * S * I;
-    if (elems > n->h_cap) {
-      if (n->h_pinned) cudaFreeHost(n->h_pinned);
-      if (cudaMallocHost((void **)&n->h_pinned, sizeof(float) * elems) != cudaSuccess) KALDI_ERR << "cudaMallocHost failed";
-      n->h_cap = elems;
+    // A caller that already holds the minibatch in page-locked memory (cudaHostAlloc / cudaHostRegister) is
+    // copied from directly; pageable memory goes through the pinned staging buffer first.  Either way ONE
+    // asynchronous H2D copy; the call returns only after the statistics are back, so the caller's buffer is
+    // free again on return.
+    const float *src = feats;
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, feats) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    if (!pinned) {
+      cudaGetLastError();   // a pageable pointer may leave cudaErrorInvalidValue behind on older drivers
+      if (elems > n->h_cap) {
+        if (n->h_pinned) cudaFreeHost(n->h_pinned);
+        n->h_pinned = nullptr; n->h_cap = 0;
+        if (cudaMallocHost((void **)&n->h_pinned, sizeof(float) * elems) != cudaSuccess) KALDI_ERR << "cudaMallocHost failed";
+        n->h_cap = elems;
+      }
+      memcpy(n->h_pinned, feats, sizeof(float) * elems);
+      src = n->h_pinned;
     }
-    memcpy(n->h_pinned, feats, sizeof(float) * elems);   // into pinned staging, then one async H2D
     auto t1 = std::chrono::steady_clock::now();
     n->feats.Resize(T * S, I, kUndefined);
-    n->feats.CopyFromHost(n->h_pinned, I);
+    n->feats.CopyFromHost(src, I);
     run_step(n, n->feats, train);
     auto t2 = std::chrono::steady_clock::now();
     double st[4];
