@@ -15,8 +15,8 @@
 //     skips the split and issues one MMA;
 //   * epilogue: tcgen05.ld 32x32b -> registers -> alpha/beta/bias -> 128-bit global stores, or a
 //     split-K partial into a workspace that splitk_reduce sums in fixed order (deterministic).
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = operand splitters during the main loop, then the epilogue (TMEM lane quadrant = warp%4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = operand splitters during the main loop, then the epilogue (TMEM lane quadrant = warp%4, two warps per quadrant split the columns).
 #include <cuda.h>
 
 #include <cstdlib>
@@ -30,7 +30,8 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;          // 32 fp32 = 128 bytes = one swizzle row
-constexpr int TC_THREADS = 192;
+constexpr int TC_SPLIT_WARPS = 8;   // operand splitters during the main loop, then the epilogue (2 per TMEM lane quadrant)
+constexpr int TC_THREADS = 64 + 32 * TC_SPLIT_WARPS;
 
 struct TcArgs {
   int M, N, K;
@@ -126,7 +127,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&conv_bar[s], 128);
+      mbar_init(&conv_bar[s], 32 * TC_SPLIT_WARPS);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&accum_bar, 1);
@@ -210,7 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else {
     // ===== operand splitters (3xTF32), then epilogue =====
-    const int et = threadIdx.x - 64;   // 0..127
+    const int et = threadIdx.x - 64;   // 0 .. 32*TC_SPLIT_WARPS-1
     if (NTERMS == 3) {
       for (int i = 0; i < nkb; i++) {
         const int s = i % STAGES;
@@ -219,7 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         float4 *lo = reinterpret_cast<float4 *>(smem + (size_t)s * STAGE_BYTES + A_BYTES + B_BYTES);
         constexpr int NV = (A_BYTES + B_BYTES) / 16;
 #pragma unroll 4
-        for (int v = et; v < NV; v += 128) {
+        for (int v = et; v < NV; v += 32 * TC_SPLIT_WARPS) {
           float4 x = hi[v];
           float4 h, l;
           h.x = u2f(f2u(x.x) & 0xffffe000u); l.x = x.x - h.x;
@@ -239,12 +240,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // shared memory (the operand stages are free: every MMA has completed) -> row-wise, fully
     // coalesced global traffic (512-byte row segments) for the alpha/beta/bias update.
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-    constexpr int EST = BN + 4;                // staging row stride (floats): conflict-free v4 stores
-    float *stg = reinterpret_cast<float *>(smem) + (size_t)quad * 32 * EST;
+    constexpr int NHALF = TC_SPLIT_WARPS / 4;  // warps sharing a quadrant split the tile's columns
+    constexpr int BNW = BN / NHALF;            // columns this warp moves
+    const int chalf = (warp - 2) / 4;          // 0 .. NHALF-1
+    const int ncol0 = n0 + chalf * BNW;        // first global column of this warp's part
+    constexpr int EST = BNW + 4;               // staging row stride (floats): conflict-free v4 stores
+    float *stg = reinterpret_cast<float *>(smem) + (size_t)(quad * NHALF + chalf) * 32 * EST;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = 0; c0 < BNW; c0 += 32) {
       uint32_t r[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(chalf * BNW + c0);
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
           "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -266,23 +271,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (vec_ok && p.beta != 0.f) {
       // beta != 0: the old C values are fetched 8 rows ahead of their use -- a load -> fma -> store chain per
       // row would expose one global-memory round trip per row (32 per tile)
-      float4 bv[BN / 128 > 0 ? BN / 128 : 1];
+      float4 bv[BNW / 128 > 0 ? BNW / 128 : 1];
 #pragma unroll
-      for (int q = 0; q < (BN / 128 > 0 ? BN / 128 : 1); q++) {
+      for (int q = 0; q < (BNW / 128 > 0 ? BNW / 128 : 1); q++) {
         const int c = lane * 4 + q * 128;
-        bv[q] = (p.bias && c < BN && n0 + c < p.N) ? *reinterpret_cast<const float4 *>(p.bias + n0 + c)
+        bv[q] = (p.bias && c < BNW && ncol0 + c < p.N) ? *reinterpret_cast<const float4 *>(p.bias + ncol0 + c)
                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       for (int r0 = 0; r0 < 32; r0 += 8) {
-        float4 old[8][BN / 128 > 0 ? BN / 128 : 1];
+        float4 old[8][BNW / 128 > 0 ? BNW / 128 : 1];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
           const int row = m0 + quad * 32 + r0 + j;
 #pragma unroll
-          for (int q = 0; q < (BN / 128 > 0 ? BN / 128 : 1); q++) {
+          for (int q = 0; q < (BNW / 128 > 0 ? BNW / 128 : 1); q++) {
             const int c = lane * 4 + q * 128;
-            old[j][q] = (row < p.M && c < BN && n0 + c < p.N)
-                            ? *reinterpret_cast<const float4 *>(p.C + (size_t)row * p.ldc + n0 + c)
+            old[j][q] = (row < p.M && c < BNW && ncol0 + c < p.N)
+                            ? *reinterpret_cast<const float4 *>(p.C + (size_t)row * p.ldc + ncol0 + c)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
@@ -292,15 +297,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (row >= p.M) break;
           const float *srow = stg + (size_t)(r0 + j) * EST;
 #pragma unroll
-          for (int q = 0; q < (BN / 128 > 0 ? BN / 128 : 1); q++) {
+          for (int q = 0; q < (BNW / 128 > 0 ? BNW / 128 : 1); q++) {
             const int c = lane * 4 + q * 128;
-            if (c < BN && n0 + c < p.N) {
+            if (c < BNW && ncol0 + c < p.N) {
               float4 v = *reinterpret_cast<const float4 *>(srow + c);
               v.x = p.alpha * v.x + bv[q].x + p.beta * old[j][q].x;
               v.y = p.alpha * v.y + bv[q].y + p.beta * old[j][q].y;
               v.z = p.alpha * v.z + bv[q].z + p.beta * old[j][q].z;
               v.w = p.alpha * v.w + bv[q].w + p.beta * old[j][q].w;
-              *reinterpret_cast<float4 *>(p.C + (size_t)row * p.ldc + n0 + c) = v;
+              *reinterpret_cast<float4 *>(p.C + (size_t)row * p.ldc + ncol0 + c) = v;
             }
           }
         }
@@ -311,15 +316,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (row >= p.M) break;
       const float *srow = stg + (size_t)rr * EST;
       if (p.splits > 1) {
-        float *wrow = p.ws + ((size_t)split * p.M + row) * p.N + n0;
-        for (int c = lane; c < BN && n0 + c < p.N; c += 32) wrow[c] = srow[c];
+        float *wrow = p.ws + ((size_t)split * p.M + row) * p.N + ncol0;
+        for (int c = lane; c < BNW && ncol0 + c < p.N; c += 32) wrow[c] = srow[c];
       } else if (vec_ok) {
-        float *crow = p.C + (size_t)row * p.ldc + n0;
-        for (int c = lane * 4; c < BN && n0 + c < p.N; c += 128) {
+        float *crow = p.C + (size_t)row * p.ldc + ncol0;
+        for (int c = lane * 4; c < BNW && ncol0 + c < p.N; c += 128) {
           float4 v = *reinterpret_cast<const float4 *>(srow + c);
           v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
           if (p.bias) {
-            const float4 b = *reinterpret_cast<const float4 *>(p.bias + n0 + c);
+            const float4 b = *reinterpret_cast<const float4 *>(p.bias + ncol0 + c);
             v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
           }
           if (p.beta != 0.f) {
@@ -329,10 +334,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           *reinterpret_cast<float4 *>(crow + c) = v;
         }
       } else {
-        float *crow = p.C + (size_t)row * p.ldc + n0;
-        for (int c = lane; c < BN && n0 + c < p.N; c += 32) {
+        float *crow = p.C + (size_t)row * p.ldc + ncol0;
+        for (int c = lane; c < BNW && ncol0 + c < p.N; c += 32) {
           float v = p.alpha * srow[c];
-          if (p.bias) v += p.bias[n0 + c];
+          if (p.bias) v += p.bias[ncol0 + c];
           if (p.beta != 0.f) v += p.beta * crow[c];
           crow[c] = v;
         }
