@@ -142,6 +142,7 @@ int eesen_b200_net_feedforward(eesen_b200_net *n, const float *feats, int T, int
     else n->frames.clear();   // no SetSeqLengths, the reference tool's own call pattern: <BiLstm> layers only
     n->feats.Resize(T * S, I, kUndefined);
     n->feats.CopyFromHost(n->h_pinned, I);
+    n->net.SetTestMode();   // net-output-extract.cc:75-76: no dropout in the forward-only path
     n->net.SetSeqLengths(n->frames);
     n->net.Feedforward(n->feats, &n->net_out);
     if (log_priors) {
