@@ -147,14 +147,39 @@ def test_oracle_matches_reference_cpu_live():
     kaldi_io.write_model(d + "/model", net)
     kaldi_io.write_batch_file(d + "/batch.bin", b)
     np.save(d + "/diff.npy", r["obj_diff"].astype(np.float32))
-    oracle.run_reference("cpu", d + "/model", d + "/batch.bin", d + "/out", lr, mom, diff_in=d + "/diff.npy")
+    info = oracle.run_reference("cpu", d + "/model", d + "/batch.bin", d + "/out", lr, mom, diff_in=d + "/diff.npy")
     ref = oracle.load_dump(d + "/out")
+    # Ctc::ErrorRateMSeq (greedy path, collapse, Levenshtein: ctc-loss.cc:235-298) runs on the CPU build too
+    err, nref = oracle.greedy_token_errors(ref["net_out"], b.frames, b.labels, b.S)
+    assert (float(info["token_err"]), int(info["ref_tokens"])) == (float(err), int(nref))
     for i in range(1, len(net.layers) + 1):
         assert_close(f"out_l{i}", on.acts[i], ref[f"out_l{i}"], atol=2e-6)
     assert_close("in_diff", r["in_diff"], ref["in_diff"], atol=1e-6, rtol=1e-4)
     assert_close("corr", on.flat_corr(), golden_arrays(ref, net), atol=2e-5, rtol=1e-4)
     m2 = kaldi_io.read_model(d + "/out/model_out")
     assert_close("params", on.flat_params(), m2.flat_params(), atol=1e-6)
+
+
+@pytest.mark.skipif(not oracle.have_reference("cpu"), reason="reference build (oracle/_ref) not present")
+@pytest.mark.parametrize("wl,seed", [("tiny", 1), ("small", 2), ("mid", 3)])
+def test_token_error_count_matches_reference(wl, seed):
+    """Ctc::ErrorRateMSeq against the restated greedy decode + edit distance, on random-weight models whose greedy
+    paths contain repeats, blanks and insertions (the statistics behind the recipes' TOKEN_ACCURACY line)."""
+    w, net, b = case(wl, seed, seed + 100)
+    for l in net.layers:                      # larger weights -> peaky posteriors -> non-trivial greedy paths
+        for k in l.params:
+            l.params[k] = (l.params[k] * 8).astype(np.float32)
+    with tempfile.TemporaryDirectory() as d:
+        kaldi_io.write_model(d + "/model", net)
+        kaldi_io.write_batch_file(d + "/batch.bin", b)
+        np.save(d + "/diff.npy", np.zeros((b.feats.shape[0], w.classes), np.float32))
+        info = oracle.run_reference("cpu", d + "/model", d + "/batch.bin", d + "/out", 0.0, 0.0, diff_in=d + "/diff.npy")
+        y = oracle.load_dump(d + "/out")["net_out"]
+    err, nref = oracle.greedy_token_errors(y, b.frames, b.labels, b.S)
+    assert int(info["ref_tokens"]) == nref == sum(len(l) for l in b.labels)
+    assert float(info["token_err"]) == float(err)
+    am = y.argmax(1)
+    assert len(np.unique(am)) > 2             # the decode really saw several symbols
 
 
 def _torch_ctc(logits, frames, labels, S):
