@@ -159,7 +159,9 @@ int main(int argc, char *argv[]) {
         if (num_jobs == 1 || job_id == 1) net.Write(target_model_filename, binary);
       }
       const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
-      KALDI_LOG << "Done " << num_done << " files, " << skipped.no_targets << " with no targets, " << skipped.too_long
+      // as the reference prints it (train-ctc-parallel.cc:247-251): utterances above --frame-limit are warned about
+      // and skipped but not counted here; "other errors" stays 0 on this path too (a bad feature dimension aborts)
+      KALDI_LOG << "Done " << num_done << " files, " << skipped.no_targets << " with no targets, " << skipped.bad_dim
                 << " with other errors. [" << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << ", "
                 << elapsed / 60 << " min, fps" << total_frames / elapsed << "]";
       KALDI_LOG << report;

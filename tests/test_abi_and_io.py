@@ -177,3 +177,46 @@ def test_feature_and_label_archives(tmp_path):
     assert raw.startswith(b"utt1 \0BFM \x04\x02\x00\x00\x00\x04\x03\x00\x00\x00")
     kaldi_io.write_label_ark(str(tmp_path / "l.ark"), keys, [[1, 2], [3]])
     assert open(tmp_path / "l.ark").read() == "utt1 1 2\nutt2 3\n"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_train_ctc_parallel")),
+                    reason="reference train-ctc-parallel (CPU build) not built")
+def test_reference_driver_reads_our_archives_and_reports_the_same_accuracy():
+    """The reference's own driver (CPU build, --cross-validate: forward + ErrorRateMSeq only) on the feature / label
+    archives and the model our writers produce: it must read them, skip what it skips (an utterance without
+    targets, one above --frame-limit) and print the TOKEN_ACCURACY the restatement computes for the rest."""
+    import re
+    import subprocess
+    from oracle import oracle
+    w, net, b = case("small", 5, 6)
+    for l in net.layers:
+        for k in l.params:
+            l.params[k] = (l.params[k] * 8).astype(np.float32)
+    utts = [b.feats[np.arange(b.frames[s]) * b.S + s] for s in range(b.S)]
+    labels = [list(map(int, l)) for l in b.labels]
+    keys = [f"utt{i:02d}" for i in range(b.S)]
+    limit = int(sorted(b.frames)[-2])                   # the longest utterance alone exceeds --frame-limit
+    longest = int(np.argmax(b.frames))
+    no_target = (longest + 1) % b.S
+    with tempfile.TemporaryDirectory() as d:
+        kaldi_io.write_model(d + "/model", net)
+        kaldi_io.write_feature_ark(d + "/feats.ark", keys, utts)
+        kaldi_io.write_label_ark(d + "/labels.ark", [k for i, k in enumerate(keys) if i != no_target],
+                                 [l for i, l in enumerate(labels) if i != no_target])
+        exe = os.path.join(ROOT, "oracle", "_ref", "ref_train_ctc_parallel")
+        r = subprocess.run([exe, "--cross-validate=true", "--num-sequence=3", f"--frame-limit={limit}", "--report-step=1000",
+                            f"ark:{d}/feats.ark", f"ark,t:{d}/labels.ark", d + "/model"], capture_output=True, text=True,
+                           timeout=600, env=dict(os.environ, OPENBLAS_NUM_THREADS="4"))
+    assert r.returncode == 0, r.stderr[-3000:]
+    log = r.stdout + r.stderr
+    acc = float(re.search(r"TOKEN_ACCURACY >> ([-0-9.e+]+)% <<", log).group(1))
+    assert "missing targets" in log and "has too many frames" in log
+    used = [i for i in range(b.S) if i not in (no_target, longest)]
+    assert re.search(rf"Done {len(used)} files, 1 with no targets", log), log[-1500:]
+    on = oracle.OracleNet(net, np.float32)
+    err = ref = 0
+    for i in used:                                       # utterance by utterance: results do not depend on the packing
+        y = on.forward(utts[i], np.array([utts[i].shape[0]], np.int32))
+        e, n = oracle.greedy_token_errors(y, [utts[i].shape[0]], [np.asarray(labels[i])], 1)
+        err += e; ref += n
+    assert abs(acc - 100.0 * (1.0 - err / ref)) < 1e-3
