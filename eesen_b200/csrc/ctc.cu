@@ -114,7 +114,9 @@ ctc_kernel(int T, int S, int K, int max_lab, const int *__restrict__ len, const 
            float *__restrict__ pzx_out, float *__restrict__ diff, int ldd, float *__restrict__ ws) {
   constexpr int PF = R <= 8 ? 4 : 2;   // emission prefetch distance (time steps)
   constexpr int LP = 32 * R;           // padded lattice width
-  extern __shared__ float occ_sm[];    // [nwarps][K]
+  // per-warp class occupancies, accumulated as 24.40 fixed point: integer addition is associative, so
+  // the shared-memory atomics below give the same bits whatever order the lanes of a pass are served in
+  extern __shared__ unsigned long long occ_sm[];    // [nwarps][K]
   __shared__ float pzx_sm;
   const int s = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -122,6 +124,10 @@ ctc_kernel(int T, int S, int K, int max_lab, const int *__restrict__ len, const 
   const int nl = lab_len[s];
   const int L = 2 * nl + 1;
   const int *lab_s = labels + (size_t)s * max_lab;
+  auto lab_at = [&](int i) {   // class of label i; ids outside [0, K) (a corrupt targets archive) read as blank
+    const int c = lab_s[i];    // instead of indexing out of bounds -- the host rejects such utterances (net.cc)
+    return (unsigned)c < (unsigned)K ? c : 0;
+  };
   float *alpha = ws + (size_t)s * T * LP;
   float *beta = ws + (size_t)S * T * LP + (size_t)s * T * LP;
 
@@ -132,7 +138,7 @@ ctc_kernel(int T, int S, int K, int max_lab, const int *__restrict__ len, const 
 #pragma unroll
     for (int r = 0; r < R; r++) {
       int j = lane * R + r;
-      cls[r] = j >= L ? -1 : ((j & 1) ? lab_s[j >> 1] : 0);
+      cls[r] = j >= L ? -1 : ((j & 1) ? lab_at(j >> 1) : 0);
       if (warp == 0) skip[r] = (j & 1) && j >= 3 && j < L && lab_s[j >> 1] != lab_s[(j >> 1) - 1];
       else skip[r] = (j & 1) && j + 2 < L && lab_s[j >> 1] != lab_s[(j >> 1) + 1];
     }
@@ -228,14 +234,15 @@ ctc_kernel(int T, int S, int K, int max_lab, const int *__restrict__ len, const 
 
   // ---- occupancies -> gradient wrt the pre-softmax activations
   const float pzx = pzx_sm;
-  float *occ = occ_sm + warp * K;
+  unsigned long long *occ = occ_sm + (size_t)warp * K;
+  constexpr float kFix = 1099511627776.f, kUnfix = 1.f / 1099511627776.f;   // 2^40
   for (int t = warp; t < T; t += nwarps) {
     float *drow = diff + ((size_t)t * S + s) * ldd;
     if (t >= Ts) {
       for (int k = lane; k < K; k += 32) drow[k] = 0.f;   // padded rows: ctc_err_ stays 0 (:1615)
       continue;
     }
-    for (int k = lane; k < K; k += 32) occ[k] = 0.f;
+    for (int k = lane; k < K; k += 32) occ[k] = 0ull;
     __syncwarp();
     const float *arow = alpha + (size_t)t * LP, *brow = beta + (size_t)t * LP;
     const float *yrow = probs + ((size_t)t * S + s) * ldp;
@@ -244,21 +251,20 @@ ctc_kernel(int T, int S, int K, int max_lab, const int *__restrict__ len, const 
     for (int j = lane; j < L; j += 32) {
       float ab = arow[j] + brow[j];
       if (j & 1) {
-        int c = lab_s[j >> 1];
+        int c = lab_at(j >> 1);
         float gam = ex2_approx(ab - pzx - logprob(yrow[c]));    // exp(log(a*b) - pzx - 2 log y) * y  (:1624 then MulElements)
-        atomicAdd(&occ[c], gam);
+        atomicAdd(&occ[c], (unsigned long long)(fminf(gam, 1048576.f) * kFix));   // each term <= 1 up to rounding
       } else {
         blank += ex2_approx(ab - pzx - lb);
       }
     }
     blank = warp_sum(blank);
     __syncwarp();
-    if (lane == 0) occ[0] += blank;
-    __syncwarp();
     float z = 0.f;
-    for (int k = lane; k < K; k += 32) z += occ[k];
+    for (int k = lane; k < K; k += 32) z += (float)occ[k] * kUnfix + (k == 0 ? blank : 0.f);
     z = warp_sum(z);                              // = -rowsum(ctc_err .* y)  (ctc-loss.cc:161-162)
-    for (int k = lane; k < K; k += 32) drow[k] = yrow[k] * z - occ[k];   // :164-168
+    for (int k = lane; k < K; k += 32)
+      drow[k] = yrow[k] * z - ((float)occ[k] * kUnfix + (k == 0 ? blank : 0.f));   // :164-168
     __syncwarp();
   }
 }
@@ -306,11 +312,23 @@ cudaError_t ctc_eval(cudaStream_t st, int T, int S, int K, int max_lab, const in
                      float *ws) {
   if (S <= 0 || T <= 0) return cudaSuccess;
   int R = ctc_R(max_lab);
-  size_t smem = sizeof(float) * 8 * K;
+  // one occupancy row of K 8-byte cells per warp: as many warps (2..8) as the opt-in shared memory holds,
+  // so that character / BPE output layers (K in the thousands) launch too -- the reference takes any K
+  int dev = 0, max_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  int nwarps = 8;
+  while (nwarps > 2 && sizeof(unsigned long long) * nwarps * (size_t)K > (size_t)max_optin - 1024) nwarps--;
+  size_t smem = sizeof(unsigned long long) * nwarps * (size_t)K;
+  if (smem > (size_t)max_optin - 1024) return cudaErrorInvalidValue;   // K > ~14 000 classes
 #define EB_CTC(RR)                                                                                        \
   case RR:                                                                                                \
-    ctc_kernel<RR><<<S, 256, smem, st>>>(T, S, K, max_lab, len, labels, lab_len, probs, ldp, pzx, diff, ldd, \
-                                         ws);                                                             \
+    if (smem > 48 * 1024) {                                                                               \
+      cudaError_t ae = cudaFuncSetAttribute(ctc_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (ae != cudaSuccess) return ae;                                                                   \
+    }                                                                                                     \
+    ctc_kernel<RR><<<S, 32 * nwarps, smem, st>>>(T, S, K, max_lab, len, labels, lab_len, probs, ldp, pzx, diff, \
+                                                 ldd, ws);                                                \
     break;
   switch (R) {
     EB_CTC(1) EB_CTC(2) EB_CTC(4) EB_CTC(8) EB_CTC(16) EB_CTC(32)

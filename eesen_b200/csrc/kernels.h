@@ -98,6 +98,8 @@ cudaError_t sgd_momentum_clip(cudaStream_t st, int num_sms, float *w, float *cor
 cudaError_t optimizer_update(cudaStream_t st, int num_sms, int mode, float *w, float *corr, float *accu,
                              const float *grad, float momentum, float eps, float rho, float one_minus_rho,
                              const SgdSegment *d_segs, int nseg, long total);
+// *d_flags = bit 0 (NaN present) | bit 1 (Inf present) over x[0, n)
+cudaError_t check_finite(cudaStream_t st, int num_sms, const float *x, long n, int *d_flags);
 cudaError_t mul_elements(cudaStream_t st, int num_sms, int N, int cols, const float *a, int lda, const float *b, int ldb,
                          float *out, int ldo);
 // scaled Bernoulli mask 0 | 1/(1-p) from a counter-based generator (per_col: one draw per column for all rows)

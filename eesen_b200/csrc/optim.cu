@@ -152,7 +152,30 @@ __global__ void col_sum_final_kernel(int K, int nblocks, const float *__restrict
   out[col] = s;
 }
 
+// bit 0: a NaN, bit 1: an Inf somewhere in x[0, n)  (Net::Check, reference net.cc:461-468 / CheckNanInf
+// utils-functions.h:118 look at the SUM on the host; element tests cannot be fooled by +inf + -inf or overflow)
+__global__ void check_finite_kernel(const float *__restrict__ x, long n, int *__restrict__ flags) {
+  int f = 0;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = x[i];
+    if (v != v) f |= 1;
+    else if (fabsf(v) == INFINITY) f |= 2;
+  }
+  f = __reduce_or_sync(0xffffffffu, f);
+  if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
+}
+
 }  // namespace
+
+cudaError_t check_finite(cudaStream_t st, int num_sms, const float *x, long n, int *d_flags) {
+  cudaError_t e = cudaMemsetAsync(d_flags, 0, sizeof(int), st);
+  if (e != cudaSuccess || n <= 0) return e;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 8 * num_sms) blocks = 8 * num_sms;
+  check_finite_kernel<<<blocks, 256, 0, st>>>(x, n, d_flags);
+  return cudaGetLastError();
+}
 
 cudaError_t sgd_momentum_clip(cudaStream_t st, int num_sms, float *w, float *corr, const float *grad,
                               float momentum, const SgdSegment *d_segs, int nseg, long total) {

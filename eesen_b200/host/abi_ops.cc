@@ -67,7 +67,7 @@ void eesen_b200_destroy(eesen_b200_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   eesen_b200_ctx::Buf *bufs[] = {&ctx->gemm_ws, &ctx->lstm_pbuf, &ctx->lstm_gsum, &ctx->lstm_flags,
-                                 &ctx->ctc_ws, &ctx->colsum_ws, &ctx->seg_buf};
+                                 &ctx->ctc_ws, &ctx->colsum_ws, &ctx->seg_buf, &ctx->flag_buf};
   for (auto *b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->nccl_comm && ctx->nccl_lib) {
@@ -441,6 +441,21 @@ int eesen_b200_ctc_eval(eesen_b200_ctx *ctx, int T, int S, int K, int max_lab, c
                                (float *)ws);
   ctx->prof_end(pe);
   return ctx->check(e, "ctc_eval");
+}
+
+int eesen_b200_check_finite(eesen_b200_ctx *ctx, const float *d_x, int64_t n, int *flags) {
+  if (!ctx || !flags || (n > 0 && !d_x) || n < 0) return EESEN_B200_EINVAL;
+  void *d;
+  int rc = ctx->reserve(ctx->flag_buf, 64, &d);
+  if (rc) return rc;
+  ctx->launches += 1;
+  int pe = ctx->prof_begin(eesen_b200_ctx::kMisc);
+  cudaError_t e = eb::check_finite(ctx->stream, ctx->num_sms, d_x, (long)n, (int *)d);
+  ctx->prof_end(pe);
+  if ((rc = ctx->check(e, "check_finite"))) return rc;
+  CTX_CHECK(cudaMemcpyAsync(flags, d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream), "memcpy(flags)");
+  CTX_CHECK(cudaStreamSynchronize(ctx->stream), "sync(flags)");
+  return 0;
 }
 
 int eesen_b200_sgd_update(eesen_b200_ctx *ctx, float *w, float *corr, const float *grad, int64_t n, float momentum,

@@ -34,13 +34,13 @@ struct Minibatch {
 class MinibatchAssembler {
  public:
   struct Counters {
-    int32 no_targets = 0, too_long = 0, bad_dim = 0;
+    int32 no_targets = 0, too_long = 0, bad_dim = 0, bad_labels = 0;
   };
 
   MinibatchAssembler(const std::string &feature_rspecifier, const std::string &targets_rspecifier, int32 feat_dim,
-                     int32 num_sequence, double frame_limit, int device = 0)
+                     int32 num_sequence, double frame_limit, int device = 0, int32 num_classes = 0)
       : feats_(feature_rspecifier), targets_(targets_rspecifier), dim_(feat_dim), num_sequence_(num_sequence),
-        frame_limit_(frame_limit), device_(device) {
+        frame_limit_(frame_limit), device_(device), num_classes_(num_classes) {
     worker_ = std::thread(&MinibatchAssembler::Run, this);
   }
 
@@ -130,6 +130,8 @@ class MinibatchAssembler {
         local.too_long++;
       } else if (m.cols != dim_) {
         KALDI_ERR << key << ": feature dim " << m.cols << " does not match the network input " << dim_;
+      } else if (!LabelsUsable(key, targets_.Value(key))) {
+        local.bad_labels++;
       } else {
         int32 cand = std::max<int32>(longest, m.rows);
         if ((double)cand * (utts->size() + 1) > frame_limit_) break;   // does not fit: starts the next minibatch
@@ -145,11 +147,31 @@ class MinibatchAssembler {
       std::unique_lock<std::mutex> lk(mu_);
       counters_.no_targets += local.no_targets;
       counters_.too_long += local.too_long;
+      counters_.bad_labels += local.bad_labels;
     }
     mb->S = utts->size();
     mb->T = longest;
     mb->dim = dim_;
     return mb->S > 0;
+  }
+
+  // The reference has no limit on the label sequence and never looks at the ids (ctc-loss.cc:116-129); here the
+  // CTC lattice of one utterance lives in the registers of one warp (<= 511 labels) and an id outside
+  // [0, num_classes) would index past the posterior row.  Such utterances are skipped with a warning (and
+  // counted) instead of aborting the run -- in a multi-rank job an abort would strand the other ranks in
+  // the all-reduce.
+  bool LabelsUsable(const std::string &key, const std::vector<int> &lab) const {
+    if (lab.size() > 511) {
+      KALDI_WARN << key << ", has too many labels; ignoring: " << lab.size() << " > 511";
+      return false;
+    }
+    if (num_classes_ > 0)
+      for (size_t i = 0; i < lab.size(); i++)
+        if (lab[i] < 0 || lab[i] >= num_classes_) {
+          KALDI_WARN << key << ", label " << lab[i] << " outside [0, " << num_classes_ << "); ignoring the utterance";
+          return false;
+        }
+    return true;
   }
 
   void Pack(Minibatch *mb, const std::vector<HostMatrix> &utts) {
@@ -173,6 +195,7 @@ class MinibatchAssembler {
   int32 dim_, num_sequence_;
   double frame_limit_;
   int device_;
+  int32 num_classes_ = 0;
   Minibatch slot_[2];
   State state_[2] = {kEmpty, kEmpty};
   int read_ = 0, held_ = -1;

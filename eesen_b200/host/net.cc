@@ -529,11 +529,13 @@ void LstmParallel::WriteData(std::ostream &os, bool binary) const {   // lstm-la
   WriteToken(os, binary, "<LearnRateCoef>"); WriteBasicType(os, binary, learn_rate_coef_);
   WriteToken(os, binary, "<MaxGrad>"); WriteBasicType(os, binary, max_grad_);
   if (has_accu_) {
-    // The reference writes the WEIGHTS a second time under <LstmAccus>, not the accumulators
-    // (lstm-layer.h:153-163 writes wei_gifo_x_ ... phole_o_c_ in both blocks).  Mirrored byte for byte:
-    // a model written here must read back in the reference exactly as the reference's own file would.
+    // DELIBERATE deviation from a reference bug: lstm-layer.h:153-163 writes the WEIGHTS (wei_gifo_x_ ...
+    // phole_o_c_) a second time under <LstmAccus>, and ReadData (:119-131) then loads them as the
+    // Adagrad/RMSProp accumulators -- after one reload sqrt(accu + eps) of a negative weight is NaN.  The real
+    // accumulators have the same shapes, so the reference reads this file exactly like its own.
+    KALDI_ASSERT((int64)host_accu_.size() == NumParams());
     WriteToken(os, binary, "<LstmAccus>");
-    WriteLstmTensors(os, binary, cell_dim_, input_dim_, host_params_);
+    WriteLstmTensors(os, binary, cell_dim_, input_dim_, host_accu_);
   }
   WriteLstmTensors(os, binary, cell_dim_, input_dim_, host_params_);
 }
@@ -764,6 +766,24 @@ void Net::Read(std::istream &is, bool binary) {
   // the reference's masks come from a std::random_device-seeded generator (kaldi-math.h:107-131): a fresh seed per
   // process unless the caller fixes one (Net::SetDropoutSeed)
   SetDropoutSeed(((uint64_t)std::random_device{}() << 32) ^ (uint64_t)std::random_device{}());
+  Check();   // net.cc:276,296
+}
+
+// Net::Check (reference net.cc:448-468): buffer counts, layer dimensions, and no NaN/Inf in the parameters.
+// The reference gathers every parameter on the host and tests the sum; here one kernel scans the parameter
+// arena in place and returns two bits.
+void Net::Check() const {
+  KALDI_ASSERT((int32)propagate_buf_.size() == NumLayers() + 1);
+  KALDI_ASSERT((int32)backpropagate_buf_.size() == NumLayers() + 1);
+  for (size_t i = 0; i + 1 < layers_.size(); i++) {
+    KALDI_ASSERT(layers_[i] != NULL);
+    KALDI_ASSERT(layers_[i]->OutputDim() == layers_[i + 1]->InputDim());
+  }
+  if (arena_size_ == 0) return;
+  int flags = 0;
+  CheckAbi(ctx_, eesen_b200_check_finite(ctx_, w_, arena_size_, &flags), "eesen_b200_check_finite");
+  if (flags & 2) KALDI_ERR << "'inf' in network parameters";
+  if (flags & 1) KALDI_ERR << "'nan' in network parameters";
 }
 
 // Lay all trainable layers out in three contiguous arenas (params / raw grads / momentum), each
@@ -863,6 +883,7 @@ void Net::Write(const std::string &file, bool binary) {
 }
 
 void Net::Write(std::ostream &os, bool binary) {
+  Check();   // net.cc:326,345
   RefreshHostCopies();
   WriteToken(os, binary, "<Nnet>");
   if (!binary) os << std::endl;
@@ -1127,11 +1148,18 @@ Ctc::~Ctc() {
 
 // label staging: [S x max_lab] padded matrix + lengths (the reference uploads the expanded
 // S x (2*max+1) matrix on every one of its 2T kernel launches, cuda-matrix.cc:882-883,948-950)
-void Ctc::Upload(const std::vector<int32> &frame_num_utt, std::vector<std::vector<int32> > &label) {
+void Ctc::Upload(const std::vector<int32> &frame_num_utt, std::vector<std::vector<int32> > &label, int32 num_classes) {
   int32 S = frame_num_utt.size();
   KALDI_ASSERT((int32)label.size() >= S);
   max_lab_ = 1;
-  for (int32 s = 0; s < S; s++) max_lab_ = std::max<int32>(max_lab_, label[s].size());
+  for (int32 s = 0; s < S; s++) {
+    max_lab_ = std::max<int32>(max_lab_, label[s].size());
+    // the reference never validates the ids (ctc-loss.cc:122-128): a label >= K reads past the posterior row
+    for (size_t l = 0; l < label[s].size(); l++)
+      if (label[s][l] < 0 || label[s][l] >= num_classes)
+        KALDI_ERR << "utterance " << s << " of the minibatch: label " << label[s][l] << " outside [0, " << num_classes
+                  << ") (the network has " << num_classes << " outputs, blank = 0)";
+  }
   // one buffer: [len S][lablen S][pzx S as float][labels S*max_lab]
   size_t ints = (size_t)3 * S + (size_t)S * max_lab_;
   GrowDevice(&d_len_, &cap_len_, ints);
@@ -1156,7 +1184,7 @@ void Ctc::EvalParallelAsync(const std::vector<int32> &frame_num_utt, const CuMat
   int32 num_frames = net_out.NumRows();
   KALDI_ASSERT(S > 0 && num_frames % S == 0);
   int32 T = num_frames / S;
-  Upload(frame_num_utt, label);
+  Upload(frame_num_utt, label, net_out.NumCols());
   CheckAbi(ctx_, eesen_b200_ctc_eval(ctx_, T, S, net_out.NumCols(), max_lab_, d_len_, d_len_ + 3 * S, d_lablen_,
                                      net_out.Data(), net_out.Stride(), d_pzx_, diff->Data(), diff->Stride()),
            "eesen_b200_ctc_eval");

@@ -279,6 +279,7 @@ class Net {
   // Replaces the done-file handshake of the reference (src/net/communicator.h:57-71,107-113).
   int32 BackpropagateShared(const CuMatrixBase<BaseFloat> *out_diff);
   void SetSeqLengths(std::vector<int> &sequence_lengths);                            // net.h:157-161
+  void Check() const;                                    // net.cc:448-468 (dims + NaN/Inf in the parameters)
   void SetTrainOptions(const NetTrainOptions &opts);
   const NetTrainOptions &GetTrainOptions() const { return opts_; }
   void SetUpdateAlgorithm(const std::string &opt);       // SGD | Adagrad | RMSProp (net.cc:481-496)
@@ -378,7 +379,7 @@ class Ctc {
   const float *DevicePzx() const { return d_pzx_; }
 
  private:
-  void Upload(const std::vector<int32> &frame_num_utt, std::vector<std::vector<int32> > &label);
+  void Upload(const std::vector<int32> &frame_num_utt, std::vector<std::vector<int32> > &label, int32 num_classes);
   eesen_b200_ctx *ctx_;
   int32 frames_ = 0, sequences_num_ = 0, ref_num_ = 0;
   float error_num_ = 0;

@@ -75,23 +75,33 @@ int main(int argc, char *argv[]) {
                                            PrecFromString(po.Str("recurrent-precision", "fp32x3"))),
              "eesen_b200_set_precision");
     if (num_jobs > 1) {
+      // Rendezvous through a file next to the model, as the reference's jobs meet through files
+      // (net/communicator.h:57-71).  A file left behind by an earlier run on the same model path must never be
+      // read as this run's id: job 1 stamps the id with its own start time, the other jobs accept only a file
+      // whose stamp is not older than a minute before their own start (the jobs of one run are started together
+      // by the recipe), and job 1 removes the file once every rank has joined the communicator.
       std::string idfile = (crossvalidate ? model_filename + ".cv" : target_model_filename) + ".ncclid";
       char id[128];
+      const long long now = (long long)std::chrono::duration_cast<std::chrono::seconds>(
+                                std::chrono::system_clock::now().time_since_epoch()).count();
       if (job_id == 1) {
+        std::remove(idfile.c_str());
         if (eesen_b200_nccl_unique_id(id)) KALDI_ERR << "ncclGetUniqueId failed";
         std::string tmp = idfile + ".tmp";
-        { std::ofstream f(tmp.c_str(), std::ios::binary); f.write(id, 128); }
+        { std::ofstream f(tmp.c_str(), std::ios::binary); f.write(id, 128); f.write((const char *)&now, sizeof(now)); }
         std::rename(tmp.c_str(), idfile.c_str());
       } else {
         for (int tries = 0;; tries++) {
           std::ifstream f(idfile.c_str(), std::ios::binary);
-          if (f.is_open() && f.read(id, 128)) break;
+          long long stamp = 0;
+          if (f.is_open() && f.read(id, 128) && f.read((char *)&stamp, sizeof(stamp)) && stamp >= now - 60) break;
           if (tries > 200000) KALDI_ERR << "timed out waiting for " << idfile;
           usleep(300);
         }
       }
       CheckAbi(ctx, eesen_b200_nccl_init(ctx, job_id - 1, num_jobs, id), "eesen_b200_nccl_init");
-      if (job_id == 1) { usleep(200000); }
+      // ncclCommInitRank returns only after all ranks have joined: nobody needs the file any more
+      if (job_id == 1) std::remove(idfile.c_str());
     }
 
     {
@@ -114,9 +124,9 @@ int main(int argc, char *argv[]) {
       int device_index = 0;
       cudaGetDevice(&device_index);
       MinibatchAssembler batches(feature_rspecifier, targets_rspecifier, net.InputDim(), num_sequence, frame_limit,
-                                 device_index);
+                                 device_index, net.OutputDim());
       int64 total_frames = 0;
-      int32 num_done = 0;
+      int32 num_done = 0, steps_since_check = 0;
       cudaStream_t stream = (cudaStream_t)eesen_b200_stream(ctx);
       cudaEvent_t h2d_done;
       cudaEventCreateWithFlags(&h2d_done, cudaEventDisableTiming);
@@ -148,6 +158,12 @@ int main(int argc, char *argv[]) {
         }
         num_done += mb->S;
         total_frames += mb->padded_frames();
+        // a diverged run is caught at the next report instead of at the final Net::Write (net.cc:448-468);
+        // every rank holds the same parameters, so every rank stops at the same step
+        if (!crossvalidate && report_step > 0 && ++steps_since_check >= report_step) {
+          net.Check();
+          steps_since_check = 0;
+        }
       }
 
       cudaEventDestroy(h2d_done);
@@ -161,8 +177,8 @@ int main(int argc, char *argv[]) {
       const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
       // as the reference prints it (train-ctc-parallel.cc:247-251): utterances above --frame-limit are warned about
       // and skipped but not counted here; "other errors" stays 0 on this path too (a bad feature dimension aborts)
-      KALDI_LOG << "Done " << num_done << " files, " << skipped.no_targets << " with no targets, " << skipped.bad_dim
-                << " with other errors. [" << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << ", "
+      KALDI_LOG << "Done " << num_done << " files, " << skipped.no_targets << " with no targets, "
+                << skipped.bad_dim + skipped.bad_labels << " with other errors. [" << (crossvalidate ? "CROSS-VALIDATION" : "TRAINING") << ", "
                 << elapsed / 60 << " min, fps" << total_frames / elapsed << "]";
       KALDI_LOG << report;
     }

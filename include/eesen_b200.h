@@ -69,6 +69,11 @@ int eesen_b200_debug_lstm_timing(eesen_b200_ctx *ctx, long long *out32, int rese
 
 /* ---------------------------------------------------------------- level 1: device operators */
 
+/* NaN/Inf scan of a device array: *flags = bit 0 (a NaN) | bit 1 (an Inf).  Replaces the host-side sum test of
+ * Net::Check / CheckNanInf (reference src/net/net.cc:461-468, src/net/utils-functions.h:118-122), which copies
+ * every parameter to the host.  Synchronises the stream (it returns a host value). */
+int eesen_b200_check_finite(eesen_b200_ctx *ctx, const float *d_x, int64_t n, int *flags);
+
 /* C = alpha*op(A)*op(B) + beta*C.  Replaces CuMatrixBase::AddMatMat -> cublasSgemm
  * (reference src/gpucompute/cuda-matrix.cc:603-639).  transA/transB: 0 = as stored, 1 = transposed;
  * (1,1) is not provided (unused by the path). */

@@ -1,0 +1,257 @@
+// tests/micro/umma_probe.cu -- hardware probe for the tcgen05 recurrent-step design.
+// Answers, on a B200:
+//   1. kind::f16 with hand-filled K-major SWIZZLE_128B tiles (no TMA): is the layout right?
+//   2. mixed operand formats (A = fp16, B = bf16) in one instruction: allowed by the hardware?
+//   3. TMEM lane layout of an M=64 accumulator (rows -> lanes (r%16) + 32*(r/16))?
+//   4. cost of one recurrent step's MMA chain: K=320 (20 k-slices), A = resident weights [M x K]
+//      (hi and lo' tiles), B = activations [N x K]; N = 32 (hi|lo') then N = 16 (hi) per k-slice.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o umma_probe umma_probe.cu
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <stdint.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#define CK(x)                                                                          \
+  do {                                                                                 \
+    cudaError_t e_ = (x);                                                              \
+    if (e_ != cudaSuccess) {                                                           \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(1);                                                                         \
+    }                                                                                  \
+  } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// byte offset of element (row r, k) in a K-major SWIZZLE_128B tile of 16-bit elements with ROWS rows
+__host__ __device__ inline size_t sw128_off(int ROWS, int r, int k) {
+  int kb = k / 64, kk = k % 64, chunk = kk / 8, within = kk % 8;
+  return (size_t)kb * ROWS * 128 + (size_t)(r / 8) * 1024 + (size_t)(r % 8) * 128 + (size_t)((chunk ^ (r % 8)) * 16) +
+         within * 2;
+}
+
+constexpr int K = 320;
+constexpr int KB = K / 64;
+
+// fmt: 0 fp16, 1 bf16
+__device__ __forceinline__ uint16_t cvt16(float x, int fmt) {
+  if (fmt == 0) return __half_as_ushort(__float2half_rn(x));
+  return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+}
+
+// out[lane][col] raw accumulator dump (128 lanes x 64 cols)
+template <int M>
+__global__ void __launch_bounds__(128, 1)
+probe_kernel(const float *A, const float *B, int NB, int afmt, int bfmt, float *out, long long *cycles, int reps,
+             int mode) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *sA = smem;                          // [M x K] hi
+  uint8_t *sA2 = sA + (size_t)M * K * 2;       // second A tile (same contents: timing only)
+  uint8_t *sB = sA2 + (size_t)M * K * 2;       // [64 x K]
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_sm;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < M * K; i += 128) {
+    int r = i / K, k = i % K;
+    uint16_t v = cvt16(A[i], afmt);
+    *reinterpret_cast<uint16_t *>(sA + sw128_off(M, r, k)) = v;
+    *reinterpret_cast<uint16_t *>(sA2 + sw128_off(M, r, k)) = v;
+  }
+  for (int i = tid; i < 64 * K; i += 128) {
+    int r = i / K, k = i % K;
+    *reinterpret_cast<uint16_t *>(sB + sw128_off(64, r, k)) = r < NB ? cvt16(B[i], bfmt) : 0;
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_sm)), "n"(128)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = tmem_base_sm;
+  const int NH = NB == 48 ? 32 : NB / 2;
+  const uint32_t idescN = (1u << 4) | ((uint32_t)afmt << 7) | ((uint32_t)bfmt << 10) | ((uint32_t)(NB >> 3) << 17) |
+                          ((uint32_t)(M >> 4) << 24);
+  const uint32_t idescH = (1u << 4) | ((uint32_t)afmt << 7) | ((uint32_t)bfmt << 10) | ((uint32_t)(NH >> 3) << 17) |
+                          ((uint32_t)(M >> 4) << 24);
+  uint32_t phase = 0;
+  long long t0 = 0, t1 = 0;
+  if (tid == 0) t0 = clock64();
+  for (int rep = 0; rep < reps; rep++) {
+    if (tid == 0) {
+      for (int kb = 0; kb < KB; kb++) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) {
+          const uint64_t ad = umma_desc(smem_u32(sA) + kb * (M * 128) + ks * 32, 16, 1024, 2);
+          const uint64_t bd = umma_desc(smem_u32(sB) + kb * (64 * 128) + ks * 32, 16, 1024, 2);
+          umma_f16(tmem_base, ad, bd, idescN, (kb | ks) != 0);
+          if (mode >= 1) {   // second weight tile against the first half of the B rows -> accumulator at column 64
+            const uint64_t ad2 = umma_desc(smem_u32(sA2) + kb * (M * 128) + ks * 32, 16, 1024, 2);
+            umma_f16(tmem_base + 64, ad2, bd, idescH, (kb | ks) != 0);
+          }
+        }
+      }
+      umma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    if (mode == 2) {   // include a TMEM read + sync in the loop (epilogue pacing)
+      uint32_t r[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(tmem_base + ((uint32_t)(warp * 32) << 16)));
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      if (r[0] == 0x12345678u) out[0] = 1.f;
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncthreads();
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    }
+  }
+  if (tid == 0) {
+    t1 = clock64();
+    cycles[0] = t1 - t0;
+  }
+  // dump 128 lanes x 128 columns
+  for (int c0 = 0; c0 < 128; c0 += 16) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+    for (int j = 0; j < 16; j++) out[(size_t)(warp * 32 + lane) * 128 + c0 + j] = __uint_as_float(r[j]);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(128) : "memory");
+  }
+}
+
+static float round16(float x, int fmt) {
+  if (fmt == 0) return __half2float(__float2half_rn(x));
+  return __bfloat162float(__float2bfloat16_rn(x));
+}
+
+template <int M>
+static void run(int NB, int afmt, int bfmt, int reps, int mode, const char *what) {
+  std::vector<float> A((size_t)M * K), B((size_t)64 * K);
+  srand(7);
+  for (auto &v : A) v = (rand() / (float)RAND_MAX - 0.5f) * 0.4f;
+  for (auto &v : B) v = (rand() / (float)RAND_MAX - 0.5f) * 2.0f;
+  float *dA, *dB, *dO;
+  long long *dC;
+  CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dO, 128 * 128 * 4)); CK(cudaMalloc(&dC, 8));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dO, 0, 128 * 128 * 4));
+  size_t smem = (size_t)M * K * 2 * 2 + 64 * K * 2 + 1024;
+  CK(cudaFuncSetAttribute(probe_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_kernel<M><<<1, 128, smem>>>(dA, dB, NB, afmt, bfmt, dO, dC, reps, mode);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("%-40s M=%d NB=%d afmt=%d bfmt=%d: LAUNCH/EXEC ERROR %s\n", what, M, NB, afmt, bfmt, cudaGetErrorString(e));
+    exit(2);
+  }
+  std::vector<float> O(128 * 128);
+  long long cyc;
+  CK(cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost));
+  // reference
+  double maxerr = 0, maxref = 0;
+  int bad = 0;
+  for (int r = 0; r < M; r++) {
+    int lane = M == 128 ? r : (r % 16) + 32 * (r / 16);
+    for (int n = 0; n < NB; n++) {
+      double s = 0;
+      for (int k = 0; k < K; k++) s += (double)round16(A[(size_t)r * K + k], afmt) * (double)round16(B[(size_t)n * K + k], bfmt);
+      double got = O[(size_t)lane * 128 + n];
+      double err = fabs(got - s);
+      if (err > maxerr) maxerr = err;
+      if (fabs(s) > maxref) maxref = fabs(s);
+      if (err > 1e-3) bad++;
+      if (mode >= 1 && n < (NB == 48 ? 32 : NB / 2)) {
+        double got2 = O[(size_t)lane * 128 + 64 + n];
+        if (fabs(got2 - s) > 1e-3) bad++;
+      }
+    }
+  }
+  printf("%-40s M=%d NB=%d afmt=%d bfmt=%d mode=%d: max|err|=%.3e (max|ref|=%.2f) bad=%d  cycles/rep=%.1f\n", what, M, NB, afmt,
+         bfmt, mode, maxerr, maxref, bad, (double)cyc / reps);
+  cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dC);
+}
+
+int main() {
+  run<128>(32, 0, 0, 1, 0, "fp16 x fp16, single pass");
+  run<128>(32, 1, 1, 1, 0, "bf16 x bf16, single pass");
+  run<64>(32, 0, 0, 1, 0, "M=64 lane layout");
+  run<64>(64, 0, 0, 1, 1, "M=64, two accumulators");
+  run<128>(32, 0, 0, 1, 1, "two weight tiles (hi: N=32, lo: N=16)");
+  // timing: 200 dependent step-chains of 20 k-slices
+  run<128>(16, 0, 0, 200, 0, "timing: 20 MMA N=16");
+  run<128>(32, 0, 0, 200, 0, "timing: 20 MMA N=32");
+  run<128>(64, 0, 0, 200, 0, "timing: 20 MMA N=64");
+  run<128>(32, 0, 0, 200, 1, "timing: 20x(N=32 + N=16), 2 A tiles");
+  run<128>(32, 0, 0, 200, 2, "timing: same + tcgen05.ld + barrier");
+  run<128>(64, 0, 0, 200, 1, "timing: 20x(N=64 + N=32)");
+  run<64>(16, 0, 0, 200, 0, "timing: M=64 20 MMA N=16");
+  run<64>(32, 0, 0, 200, 0, "timing: M=64 20 MMA N=32");
+  run<64>(64, 0, 0, 200, 0, "timing: M=64 20 MMA N=64");
+  run<64>(64, 0, 0, 200, 1, "timing: M=64 20x(N=64 + N=32)");
+  run<64>(32, 0, 0, 200, 1, "timing: M=64 20x(N=32 + N=16)");
+  // (A = fp16 with B = bf16 in one instruction: "illegal instruction" on B200 -- measured, removed)
+  return 0;
+}
