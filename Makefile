@@ -14,7 +14,7 @@ OBJDIR  := build
 LIBDIR  := eesen_b200/lib
 BINDIR  := eesen_b200/bin
 
-CU_SRCS := gemm gemm_tc lstm ctc optim
+CU_SRCS := gemm gemm_tc lstm lstm_tc ctc optim
 CC_SRCS := base net abi_ops abi_net
 CU_OBJS := $(patsubst %,$(OBJDIR)/%.cu.o,$(CU_SRCS))
 CC_OBJS := $(patsubst %,$(OBJDIR)/%.cc.o,$(CC_SRCS))
@@ -23,7 +23,7 @@ BINS    := train-ctc-parallel net-output-extract format-to-nonparallel net-chang
 
 all: $(LIBDIR)/libeesen_b200.so $(patsubst %,$(BINDIR)/%,$(BINS))
 
-$(OBJDIR)/%.cu.o: eesen_b200/csrc/%.cu eesen_b200/csrc/common.cuh eesen_b200/csrc/kernels.h
+$(OBJDIR)/%.cu.o: eesen_b200/csrc/%.cu eesen_b200/csrc/common.cuh eesen_b200/csrc/kernels.h eesen_b200/csrc/tc_common.cuh
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

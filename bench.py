@@ -16,9 +16,12 @@ Rank 0 prints ONE JSON line:
   e2e        same metric through the public C-ABI call with HOST buffers (page-locked host memory; H2D of
              the packed features and D2H of the statistics inside the timed region)
   roofline   dominant kernel category of the step, measured live with CUDA events
+  roofline_step  the whole step against the HBM roof (SURVEY.md 8d bytes per valid frame)
   cpu_baseline  the reference's own cpucompute path (oracle/_ref/ref_dump_cpu = unmodified reference
              objects) + the restated CTC (the reference has no CPU CTC) on a bounded sample, N=1 only
---impl reference times that CPU arm as the main line.
+  gpu_reference  the reference's own gpucompute kernels (oracle/_ref/ref_dump_gpu) on the same GPU and batch, N=1 only
+  replicas_identical  (N > 1) sha256 of every rank's parameters after the timed steps agree
+--impl reference times the CPU arm as the main line, on the full minibatch (at most 2 timed steps are executed).
 """
 from __future__ import annotations
 
@@ -40,7 +43,8 @@ from eesen_b200 import kaldi_io, synth  # noqa: E402
 
 METRIC = "ctc_train_frames_per_sec"
 UNIT = "frames/s"
-REF_SAMPLE_UTTS = 8  # bounded CPU sample: this many utterances of the same workload per step
+REF_SAMPLE_UTTS = 8  # bounded CPU sample inside the GPU arm's line: this many utterances of the same workload per step
+REF_MAX_STEPS = 2    # --impl reference: full minibatch, at most this many timed steps (tens of seconds each)
 
 
 def load_peaks():
@@ -107,7 +111,7 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_arm(w, steps: int, warmup: int, tmp: str):
+def cpu_reference_arm(w, steps: int, warmup: int, tmp: str, sample_utts: int = REF_SAMPLE_UTTS):
     """Times the reference's CPU implementation of the path on this box's host cores.
 
     oracle/_ref/ref_dump_cpu = UNMODIFIED reference objects (Net fwd/bwd/update on cpucompute with
@@ -117,11 +121,16 @@ def cpu_reference_arm(w, steps: int, warmup: int, tmp: str):
     from oracle import oracle  # test/bench-only import: the checker as the CPU baseline
     cores = os.cpu_count() or 1
     net = synth.make_model(w, seed=0)
-    b = synth.make_batch(w, seed=1, S=REF_SAMPLE_UTTS)
+    b = synth.make_batch(w, seed=1, S=sample_utts)
     model = os.path.join(tmp, "ref_model")
     batch = os.path.join(tmp, "ref_batch.bin")
     kaldi_io.write_model(model, net)
     kaldi_io.write_batch_file(batch, b)
+    # thread-count probe on a small sample (one untimed step each), the timing itself on `b`
+    probe = batch
+    if sample_utts > REF_SAMPLE_UTTS:
+        probe = os.path.join(tmp, "ref_probe.bin")
+        kaldi_io.write_batch_file(probe, synth.make_batch(w, seed=1, S=REF_SAMPLE_UTTS))
     sample = (f"{b.S} utterances of the {w.name} workload per step ({b.valid_frames} valid / "
               f"{b.feats.shape[0]} padded frames)")
     # CTC restatement on the sample (fp32 port, single thread)
@@ -137,7 +146,7 @@ def cpu_reference_arm(w, steps: int, warmup: int, tmp: str):
         best = None
         for th in sorted({min(cores, c) for c in (8, 16, 32)}):
             try:
-                info = oracle.run_reference("cpu", model, batch, os.path.join(tmp, "ref_out"), w.learn_rate,
+                info = oracle.run_reference("cpu", model, probe, os.path.join(tmp, "ref_out"), w.learn_rate,
                                             w.momentum, steps=1, time_only=True, threads=th, timeout=120)
             except Exception:
                 continue
@@ -168,17 +177,48 @@ def run_reference_impl(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # the SAME configuration as the GPU arm: the full w.S-utterance minibatch per step.  One such step takes the
+    # host cores tens of seconds, so at most REF_MAX_STEPS timed steps (after at most one warm-up step) are
+    # executed whatever --steps / --warmup ask for; `sample` says how many were.
+    run_steps, run_warm = min(args.steps, REF_MAX_STEPS), min(args.warmup, 1)
     with tempfile.TemporaryDirectory() as tmp:
-        cb = cpu_reference_arm(w, args.steps, args.warmup, tmp)
+        cb = cpu_reference_arm(w, run_steps, run_warm, tmp, sample_utts=args.ref_utts or w.S)
+    cb["sample"] += f"; {run_steps} timed step(s) after {run_warm} warm-up executed of --steps {args.steps} --warmup {args.warmup}"
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w.name, "utts_per_gpu": w.S, "parallelism": "cpu host cores"},
+            "config": {"workload": w.name, "layers": w.layers, "cells_per_direction": w.cells, "input_dim": w.in_dim,
+                       "classes": w.classes, "utts_per_gpu": args.ref_utts or w.S, "frames_per_utt": [w.t_lo, w.t_hi],
+                       "parallelism": "cpu host cores", "storage": "fp32", "learn_rate": w.learn_rate,
+                       "momentum": w.momentum, "frames_counted": "valid (unpadded) frames"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "note")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
     return 0
+
+
+def gpu_reference_leg(w, tmp: str, steps: int = 2):
+    """The reference's OWN kernels (src/gpucompute, unmodified, compiled for sm_100a: oracle/_ref/ref_dump_gpu)
+    on the same B200 and the same full minibatch: one warm-up + `steps` timed train steps."""
+    from oracle import oracle  # bench-only: the reference as a timed comparator, never on the product path
+    if not oracle.have_reference("gpu"):
+        return {"value": None, "unit": UNIT, "unavailable": "oracle/_ref/ref_dump_gpu not built"}
+    net = synth.make_model(w, seed=0)
+    b = synth.make_batch(w, seed=1)
+    model, batch = os.path.join(tmp, "gref_model"), os.path.join(tmp, "gref_batch.bin")
+    kaldi_io.write_model(model, net)
+    kaldi_io.write_batch_file(batch, b)
+    try:
+        info = oracle.run_reference("gpu", model, batch, os.path.join(tmp, "gref_out"), w.learn_rate, w.momentum,
+                                    steps=steps + 1, time_only=True, timeout=300)
+    except Exception as e:
+        return {"value": None, "unit": UNIT, "unavailable": str(e)[-300:]}
+    st = info["step_seconds"][1:]
+    sec = float(np.mean(st))
+    return {"value": b.valid_frames / sec, "unit": UNIT, "seconds_per_step": sec, "steps": len(st), "kind": "reference gpucompute",
+            "sample": f"{b.S} utterances of the {w.name} workload ({b.valid_frames} valid / {b.feats.shape[0]} padded frames)",
+            "note": "unmodified reference src/gpucompute + src/net built for sm_100a, its own cuBLAS calls and per-kernel device syncs"}
 
 
 # --------------------------------------------------------------------------------------- GPU arm
@@ -338,6 +378,15 @@ def run_ours(args, w):
         ms_alt = a0.elapsed_time(a1)
         ctx.set_precision(args.gemm_precision, args.recurrent_precision)
 
+    # correctness next to speed: every replica must hold bit-identical parameters after the timed steps
+    replicas_identical = None
+    if world > 1:
+        import hashlib
+        digest = hashlib.sha256(np.ascontiguousarray(net.params()).tobytes()).hexdigest()
+        digests = [None] * world
+        dist.all_gather_object(digests, digest)
+        replicas_identical = all(d == digests[0] for d in digests)
+
     t = torch.tensor([ms_dev, t_e2e * 1e3, float(frames_dev), float(padded_dev), ms_alt or 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = t.clone()
@@ -387,12 +436,26 @@ def run_ours(args, w):
             dom = "gemm"
         line["roofline"] = allr[dom]
         line["rooflines_other"] = {k: v for k, v in allr.items() if k != dom}
+        # whole step against the HBM roof: SURVEY.md 8(d) algorithmic bytes per valid frame (374.7 KB for C2,
+        # 753 KB for C4; weights excluded) x valid frames / step time -- the figure north_star's 70 % refers to
+        max_lab = int(np.mean([max(len(l) for l in b.labels) for b in pool]))
+        by_frame = synth.hbm_bytes_per_frame(w, max_lab)
+        ach = by_frame * (frames_all / world) / (ms_dev * 1e-3) / 1e9      # per GPU
+        line["roofline_step"] = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                 "frac": ach / peaks["hbm_gbs"], "peak_source": peaks["source"],
+                                 "algorithmic_bytes_per_valid_frame": by_frame,
+                                 "note": "per GPU; the recurrence is latency-bound at 64 utterances per GPU (T dependent steps per layer and pass)"}
+        if world > 1:
+            line["replicas_identical"] = replicas_identical
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_reference_arm(w, 1, 0, tmp)
             except Exception as e:  # the checker is optional for the measurement itself
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"failed: {e}"}
+        if world == 1 and not args.no_gpu_reference:
+            # the context must not hold the GPU's memory hostage while the reference allocates its ~3 GB
+            line["gpu_reference"] = gpu_reference_leg(w, tmp)
         print(json.dumps(line), flush=True)
     net.close()
     ctx.close()
@@ -413,6 +476,8 @@ def main():
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the informational TF32 pass")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference's own gpucompute kernels")
+    ap.add_argument("--ref-utts", type=int, default=0, help="--impl reference: utterances per step (default: the full minibatch)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = synth.WORKLOADS[args.workload]

@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "tc_common.cuh"
 
 namespace eb {
 
@@ -42,53 +43,6 @@ struct TcArgs {
   float *ws;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-
-__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout).
-//   K-major operand : LayoutType::SWIZZLE_128B (2): rows of 128 B, 8-row atoms, SBO = 1024 B between atoms
-//   MN-major tf32   : LayoutType::SWIZZLE_128B_BASE32B (1) -- the only MN-major layout for 32-bit operands
-//                     (cutlass sm100_common.inl:92): rows of 128 B = 32 elements along M/N, 4-k-row atoms
-//                     (Swizzle<2,5,2>), SBO = 512 B between k atoms, LBO between 32-wide M/N groups
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3fff);             // start address  [0,14)
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;   // leading byte offset [16,30)
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;   // stride byte offset  [32,46)
-  d |= (uint64_t)1 << 46;                              // descriptor version 1 (Blackwell)
-  d |= (uint64_t)layout << 61;                         // LayoutType
-  return d;
-}
-
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n.reg .pred p;\n"
@@ -97,10 +51,122 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
-               : "memory");
-}
+// Epilogue shared by the tf32 and the bf16 kernels: TMEM (lane = output row) -> registers -> this warp's
+// private 32 x BNW staging tile in shared memory (the operand stages are free: every MMA has completed) ->
+// row-wise, fully coalesced global traffic (512-byte row segments) for the alpha/beta/bias update.
+template <int BN>
+__device__ __forceinline__ void tc_epilogue(uint8_t *smem, uint64_t *accum_bar, uint32_t tmem_base, const TcArgs &p,
+                                            int warp, int lane, int m0, int n0, int split) {
+    mbar_wait(accum_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    // Epilogue: TMEM (lane = output row) -> registers -> this warp's private 32 x BN staging tile in
+    // shared memory (the operand stages are free: every MMA has completed) -> row-wise, fully
+    // coalesced global traffic (512-byte row segments) for the alpha/beta/bias update.
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    constexpr int NHALF = TC_SPLIT_WARPS / 4;  // warps sharing a quadrant split the tile's columns
+    constexpr int BNW = BN / NHALF;            // columns this warp moves
+    const int chalf = (warp - 2) / 4;          // 0 .. NHALF-1
+    const int ncol0 = n0 + chalf * BNW;        // first global column of this warp's part
+    constexpr int EST = BNW + 4;               // staging row stride (floats): conflict-free v4 stores
+    float *stg = reinterpret_cast<float *>(smem) + (size_t)(quad * NHALF + chalf) * 32 * EST;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BNW; c0 += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(chalf * BNW + c0);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      float4 *dst = reinterpret_cast<float4 *>(stg + (size_t)lane * EST + c0);
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        dst[j] = make_float4(u2f(r[4 * j]), u2f(r[4 * j + 1]), u2f(r[4 * j + 2]), u2f(r[4 * j + 3]));
+    }
+    __syncwarp();
+    const bool vec_ok = (p.ldc & 3) == 0 && (p.N & 3) == 0 && p.splits == 1 && ((uintptr_t)p.C & 15) == 0 &&
+                        ((uintptr_t)p.bias & 15) == 0;
+    if (vec_ok && p.beta != 0.f) {
+      // beta != 0: the old C values are fetched 8 rows ahead of their use -- a load -> fma -> store chain per
+      // row would expose one global-memory round trip per row (32 per tile)
+      float4 bv[BNW / 128 > 0 ? BNW / 128 : 1];
+#pragma unroll
+      for (int q = 0; q < (BNW / 128 > 0 ? BNW / 128 : 1); q++) {
+        const int c = lane * 4 + q * 128;
+        bv[q] = (p.bias && c < BNW && ncol0 + c < p.N) ? *reinterpret_cast<const float4 *>(p.bias + ncol0 + c)
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      for (int r0 = 0; r0 < 32; r0 += 8) {
+        float4 old[8][BNW / 128 > 0 ? BNW / 128 : 1];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int row = m0 + quad * 32 + r0 + j;
+#pragma unroll
+          for (int q = 0; q < (BNW / 128 > 0 ? BNW / 128 : 1); q++) {
+            const int c = lane * 4 + q * 128;
+            old[j][q] = (row < p.M && c < BNW && ncol0 + c < p.N)
+                            ? *reinterpret_cast<const float4 *>(p.C + (size_t)row * p.ldc + ncol0 + c)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int row = m0 + quad * 32 + r0 + j;
+          if (row >= p.M) break;
+          const float *srow = stg + (size_t)(r0 + j) * EST;
+#pragma unroll
+          for (int q = 0; q < (BNW / 128 > 0 ? BNW / 128 : 1); q++) {
+            const int c = lane * 4 + q * 128;
+            if (c < BNW && ncol0 + c < p.N) {
+              float4 v = *reinterpret_cast<const float4 *>(srow + c);
+              v.x = p.alpha * v.x + bv[q].x + p.beta * old[j][q].x;
+              v.y = p.alpha * v.y + bv[q].y + p.beta * old[j][q].y;
+              v.z = p.alpha * v.z + bv[q].z + p.beta * old[j][q].z;
+              v.w = p.alpha * v.w + bv[q].w + p.beta * old[j][q].w;
+              *reinterpret_cast<float4 *>(p.C + (size_t)row * p.ldc + ncol0 + c) = v;
+            }
+          }
+        }
+      }
+    } else
+    for (int rr = 0; rr < 32; rr++) {
+      const int row = m0 + quad * 32 + rr;
+      if (row >= p.M) break;
+      const float *srow = stg + (size_t)rr * EST;
+      if (p.splits > 1) {
+        float *wrow = p.ws + ((size_t)split * p.M + row) * p.N + ncol0;
+        for (int c = lane; c < BNW && ncol0 + c < p.N; c += 32) wrow[c] = srow[c];
+      } else if (vec_ok) {
+        float *crow = p.C + (size_t)row * p.ldc + ncol0;
+        for (int c = lane * 4; c < BNW && ncol0 + c < p.N; c += 128) {
+          float4 v = *reinterpret_cast<const float4 *>(srow + c);
+          v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
+          if (p.bias) {
+            const float4 b = *reinterpret_cast<const float4 *>(p.bias + ncol0 + c);
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+          }
+          if (p.beta != 0.f) {
+            const float4 o = *reinterpret_cast<const float4 *>(crow + c);
+            v.x += p.beta * o.x; v.y += p.beta * o.y; v.z += p.beta * o.z; v.w += p.beta * o.w;
+          }
+          *reinterpret_cast<float4 *>(crow + c) = v;
+        }
+      } else {
+        float *crow = p.C + (size_t)row * p.ldc + ncol0;
+        for (int c = lane; c < BNW && ncol0 + c < p.N; c += 32) {
+          float v = p.alpha * srow[c];
+          if (p.bias) v += p.bias[ncol0 + c];
+          if (p.beta != 0.f) v += p.beta * crow[c];
+          crow[c] = v;
+        }
+      }
+    }
+  }
 
 // TA: 0 = A stored [M x K] (K-major operand), 1 = A stored [K x M] (MN-major operand)
 // TB: 1 = B stored [N x K] (K-major operand), 0 = B stored [K x N] (MN-major operand)
@@ -234,115 +300,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_arrive(&conv_bar[s]);
       }
     }
-    mbar_wait(&accum_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    // Epilogue: TMEM (lane = output row) -> registers -> this warp's private 32 x BN staging tile in
-    // shared memory (the operand stages are free: every MMA has completed) -> row-wise, fully
-    // coalesced global traffic (512-byte row segments) for the alpha/beta/bias update.
-    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-    constexpr int NHALF = TC_SPLIT_WARPS / 4;  // warps sharing a quadrant split the tile's columns
-    constexpr int BNW = BN / NHALF;            // columns this warp moves
-    const int chalf = (warp - 2) / 4;          // 0 .. NHALF-1
-    const int ncol0 = n0 + chalf * BNW;        // first global column of this warp's part
-    constexpr int EST = BNW + 4;               // staging row stride (floats): conflict-free v4 stores
-    float *stg = reinterpret_cast<float *>(smem) + (size_t)(quad * NHALF + chalf) * 32 * EST;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BNW; c0 += 32) {
-      uint32_t r[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(chalf * BNW + c0);
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-      float4 *dst = reinterpret_cast<float4 *>(stg + (size_t)lane * EST + c0);
-#pragma unroll
-      for (int j = 0; j < 8; j++)
-        dst[j] = make_float4(u2f(r[4 * j]), u2f(r[4 * j + 1]), u2f(r[4 * j + 2]), u2f(r[4 * j + 3]));
-    }
-    __syncwarp();
-    const bool vec_ok = (p.ldc & 3) == 0 && (p.N & 3) == 0 && p.splits == 1 && ((uintptr_t)p.C & 15) == 0 &&
-                        ((uintptr_t)p.bias & 15) == 0;
-    if (vec_ok && p.beta != 0.f) {
-      // beta != 0: the old C values are fetched 8 rows ahead of their use -- a load -> fma -> store chain per
-      // row would expose one global-memory round trip per row (32 per tile)
-      float4 bv[BNW / 128 > 0 ? BNW / 128 : 1];
-#pragma unroll
-      for (int q = 0; q < (BNW / 128 > 0 ? BNW / 128 : 1); q++) {
-        const int c = lane * 4 + q * 128;
-        bv[q] = (p.bias && c < BNW && ncol0 + c < p.N) ? *reinterpret_cast<const float4 *>(p.bias + ncol0 + c)
-                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      for (int r0 = 0; r0 < 32; r0 += 8) {
-        float4 old[8][BNW / 128 > 0 ? BNW / 128 : 1];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const int row = m0 + quad * 32 + r0 + j;
-#pragma unroll
-          for (int q = 0; q < (BNW / 128 > 0 ? BNW / 128 : 1); q++) {
-            const int c = lane * 4 + q * 128;
-            old[j][q] = (row < p.M && c < BNW && ncol0 + c < p.N)
-                            ? *reinterpret_cast<const float4 *>(p.C + (size_t)row * p.ldc + ncol0 + c)
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const int row = m0 + quad * 32 + r0 + j;
-          if (row >= p.M) break;
-          const float *srow = stg + (size_t)(r0 + j) * EST;
-#pragma unroll
-          for (int q = 0; q < (BNW / 128 > 0 ? BNW / 128 : 1); q++) {
-            const int c = lane * 4 + q * 128;
-            if (c < BNW && ncol0 + c < p.N) {
-              float4 v = *reinterpret_cast<const float4 *>(srow + c);
-              v.x = p.alpha * v.x + bv[q].x + p.beta * old[j][q].x;
-              v.y = p.alpha * v.y + bv[q].y + p.beta * old[j][q].y;
-              v.z = p.alpha * v.z + bv[q].z + p.beta * old[j][q].z;
-              v.w = p.alpha * v.w + bv[q].w + p.beta * old[j][q].w;
-              *reinterpret_cast<float4 *>(p.C + (size_t)row * p.ldc + ncol0 + c) = v;
-            }
-          }
-        }
-      }
-    } else
-    for (int rr = 0; rr < 32; rr++) {
-      const int row = m0 + quad * 32 + rr;
-      if (row >= p.M) break;
-      const float *srow = stg + (size_t)rr * EST;
-      if (p.splits > 1) {
-        float *wrow = p.ws + ((size_t)split * p.M + row) * p.N + ncol0;
-        for (int c = lane; c < BNW && ncol0 + c < p.N; c += 32) wrow[c] = srow[c];
-      } else if (vec_ok) {
-        float *crow = p.C + (size_t)row * p.ldc + ncol0;
-        for (int c = lane * 4; c < BNW && ncol0 + c < p.N; c += 128) {
-          float4 v = *reinterpret_cast<const float4 *>(srow + c);
-          v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
-          if (p.bias) {
-            const float4 b = *reinterpret_cast<const float4 *>(p.bias + ncol0 + c);
-            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-          }
-          if (p.beta != 0.f) {
-            const float4 o = *reinterpret_cast<const float4 *>(crow + c);
-            v.x += p.beta * o.x; v.y += p.beta * o.y; v.z += p.beta * o.z; v.w += p.beta * o.w;
-          }
-          *reinterpret_cast<float4 *>(crow + c) = v;
-        }
-      } else {
-        float *crow = p.C + (size_t)row * p.ldc + ncol0;
-        for (int c = lane; c < BNW && ncol0 + c < p.N; c += 32) {
-          float v = p.alpha * srow[c];
-          if (p.bias) v += p.bias[ncol0 + c];
-          if (p.beta != 0.f) v += p.beta * crow[c];
-          crow[c] = v;
-        }
-      }
-    }
+    tc_epilogue<BN>(smem, &accum_bar, tmem_base, p, warp, lane, m0, n0, split);
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -350,6 +308,143 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------ bf16 operands
+// kind::f16 (bf16 x bf16 -> fp32 in TMEM) for BASELINE config 4 ("bf16 tensor-core gate GEMM").  Operands are
+// bf16 copies of the fp32 matrices (f32_to_bf16_kernel below: 6 bytes of HBM traffic per element, against
+// (M+N)*K*4 bytes that an in-kernel conversion of fp32 tiles would pull through L2 for EVERY tile -- at 128x256
+// tiles an fp32-sourced bf16 GEMM is L2-bound at ~30 % of the tensor peak).  Same TMA / mbarrier / TMEM
+// structure as the tf32 kernel, no splitter role: one MMA per 16-wide k-slice, 64-wide k-blocks (128-byte
+// swizzle rows), 4-8 pipeline stages.
+//   K-major operand : box {64 k, rows}, LayoutType::SWIZZLE_128B, 8-row atoms 1024 B apart (SBO), k-slice = +32 B
+//   MN-major operand: box {64 mn, 64 k} per 64-wide m/n group (LBO = 8192 B), 8-k-row atoms 1024 B apart (SBO),
+//                     k-slice of 16 rows = +2048 B   (canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units)
+constexpr int TC16_BK = 64;
+
+template <int BN, int TA, int TB, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs p) {
+  constexpr int A_BYTES = TC_BM * TC16_BK * 2;
+  constexpr int B_BYTES = BN * TC16_BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_sm;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int split = blockIdx.z;
+  const int kb_total = (p.K + TC16_BK - 1) / TC16_BK;
+  const int kb_beg = split * p.kblocks_per_split;
+  const int kb_end = min(kb_total, kb_beg + p.kblocks_per_split);
+  const int nkb = kb_end - kb_beg;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_sm)),
+                 "n"(BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = tmem_base_sm;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % STAGES;
+        if (i >= STAGES) mbar_wait(&empty_bar[s], ((i / STAGES) - 1) & 1);
+        uint8_t *sa = smem + (size_t)s * STAGE_BYTES;
+        uint8_t *sb = sa + A_BYTES;
+        mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+        const int k0 = (kb_beg + i) * TC16_BK;
+        if (TA == 0) {
+          tma_load_2d(sa, &mapA, k0, m0, &full_bar[s]);              // box {64 k, 128 m}
+        } else {
+#pragma unroll
+          for (int g = 0; g < TC_BM / 64; g++)                        // box {64 m, 64 k} per 64-wide M group
+            tma_load_2d(sa + g * (TC16_BK * 128), &mapA, m0 + g * 64, k0, &full_bar[s]);
+        }
+        if (TB == 1) {
+          tma_load_2d(sb, &mapB, k0, n0, &full_bar[s]);              // box {64 k, BN n}
+        } else {
+#pragma unroll
+          for (int g = 0; g < BN / 64; g++)
+            tma_load_2d(sb + g * (TC16_BK * 128), &mapB, n0 + g * 64, k0, &full_bar[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), majors, N >> 3, M >> 4
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TA ? 1 : 0) << 15) |
+                             ((uint32_t)(TB ? 0 : 1) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % STAGES;
+        mbar_wait(&full_bar[s], (i / STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC16_BK / 16; k++) {
+          const uint32_t a_off = TA == 0 ? k * 32 : k * 2048;
+          const uint32_t b_off = TB == 1 ? k * 32 : k * 2048;
+          const uint32_t a_lbo = TA == 0 ? 16 : TC16_BK * 128, b_lbo = TB == 1 ? 16 : TC16_BK * 128;
+          const uint64_t ad = umma_desc(sa + a_off, a_lbo, 1024, 2);
+          const uint64_t bd = umma_desc(sb + b_off, b_lbo, 1024, 2);
+          umma_f16(tmem_base, ad, bd, idesc, (i | k) != 0);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&accum_bar);
+    }
+  } else {
+    tc_epilogue<BN>(smem, &accum_bar, tmem_base, p, warp, lane, m0, n0, split);
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+
+// fp32 [rows x cols] (ld lds) -> bf16 [rows x cols] (ld ldd, a multiple of 8), round to nearest even
+__global__ void f32_to_bf16_kernel(const float *__restrict__ src, long rows, int cols, long lds, uint16_t *__restrict__ dst,
+                                   int ldd) {
+  const int c8 = (cols + 7) / 8;
+  const long n = rows * c8;
+  const bool vec = (lds & 3) == 0 && (((uintptr_t)src) & 15) == 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / c8;
+    const int c = (int)(i - r * c8) * 8;
+    const float *sp = src + r * lds + c;
+    float v[8];
+    if (vec && c + 8 <= cols) {
+      const float4 a = __ldcs(reinterpret_cast<const float4 *>(sp)), b = __ldcs(reinterpret_cast<const float4 *>(sp) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = c + j < cols ? sp[j] : 0.f;
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(w[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+    *reinterpret_cast<uint4 *>(dst + r * ldd + c) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -465,6 +560,43 @@ cudaError_t launch_tc_layout(cudaStream_t st, const CUtensorMap &ma, const CUten
   return nterms == 3 ? launch_tc<64, TA, TB, 3>(st, ma, mb, p) : launch_tc<64, TA, TB, 1>(st, ma, mb, p);
 }
 
+// ---- bf16 path (precision 2)
+bool make_map16(CUtensorMap *map, const void *base, long rows, long cols, long ld, int box_cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BN, int TA, int TB>
+cudaError_t launch_tc16(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const TcArgs &p) {
+  constexpr int STAGES = BN == 256 ? 4 : BN == 128 ? 6 : 8;
+  constexpr int SMEM = STAGES * (TC_BM * TC16_BK * 2 + BN * TC16_BK * 2) + 1024;
+  auto kern = gemm_tc16_kernel<BN, TA, TB, STAGES>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  dim3 grid((p.N + BN - 1) / BN, (p.M + TC_BM - 1) / TC_BM, p.splits);
+  kern<<<grid, TC_THREADS, SMEM, st>>>(ma, mb, p);
+  return cudaGetLastError();
+}
+
+template <int TA, int TB>
+cudaError_t launch_tc16_layout(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const TcArgs &p, int bn) {
+  if (bn == 256) return launch_tc16<256, TA, TB>(st, ma, mb, p);
+  if (bn == 128) return launch_tc16<128, TA, TB>(st, ma, mb, p);
+  return launch_tc16<64, TA, TB>(st, ma, mb, p);
+}
+
 }  // namespace
 
 bool gemm_tc_supported(int transA, int transB, int M, int N, int K, const float *A, int lda, const float *B, int ldb,
@@ -543,6 +675,60 @@ cudaError_t gemm_tc(cudaStream_t st, int num_sms, int transA, int transB, int M,
   else if (transA == 0 && transB == 0) e = launch_tc_layout<0, 0>(st, ma, mb, p, nterms, bn);
   else if (transA == 1 && transB == 0) e = launch_tc_layout<1, 0>(st, ma, mb, p, nterms, bn);
   else return cudaErrorInvalidValue;
+  if (e != cudaSuccess) return e;
+  if (p.splits > 1) {
+    size_t n = (size_t)M * N;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 4 * num_sms) blocks = 4 * num_sms;
+    tc_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+size_t gemm_tc16_operand_bytes(long rows, int cols) { return (size_t)rows * (size_t)((cols + 7) & ~7) * 2; }
+
+cudaError_t convert_bf16(cudaStream_t st, int num_sms, const float *src, long rows, int cols, long lds, void *dst) {
+  if (rows <= 0 || cols <= 0) return cudaSuccess;
+  const int ldd = (cols + 7) & ~7;
+  const long n = rows * (ldd / 8);
+  long blocks = (n + 255) / 256;
+  if (blocks > 16L * num_sms) blocks = 16L * num_sms;
+  f32_to_bf16_kernel<<<(int)blocks, 256, 0, st>>>(src, rows, cols, lds, (uint16_t *)dst, ldd);
+  return cudaGetLastError();
+}
+
+// A16 / B16: bf16 copies made by convert_bf16 (dense, ld = cols rounded up to 8) of the matrices AS STORED:
+// A [M x K] (transA = 0) or [K x M] (transA = 1); B [N x K] (transB = 1) or [K x N] (transB = 0).
+cudaError_t gemm_tc16(cudaStream_t st, int num_sms, int transA, int transB, int M, int N, int K, float alpha,
+                      const void *A16, const void *B16, float beta, float *C, int ldc, const float *bias, float *ws,
+                      size_t ws_bytes) {
+  if (transA && transB) return cudaErrorInvalidValue;
+  const int bn = pick_bn(M, N, K);
+  CUtensorMap ma, mb;
+  bool ok;
+  ok = transA == 0 ? make_map16(&ma, A16, M, K, (K + 7) & ~7, TC16_BK, TC_BM) : make_map16(&ma, A16, K, M, (M + 7) & ~7, 64, TC16_BK);
+  ok = ok && (transB == 1 ? make_map16(&mb, B16, N, K, (K + 7) & ~7, TC16_BK, bn) : make_map16(&mb, B16, K, N, (N + 7) & ~7, 64, TC16_BK));
+  if (!ok) return cudaErrorInvalidValue;
+  TcArgs p;
+  p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.alpha = alpha; p.beta = beta; p.ws = ws;
+  const int kb = (K + TC16_BK - 1) / TC16_BK;
+  p.splits = 1;
+  p.kblocks_per_split = kb;
+  long tiles = (long)((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn);
+  if (tiles < num_sms && K >= 4096 && ws) {
+    int splits = pick_splits(tiles, kb, num_sms);
+    while (splits > 1 && (size_t)splits * M * N * sizeof(float) > ws_bytes) splits--;
+    if (splits > 1) {
+      int per = (kb + splits - 1) / splits;
+      p.kblocks_per_split = per;
+      p.splits = (kb + per - 1) / per;
+    }
+  }
+  cudaError_t e;
+  if (transA == 0 && transB == 1) e = launch_tc16_layout<0, 1>(st, ma, mb, p, bn);
+  else if (transA == 0 && transB == 0) e = launch_tc16_layout<0, 0>(st, ma, mb, p, bn);
+  else e = launch_tc16_layout<1, 0>(st, ma, mb, p, bn);
   if (e != cudaSuccess) return e;
   if (p.splits > 1) {
     size_t n = (size_t)M * N;

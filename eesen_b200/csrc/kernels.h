@@ -21,6 +21,13 @@ cudaError_t gemm_tc(cudaStream_t st, int num_sms, int transA, int transB, int M,
                     const float *A, int lda, const float *B, int ldb, float beta, float *C, int ldc,
                     const float *bias, int precision, float *ws, size_t ws_bytes);
 
+// bf16 arithmetic (precision 2, BASELINE config 4): tcgen05 kind::f16 on bf16 copies of the operands
+size_t gemm_tc16_operand_bytes(long rows, int cols);
+cudaError_t convert_bf16(cudaStream_t st, int num_sms, const float *src, long rows, int cols, long lds, void *dst);
+cudaError_t gemm_tc16(cudaStream_t st, int num_sms, int transA, int transB, int M, int N, int K, float alpha,
+                      const void *A16, const void *B16, float beta, float *C, int ldc, const float *bias, float *ws,
+                      size_t ws_bytes);
+
 // lstm.cu -- persistent recurrent kernels (both directions in one cooperative launch)
 struct LstmDirParams {
   const float *wm;  // [4C x C] recurrent weights, row blocks g,i,f,o
@@ -57,6 +64,7 @@ struct LstmBwdArgs {
   int ldr = 0, rmask_per_step = 0;
 };
 struct LstmPlan {
+  int engine;            // 0: warp-level mma.sync kernels (lstm.cu), 1: tcgen05 kernels (lstm_tc.cu)
   int nut, nct, ksplit;  // utterance tiles / cell tiles per CTA, K-split warps (fwd)
   int groups, slices;    // grid = (slices, groups, ndir)
   int ndir;              // 2: BiLstmParallel (fw + bw cells), 1: LstmParallel (fw cells only)
@@ -73,6 +81,13 @@ cudaError_t lstm_reduce_gsum(cudaStream_t st, const LstmPlan &plan, int C, const
                              float *db /*[4C]*/, float *dpi, float *dpf, float *dpo, int dir);
 
 int lstm_debug_timing(long long *out32, int reset);  // 1 if built with -DEB_LSTM_TIMING
+
+// lstm_tc.cu -- the same recurrences with the per-step product on tcgen05 (fp16 hi/lo' split, TMEM accumulator);
+// lstm_plan() returns such a plan (engine = 1) when the shape allows, EESEN_B200_LSTM_ENGINE=legacy forces lstm.cu
+LstmPlan lstm_tc_plan(int S, int C, int num_sms, size_t max_smem, int ndir);
+cudaError_t lstm_tc_forward(cudaStream_t st, const LstmPlan &plan, const LstmFwdArgs &a);
+cudaError_t lstm_tc_backward(cudaStream_t st, const LstmPlan &plan, const LstmBwdArgs &a);
+int lstm_tc_debug_timing(long long *out32, int reset);
 
 // ctc.cu
 cudaError_t softmax_rows(cudaStream_t st, int N, int K, const float *logits, int ld, float *probs, int ldp,

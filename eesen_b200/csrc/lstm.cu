@@ -26,6 +26,9 @@
 
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+#include <cstring>
+
 namespace eb {
 
 #ifdef EB_LSTM_TIMING
@@ -560,7 +563,12 @@ cudaError_t launch_bwd(cudaStream_t st, const LstmPlan &pl, const LstmBwdArgs &a
 
 int lstm_debug_timing(long long *out32, int reset) {
 #ifdef EB_LSTM_TIMING
-  if (out32) cudaMemcpyFromSymbol(out32, g_lstm_timing, sizeof(long long) * 32);
+  if (out32) {
+    cudaMemcpyFromSymbol(out32, g_lstm_timing, sizeof(long long) * 32);
+    long long tc[32];
+    if (lstm_tc_debug_timing(tc, reset))
+      for (int i = 0; i < 32; i++) out32[i] += tc[i];   // only one engine runs per build-and-measure session
+  }
   if (reset) {
     long long z[32] = {0};
     cudaMemcpyToSymbol(g_lstm_timing, z, sizeof(z));
@@ -572,9 +580,20 @@ int lstm_debug_timing(long long *out32, int reset) {
 #endif
 }
 
+// read at every plan (not cached): the tests switch engines inside one process
+static bool legacy_engine_forced() {
+  const char *e = getenv("EESEN_B200_LSTM_ENGINE");
+  return e && strcmp(e, "legacy") == 0;
+}
+
 LstmPlan lstm_plan(int S, int C, int num_sms, size_t max_smem, int ndir) {
+  if (!legacy_engine_forced()) {
+    LstmPlan tc = lstm_tc_plan(S, C, num_sms, max_smem, ndir);
+    if (tc.valid) return tc;
+  }
   LstmPlan best;
   best.valid = 0;
+  best.engine = 0;
   best.ndir = ndir;
   long best_work = -1;
   if (C % 8 != 0 || C <= 0 || S <= 0 || ndir < 1 || ndir > 2) return best;
@@ -618,6 +637,7 @@ LstmPlan lstm_plan(int S, int C, int num_sms, size_t max_smem, int ndir) {
 
 cudaError_t lstm_forward(cudaStream_t st, const LstmPlan &plan, const LstmFwdArgs &a) {
   if (!plan.valid) return cudaErrorInvalidConfiguration;
+  if (plan.engine == 1) return lstm_tc_forward(st, plan, a);
   if (a.drop < 0 || a.drop > 2 || (a.drop != 0 && !a.rmask)) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(a.xbuf, 0, plan.xbuf_bytes, st);
   if (e != cudaSuccess) return e;
@@ -626,6 +646,7 @@ cudaError_t lstm_forward(cudaStream_t st, const LstmPlan &plan, const LstmFwdArg
 
 cudaError_t lstm_backward(cudaStream_t st, const LstmPlan &plan, const LstmBwdArgs &a) {
   if (!plan.valid) return cudaErrorInvalidConfiguration;
+  if (plan.engine == 1) return lstm_tc_backward(st, plan, a);
   if (a.drop < 0 || a.drop > 2 || (a.drop != 0 && !a.rmask)) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(a.pbuf, 0, plan.pbuf_floats * sizeof(float), st);
   if (e != cudaSuccess) return e;

@@ -1,0 +1,643 @@
+// eesen_b200/csrc/lstm_tc.cu -- persistent recurrent kernels on the 5th-generation tensor cores.
+//
+// Same contract as lstm.cu (reference BiLstmParallel::PropagateFncVanillaPass{Forward,Backward}
+// bilstm-parallel-layer.h:112-149,166-205 and BackpropagateFncVanillaPass* :450-499,541-590 plus the
+// bias / peephole reductions :507-510,598-601): ONE cooperative launch per layer and pass runs all T
+// steps of both directions.  What changes is the per-step product m_{t-1} * Wm^T (forward) and
+// d(gates) * Wm (backward): it runs as tcgen05.mma kind::f16 with the accumulator in TMEM instead
+// of 60 warp-level mma.sync per warp and step.
+//
+// Decomposition: CTA(dir, group, slice) owns 32 cells (= 128 gate rows = one M=128 tile) of one direction
+// for a group of 16 utterances.  Its rows of Wm stay resident in shared memory for the whole sequence as
+// TWO fp16 tiles in the canonical K-major SWIZZLE_128B layout the tensor core reads directly:
+//   W = W_hi + 2^-11 * W_lo'        W_hi = fp16(W),  W_lo' = fp16((W - W_hi) * 2^11)
+// and the per-step activations are split the same way, stacked along N:
+//   B = [ x_hi (16 utterances) ; x_lo' (16 utterances) ]          (32 x K, K-major)
+// Two MMAs per 16-wide k-slice:  X += W_hi * B  (N = 32: hi*hi | hi*lo'),  Y += W_lo' * B[0:16]  (N = 16:
+// lo'*hi); result = X[:, u] + 2^-11 * (X[:, 16+u] + Y[:, u]) -- the dropped lo'*lo' term is 2^-22 relative,
+// the same fidelity class as the 3xTF32 split of lstm.cu (both operands carry 22 mantissa bits; fp16 x fp16
+// products are exact in the fp32 accumulator).  Forward: |m| < 1, so fp16 never overflows.  Backward:
+// d(gates) has no fixed range, so every utterance column is scaled by its own power of two (exact) to
+// [2^13, 2^14) before the split and scaled back in the epilogue.  (One instruction cannot mix fp16 and bf16
+// operands on sm_100a -- measured, tests/micro/umma_probe.cu -- hence the scaling instead of a bf16 split.)
+//
+// Exchange between the CTAs of one (dir, group): the "LL" tagged 8-byte words of lstm.cu (common.cuh); the
+// forward payload is the already split pair (hi | lo' << 16), so the ten consumers of a word do no arithmetic.
+// 256 threads: every warp stages the exchanged words into the B tile, evaluates the gates (two (cell, utterance)
+// pairs per thread) and owns a part of the TMEM -> register epilogue (lane quadrant = warp % 4); warp 0
+// additionally allocates TMEM and issues the MMAs from one elected lane while the others wait for the commit.
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace eb {
+
+#ifdef EB_LSTM_TIMING
+__device__ long long g_lstm_tc_timing[2][16];
+#define TC_T0() long long tk_ = clock64()
+#define TC_TICK(kernel, i)                                                          \
+  do {                                                                              \
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {        \
+      long long n_ = clock64();                                                     \
+      g_lstm_tc_timing[kernel][i] += n_ - tk_;                                      \
+      tk_ = n_;                                                                     \
+    }                                                                               \
+  } while (0)
+#else
+#define TC_T0()
+#define TC_TICK(kernel, i)
+#endif
+
+namespace {
+
+constexpr int TCL_CS = 32;        // cells per slice (x 4 gates = the 128 rows of one UMMA tile)
+constexpr int TCL_UG = 16;        // utterances per group
+constexpr int TCL_WORKERS = 256;  // worker threads (8 warps)
+constexpr int TCL_THREADS = TCL_WORKERS;   // 8 warps = 2 per SM sub-partition (a 9th warp would cap every thread at 168 registers)
+constexpr float kLoScale = 2048.f, kLoUnscale = 1.f / 2048.f;
+
+// byte offset of element (row r, k) of a K-major SWIZZLE_128B tile of 16-bit elements with `rows` rows:
+// 64-wide k-blocks of rows*128 bytes, 8-row atoms of 1024 bytes, 16-byte chunks XOR-swizzled by (row & 7)
+__device__ __forceinline__ uint32_t sw128_off(int rows, int r, int k) {
+  const int kb = k >> 6, kk = k & 63;
+  return (uint32_t)(kb * rows * 128 + (r >> 3) * 1024 + (r & 7) * 128 + ((((kk >> 3) ^ (r & 7)) << 4)) + ((kk & 7) << 1));
+}
+
+__device__ __forceinline__ void split_f16(float x, uint32_t &hi, uint32_t &lo) {
+  const __half h = __float2half_rn(x);
+  hi = (uint32_t)__half_as_ushort(h);
+  lo = (uint32_t)__half_as_ushort(__float2half_rn((x - __half2float(h)) * kLoScale));
+}
+
+__device__ __forceinline__ void st_tagged_u32(uint2 *p, uint32_t v, unsigned tag) {
+  asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};\n" ::"l"(p), "r"(v), "r"(tag) : "memory");
+}
+
+__device__ __forceinline__ void named_bar_workers() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+// instruction descriptor, kind::f16: D = F32, A = B = F16, both K-major
+__device__ __forceinline__ uint32_t idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------ forward
+template <int DROP>
+__global__ void __launch_bounds__(TCL_THREADS, 1)
+lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int C = a.C, S = a.S, T = a.T;
+  const int KB = C >> 6;                                  // 64-wide k-blocks (C % 64 == 0)
+  uint8_t *Whi = smem;                                    // [KB][128 rows][128 B]
+  uint8_t *Wlo = Whi + (size_t)KB * 16384;
+  uint8_t *Bt = Wlo + (size_t)KB * 16384;                 // [KB][32 rows][128 B]: rows 0-15 hi, 16-31 lo'
+  float *stg = reinterpret_cast<float *>(Bt + (size_t)KB * 4096);   // [4 gates][16 utts][32 cells]
+  __shared__ uint64_t b_full, mma_done;
+  __shared__ uint32_t tmem_base_sm;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slice = blockIdx.x, group = blockIdx.y, dir = blockIdx.z;
+  const LstmDirParams P = a.p[dir];
+  uint2 *xbuf = reinterpret_cast<uint2 *>(a.xbuf);       // [2 parity][ndir][groups][16][C] tagged words
+  const int s0 = a.s_begin, s1 = a.s_begin + a.s_count;
+
+  // ---- resident weights: row = gate*32 + local cell, split into the two fp16 tiles
+  for (int idx = tid; idx < 128 * C; idx += TCL_THREADS) {
+    const int r = idx / C, k = idx - r * C;
+    const int q = r >> 5, c_ = r & 31;
+    const float w = P.wm[((size_t)q * C + slice * TCL_CS + c_) * C + k];
+    uint32_t h, l;
+    split_f16(w, h, l);
+    const uint32_t off = sw128_off(128, r, k);
+    *reinterpret_cast<uint16_t *>(Whi + off) = (uint16_t)h;
+    *reinterpret_cast<uint16_t *>(Wlo + off) = (uint16_t)l;
+  }
+  for (int idx = tid; idx < KB * 1024; idx += TCL_THREADS) reinterpret_cast<uint32_t *>(Bt)[idx] = 0u;
+  if (tid == 0) {
+    mbar_init(&b_full, TCL_WORKERS);
+    mbar_init(&mma_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_sm)), "n"(64)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = tmem_base_sm;
+
+  {
+    // ===== workers =====
+    const int cl = lane, up = warp;                        // gate phase: local cell, utterance pair
+    const int cell = slice * TCL_CS + cl;
+    int uidx[2], lenu[2];
+    bool valid[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      uidx[e] = s0 + group * TCL_UG + 2 * up + e;
+      valid[e] = uidx[e] < s1;
+      lenu[e] = (a.len && valid[e]) ? a.len[uidx[e]] : 0;   // NULL: uni-directional (no masking)
+    }
+    const float ppi = P.pi[cell], ppf = P.pf[cell], ppo = P.po[cell];
+    float cprev[2] = {0.f, 0.f};
+    float pre[4][2];
+    float rmk[2] = {1.f, 1.f};
+    auto load_pre = [&](int t) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const float *row = a.G + ((size_t)t * S + (valid[e] ? uidx[e] : 0)) * a.ldg + (size_t)dir * 4 * C + cell;
+#pragma unroll
+        for (int q = 0; q < 4; q++) pre[q][e] = valid[e] ? __ldcs(row + (size_t)q * C) : 0.f;
+        if (DROP != 0)
+          rmk[e] = valid[e] ? __ldg(a.rmask + (size_t)(a.rmask_per_step ? (size_t)t * S + uidx[e] : (size_t)uidx[e]) * a.ldr +
+                                    (size_t)dir * C + cell)
+                            : 0.f;
+      }
+    };
+    load_pre(dir == 0 ? 0 : T - 1);
+    const int c8n = C >> 3;                                // 8-cell chunks per utterance row
+    const int quad = warp & 3, uh = warp >> 2;             // epilogue: TMEM lane quadrant (= gate), utterance half
+
+    for (int step = 0; step < T; step++) {
+      const int t = dir == 0 ? step : T - 1 - step;
+      float acc[4][2];
+#pragma unroll
+      for (int q = 0; q < 4; q++) { acc[q][0] = 0.f; acc[q][1] = 0.f; }
+      TC_T0();
+      if (step > 0) {
+        // ---- stage m_{t-1} of the group: spin on the tagged words, write the hi / lo' rows of the B tile
+        const uint4 *xr = reinterpret_cast<const uint4 *>(
+            xbuf + ((size_t)(((step - 1) & 1) * ndir + dir) * groups + group) * TCL_UG * C);
+        const unsigned want = (unsigned)step;
+        for (int v = tid; v < TCL_UG * c8n; v += TCL_WORKERS) {
+          const int u = v / c8n, c8 = v - u * c8n;
+          uint4 hi4 = make_uint4(0u, 0u, 0u, 0u), lo4 = hi4;
+          if (s0 + group * TCL_UG + u < s1) {
+            const uint4 *src = xr + ((size_t)u * C + c8 * 8) / 2;
+            uint4 q0, q1, q2, q3;
+            bool ok;
+            do {
+              q0 = ld_tagged2(src); q1 = ld_tagged2(src + 1); q2 = ld_tagged2(src + 2); q3 = ld_tagged2(src + 3);
+              ok = q0.y == want && q0.w == want && q1.y == want && q1.w == want && q2.y == want && q2.w == want &&
+                   q3.y == want && q3.w == want;
+            } while (!ok);
+            hi4 = make_uint4(__byte_perm(q0.x, q0.z, 0x5410), __byte_perm(q1.x, q1.z, 0x5410),
+                             __byte_perm(q2.x, q2.z, 0x5410), __byte_perm(q3.x, q3.z, 0x5410));
+            lo4 = make_uint4(__byte_perm(q0.x, q0.z, 0x7632), __byte_perm(q1.x, q1.z, 0x7632),
+                             __byte_perm(q2.x, q2.z, 0x7632), __byte_perm(q3.x, q3.z, 0x7632));
+          }
+          const int k0 = c8 * 8;
+          *reinterpret_cast<uint4 *>(Bt + sw128_off(32, u, k0)) = hi4;
+          *reinterpret_cast<uint4 *>(Bt + sw128_off(32, 16 + u, k0)) = lo4;
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
+        mbar_arrive(&b_full);
+        TC_TICK(0, 0);
+        if (warp == 0) {
+          // ===== MMA issue: 2 instructions per 16-wide k-slice, one commit =====
+          mbar_wait(&b_full, (uint32_t)((step - 1) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          if (elect_one()) {
+            const uint32_t idN = idesc_f16(128, 32), idH = idesc_f16(128, 16);
+            const uint32_t whi = smem_u32(Whi), wlo = smem_u32(Wlo), bt = smem_u32(Bt);
+            for (int kb = 0; kb < KB; kb++) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ks++) {
+                const uint64_t bd = umma_desc(bt + kb * 4096 + ks * 32, 16, 1024, 2);
+                umma_f16(tmem_base, umma_desc(whi + kb * 16384 + ks * 32, 16, 1024, 2), bd, idN, (kb | ks) != 0);
+                umma_f16(tmem_base + 32, umma_desc(wlo + kb * 16384 + ks * 32, 16, 1024, 2), bd, idH, (kb | ks) != 0);
+              }
+            }
+            umma_commit(&mma_done);
+          }
+          __syncwarp();
+        }
+        // ---- the product runs on the tensor pipe; wait for its commit
+        mbar_wait(&mma_done, (uint32_t)((step - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        TC_TICK(0, 1);
+        {
+          uint32_t x0[8], x1[8], y0[8];
+          const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16);
+          tmem_ld8(tl + 8 * uh, x0);
+          tmem_ld8(tl + 16 + 8 * uh, x1);
+          tmem_ld8(tl + 32 + 8 * uh, y0);
+          tmem_ld_wait();
+          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+          float *dst = stg + ((size_t)(quad * TCL_UG + 8 * uh)) * 32 + lane;
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            dst[j * 32] = u2f(x0[j]) + (u2f(x1[j]) + u2f(y0[j])) * kLoUnscale;
+        }
+        named_bar_workers();
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          acc[q][0] = stg[(q * TCL_UG + 2 * up) * 32 + cl];
+          acc[q][1] = stg[(q * TCL_UG + 2 * up + 1) * 32 + cl];
+        }
+        TC_TICK(0, 2);
+      }
+
+      // ---- gates, cell update (bilstm-parallel-layer.h:127-147), padding mask of the backward cells (:201-204)
+      float sg[2], si[2], sf[2], so[2], sc[2], sm[2];
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        float yg = pre[0][e] + acc[0][e];
+        float yi = pre[1][e] + acc[1][e] + cprev[e] * ppi;
+        float yf = pre[2][e] + acc[2][e] + cprev[e] * ppf;
+        float gi = sigmoidf_(yi), gf = sigmoidf_(yf), gg = tanhf_(yg);
+        float c;
+        if (DROP == 0) c = gg * gi + cprev[e] * gf;
+        else if (DROP == 1) c = rmk[e] * (gg * gi) + cprev[e] * gf;
+        else c = rmk[e] * (gg * gi + cprev[e] * gf);
+        float h = tanhf_(c);
+        float go = sigmoidf_(pre[3][e] + acc[3][e] + c * ppo);
+        float m = h * go;
+        const bool keep = valid[e] && !(dir == 1 && t >= lenu[e]);
+        sg[e] = keep ? gg : 0.f; si[e] = keep ? gi : 0.f; sf[e] = keep ? gf : 0.f; so[e] = keep ? go : 0.f;
+        sc[e] = keep ? c : 0.f; sm[e] = keep ? m : 0.f;
+        cprev[e] = sc[e];
+      }
+      // only m is on the inter-CTA critical path: publish it first (already split, tagged word, no fence)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        if (valid[e]) {
+          if (step + 1 < T) {
+            uint32_t h, l;
+            split_f16(sm[e], h, l);
+            st_tagged_u32(xbuf + (((size_t)((step & 1) * ndir + dir) * groups + group) * TCL_UG + 2 * up + e) * C + cell,
+                          h | (l << 16), (unsigned)step + 1u);
+          }
+          __stcs(a.out + ((size_t)t * S + uidx[e]) * a.ldo + (size_t)dir * C + cell, sm[e]);
+        }
+      }
+      TC_TICK(0, 3);
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        if (valid[e]) {
+          float *grow = a.G + ((size_t)t * S + uidx[e]) * a.ldg + (size_t)dir * 4 * C + cell;
+          __stcs(grow, sg[e]); __stcs(grow + (size_t)C, si[e]);
+          __stcs(grow + (size_t)2 * C, sf[e]); __stcs(grow + (size_t)3 * C, so[e]);
+          __stcs(a.cell + ((size_t)t * S + uidx[e]) * a.ldc + (size_t)dir * C + cell, sc[e]);
+        }
+      }
+      if (step + 1 < T) load_pre(dir == 0 ? t + 1 : t - 1);
+      TC_TICK(0, 4);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(64) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------ backward
+// Partial d_m of ALL C cells from this CTA's 128 gate rows:  P[j, u] = sum_r Wm[r, j] * D[u, r]
+// A = Wm^T tiles [j rows x 128 k] (hi, lo'), M tiles of 128 rows plus one of 64 when C % 128 == 64;
+// B = D (scaled per utterance, hi rows 0-15 | lo' rows 16-31) [32 x 128 k].
+template <int DROP>
+__global__ void __launch_bounds__(TCL_THREADS, 1)
+lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int C = a.C, S = a.S, T = a.T;
+  const int n128 = C >> 7, rem64 = (C & 127) ? 1 : 0, MT = n128 + rem64;
+  uint8_t *Ahi = smem;                                    // per M tile: [2 k-blocks][rows][128 B]; tile mt at mt*128*256 B
+  uint8_t *Alo = Ahi + (size_t)C * 256;
+  uint8_t *Bt = Alo + (size_t)C * 256;                    // [2 k-blocks][32 rows][128 B]
+  float *scl = reinterpret_cast<float *>(Bt + 8192);      // [16] inverse column scales
+  __shared__ uint64_t b_full, mma_done;
+  __shared__ uint32_t tmem_base_sm;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slice = blockIdx.x, group = blockIdx.y, dir = blockIdx.z;
+  const LstmDirParams P = a.p[dir];
+  uint2 *pbuf = reinterpret_cast<uint2 *>(a.pbuf);       // [2 parity][ndir][groups][slices][16][C] tagged partial d_m
+  const int s0 = a.s_begin, s1 = a.s_begin + a.s_count;
+
+  // A[j, k = gate*32 + c] = Wm[gate*C + slice*32 + c][j]
+  for (int idx = tid; idx < 128 * C; idx += TCL_THREADS) {
+    const int kk = idx / C, j = idx - kk * C;             // j fastest: coalesced reads of the Wm row
+    const int q = kk >> 5, c_ = kk & 31;
+    const float w = P.wm[((size_t)q * C + slice * TCL_CS + c_) * C + j];
+    uint32_t h, l;
+    split_f16(w, h, l);
+    const int mt = j >> 7;
+    const int rows = mt < n128 ? 128 : 64;
+    const uint32_t off = (uint32_t)mt * 128 * 256 + sw128_off(rows, j & 127, kk);
+    *reinterpret_cast<uint16_t *>(Ahi + off) = (uint16_t)h;
+    *reinterpret_cast<uint16_t *>(Alo + off) = (uint16_t)l;
+  }
+  for (int idx = tid; idx < 2048; idx += TCL_THREADS) reinterpret_cast<uint32_t *>(Bt)[idx] = 0u;
+  if (tid == 0) {
+    mbar_init(&b_full, TCL_WORKERS);
+    mbar_init(&mma_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_sm)), "n"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = tmem_base_sm;
+
+  {
+    // ===== workers: two (cell, utterance) items per thread =====
+    const int cl = lane, up = warp;
+    const int cell = slice * TCL_CS + cl;
+    int uidx[2];
+    bool ok[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      uidx[e] = s0 + group * TCL_UG + 2 * up + e;
+      ok[e] = uidx[e] < s1;
+    }
+    const float ppi = P.pi[cell], ppf = P.pf[cell], ppo = P.po[cell];
+    float dc_next[2] = {0.f, 0.f}, f_next[2] = {0.f, 0.f}, di_next[2] = {0.f, 0.f}, df_next[2] = {0.f, 0.f};
+    float dcm_next[2] = {0.f, 0.f};
+    float sb[4][2], spi[2] = {0.f, 0.f}, spf[2] = {0.f, 0.f}, spo[2] = {0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; q++) { sb[q][0] = 0.f; sb[q][1] = 0.f; }
+    float vg[2], vi[2], vf[2], vo[2], vc[2], vcp[2], vd[2], vr[2] = {1.f, 1.f};
+    const int tstep = dir == 0 ? -1 : 1;   // time order of the forward pass: c_prev lives at t + tstep
+    auto prefetch = [&](int t) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        if (!ok[e]) { vg[e] = vi[e] = vf[e] = vo[e] = vc[e] = vcp[e] = vd[e] = 0.f; continue; }
+        const int u = uidx[e];
+        const float *grow = a.G + ((size_t)t * S + u) * a.ldg + (size_t)dir * 4 * C + cell;
+        vg[e] = __ldcs(grow); vi[e] = __ldcs(grow + (size_t)C); vf[e] = __ldcs(grow + (size_t)2 * C); vo[e] = __ldcs(grow + (size_t)3 * C);
+        vc[e] = __ldcs(a.cell + ((size_t)t * S + u) * a.ldc + (size_t)dir * C + cell);
+        const int tp = t + tstep;
+        vcp[e] = (tp >= 0 && tp < T) ? __ldcs(a.cell + ((size_t)tp * S + u) * a.ldc + (size_t)dir * C + cell) : 0.f;
+        vd[e] = __ldcs(a.dout + ((size_t)t * S + u) * a.ldd + (size_t)dir * C + cell);
+        if (DROP != 0)
+          vr[e] = __ldg(a.rmask + (size_t)(a.rmask_per_step ? (size_t)t * S + u : (size_t)u) * a.ldr + (size_t)dir * C + cell);
+      }
+    };
+    prefetch(dir == 0 ? T - 1 : 0);
+    const size_t pstride_slice = (size_t)TCL_UG * C;
+    const int quad = warp & 3, uh = warp >> 2;
+
+    for (int step = 0; step < T; step++) {
+      const int t = dir == 0 ? T - 1 - step : step;
+      TC_T0();
+      float dm[2] = {vd[0], vd[1]};
+      if (step > 0) {
+        // ---- d_m of this thread's items: the `slices` tagged partials, summed in fixed order (:470 / :561)
+        const uint2 *pb = pbuf + ((size_t)((((step - 1) & 1) * ndir + dir) * groups + group) * slices) * pstride_slice + cell;
+        const unsigned want = (unsigned)step;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          if (!ok[e]) continue;
+          const uint2 *pe = pb + (size_t)(2 * up + e) * C;
+          float s_ = 0.f;
+          uint2 q[12];                                      // slices <= 12 (C <= 384, lstm_tc_plan)
+          bool all;
+          do {   // issue the loads together, retry until every tag has arrived
+            all = true;
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+              if (i < slices) {
+                q[i] = ld_tagged(pe + (size_t)i * pstride_slice);
+                all = all && (q[i].y == want);
+              }
+            }
+          } while (!all);
+#pragma unroll
+          for (int i = 0; i < 12; i++)
+            if (i < slices) s_ += __uint_as_float(q[i].x);   // fixed order: deterministic
+          dm[e] += s_;
+        }
+      }
+      TC_TICK(1, 0);
+      float dgt[4][2];
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        float dg = 0.f, di = 0.f, df = 0.f, dO = 0.f;
+        if (ok[e]) {
+          float h = tanhf_(vc[e]);
+          float dh = dm[e] * vo[e] * (1.f - h * h);                               // :473-474
+          dO = dm[e] * h * vo[e] * (1.f - vo[e]);                                 // :477-478
+          float dc, dcm;
+          if (DROP == 0) {
+            dc = dh + dc_next[e] * f_next[e] + di_next[e] * ppi + df_next[e] * ppf + dO * ppo;   // :481-485
+            dcm = dc;
+          } else {
+            dc = dh + di_next[e] * ppi + df_next[e] * ppf + dO * ppo + (DROP == 2 ? dcm_next[e] : dc_next[e]) * f_next[e];
+            dcm = dc * vr[e];
+          }
+          df = (DROP == 2 ? dcm : dc) * vcp[e] * vf[e] * (1.f - vf[e]);           // :488-489 / :715-719
+          di = dcm * vg[e] * vi[e] * (1.f - vi[e]);                               // :492-493 / :723
+          dg = dcm * vi[e] * (1.f - vg[e] * vg[e]);                               // :496-497 / :727
+          dc_next[e] = dc; dcm_next[e] = dcm; f_next[e] = vf[e]; di_next[e] = di; df_next[e] = df;
+          float *drow = a.DG + ((size_t)t * S + uidx[e]) * a.lddg + (size_t)dir * 4 * C + cell;
+          drow[0] = dg; drow[(size_t)C] = di; drow[(size_t)2 * C] = df; drow[(size_t)3 * C] = dO;
+          sb[0][e] += dg; sb[1][e] += di; sb[2][e] += df; sb[3][e] += dO;         // :507 / :598
+          spi[e] += di * vcp[e]; spf[e] += df * vcp[e]; spo[e] += dO * vc[e];     // :508-510 / :599-601
+        }
+        dgt[0][e] = dg; dgt[1][e] = di; dgt[2][e] = df; dgt[3][e] = dO;
+      }
+      if (step + 1 == T) break;   // the last step's recurrent contribution is never consumed
+      // ---- D operand: every utterance column scaled by its own power of two into [2^13, 2^14), fp16 hi / lo'
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        float mx = fmaxf(fmaxf(fabsf(dgt[0][e]), fabsf(dgt[1][e])), fmaxf(fabsf(dgt[2][e]), fabsf(dgt[3][e])));
+        const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));   // non-negative floats order like their bits
+        int ex = (int)(mb >> 23) - 127;                    // floor(log2(max)); -127 for zero / subnormal columns
+        int kexp = 13 - ex;
+        kexp = kexp > 120 ? 120 : (kexp < -120 ? -120 : kexp);
+        if (mb == 0u || mb >= 0x7f800000u) kexp = 0;       // all-zero column, or inf/nan (propagates as it is)
+        const float sc = __uint_as_float((uint32_t)(kexp + 127) << 23);
+        if (lane == 0) scl[2 * up + e] = __uint_as_float((uint32_t)(127 - kexp) << 23);
+        const int u = 2 * up + e;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          uint32_t h, l;
+          split_f16(dgt[q][e] * sc, h, l);
+          *reinterpret_cast<uint16_t *>(Bt + sw128_off(32, u, q * 32 + cl)) = (uint16_t)h;
+          *reinterpret_cast<uint16_t *>(Bt + sw128_off(32, 16 + u, q * 32 + cl)) = (uint16_t)l;
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      mbar_arrive(&b_full);
+      TC_TICK(1, 1);
+      if (warp == 0) {
+        // ===== MMA issue (the last step's partial is never consumed: T-1 products) =====
+        mbar_wait(&b_full, (uint32_t)(step & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        if (elect_one()) {
+          const uint32_t ahi = smem_u32(Ahi), alo = smem_u32(Alo), bt = smem_u32(Bt);
+          for (int mt = 0; mt < MT; mt++) {
+            const int rows = mt < n128 ? 128 : 64;
+            const uint32_t idN = idesc_f16(rows, 32), idH = idesc_f16(rows, 16);
+            const uint32_t tb = (uint32_t)mt * 128 * 256;
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++) {
+              const int kb = ks >> 2, k4 = ks & 3;
+              const uint64_t bd = umma_desc(bt + kb * 4096 + k4 * 32, 16, 1024, 2);
+              umma_f16(tmem_base + mt * 48, umma_desc(ahi + tb + kb * rows * 128 + k4 * 32, 16, 1024, 2), bd, idN, ks != 0);
+              umma_f16(tmem_base + mt * 48 + 32, umma_desc(alo + tb + kb * rows * 128 + k4 * 32, 16, 1024, 2), bd, idH, ks != 0);
+            }
+          }
+          umma_commit(&mma_done);
+        }
+        __syncwarp();
+      }
+      prefetch(t + tstep);
+      mbar_wait(&mma_done, (uint32_t)(step & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      TC_TICK(1, 2);
+      {
+        uint2 *pw = pbuf + ((size_t)((((step & 1) * ndir + dir) * groups + group) * slices + slice)) * pstride_slice;
+        const unsigned tagw = (unsigned)step + 1u;
+        float inv[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) inv[j] = scl[8 * uh + j];
+        for (int mt = 0; mt < MT; mt++) {
+          const bool full = mt < n128;
+          uint32_t x0[8], x1[8], y0[8];
+          const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 48);
+          tmem_ld8(tl + 8 * uh, x0);
+          tmem_ld8(tl + 16 + 8 * uh, x1);
+          tmem_ld8(tl + 32 + 8 * uh, y0);
+          tmem_ld_wait();
+          // M = 128: lane = row; M = 64: rows 16*quad .. +15 sit in lanes 0-15 of every quadrant
+          const int j = full ? mt * 128 + quad * 32 + lane : mt * 128 + quad * 16 + lane;
+          if (full || lane < 16) {
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) {
+              const float pv = (u2f(x0[jj]) + (u2f(x1[jj]) + u2f(y0[jj])) * kLoUnscale) * inv[jj];
+              st_tagged(pw + (size_t)(8 * uh + jj) * C + j, pv, tagw);
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      }
+      TC_TICK(1, 3);
+    }
+
+    // ---- bias / peephole gradient partial sums of this (dir, group): reduce over the CTA's 16 utterances
+    named_bar_workers();
+    float *red = reinterpret_cast<float *>(smem);   // [7][16 utts][32 cells] (the weights are no longer needed:
+                                                    //  every MMA was committed and waited for)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int u = 2 * up + e;
+      float v[7] = {sb[0][e], sb[1][e], sb[2][e], sb[3][e], spi[e], spf[e], spo[e]};
+#pragma unroll
+      for (int q = 0; q < 7; q++) red[(q * TCL_UG + u) * 32 + cl] = v[q];
+    }
+    named_bar_workers();
+    if (tid < 7 * 32) {
+      const int q = tid >> 5, c_ = tid & 31;
+      float s_ = 0.f;
+      for (int uu = 0; uu < TCL_UG; uu++) s_ += red[(q * TCL_UG + uu) * 32 + c_];
+      a.gsum[(((size_t)dir * groups + group) * 7 + q) * C + slice * TCL_CS + c_] = s_;
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(256) : "memory");
+  }
+}
+
+size_t tc_fwd_smem(int C) { return (size_t)(C / 64) * (2 * 16384 + 4096) + 4 * TCL_UG * 32 * sizeof(float) + 1024; }
+size_t tc_bwd_smem(int C) { return (size_t)C * 512 + 8192 + 64 + 1024; }
+
+}  // namespace
+
+int lstm_tc_debug_timing(long long *out32, int reset) {
+#ifdef EB_LSTM_TIMING
+  if (out32) cudaMemcpyFromSymbol(out32, g_lstm_tc_timing, sizeof(long long) * 32);
+  if (reset) {
+    long long z[32] = {0};
+    cudaMemcpyToSymbol(g_lstm_tc_timing, z, sizeof(z));
+  }
+  return 1;
+#else
+  (void)out32; (void)reset;
+  return 0;
+#endif
+}
+
+// Plan of the tensor-core engine (engine = 1): valid when the cells of a direction tile into 64-wide k-blocks,
+// the resident tiles fit shared memory and one co-resident grid holds every (dir, group, slice).
+LstmPlan lstm_tc_plan(int S, int C, int num_sms, size_t max_smem, int ndir) {
+  LstmPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  pl.ndir = ndir;
+  if (C % 64 != 0 || C < 64 || S <= 0 || ndir < 1 || ndir > 2) return pl;
+  const int groups = (S + TCL_UG - 1) / TCL_UG, slices = C / TCL_CS;
+  const size_t sf = tc_fwd_smem(C), sb = tc_bwd_smem(C);
+  if ((long)ndir * groups * slices > num_sms || sf > max_smem || sb > max_smem || slices > 12) return pl;
+  pl.engine = 1;
+  pl.nut = 2; pl.nct = 4; pl.ksplit = 1;
+  pl.groups = groups; pl.slices = slices;
+  pl.threads = TCL_THREADS;
+  pl.smem_fwd = sf; pl.smem_bwd = sb;
+  pl.pbuf_floats = (size_t)2 * 2 * ndir * groups * slices * TCL_UG * C;   // 8-byte tagged words
+  pl.xbuf_bytes = (size_t)2 * ndir * groups * TCL_UG * C * 8;
+  pl.gsum_floats = (size_t)2 * groups * 7 * C;
+  pl.valid = 1;
+  return pl;
+}
+
+cudaError_t lstm_tc_forward(cudaStream_t st, const LstmPlan &pl, const LstmFwdArgs &a) {
+  if (!pl.valid || pl.engine != 1) return cudaErrorInvalidConfiguration;
+  if (a.drop < 0 || a.drop > 2 || (a.drop != 0 && !a.rmask)) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(a.xbuf, 0, pl.xbuf_bytes, st);
+  if (e != cudaSuccess) return e;
+  dim3 grid(pl.slices, pl.groups, pl.ndir), block(pl.threads);
+  int groups = pl.groups, ndir = pl.ndir;
+  LstmFwdArgs args = a;
+  void *kargs[] = {&args, &groups, &ndir};
+  const void *fn = a.drop == 0 ? (const void *)lstm_tc_fwd_kernel<0>
+                   : a.drop == 1 ? (const void *)lstm_tc_fwd_kernel<1> : (const void *)lstm_tc_fwd_kernel<2>;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_fwd);
+  if (e != cudaSuccess) return e;
+  return cudaLaunchCooperativeKernel(fn, grid, block, kargs, pl.smem_fwd, st);
+}
+
+cudaError_t lstm_tc_backward(cudaStream_t st, const LstmPlan &pl, const LstmBwdArgs &a) {
+  if (!pl.valid || pl.engine != 1) return cudaErrorInvalidConfiguration;
+  if (a.drop < 0 || a.drop > 2 || (a.drop != 0 && !a.rmask)) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(a.pbuf, 0, pl.pbuf_floats * sizeof(float), st);
+  if (e != cudaSuccess) return e;
+  dim3 grid(pl.slices, pl.groups, pl.ndir), block(pl.threads);
+  int groups = pl.groups, slices = pl.slices, ndir = pl.ndir;
+  LstmBwdArgs args = a;
+  void *kargs[] = {&args, &groups, &slices, &ndir};
+  const void *fn = a.drop == 0 ? (const void *)lstm_tc_bwd_kernel<0>
+                   : a.drop == 1 ? (const void *)lstm_tc_bwd_kernel<1> : (const void *)lstm_tc_bwd_kernel<2>;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bwd);
+  if (e != cudaSuccess) return e;
+  return cudaLaunchCooperativeKernel(fn, grid, block, kargs, pl.smem_bwd, st);
+}
+
+}  // namespace eb

@@ -67,7 +67,7 @@ void eesen_b200_destroy(eesen_b200_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   eesen_b200_ctx::Buf *bufs[] = {&ctx->gemm_ws, &ctx->lstm_pbuf, &ctx->lstm_gsum, &ctx->lstm_flags,
-                                 &ctx->ctc_ws, &ctx->colsum_ws, &ctx->seg_buf, &ctx->flag_buf};
+                                 &ctx->ctc_ws, &ctx->colsum_ws, &ctx->seg_buf, &ctx->flag_buf, &ctx->bf16_a, &ctx->bf16_b};
   for (auto *b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->nccl_comm && ctx->nccl_lib) {
@@ -103,8 +103,37 @@ static int do_gemm(eesen_b200_ctx *ctx, int ta, int tb, int M, int N, int K, flo
                    long sA, const float *B, int ldb, long sB, float beta, float *C, int ldc, long sC,
                    const float *bias, long sBias, int batch) {
   void *ws = nullptr;
-  // tensor-core engine: tcgen05/TMEM/TMA (gemm_tc.cu) for fp32x3 / tf32; the warp-level mma.sync
-  // kernel (gemm.cu) serves the bf16 mode and EESEN_B200_GEMM_ENGINE=legacy (A/B measurements)
+  // tensor-core engine: tcgen05/TMEM/TMA (gemm_tc.cu) for every arithmetic mode -- kind::tf32 for fp32x3 / tf32,
+  // kind::f16 on bf16 copies of the operands for bf16 (BASELINE config 4); the warp-level mma.sync kernel
+  // (gemm.cu) is kept for EESEN_B200_GEMM_ENGINE=legacy (A/B measurements) and matrices TMA cannot address
+  if (ctx->gemm_engine == 0 && ctx->gemm_prec == 2 && !(ta && tb) && M > 0 && N > 0 && K > 0 &&
+      eb::gemm_tc_supported(ta, tb, M, N, K, A, 4, B, 4, 0)) {
+    size_t need_tc = eb::gemm_tc_workspace_bytes(M, N, K, ctx->num_sms);
+    if (need_tc) {
+      int rc = ctx->reserve(ctx->gemm_ws, need_tc, &ws);
+      if (rc) return rc;
+    }
+    // operands as stored: A [M x K] or [K x M], B [N x K] or [K x N]
+    const long ar = ta ? K : M, br = tb ? N : K;
+    const int ac = ta ? M : K, bc = tb ? K : N;
+    void *a16 = nullptr, *b16 = nullptr;
+    int rc;
+    if ((rc = ctx->reserve(ctx->bf16_a, eb::gemm_tc16_operand_bytes(ar, ac), &a16))) return rc;
+    if ((rc = ctx->reserve(ctx->bf16_b, eb::gemm_tc16_operand_bytes(br, bc), &b16))) return rc;
+    for (int b = 0; b < batch; b++) {
+      int pe = ctx->prof_begin(eesen_b200_ctx::kGemm);
+      cudaError_t e = cudaSuccess;
+      if (b == 0 || sA != 0) { e = eb::convert_bf16(ctx->stream, ctx->num_sms, A + b * sA, ar, ac, lda, a16); ctx->launches += 1; }
+      if (e == cudaSuccess && (b == 0 || sB != 0)) { e = eb::convert_bf16(ctx->stream, ctx->num_sms, B + b * sB, br, bc, ldb, b16); ctx->launches += 1; }
+      if (e == cudaSuccess)
+        e = eb::gemm_tc16(ctx->stream, ctx->num_sms, ta, tb, M, N, K, alpha, a16, b16, beta, C + b * sC, ldc,
+                          bias ? bias + b * sBias : nullptr, (float *)ws, ws ? ctx->gemm_ws.bytes : 0);
+      ctx->prof_end(pe);
+      ctx->launches += 1;
+      if ((rc = ctx->check(e, "gemm_tc16"))) return rc;
+    }
+    return 0;
+  }
   if (ctx->gemm_engine == 0 && eb::gemm_tc_supported(ta, tb, M, N, K, A, lda, B, ldb, ctx->gemm_prec) &&
       (batch == 1 || ((sA & 3) == 0 && (sB & 3) == 0))) {
     size_t need_tc = eb::gemm_tc_workspace_bytes(M, N, K, ctx->num_sms);
@@ -445,7 +474,7 @@ int eesen_b200_ctc_eval(eesen_b200_ctx *ctx, int T, int S, int K, int max_lab, c
 
 int eesen_b200_check_finite(eesen_b200_ctx *ctx, const float *d_x, int64_t n, int *flags) {
   if (!ctx || !flags || (n > 0 && !d_x) || n < 0) return EESEN_B200_EINVAL;
-  void *d;
+  void *d = nullptr;
   int rc = ctx->reserve(ctx->flag_buf, 64, &d);
   if (rc) return rc;
   ctx->launches += 1;

@@ -26,7 +26,7 @@ struct eesen_b200_ctx {
     void *p = nullptr;
     size_t bytes = 0;
   };
-  Buf gemm_ws, lstm_pbuf, lstm_gsum, lstm_flags, ctc_ws, colsum_ws, seg_buf, flag_buf;
+  Buf gemm_ws, lstm_pbuf, lstm_gsum, lstm_flags, ctc_ws, colsum_ws, seg_buf, flag_buf, bf16_a, bf16_b;
 
   // optional per-category kernel timing with CUDA events on `stream` (bench.py roofline)
   enum { kGemm = 0, kLstmFwd, kLstmBwd, kSoftmax, kCtc, kSgd, kAllReduce, kMisc, kNumCat };

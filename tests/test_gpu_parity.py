@@ -66,6 +66,13 @@ def test_gemm(ctx, ta, tb, M, N, K, prec, tol):
         tol = 2.5e-5   # fp32 accumulation in TMEM over long K (tensor-core accumulate rounding), ~6e-6 relative
     assert_close("gemm", got[:, :N] / scale, ref / scale, atol=tol)
     assert np.array_equal(got[:, N:], C0[:, N:])   # padding columns of C untouched
+    if prec == "bf16":
+        # the bf16 mode is tcgen05 kind::f16 on round-to-nearest-even bf16 copies of the operands with fp32
+        # accumulation: against the exact product of the ROUNDED operands only the accumulation order is left
+        r16 = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(torch.bfloat16).to(torch.float64).numpy()
+        a = r16(A[:, :Ash[1]]); b = r16(B[:, :Bsh[1]])
+        ref16 = 0.5 * ((a.T if ta else a) @ (b.T if tb else b)) + 0.25 * C0[:, :N]
+        assert_close("gemm_bf16_rounded_operands", got[:, :N] / scale, ref16 / scale, atol=2.5e-5 if K >= 512 else 5e-6)
 
 
 @pytest.mark.parametrize("N,K", [(7, 5), (1000, 46), (333, 300)])
@@ -139,10 +146,19 @@ def test_ctc_eval_vs_oracle(ctx, seed, S, T, K, maxlab):
 
 @pytest.mark.parametrize("S,T,I,C", [(4, 9, 8, 16), (2, 30, 40, 128), (20, 17, 40, 64), (16, 40, 40, 320), (3, 5, 64, 24),
                                      (100, 7, 40, 320), (1, 1, 40, 64)])   # 100 utts: two utterance chunks (64 + 36)
-@pytest.mark.parametrize("rec", ["fp32x3", "tf32"])
-def test_bilstm_layer_vs_oracle(ctx, S, T, I, C, rec):
-    """Level-1 BiLSTM forward/backward of one layer against the fp64 oracle, ragged lengths."""
+@pytest.mark.parametrize("rec", ["fp32x3", "tf32", "legacy-engine"])
+def test_bilstm_layer_vs_oracle(ctx, S, T, I, C, rec, monkeypatch):
+    """Level-1 BiLSTM forward/backward of one layer against the fp64 oracle, ragged lengths.  Shapes with
+    cells % 64 == 0 run on the tcgen05 recurrent kernels (lstm_tc.cu), the others -- and every shape under
+    EESEN_B200_LSTM_ENGINE=legacy -- on the warp-level kernels (lstm.cu): same tolerances for both."""
     torch = torch_()
+    if rec == "legacy-engine":
+        if C % 64 != 0:
+            pytest.skip("already on the warp-level kernels")
+        monkeypatch.setenv("EESEN_B200_LSTM_ENGINE", "legacy")
+        rec = "fp32x3"
+    else:
+        monkeypatch.delenv("EESEN_B200_LSTM_ENGINE", raising=False)
     rng = np.random.default_rng(S * 1000 + T)
     frames = np.sort(rng.integers(max(1, T // 2), T + 1, size=S))[::-1].astype(np.int32)
     frames[0] = T
