@@ -10,12 +10,12 @@ CXX     := g++
 ARCH    := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall $(if $(TIMING),-DEB_LSTM_TIMING,)
 CXXFLAGS:= -O2 -std=c++17 -fPIC -Wall -I$(CUDA)/include
-OBJDIR  := build
-LIBDIR  := eesen_b200/lib
+OBJDIR  ?= build
+LIBDIR  ?= eesen_b200/lib
 BINDIR  := eesen_b200/bin
 
-CU_SRCS := gemm gemm_tc lstm lstm_tc ctc optim
-CC_SRCS := base net abi_ops abi_net
+CU_SRCS := gemm gemm_tc lstm lstm_tc ctc optim decode
+CC_SRCS := base net abi_ops abi_net abi_decode
 CU_OBJS := $(patsubst %,$(OBJDIR)/%.cu.o,$(CU_SRCS))
 CC_OBJS := $(patsubst %,$(OBJDIR)/%.cc.o,$(CC_SRCS))
 

@@ -23,7 +23,7 @@ class EesenB200Error(RuntimeError):
 
 
 class BilstmParams(C.Structure):
-    _fields_ = [(n, C.c_void_p * 2) for n in ("wx", "wm", "bias", "pi", "pf", "po")]
+    _fields_ = [(n, C.c_void_p * 2) for n in ("wx", "wm", "bias", "pi", "pf", "po")] + [("ldwx", C.c_int), ("ldwm", C.c_int)]
 
 
 class SgdSegment(C.Structure):
@@ -37,9 +37,10 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise EesenB200Error(f"{LIB_PATH} not built: run `make` (or __graft_entry__.build()) first")
-    lib = C.CDLL(LIB_PATH)
+    path = os.environ.get("EESEN_B200_LIB", LIB_PATH)   # instrumented builds (make TIMING=1 LIBDIR=...) for tests/lstm_timing.py
+    if not os.path.exists(path):
+        raise EesenB200Error(f"{path} not built: run `make` (or __graft_entry__.build()) first")
+    lib = C.CDLL(path)
     lib.eesen_b200_last_error.restype = C.c_char_p
     lib.eesen_b200_last_error.argtypes = [C.c_void_p]
     lib.eesen_b200_stream.restype = C.c_void_p
@@ -125,22 +126,24 @@ class Context:
                                             C.c_float(beta), _p(Cm), ldc), "gemm")
 
     @staticmethod
-    def _pack(tensors12) -> BilstmParams:
+    def _pack(tensors12, ldwx=0, ldwm=0) -> BilstmParams:
+        """ldwx / ldwm: row strides of the wx / wm matrices in floats (0 = dense), e.g. pitched reference weights"""
         s = BilstmParams()
         names = ("wx", "wm", "bias", "pi", "pf", "po")
         for d in range(2):
             for k, n in enumerate(names):
                 getattr(s, n)[d] = tensors12[d * 6 + k].data_ptr()
+        s.ldwx, s.ldwm = ldwx, ldwm
         return s
 
-    def bilstm_forward(self, T, S, I, Cc, d_len, x, ldx, params12, gates, cell, out, ldo):
-        p = self._pack(params12)
+    def bilstm_forward(self, T, S, I, Cc, d_len, x, ldx, params12, gates, cell, out, ldo, ldwx=0, ldwm=0):
+        p = self._pack(params12, ldwx, ldwm)
         self.check(self.lib.eesen_b200_bilstm_forward(self.h, T, S, I, Cc, _p(d_len), _p(x), ldx, C.byref(p),
                                                       _p(gates), _p(cell), _p(out), ldo), "bilstm_forward")
 
     def bilstm_backward(self, T, S, I, Cc, x, ldx, params12, gates, cell, out, ldo, dout, ldd, dgates, dx, lddx,
-                        grads12):
-        p, g = self._pack(params12), self._pack(grads12)
+                        grads12, ldwx=0, ldwm=0, gldwx=0, gldwm=0):
+        p, g = self._pack(params12, ldwx, ldwm), self._pack(grads12, gldwx, gldwm)
         self.check(self.lib.eesen_b200_bilstm_backward(self.h, T, S, I, Cc, _p(x), ldx, C.byref(p), _p(gates),
                                                        _p(cell), _p(out), ldo, _p(dout), ldd, _p(dgates), _p(dx),
                                                        lddx, C.byref(g)), "bilstm_backward")

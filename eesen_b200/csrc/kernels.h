@@ -31,6 +31,7 @@ cudaError_t gemm_tc16(cudaStream_t st, int num_sms, int transA, int transB, int 
 // lstm.cu -- persistent recurrent kernels (both directions in one cooperative launch)
 struct LstmDirParams {
   const float *wm;  // [4C x C] recurrent weights, row blocks g,i,f,o
+  int ldwm;         // row stride of wm in floats (>= C)
   const float *pi, *pf, *po;  // [C] peepholes
 };
 struct LstmFwdArgs {
@@ -73,7 +74,8 @@ struct LstmPlan {
   size_t pbuf_floats, gsum_floats, xbuf_bytes;
   int valid;
 };
-LstmPlan lstm_plan(int S, int C, int num_sms, size_t max_smem, int ndir = 2);
+// pass: 0 = forward, 1 = backward (the engines are chosen per pass, lstm.cu:engine_for_pass)
+LstmPlan lstm_plan(int S, int C, int num_sms, size_t max_smem, int ndir = 2, int pass = 0);
 cudaError_t lstm_forward(cudaStream_t st, const LstmPlan &plan, const LstmFwdArgs &a);
 cudaError_t lstm_backward(cudaStream_t st, const LstmPlan &plan, const LstmBwdArgs &a);
 // bias/peephole gradient from the per-group sums: dst[7 blocks] = sum_groups gsum
@@ -100,6 +102,21 @@ size_t ctc_workspace_floats(int T, int S, int max_lab);
 cudaError_t ctc_eval(cudaStream_t st, int T, int S, int K, int max_lab, const int *len, const int *labels,
                      const int *lab_len, const float *probs, int ldp, float *pzx, float *diff, int ldd,
                      float *ws);
+
+// decode.cu -- one-best WFST token passing for a batch of utterances (reference src/decoder/lattice-faster-decoder.cc)
+struct DecodeGraph {      // device pointers; CSR over states, emitting arcs of a state first, then its epsilon arcs
+  int num_states, num_arcs, start;
+  const int *row;         // [num_states + 1]
+  const int *eps;         // [num_states]     first epsilon-input arc of the state
+  const int *ilabel, *olabel, *nextstate, *arc_from;   // [num_arcs]
+  const float *weight;    // [num_arcs] graph cost
+  const float *final_cost;   // [num_states], +inf = not final
+};
+size_t decode_workspace_bytes(int S, int num_states, int frame_cap, int wl_cap, int tok_cap);
+cudaError_t decode_best_path(cudaStream_t st, int num_sms, const DecodeGraph &g, int S, int T, const int *h_frames,
+                             const float *d_loglikes, int ld, float scale, float beam, void *ws, int frame_cap,
+                             int wl_cap, int tok_cap, int *d_out_labels, int max_out, int *d_out_len, float *d_out_cost,
+                             int *err_bits, long *closure_rounds);
 
 // optim.cu
 struct SgdSegment {

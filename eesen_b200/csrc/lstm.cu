@@ -113,7 +113,7 @@ lstm_fwd_kernel(LstmFwdArgs a, int groups, unsigned expected_per_step) {
     int gate = mt * 2 + (e & 1);
     int k = ks * 8 + tt + ((e & 2) ? 4 : 0);
     int cellw = (slice * NCT + c_) * 8 + gg;
-    Wsm[idx] = cellw < C ? P.wm[((size_t)gate * C + cellw) * C + k] : 0.f;
+    Wsm[idx] = cellw < C ? P.wm[((size_t)gate * C + cellw) * P.ldwm + k] : 0.f;
   }
 
   const int cell = (slice * NCT + ct) * 8 + g;  // this lane's cell (finalising warps)
@@ -340,7 +340,7 @@ lstm_bwd_kernel(LstmBwdArgs a, int groups, int slices, unsigned expected_per_ste
     int j = mt * 16 + gg + ((e & 1) ? 8 : 0);     // output cell (M index)
     int gate = rl / (8 * NCT), rem = rl % (8 * NCT);
     int cellw = slice * NCT * 8 + rem;
-    Wsm[idx] = (cellw < C && j < C) ? P.wm[((size_t)gate * C + cellw) * C + j] : 0.f;
+    Wsm[idx] = (cellw < C && j < C) ? P.wm[((size_t)gate * C + cellw) * P.ldwm + j] : 0.f;
   }
 
   // per-item state
@@ -580,14 +580,20 @@ int lstm_debug_timing(long long *out32, int reset) {
 #endif
 }
 
-// read at every plan (not cached): the tests switch engines inside one process
-static bool legacy_engine_forced() {
+// Engine per pass, read at every plan (not cached: the tests switch engines inside one process).
+//   EESEN_B200_LSTM_ENGINE unset : forward on tcgen05 (lstm_tc.cu) where the shape allows, backward on the warp-level
+//                                  kernels below (measured on C2: tcgen05 forward 7.4 ms vs 10.2 ms per step; the
+//                                  tcgen05 backward is correct but its reduce-scatter exchange is slower, 13 vs 10.8 ms)
+//   "legacy" : both passes here;  "tc" : both passes on tcgen05
+static int engine_for_pass(int pass) {
   const char *e = getenv("EESEN_B200_LSTM_ENGINE");
-  return e && strcmp(e, "legacy") == 0;
+  if (e && strcmp(e, "legacy") == 0) return 0;
+  if (e && strcmp(e, "tc") == 0) return 1;
+  return pass == 0 ? 1 : 0;
 }
 
-LstmPlan lstm_plan(int S, int C, int num_sms, size_t max_smem, int ndir) {
-  if (!legacy_engine_forced()) {
+LstmPlan lstm_plan(int S, int C, int num_sms, size_t max_smem, int ndir, int pass) {
+  if (engine_for_pass(pass) == 1) {
     LstmPlan tc = lstm_tc_plan(S, C, num_sms, max_smem, ndir);
     if (tc.valid) return tc;
   }

@@ -21,8 +21,11 @@
 // [2^13, 2^14) before the split and scaled back in the epilogue.  (One instruction cannot mix fp16 and bf16
 // operands on sm_100a -- measured, tests/micro/umma_probe.cu -- hence the scaling instead of a bf16 split.)
 //
-// Exchange between the CTAs of one (dir, group): the "LL" tagged 8-byte words of lstm.cu (common.cuh); the
-// forward payload is the already split pair (hi | lo' << 16), so the ten consumers of a word do no arithmetic.
+// Exchange between the CTAs of one (dir, group): "LL" style tagged words as in lstm.cu, but 4 bytes wide -- the
+// step tag is ONE bit that replaces the least significant bit of the payload (of lo' forward: 2^-21 relative; of
+// the fp32 partial d_m backward: 2^-24 relative), so a step moves half the bytes of an 8-byte word protocol through
+// L2.  A buffer is reused every second step with the bit flipped ((step >> 1) & 1); buffers start as 0xFF bytes.
+// The forward payload is the already split pair (hi | lo' << 16): the ten consumers of a word do no arithmetic.
 // 256 threads: every warp stages the exchanged words into the B tile, evaluates the gates (two (cell, utterance)
 // pairs per thread) and owns a part of the TMEM -> register epilogue (lane quadrant = warp % 4); warp 0
 // additionally allocates TMEM and issues the MMAs from one elected lane while the others wait for the commit.
@@ -38,19 +41,30 @@
 namespace eb {
 
 #ifdef EB_LSTM_TIMING
+// debug build only (make TIMING=1): per-phase clock64 deltas of thread 0 of CTA (0,0,0), accumulated in REGISTERS
+// and written once at the end (a global read-modify-write per tick would stall the MMA-issuing warp on an L2 round
+// trip five times per step)
 __device__ long long g_lstm_tc_timing[2][16];
 #define TC_T0() long long tk_ = clock64()
+#define TC_ACC_DECL() long long tacc_[6] = {0, 0, 0, 0, 0, 0}
 #define TC_TICK(kernel, i)                                                          \
   do {                                                                              \
     if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {        \
       long long n_ = clock64();                                                     \
-      g_lstm_tc_timing[kernel][i] += n_ - tk_;                                      \
+      tacc_[i] += n_ - tk_;                                                         \
       tk_ = n_;                                                                     \
     }                                                                               \
   } while (0)
+#define TC_FLUSH(kernel)                                                            \
+  do {                                                                              \
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)          \
+      for (int i_ = 0; i_ < 6; i_++) g_lstm_tc_timing[kernel][i_] += tacc_[i_];     \
+  } while (0)
 #else
 #define TC_T0()
+#define TC_ACC_DECL()
 #define TC_TICK(kernel, i)
+#define TC_FLUSH(kernel)
 #endif
 
 namespace {
@@ -74,8 +88,52 @@ __device__ __forceinline__ void split_f16(float x, uint32_t &hi, uint32_t &lo) {
   lo = (uint32_t)__half_as_ushort(__float2half_rn((x - __half2float(h)) * kLoScale));
 }
 
-__device__ __forceinline__ void st_tagged_u32(uint2 *p, uint32_t v, unsigned tag) {
-  asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};\n" ::"l"(p), "r"(v), "r"(tag) : "memory");
+// instruction descriptor, kind::f16: D = F32, A = B = F16, both K-major
+__device__ __forceinline__ uint32_t idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// 4-byte exchange words, relaxed at gpu scope (served by L2, never by a stale L1 line)
+__device__ __forceinline__ void st_word(uint32_t *p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.b32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_word(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.b32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_word4(const uint4 *p) {
+  uint4 q;
+  asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(p) : "memory");
+  return q;
+}
+
+// One recurrent step's MMAs from the elected lane: fully unrolled, descriptors = 64-bit base + constant
+// (SASS: back-to-back UTCHMMA with one UIADD3.64 in between; a loop with run-time offsets costs ~45 clk per MMA).
+template <int KB>
+__device__ __forceinline__ void issue_fwd_mmas(uint64_t dWhi, uint64_t dWlo, uint64_t dB, uint32_t tmem, uint32_t idN,
+                                               uint32_t idH) {
+#pragma unroll
+  for (int kb = 0; kb < KB; kb++) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+      const uint64_t bd = dB + (uint64_t)((kb * 4096 + ks * 32) >> 4);
+      umma_f16(tmem, dWhi + (uint64_t)((kb * 16384 + ks * 32) >> 4), bd, idN, (kb | ks) != 0);
+      umma_f16(tmem + 32, dWlo + (uint64_t)((kb * 16384 + ks * 32) >> 4), bd, idH, (kb | ks) != 0);
+    }
+  }
+}
+template <int ROWS>
+__device__ __forceinline__ void issue_bwd_tile(uint64_t dAhi, uint64_t dAlo, uint64_t dB, uint32_t tmem) {
+  const uint32_t idN = idesc_f16(ROWS, 32), idH = idesc_f16(ROWS, 16);
+#pragma unroll
+  for (int ks = 0; ks < 8; ks++) {
+    const int kb = ks >> 2, k4 = ks & 3;
+    const uint64_t bd = dB + (uint64_t)((kb * 4096 + k4 * 32) >> 4);
+    umma_f16(tmem, dAhi + (uint64_t)((kb * ROWS * 128 + k4 * 32) >> 4), bd, idN, ks != 0);
+    umma_f16(tmem + 32, dAlo + (uint64_t)((kb * ROWS * 128 + k4 * 32) >> 4), bd, idH, ks != 0);
+  }
 }
 
 __device__ __forceinline__ void named_bar_workers() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
@@ -87,10 +145,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
-// instruction descriptor, kind::f16: D = F32, A = B = F16, both K-major
-__device__ __forceinline__ uint32_t idesc_f16(int M, int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 // ------------------------------------------------------------------------------------ forward
 template <int DROP>
@@ -110,19 +164,30 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slice = blockIdx.x, group = blockIdx.y, dir = blockIdx.z;
   const LstmDirParams P = a.p[dir];
-  uint2 *xbuf = reinterpret_cast<uint2 *>(a.xbuf);       // [2 parity][ndir][groups][16][C] tagged words
+  uint32_t *xbuf = reinterpret_cast<uint32_t *>(a.xbuf);  // [2 parity][ndir][groups][16][C] 4-byte tagged words
   const int s0 = a.s_begin, s1 = a.s_begin + a.s_count;
 
-  // ---- resident weights: row = gate*32 + local cell, split into the two fp16 tiles
-  for (int idx = tid; idx < 128 * C; idx += TCL_THREADS) {
-    const int r = idx / C, k = idx - r * C;
-    const int q = r >> 5, c_ = r & 31;
-    const float w = P.wm[((size_t)q * C + slice * TCL_CS + c_) * C + k];
-    uint32_t h, l;
-    split_f16(w, h, l);
-    const uint32_t off = sw128_off(128, r, k);
-    *reinterpret_cast<uint16_t *>(Whi + off) = (uint16_t)h;
-    *reinterpret_cast<uint16_t *>(Wlo + off) = (uint16_t)l;
+  // ---- resident weights: row = gate*32 + local cell, split into the two fp16 tiles (8 loads in flight per thread)
+  for (int base = 0; base < 128 * C; base += 8 * TCL_THREADS) {
+    float w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int idx = base + i * TCL_THREADS + tid;
+      const int r = idx / C, k = idx - r * C;
+      w[i] = idx < 128 * C ? __ldg(P.wm + ((size_t)(r >> 5) * C + slice * TCL_CS + (r & 31)) * P.ldwm + k) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int idx = base + i * TCL_THREADS + tid;
+      if (idx < 128 * C) {
+        const int r = idx / C, k = idx - r * C;
+        uint32_t h, l;
+        split_f16(w[i], h, l);
+        const uint32_t off = sw128_off(128, r, k);
+        *reinterpret_cast<uint16_t *>(Whi + off) = (uint16_t)h;
+        *reinterpret_cast<uint16_t *>(Wlo + off) = (uint16_t)l;
+      }
+    }
   }
   for (int idx = tid; idx < KB * 1024; idx += TCL_THREADS) reinterpret_cast<uint32_t *>(Bt)[idx] = 0u;
   if (tid == 0) {
@@ -172,7 +237,10 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
     load_pre(dir == 0 ? 0 : T - 1);
     const int c8n = C >> 3;                                // 8-cell chunks per utterance row
     const int quad = warp & 3, uh = warp >> 2;             // epilogue: TMEM lane quadrant (= gate), utterance half
+    const uint64_t dWhi = umma_desc(smem_u32(Whi), 16, 1024, 2), dWlo = umma_desc(smem_u32(Wlo), 16, 1024, 2),
+                   dBt = umma_desc(smem_u32(Bt), 16, 1024, 2);
 
+    TC_ACC_DECL();
     for (int step = 0; step < T; step++) {
       const int t = dir == 0 ? step : T - 1 - step;
       float acc[4][2];
@@ -183,23 +251,38 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
         // ---- stage m_{t-1} of the group: spin on the tagged words, write the hi / lo' rows of the B tile
         const uint4 *xr = reinterpret_cast<const uint4 *>(
             xbuf + ((size_t)(((step - 1) & 1) * ndir + dir) * groups + group) * TCL_UG * C);
-        const unsigned want = (unsigned)step;
-        for (int v = tid; v < TCL_UG * c8n; v += TCL_WORKERS) {
+        const uint32_t want = (uint32_t)(((step - 1) >> 1) & 1) << 16;   // tag bit of the data produced at step-1
+        // every thread owns up to 3 chunks (utterance u, 8 cells): ALL their loads go out before the first check
+        // (a chunk-after-chunk loop would serialise one L2 round trip per chunk), then whatever is still missing
+        // is polled again
+        constexpr int MAXT = 3;                            // 16 * (C/8) / 256 <= 3 for C <= 384
+        uint4 q[MAXT][2];
+        const uint4 *src[MAXT];
+        bool live[MAXT];
+#pragma unroll
+        for (int i = 0; i < MAXT; i++) {
+          const int v = tid + i * TCL_WORKERS;
+          const int u = v / c8n, c8 = v - u * c8n;
+          live[i] = v < TCL_UG * c8n && s0 + group * TCL_UG + u < s1;
+          src[i] = xr + ((size_t)u * C + c8 * 8) / 4;
+          if (live[i]) { q[i][0] = ld_word4(src[i]); q[i][1] = ld_word4(src[i] + 1); }
+        }
+#pragma unroll
+        for (int i = 0; i < MAXT; i++) {
+          const int v = tid + i * TCL_WORKERS;
+          if (v >= TCL_UG * c8n) continue;
           const int u = v / c8n, c8 = v - u * c8n;
           uint4 hi4 = make_uint4(0u, 0u, 0u, 0u), lo4 = hi4;
-          if (s0 + group * TCL_UG + u < s1) {
-            const uint4 *src = xr + ((size_t)u * C + c8 * 8) / 2;
-            uint4 q0, q1, q2, q3;
-            bool ok;
-            do {
-              q0 = ld_tagged2(src); q1 = ld_tagged2(src + 1); q2 = ld_tagged2(src + 2); q3 = ld_tagged2(src + 3);
-              ok = q0.y == want && q0.w == want && q1.y == want && q1.w == want && q2.y == want && q2.w == want &&
-                   q3.y == want && q3.w == want;
-            } while (!ok);
-            hi4 = make_uint4(__byte_perm(q0.x, q0.z, 0x5410), __byte_perm(q1.x, q1.z, 0x5410),
-                             __byte_perm(q2.x, q2.z, 0x5410), __byte_perm(q3.x, q3.z, 0x5410));
-            lo4 = make_uint4(__byte_perm(q0.x, q0.z, 0x7632), __byte_perm(q1.x, q1.z, 0x7632),
-                             __byte_perm(q2.x, q2.z, 0x7632), __byte_perm(q3.x, q3.z, 0x7632));
+          if (live[i]) {
+            while (((((q[i][0].x ^ want) | (q[i][0].y ^ want) | (q[i][0].z ^ want) | (q[i][0].w ^ want) |
+                      (q[i][1].x ^ want) | (q[i][1].y ^ want) | (q[i][1].z ^ want) | (q[i][1].w ^ want)) & 0x10000u)) != 0u) {
+              q[i][0] = ld_word4(src[i]); q[i][1] = ld_word4(src[i] + 1);
+            }
+            hi4 = make_uint4(__byte_perm(q[i][0].x, q[i][0].y, 0x5410), __byte_perm(q[i][0].z, q[i][0].w, 0x5410),
+                             __byte_perm(q[i][1].x, q[i][1].y, 0x5410), __byte_perm(q[i][1].z, q[i][1].w, 0x5410));
+            // the tag bit (LSB of every lo' half) is cleared again: a zero stays an exact zero
+            lo4 = make_uint4(__byte_perm(q[i][0].x, q[i][0].y, 0x7632) & 0xfffefffeu, __byte_perm(q[i][0].z, q[i][0].w, 0x7632) & 0xfffefffeu,
+                             __byte_perm(q[i][1].x, q[i][1].y, 0x7632) & 0xfffefffeu, __byte_perm(q[i][1].z, q[i][1].w, 0x7632) & 0xfffefffeu);
           }
           const int k0 = c8 * 8;
           *reinterpret_cast<uint4 *>(Bt + sw128_off(32, u, k0)) = hi4;
@@ -214,14 +297,13 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           if (elect_one()) {
             const uint32_t idN = idesc_f16(128, 32), idH = idesc_f16(128, 16);
-            const uint32_t whi = smem_u32(Whi), wlo = smem_u32(Wlo), bt = smem_u32(Bt);
-            for (int kb = 0; kb < KB; kb++) {
-#pragma unroll
-              for (int ks = 0; ks < 4; ks++) {
-                const uint64_t bd = umma_desc(bt + kb * 4096 + ks * 32, 16, 1024, 2);
-                umma_f16(tmem_base, umma_desc(whi + kb * 16384 + ks * 32, 16, 1024, 2), bd, idN, (kb | ks) != 0);
-                umma_f16(tmem_base + 32, umma_desc(wlo + kb * 16384 + ks * 32, 16, 1024, 2), bd, idH, (kb | ks) != 0);
-              }
+            switch (KB) {
+              case 1: issue_fwd_mmas<1>(dWhi, dWlo, dBt, tmem_base, idN, idH); break;
+              case 2: issue_fwd_mmas<2>(dWhi, dWlo, dBt, tmem_base, idN, idH); break;
+              case 3: issue_fwd_mmas<3>(dWhi, dWlo, dBt, tmem_base, idN, idH); break;
+              case 4: issue_fwd_mmas<4>(dWhi, dWlo, dBt, tmem_base, idN, idH); break;
+              case 5: issue_fwd_mmas<5>(dWhi, dWlo, dBt, tmem_base, idN, idH); break;
+              default: issue_fwd_mmas<6>(dWhi, dWlo, dBt, tmem_base, idN, idH); break;
             }
             umma_commit(&mma_done);
           }
@@ -280,8 +362,8 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
           if (step + 1 < T) {
             uint32_t h, l;
             split_f16(sm[e], h, l);
-            st_tagged_u32(xbuf + (((size_t)((step & 1) * ndir + dir) * groups + group) * TCL_UG + 2 * up + e) * C + cell,
-                          h | (l << 16), (unsigned)step + 1u);
+            st_word(xbuf + (((size_t)((step & 1) * ndir + dir) * groups + group) * TCL_UG + 2 * up + e) * C + cell,
+                    h | ((l & 0xfffeu) << 16) | ((uint32_t)((step >> 1) & 1) << 16));   // tag = LSB of lo'
           }
           __stcs(a.out + ((size_t)t * S + uidx[e]) * a.ldo + (size_t)dir * C + cell, sm[e]);
         }
@@ -299,6 +381,7 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
       if (step + 1 < T) load_pre(dir == 0 ? t + 1 : t - 1);
       TC_TICK(0, 4);
     }
+    TC_FLUSH(0);
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -324,32 +407,43 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
   uint8_t *Alo = Ahi + (size_t)C * 256;
   uint8_t *Bt = Alo + (size_t)C * 256;                    // [2 k-blocks][32 rows][128 B]
   float *scl = reinterpret_cast<float *>(Bt + 8192);      // [16] inverse column scales
-  __shared__ uint64_t b_full, mma_done;
+  __shared__ uint64_t b_full, mma_done[3];   // one commit barrier per M tile (C <= 384: at most 3 tiles)
   __shared__ uint32_t tmem_base_sm;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slice = blockIdx.x, group = blockIdx.y, dir = blockIdx.z;
   const LstmDirParams P = a.p[dir];
-  uint2 *pbuf = reinterpret_cast<uint2 *>(a.pbuf);       // [2 parity][ndir][groups][slices][16][C] tagged partial d_m
+  uint32_t *pbuf = reinterpret_cast<uint32_t *>(a.pbuf);  // [2 parity][ndir][groups][slices][16][C] partial d_m, tag in the LSB
   const int s0 = a.s_begin, s1 = a.s_begin + a.s_count;
 
-  // A[j, k = gate*32 + c] = Wm[gate*C + slice*32 + c][j]
-  for (int idx = tid; idx < 128 * C; idx += TCL_THREADS) {
-    const int kk = idx / C, j = idx - kk * C;             // j fastest: coalesced reads of the Wm row
-    const int q = kk >> 5, c_ = kk & 31;
-    const float w = P.wm[((size_t)q * C + slice * TCL_CS + c_) * C + j];
-    uint32_t h, l;
-    split_f16(w, h, l);
-    const int mt = j >> 7;
-    const int rows = mt < n128 ? 128 : 64;
-    const uint32_t off = (uint32_t)mt * 128 * 256 + sw128_off(rows, j & 127, kk);
-    *reinterpret_cast<uint16_t *>(Ahi + off) = (uint16_t)h;
-    *reinterpret_cast<uint16_t *>(Alo + off) = (uint16_t)l;
+  // A[j, k = gate*32 + c] = Wm[gate*C + slice*32 + c][j]   (j fastest: coalesced reads of the Wm rows, 8 in flight)
+  for (int base = 0; base < 128 * C; base += 8 * TCL_THREADS) {
+    float w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int idx = base + i * TCL_THREADS + tid;
+      const int kk = idx / C, j = idx - kk * C;
+      w[i] = idx < 128 * C ? __ldg(P.wm + ((size_t)(kk >> 5) * C + slice * TCL_CS + (kk & 31)) * P.ldwm + j) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int idx = base + i * TCL_THREADS + tid;
+      if (idx < 128 * C) {
+        const int kk = idx / C, j = idx - kk * C;
+        uint32_t h, l;
+        split_f16(w[i], h, l);
+        const int mt = j >> 7;
+        const int rows = mt < n128 ? 128 : 64;
+        const uint32_t off = (uint32_t)mt * 128 * 256 + sw128_off(rows, j & 127, kk);
+        *reinterpret_cast<uint16_t *>(Ahi + off) = (uint16_t)h;
+        *reinterpret_cast<uint16_t *>(Alo + off) = (uint16_t)l;
+      }
+    }
   }
   for (int idx = tid; idx < 2048; idx += TCL_THREADS) reinterpret_cast<uint32_t *>(Bt)[idx] = 0u;
   if (tid == 0) {
     mbar_init(&b_full, TCL_WORKERS);
-    mbar_init(&mma_done, 1);
+    for (int i = 0; i < 3; i++) mbar_init(&mma_done[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
@@ -400,35 +494,43 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
     prefetch(dir == 0 ? T - 1 : 0);
     const size_t pstride_slice = (size_t)TCL_UG * C;
     const int quad = warp & 3, uh = warp >> 2;
+    const uint64_t dAhi = umma_desc(smem_u32(Ahi), 16, 1024, 2), dAlo = umma_desc(smem_u32(Alo), 16, 1024, 2),
+                   dBt = umma_desc(smem_u32(Bt), 16, 1024, 2);
 
+    TC_ACC_DECL();
     for (int step = 0; step < T; step++) {
       const int t = dir == 0 ? T - 1 - step : step;
       TC_T0();
       float dm[2] = {vd[0], vd[1]};
       if (step > 0) {
         // ---- d_m of this thread's items: the `slices` tagged partials, summed in fixed order (:470 / :561)
-        const uint2 *pb = pbuf + ((size_t)((((step - 1) & 1) * ndir + dir) * groups + group) * slices) * pstride_slice + cell;
-        const unsigned want = (unsigned)step;
+        const uint32_t *pb = pbuf + ((size_t)((((step - 1) & 1) * ndir + dir) * groups + group) * slices) * pstride_slice + cell;
+        const uint32_t want = (uint32_t)(((step - 1) >> 1) & 1);
+        uint32_t q[2][12];                                  // slices <= 12 (C <= 384, lstm_tc_plan)
+        // the loads of BOTH items go out together (one L2 round trip when everything is there) ...
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const uint32_t *pe = pb + (size_t)(2 * up + e) * C;
+#pragma unroll
+          for (int i = 0; i < 12; i++)
+            if (i < slices && ok[e]) q[e][i] = ld_word(pe + (size_t)i * pstride_slice);
+        }
+        // ... then only the words that have not arrived yet are polled again
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const uint32_t *pe = pb + (size_t)(2 * up + e) * C;
+#pragma unroll
+          for (int i = 0; i < 12; i++)
+            if (i < slices && ok[e])
+              while ((q[e][i] & 1u) != want) q[e][i] = ld_word(pe + (size_t)i * pstride_slice);
+        }
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           if (!ok[e]) continue;
-          const uint2 *pe = pb + (size_t)(2 * up + e) * C;
           float s_ = 0.f;
-          uint2 q[12];                                      // slices <= 12 (C <= 384, lstm_tc_plan)
-          bool all;
-          do {   // issue the loads together, retry until every tag has arrived
-            all = true;
-#pragma unroll
-            for (int i = 0; i < 12; i++) {
-              if (i < slices) {
-                q[i] = ld_tagged(pe + (size_t)i * pstride_slice);
-                all = all && (q[i].y == want);
-              }
-            }
-          } while (!all);
 #pragma unroll
           for (int i = 0; i < 12; i++)
-            if (i < slices) s_ += __uint_as_float(q[i].x);   // fixed order: deterministic
+            if (i < slices) s_ += __uint_as_float(q[e][i] & 0xfffffffeu);   // tag bit cleared; fixed order: deterministic
           dm[e] += s_;
         }
       }
@@ -489,34 +591,31 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
         mbar_wait(&b_full, (uint32_t)(step & 1));
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         if (elect_one()) {
-          const uint32_t ahi = smem_u32(Ahi), alo = smem_u32(Alo), bt = smem_u32(Bt);
+          // one commit per M tile: the epilogue (TMEM -> tagged words) of tile mt runs while the tensor pipe is
+          // still working on tile mt+1
           for (int mt = 0; mt < MT; mt++) {
-            const int rows = mt < n128 ? 128 : 64;
-            const uint32_t idN = idesc_f16(rows, 32), idH = idesc_f16(rows, 16);
-            const uint32_t tb = (uint32_t)mt * 128 * 256;
-#pragma unroll
-            for (int ks = 0; ks < 8; ks++) {
-              const int kb = ks >> 2, k4 = ks & 3;
-              const uint64_t bd = umma_desc(bt + kb * 4096 + k4 * 32, 16, 1024, 2);
-              umma_f16(tmem_base + mt * 48, umma_desc(ahi + tb + kb * rows * 128 + k4 * 32, 16, 1024, 2), bd, idN, ks != 0);
-              umma_f16(tmem_base + mt * 48 + 32, umma_desc(alo + tb + kb * rows * 128 + k4 * 32, 16, 1024, 2), bd, idH, ks != 0);
-            }
+            const uint64_t toff = (uint64_t)((mt * 128 * 256) >> 4);
+            if (mt < n128) issue_bwd_tile<128>(dAhi + toff, dAlo + toff, dBt, tmem_base + mt * 48);
+            else issue_bwd_tile<64>(dAhi + toff, dAlo + toff, dBt, tmem_base + mt * 48);
+            umma_commit(&mma_done[mt]);
           }
-          umma_commit(&mma_done);
         }
         __syncwarp();
       }
       prefetch(t + tstep);
-      mbar_wait(&mma_done, (uint32_t)(step & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       TC_TICK(1, 2);
       {
-        uint2 *pw = pbuf + ((size_t)((((step & 1) * ndir + dir) * groups + group) * slices + slice)) * pstride_slice;
-        const unsigned tagw = (unsigned)step + 1u;
+        uint32_t *pw = pbuf + ((size_t)((((step & 1) * ndir + dir) * groups + group) * slices + slice)) * pstride_slice;
+        const uint32_t tagw = (uint32_t)((step >> 1) & 1);
         float inv[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) inv[j] = scl[8 * uh + j];
         for (int mt = 0; mt < MT; mt++) {
+          mbar_wait(&mma_done[mt], (uint32_t)(step & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          if (mt == 0) {   // the column scales were written by the other warps before they arrived on b_full: read
+                           // them only behind the first commit (which is behind b_full)
+#pragma unroll
+            for (int j = 0; j < 8; j++) inv[j] = scl[8 * uh + j];
+          }
           const bool full = mt < n128;
           uint32_t x0[8], x1[8], y0[8];
           const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 48);
@@ -530,7 +629,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
 #pragma unroll
             for (int jj = 0; jj < 8; jj++) {
               const float pv = (u2f(x0[jj]) + (u2f(x1[jj]) + u2f(y0[jj])) * kLoUnscale) * inv[jj];
-              st_tagged(pw + (size_t)(8 * uh + jj) * C + j, pv, tagw);
+              st_word(pw + (size_t)(8 * uh + jj) * C + j, (__float_as_uint(pv) & 0xfffffffeu) | tagw);   // tag = LSB
             }
           }
         }
@@ -539,6 +638,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
       TC_TICK(1, 3);
     }
 
+    TC_FLUSH(1);
     // ---- bias / peephole gradient partial sums of this (dir, group): reduce over the CTA's 16 utterances
     named_bar_workers();
     float *red = reinterpret_cast<float *>(smem);   // [7][16 utts][32 cells] (the weights are no longer needed:
@@ -601,8 +701,8 @@ LstmPlan lstm_tc_plan(int S, int C, int num_sms, size_t max_smem, int ndir) {
   pl.groups = groups; pl.slices = slices;
   pl.threads = TCL_THREADS;
   pl.smem_fwd = sf; pl.smem_bwd = sb;
-  pl.pbuf_floats = (size_t)2 * 2 * ndir * groups * slices * TCL_UG * C;   // 8-byte tagged words
-  pl.xbuf_bytes = (size_t)2 * ndir * groups * TCL_UG * C * 8;
+  pl.pbuf_floats = (size_t)2 * ndir * groups * slices * TCL_UG * C;       // 4-byte words, tag in the LSB
+  pl.xbuf_bytes = (size_t)2 * ndir * groups * TCL_UG * C * 4;
   pl.gsum_floats = (size_t)2 * groups * 7 * C;
   pl.valid = 1;
   return pl;
@@ -611,7 +711,7 @@ LstmPlan lstm_tc_plan(int S, int C, int num_sms, size_t max_smem, int ndir) {
 cudaError_t lstm_tc_forward(cudaStream_t st, const LstmPlan &pl, const LstmFwdArgs &a) {
   if (!pl.valid || pl.engine != 1) return cudaErrorInvalidConfiguration;
   if (a.drop < 0 || a.drop > 2 || (a.drop != 0 && !a.rmask)) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(a.xbuf, 0, pl.xbuf_bytes, st);
+  cudaError_t e = cudaMemsetAsync(a.xbuf, 0xff, pl.xbuf_bytes, st);   // tag bit 1 = "not the data of steps 0 / 1"
   if (e != cudaSuccess) return e;
   dim3 grid(pl.slices, pl.groups, pl.ndir), block(pl.threads);
   int groups = pl.groups, ndir = pl.ndir;
@@ -627,7 +727,7 @@ cudaError_t lstm_tc_forward(cudaStream_t st, const LstmPlan &pl, const LstmFwdAr
 cudaError_t lstm_tc_backward(cudaStream_t st, const LstmPlan &pl, const LstmBwdArgs &a) {
   if (!pl.valid || pl.engine != 1) return cudaErrorInvalidConfiguration;
   if (a.drop < 0 || a.drop > 2 || (a.drop != 0 && !a.rmask)) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(a.pbuf, 0, pl.pbuf_floats * sizeof(float), st);
+  cudaError_t e = cudaMemsetAsync(a.pbuf, 0xff, pl.pbuf_floats * sizeof(float), st);
   if (e != cudaSuccess) return e;
   dim3 grid(pl.slices, pl.groups, pl.ndir), block(pl.threads);
   int groups = pl.groups, slices = pl.slices, ndir = pl.ndir;

@@ -56,7 +56,17 @@ int eesen_b200_create(eesen_b200_ctx **out, int device) {
     const char *eng = getenv("EESEN_B200_GEMM_ENGINE");
     ctx->gemm_engine = (eng && std::string(eng) == "legacy") ? 1 : 0;
   }
-  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  {
+    const char *ov = getenv("EESEN_B200_OVERLAP");
+    ctx->overlap = (ov && ov[0] == '0') ? 0 : 1;
+  }
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // lo = numerically greatest = lowest priority
+  e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return (int)e; }
+  e = cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_lo);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return (int)e; }
   *out = ctx;
   return 0;
@@ -65,8 +75,9 @@ int eesen_b200_create(eesen_b200_ctx **out, int device) {
 void eesen_b200_destroy(eesen_b200_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  ctx->join_side();
   cudaStreamSynchronize(ctx->stream);
-  eesen_b200_ctx::Buf *bufs[] = {&ctx->gemm_ws, &ctx->lstm_pbuf, &ctx->lstm_gsum, &ctx->lstm_flags,
+  eesen_b200_ctx::Buf *bufs[] = {&ctx->decode_ws, &ctx->gemm_ws_side, &ctx->bf16_a_side, &ctx->bf16_b_side,&ctx->gemm_ws, &ctx->lstm_pbuf, &ctx->lstm_gsum, &ctx->lstm_flags,
                                  &ctx->ctc_ws, &ctx->colsum_ws, &ctx->seg_buf, &ctx->flag_buf, &ctx->bf16_a, &ctx->bf16_b};
   for (auto *b : bufs)
     if (b->p) cudaFree(b->p);
@@ -76,6 +87,9 @@ void eesen_b200_destroy(eesen_b200_ctx *ctx) {
     if (f) f(ctx->nccl_comm);
   }
   cudaStreamDestroy(ctx->stream);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   delete ctx;
 }
 
@@ -92,6 +106,7 @@ int eesen_b200_set_precision(eesen_b200_ctx *ctx, int gemm_precision, int recurr
 }
 
 int eesen_b200_synchronize(eesen_b200_ctx *ctx) {
+  ctx->join_side();
   CTX_CHECK(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
   return 0;
 }
@@ -101,8 +116,11 @@ long eesen_b200_launch_count(const eesen_b200_ctx *ctx) { return ctx->launches; 
 
 static int do_gemm(eesen_b200_ctx *ctx, int ta, int tb, int M, int N, int K, float alpha, const float *A, int lda,
                    long sA, const float *B, int ldb, long sB, float beta, float *C, int ldc, long sC,
-                   const float *bias, long sBias, int batch) {
+                   const float *bias, long sBias, int batch, bool on_side = false) {
   void *ws = nullptr;
+  cudaStream_t st = on_side ? ctx->side : ctx->stream;
+  eesen_b200_ctx::Buf &gemm_ws = on_side ? ctx->gemm_ws_side : ctx->gemm_ws;
+  eesen_b200_ctx::Buf &bf16_a = on_side ? ctx->bf16_a_side : ctx->bf16_a, &bf16_b = on_side ? ctx->bf16_b_side : ctx->bf16_b;
   // tensor-core engine: tcgen05/TMEM/TMA (gemm_tc.cu) for every arithmetic mode -- kind::tf32 for fp32x3 / tf32,
   // kind::f16 on bf16 copies of the operands for bf16 (BASELINE config 4); the warp-level mma.sync kernel
   // (gemm.cu) is kept for EESEN_B200_GEMM_ENGINE=legacy (A/B measurements) and matrices TMA cannot address
@@ -110,7 +128,7 @@ static int do_gemm(eesen_b200_ctx *ctx, int ta, int tb, int M, int N, int K, flo
       eb::gemm_tc_supported(ta, tb, M, N, K, A, 4, B, 4, 0)) {
     size_t need_tc = eb::gemm_tc_workspace_bytes(M, N, K, ctx->num_sms);
     if (need_tc) {
-      int rc = ctx->reserve(ctx->gemm_ws, need_tc, &ws);
+      int rc = ctx->reserve(gemm_ws, need_tc, &ws);
       if (rc) return rc;
     }
     // operands as stored: A [M x K] or [K x M], B [N x K] or [K x N]
@@ -118,16 +136,16 @@ static int do_gemm(eesen_b200_ctx *ctx, int ta, int tb, int M, int N, int K, flo
     const int ac = ta ? M : K, bc = tb ? K : N;
     void *a16 = nullptr, *b16 = nullptr;
     int rc;
-    if ((rc = ctx->reserve(ctx->bf16_a, eb::gemm_tc16_operand_bytes(ar, ac), &a16))) return rc;
-    if ((rc = ctx->reserve(ctx->bf16_b, eb::gemm_tc16_operand_bytes(br, bc), &b16))) return rc;
+    if ((rc = ctx->reserve(bf16_a, eb::gemm_tc16_operand_bytes(ar, ac), &a16))) return rc;
+    if ((rc = ctx->reserve(bf16_b, eb::gemm_tc16_operand_bytes(br, bc), &b16))) return rc;
     for (int b = 0; b < batch; b++) {
-      int pe = ctx->prof_begin(eesen_b200_ctx::kGemm);
+      int pe = ctx->prof_begin(eesen_b200_ctx::kGemm, on_side);
       cudaError_t e = cudaSuccess;
-      if (b == 0 || sA != 0) { e = eb::convert_bf16(ctx->stream, ctx->num_sms, A + b * sA, ar, ac, lda, a16); ctx->launches += 1; }
-      if (e == cudaSuccess && (b == 0 || sB != 0)) { e = eb::convert_bf16(ctx->stream, ctx->num_sms, B + b * sB, br, bc, ldb, b16); ctx->launches += 1; }
+      if (b == 0 || sA != 0) { e = eb::convert_bf16(st, ctx->num_sms, A + b * sA, ar, ac, lda, a16); ctx->launches += 1; }
+      if (e == cudaSuccess && (b == 0 || sB != 0)) { e = eb::convert_bf16(st, ctx->num_sms, B + b * sB, br, bc, ldb, b16); ctx->launches += 1; }
       if (e == cudaSuccess)
-        e = eb::gemm_tc16(ctx->stream, ctx->num_sms, ta, tb, M, N, K, alpha, a16, b16, beta, C + b * sC, ldc,
-                          bias ? bias + b * sBias : nullptr, (float *)ws, ws ? ctx->gemm_ws.bytes : 0);
+        e = eb::gemm_tc16(st, ctx->num_sms, ta, tb, M, N, K, alpha, a16, b16, beta, C + b * sC, ldc,
+                          bias ? bias + b * sBias : nullptr, (float *)ws, ws ? gemm_ws.bytes : 0);
       ctx->prof_end(pe);
       ctx->launches += 1;
       if ((rc = ctx->check(e, "gemm_tc16"))) return rc;
@@ -138,14 +156,14 @@ static int do_gemm(eesen_b200_ctx *ctx, int ta, int tb, int M, int N, int K, flo
       (batch == 1 || ((sA & 3) == 0 && (sB & 3) == 0))) {
     size_t need_tc = eb::gemm_tc_workspace_bytes(M, N, K, ctx->num_sms);
     if (need_tc) {
-      int rc = ctx->reserve(ctx->gemm_ws, need_tc, &ws);
+      int rc = ctx->reserve(gemm_ws, need_tc, &ws);
       if (rc) return rc;
     }
     for (int b = 0; b < batch; b++) {
-      int pe = ctx->prof_begin(eesen_b200_ctx::kGemm);
-      cudaError_t e = eb::gemm_tc(ctx->stream, ctx->num_sms, ta, tb, M, N, K, alpha, A + b * sA, lda, B + b * sB, ldb,
+      int pe = ctx->prof_begin(eesen_b200_ctx::kGemm, on_side);
+      cudaError_t e = eb::gemm_tc(st, ctx->num_sms, ta, tb, M, N, K, alpha, A + b * sA, lda, B + b * sB, ldb,
                                   beta, C + b * sC, ldc, bias ? bias + b * sBias : nullptr, ctx->gemm_prec,
-                                  (float *)ws, ws ? ctx->gemm_ws.bytes : 0);
+                                  (float *)ws, ws ? gemm_ws.bytes : 0);
       ctx->prof_end(pe);
       ctx->launches += 1;
       int rc = ctx->check(e, "gemm_tc");
@@ -155,12 +173,12 @@ static int do_gemm(eesen_b200_ctx *ctx, int ta, int tb, int M, int N, int K, flo
   }
   size_t need = eb::gemm_workspace_bytes(M, N, K, batch, ctx->num_sms);
   if (K >= 4096) {
-    int rc = ctx->reserve(ctx->gemm_ws, need, &ws);
+    int rc = ctx->reserve(gemm_ws, need, &ws);
     if (rc) return rc;
   }
-  int pe = ctx->prof_begin(eesen_b200_ctx::kGemm);
-  cudaError_t e = eb::gemm(ctx->stream, ctx->num_sms, ta, tb, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc,
-                           sC, bias, sBias, batch, ctx->gemm_prec, (float *)ws, ws ? ctx->gemm_ws.bytes : 0);
+  int pe = ctx->prof_begin(eesen_b200_ctx::kGemm, on_side);
+  cudaError_t e = eb::gemm(st, ctx->num_sms, ta, tb, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc,
+                           sC, bias, sBias, batch, ctx->gemm_prec, (float *)ws, ws ? gemm_ws.bytes : 0);
   ctx->prof_end(pe);
   ctx->launches += 1;
   return ctx->check(e, "gemm");
@@ -175,13 +193,13 @@ int eesen_b200_gemm(eesen_b200_ctx *ctx, int transA, int transB, int M, int N, i
 // Picks the resident-weight plan.  The recurrence is independent per utterance, so a minibatch that
 // does not fit one co-resident grid (e.g. 128 utterances at C=320) is processed in utterance chunks
 // of the largest size that does: chunk = S, else the largest multiple of 8 in {64, 32, 16, 8}.
-static int lstm_prepare(eesen_b200_ctx *ctx, int ndir, int S, int C, eb::LstmPlan *plan, int *chunk, float **pbuf,
+static int lstm_prepare(eesen_b200_ctx *ctx, int ndir, int pass, int S, int C, eb::LstmPlan *plan, int *chunk, float **pbuf,
                         float **gsum, void **xbuf) {
   const int cands[5] = {S, 64, 32, 16, 8};
   plan->valid = 0;
   for (int i = 0; i < 5 && !plan->valid; i++) {
     if (cands[i] > S || cands[i] <= 0) continue;
-    *plan = eb::lstm_plan(cands[i], C, ctx->num_sms, ctx->max_smem, ndir);
+    *plan = eb::lstm_plan(cands[i], C, ctx->num_sms, ctx->max_smem, ndir, pass);
     *chunk = cands[i];
   }
   if (!plan->valid)
@@ -208,19 +226,21 @@ static int lstm_forward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I,
   float *pbuf, *gsum;
   void *xbuf;
   int chunk = S;
-  int rc = lstm_prepare(ctx, ndir, S, C, &plan, &chunk, &pbuf, &gsum, &xbuf);
+  int rc = lstm_prepare(ctx, ndir, 0, S, C, &plan, &chunk, &pbuf, &gsum, &xbuf);
   if (rc) return rc;
   // input-side gate pre-activations for both directions: G[:, d*4C..] = x * Wx_d^T + b_d
   // (bilstm-parallel-layer.h:109-110,163-164).  Batched over the direction when the two weight
   // blocks are equally strided (they are in the Net arena), else two launches.
   long sW = ndir == 2 ? p->wx[1] - p->wx[0] : 0, sB = ndir == 2 ? p->bias[1] - p->bias[0] : 0;
   const int N = T * S, ldg = ndir * 4 * C;
+  const int ldwx = p->ldwx > 0 ? p->ldwx : I, ldwm = p->ldwm > 0 ? p->ldwm : C;
+  if (ldwx < I || ldwm < C) return ctx->fail(EESEN_B200_EINVAL, "ldwx / ldwm smaller than the matrix width");
   if (ndir == 2 && sW > 0 && (sW & 3) == 0 && sB > 0) {
-    rc = do_gemm(ctx, 0, 1, N, 4 * C, I, 1.f, x, ldx, 0, p->wx[0], I, sW, 0.f, gates, ldg, 4 * C, p->bias[0], sB, 2);
+    rc = do_gemm(ctx, 0, 1, N, 4 * C, I, 1.f, x, ldx, 0, p->wx[0], ldwx, sW, 0.f, gates, ldg, 4 * C, p->bias[0], sB, 2);
     if (rc) return rc;
   } else {
     for (int d = 0; d < ndir; d++) {
-      rc = do_gemm(ctx, 0, 1, N, 4 * C, I, 1.f, x, ldx, 0, p->wx[d], I, 0, 0.f, gates + (size_t)d * 4 * C, ldg, 0,
+      rc = do_gemm(ctx, 0, 1, N, 4 * C, I, 1.f, x, ldx, 0, p->wx[d], ldwx, 0, 0.f, gates + (size_t)d * 4 * C, ldg, 0,
                    p->bias[d], 0, 1);
       if (rc) return rc;
     }
@@ -232,7 +252,7 @@ static int lstm_forward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I,
   a.out = out; a.ldo = ldo;
   for (int d = 0; d < 2; d++) {
     const int q = d < ndir ? d : 0;
-    a.p[d].wm = p->wm[q]; a.p[d].pi = p->pi[q]; a.p[d].pf = p->pf[q]; a.p[d].po = p->po[q];
+    a.p[d].wm = p->wm[q]; a.p[d].ldwm = ldwm; a.p[d].pi = p->pi[q]; a.p[d].pf = p->pf[q]; a.p[d].po = p->po[q];
   }
   a.xbuf = xbuf;
   a.precision = ctx->rec_prec;
@@ -305,10 +325,14 @@ static int lstm_backward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I
   float *pbuf, *gsum;
   void *xbuf;
   int chunk = S;
-  int rc = lstm_prepare(ctx, ndir, S, C, &plan, &chunk, &pbuf, &gsum, &xbuf);
+  int rc = lstm_prepare(ctx, ndir, 1, S, C, &plan, &chunk, &pbuf, &gsum, &xbuf);
   if (rc) return rc;
   const int nchunks = (S + chunk - 1) / chunk;
   const int ldg = ndir * 4 * C;
+  const int ldwx = p->ldwx > 0 ? p->ldwx : I, ldwm = p->ldwm > 0 ? p->ldwm : C;
+  const int gldwx = gr->ldwx > 0 ? gr->ldwx : I, gldwm = gr->ldwm > 0 ? gr->ldwm : C;
+  if (ldwx < I || ldwm < C || gldwx < I || gldwm < C)
+    return ctx->fail(EESEN_B200_EINVAL, "ldwx / ldwm smaller than the matrix width");
   eb::LstmBwdArgs a;
   a.T = T; a.S = S; a.C = C;
   a.G = gates; a.ldg = ldg;
@@ -317,7 +341,7 @@ static int lstm_backward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I
   a.DG = dgates; a.lddg = ldg;
   for (int d = 0; d < 2; d++) {
     const int q = d < ndir ? d : 0;
-    a.p[d].wm = p->wm[q]; a.p[d].pi = p->pi[q]; a.p[d].pf = p->pf[q]; a.p[d].po = p->po[q];
+    a.p[d].wm = p->wm[q]; a.p[d].ldwm = ldwm; a.p[d].pi = p->pi[q]; a.p[d].pf = p->pf[q]; a.p[d].po = p->po[q];
   }
   a.pbuf = pbuf; a.gsum = gsum;
   a.precision = ctx->rec_prec;
@@ -343,21 +367,26 @@ static int lstm_backward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I
   // dx = DG_fw * Wx_fw + DG_bw * Wx_bw   (:502 beta=0, :593 beta=1)
   if (dx) {
     for (int d = 0; d < ndir; d++) {
-      rc = do_gemm(ctx, 0, 0, N, I, 4 * C, 1.f, dgates + (size_t)d * 4 * C, ldg, 0, p->wx[d], I, 0,
+      rc = do_gemm(ctx, 0, 0, N, I, 4 * C, 1.f, dgates + (size_t)d * 4 * C, ldg, 0, p->wx[d], ldwx, 0,
                    d == 0 ? 0.f : 1.f, dx, lddx, 0, nullptr, 0, 1);
       if (rc) return rc;
     }
   }
+  // The weight-gradient products below are consumed only by the all-reduce / update at the end of the step: they go
+  // to the side stream (forked here, after the recurrent kernel and the bias / peephole sums) and overlap with the
+  // dX product above and with the recurrent backward of the layer below.
+  const bool sd = ctx->overlap != 0;
+  if (sd) ctx->fork_side();
   long sGW = ndir == 2 ? gr->wx[1] - gr->wx[0] : 0, sGM = ndir == 2 ? gr->wm[1] - gr->wm[0] : 0;
   bool batched = ndir == 2 && sGW > 0 && (sGW & 3) == 0 && sGM > 0 && (sGM & 3) == 0;
   // Wx grad = DG^T * x   (:505 / :596), both directions batched
   if (batched) {
-    rc = do_gemm(ctx, 1, 0, 4 * C, I, N, 1.f, dgates, ldg, 4 * C, x, ldx, 0, 0.f, gr->wx[0], I, sGW, nullptr, 0, 2);
+    rc = do_gemm(ctx, 1, 0, 4 * C, I, N, 1.f, dgates, ldg, 4 * C, x, ldx, 0, 0.f, gr->wx[0], gldwx, sGW, nullptr, 0, 2, sd);
     if (rc) return rc;
   } else {
     for (int d = 0; d < ndir; d++) {
-      rc = do_gemm(ctx, 1, 0, 4 * C, I, N, 1.f, dgates + (size_t)d * 4 * C, ldg, 0, x, ldx, 0, 0.f, gr->wx[d], I, 0,
-                   nullptr, 0, 1);
+      rc = do_gemm(ctx, 1, 0, 4 * C, I, N, 1.f, dgates + (size_t)d * 4 * C, ldg, 0, x, ldx, 0, 0.f, gr->wx[d], gldwx, 0,
+                   nullptr, 0, 1, sd);
       if (rc) return rc;
     }
   }
@@ -365,17 +394,17 @@ static int lstm_backward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I
   //                          bw pairs DG rows [0, N-S) with out rows [S, N) (:597)
   if (T > 1) {
     const int Nm = N - S;
-    rc = do_gemm(ctx, 1, 0, 4 * C, C, Nm, 1.f, dgates + (size_t)S * ldg, ldg, 0, out, ldo, 0, 0.f, gr->wm[0], C, 0,
-                 nullptr, 0, 1);
+    rc = do_gemm(ctx, 1, 0, 4 * C, C, Nm, 1.f, dgates + (size_t)S * ldg, ldg, 0, out, ldo, 0, 0.f, gr->wm[0], gldwm, 0,
+                 nullptr, 0, 1, sd);
     if (rc) return rc;
     if (ndir == 2) {
       rc = do_gemm(ctx, 1, 0, 4 * C, C, Nm, 1.f, dgates + 4 * C, ldg, 0, out + (size_t)S * ldo + C, ldo, 0, 0.f,
-                   gr->wm[1], C, 0, nullptr, 0, 1);
+                   gr->wm[1], gldwm, 0, nullptr, 0, 1, sd);
       if (rc) return rc;
     }
   } else {
     for (int d = 0; d < ndir; d++)
-      CTX_CHECK(cudaMemsetAsync(gr->wm[d], 0, sizeof(float) * 4 * C * C, ctx->stream), "memset");
+      CTX_CHECK(cudaMemset2DAsync(gr->wm[d], sizeof(float) * gldwm, 0, sizeof(float) * C, 4 * C, sd ? ctx->side : ctx->stream), "memset");
   }
   return 0;
 }
@@ -474,6 +503,7 @@ int eesen_b200_ctc_eval(eesen_b200_ctx *ctx, int T, int S, int K, int max_lab, c
 
 int eesen_b200_check_finite(eesen_b200_ctx *ctx, const float *d_x, int64_t n, int *flags) {
   if (!ctx || !flags || (n > 0 && !d_x) || n < 0) return EESEN_B200_EINVAL;
+  ctx->join_side();
   void *d = nullptr;
   int rc = ctx->reserve(ctx->flag_buf, 64, &d);
   if (rc) return rc;
@@ -490,6 +520,7 @@ int eesen_b200_check_finite(eesen_b200_ctx *ctx, const float *d_x, int64_t n, in
 int eesen_b200_sgd_update(eesen_b200_ctx *ctx, float *w, float *corr, const float *grad, int64_t n, float momentum,
                           const eesen_b200_sgd_segment *segments, int nseg) {
   if (!ctx || !w || !corr || !grad || !segments || nseg < 1) return EESEN_B200_EINVAL;
+  ctx->join_side();
   std::vector<eb::SgdSegment> h(nseg);
   for (int i = 0; i < nseg; i++) {
     h[i].offset = segments[i].offset; h[i].count = segments[i].count;
@@ -547,7 +578,7 @@ int eesen_b200_nccl_init(eesen_b200_ctx *ctx, int rank, int nranks, const char i
   return 0;
 }
 
-int eesen_b200_allreduce_sum(eesen_b200_ctx *ctx, float *buf, int64_t n) {
+static int allreduce_impl(eesen_b200_ctx *ctx, float *buf, int64_t n, bool on_side) {
   if (!ctx || !buf) return EESEN_B200_EINVAL;
   if (ctx->nranks == 1) return 0;
   if (!ctx->nccl_comm) return ctx->fail(EESEN_B200_ENCCL, "NCCL communicator not initialised");
@@ -556,11 +587,28 @@ int eesen_b200_allreduce_sum(eesen_b200_ctx *ctx, float *buf, int64_t n) {
   static ar_t f = nullptr;
   if (!f) f = (ar_t)dlsym(ctx->nccl_lib, "ncclAllReduce");
   if (!f) return ctx->fail(EESEN_B200_ENCCL, "ncclAllReduce not found");
-  int pe = ctx->prof_begin(eesen_b200_ctx::kAllReduce);
-  int r = f(buf, buf, (size_t)n, 7, 0, ctx->nccl_comm, ctx->stream);
+  int pe = ctx->prof_begin(eesen_b200_ctx::kAllReduce, on_side);
+  int r = f(buf, buf, (size_t)n, 7, 0, ctx->nccl_comm, on_side ? ctx->side : ctx->stream);
   ctx->prof_end(pe);
   if (r != 0) return ctx->fail(EESEN_B200_ENCCL, "ncclAllReduce failed with code " + std::to_string(r));
   return 0;
+}
+
+int eesen_b200_allreduce_sum(eesen_b200_ctx *ctx, float *buf, int64_t n) {
+  if (ctx) ctx->join_side();
+  return allreduce_impl(ctx, buf, n, false);
+}
+
+// Bucketed variant for the layer loop of Net::Backpropagate (reference update order, src/net/net.cc:98-105): the
+// gradient block of a layer is reduced on the side stream as soon as it is final -- behind that layer's
+// weight-gradient products, in front of the next layer's -- while `stream` keeps back-propagating.  Everything
+// queued on `stream` so far (bias / peephole sums, affine gradients) is waited for first.
+int eesen_b200_allreduce_sum_overlapped(eesen_b200_ctx *ctx, float *buf, int64_t n) {
+  if (!ctx) return EESEN_B200_EINVAL;
+  if (ctx->nranks == 1) return 0;
+  if (!ctx->overlap) return allreduce_impl(ctx, buf, n, false);
+  ctx->fork_side();
+  return allreduce_impl(ctx, buf, n, true);
 }
 
 int eesen_b200_profile(eesen_b200_ctx *ctx, int enable, double *ms, long *counts) {

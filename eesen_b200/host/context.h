@@ -27,29 +27,54 @@ struct eesen_b200_ctx {
     size_t bytes = 0;
   };
   Buf gemm_ws, lstm_pbuf, lstm_gsum, lstm_flags, ctc_ws, colsum_ws, seg_buf, flag_buf, bf16_a, bf16_b;
+  Buf gemm_ws_side, bf16_a_side, bf16_b_side;   // the side stream's own scratch
+  Buf decode_ws;
+
+  // Side stream (lower priority): work nothing on the critical path waits for -- the weight-gradient products of
+  // layer l and the all-reduce of its gradient block run here while `stream` carries dX and the recurrent backward
+  // of layer l-1 (the tcgen05 recurrent kernels occupy 80 of the 148 SMs).  fork_side(): side waits for everything
+  // queued on `stream` so far; join_side(): `stream` waits for everything queued on side.  Every consumer of the
+  // gradient arena (all-reduce, optimiser, host reads, eesen_b200_synchronize) joins first.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool side_pending = false;
+  int overlap = 1;   // EESEN_B200_OVERLAP=0: everything on `stream` (A/B measurements)
+  void fork_side() {
+    cudaEventRecord(ev_fork, stream);
+    cudaStreamWaitEvent(side, ev_fork, 0);
+    side_pending = true;
+  }
+  void join_side() {
+    if (!side_pending) return;
+    cudaEventRecord(ev_join, side);
+    cudaStreamWaitEvent(stream, ev_join, 0);
+    side_pending = false;
+  }
 
   // optional per-category kernel timing with CUDA events on `stream` (bench.py roofline)
   enum { kGemm = 0, kLstmFwd, kLstmBwd, kSoftmax, kCtc, kSgd, kAllReduce, kMisc, kNumCat };
-  struct ProfEv { cudaEvent_t a, b; int cat; };
+  struct ProfEv { cudaEvent_t a, b; int cat; cudaStream_t st; };
   bool prof_on = false;
   std::vector<ProfEv> prof_events;
   std::vector<ProfEv> prof_pool;
   double prof_ms[kNumCat] = {0};
   long prof_count[kNumCat] = {0};
-  int prof_begin(int cat) {
+  int prof_begin(int cat, bool on_side = false) {
     if (!prof_on) return -1;
     ProfEv e;
     if (!prof_pool.empty()) { e = prof_pool.back(); prof_pool.pop_back(); }
     else { cudaEventCreate(&e.a); cudaEventCreate(&e.b); }
     e.cat = cat;
-    cudaEventRecord(e.a, stream);
+    e.st = on_side ? side : stream;
+    cudaEventRecord(e.a, e.st);
     prof_events.push_back(e);
     return (int)prof_events.size() - 1;
   }
   void prof_end(int idx) {
-    if (idx >= 0) cudaEventRecord(prof_events[idx].b, stream);
+    if (idx >= 0) cudaEventRecord(prof_events[idx].b, prof_events[idx].st);
   }
   void prof_collect() {
+    join_side();
     cudaStreamSynchronize(stream);
     for (auto &e : prof_events) {
       float ms = 0.f;
@@ -78,6 +103,7 @@ struct eesen_b200_ctx {
     if (bytes > b.bytes) {
       if (b.p) {
         cudaError_t e = cudaStreamSynchronize(stream);
+        if (e == cudaSuccess && side) e = cudaStreamSynchronize(side);
         if (e != cudaSuccess) return check(e, "cudaStreamSynchronize");
         cudaFree(b.p);
         b.p = nullptr;

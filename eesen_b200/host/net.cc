@@ -16,6 +16,11 @@ namespace eesen {
 
 static eesen_b200_ctx *g_ctx = nullptr;  // the process-wide device context (reference: CuDevice singleton)
 static cudaStream_t Stream() { return g_ctx ? g_ctx->stream : (cudaStream_t)0; }
+// host-visible results need BOTH streams drained (the weight-gradient products run on the side stream)
+static cudaError_t SyncStream() {
+  if (g_ctx) g_ctx->join_side();
+  return cudaStreamSynchronize(Stream());
+}
 
 #define CU_CHECK(call)                                                                  \
   do {                                                                                  \
@@ -60,12 +65,12 @@ void CuMatrixBase<Real>::CopyToHost(Real *dst, int32 ld) const {
   if (num_rows_ == 0) return;
   if (stride_ == num_cols_ && ld == num_cols_) {
     CU_CHECK(cudaMemcpyAsync(dst, data_, sizeof(Real) * (size_t)num_rows_ * num_cols_, cudaMemcpyDeviceToHost, Stream()));
-    CU_CHECK(cudaStreamSynchronize(Stream()));
+    CU_CHECK(SyncStream());
     return;
   }
   CU_CHECK(cudaMemcpy2DAsync(dst, sizeof(Real) * ld, data_, sizeof(Real) * stride_, sizeof(Real) * num_cols_,
                              num_rows_, cudaMemcpyDeviceToHost, Stream()));
-  CU_CHECK(cudaStreamSynchronize(Stream()));
+  CU_CHECK(SyncStream());
 }
 
 template <typename Real>
@@ -74,7 +79,7 @@ void CuMatrix<Real>::Resize(int32 rows, int32 cols, MatrixResizeType t) {
   size_t need = (size_t)rows * stride;
   if (need > capacity_) {
     if (this->data_) {
-      CU_CHECK(cudaStreamSynchronize(Stream()));
+      CU_CHECK(SyncStream());
       CU_CHECK(cudaFree(this->data_));
       this->data_ = nullptr;
     }
@@ -306,6 +311,8 @@ void BiLstmParallel::WriteData(std::ostream &os, bool binary) const {
 
 void BiLstmParallel::Params(eesen_b200_bilstm_params *p, eesen_b200_bilstm_grads *g) const {
   const int64 C = cell_dim_, I = input_dim_;
+  if (p) { p->ldwx = 0; p->ldwm = 0; }   // the arena holds the matrices densely
+  if (g) { g->ldwx = 0; g->ldwm = 0; }
   const int64 dir_stride = 4 * C * I + 4 * C * C + 4 * C + 3 * C;
   for (int d = 0; d < 2; d++) {
     int64 o = d * dir_stride;
@@ -325,7 +332,7 @@ void BiLstmParallel::SetSeqLengths(std::vector<int> &sequence_lengths) {
   int32 S = sequence_lengths.size();
   if (S == 0) return;
   if (S > d_len_cap_) {
-    if (d_len_) { CU_CHECK(cudaStreamSynchronize(Stream())); CU_CHECK(cudaFree(d_len_)); }
+    if (d_len_) { CU_CHECK(SyncStream()); CU_CHECK(cudaFree(d_len_)); }
     CU_CHECK(cudaMalloc((void **)&d_len_, sizeof(int) * S));
     d_len_cap_ = S;
   }
@@ -372,7 +379,7 @@ void BiLstmParallel::PrepareMask(CuMatrix<BaseFloat> *mask, int32 rows, BaseFloa
   if (!inj.empty()) {
     if (inj_rows != rows) KALDI_ERR << "injected dropout mask has " << inj_rows << " rows, this minibatch needs " << rows;
     mask->CopyFromHost(inj.data(), w);
-    CU_CHECK(cudaStreamSynchronize(Stream()));   // inj may be replaced by the caller right after
+    CU_CHECK(SyncStream());   // inj may be replaced by the caller right after
     return;
   }
   CheckAbi(ctx_, eesen_b200_dropout_mask(ctx_, rows, w, mask->Data(), mask->Stride(), p, per_col ? 1 : 0, drop_seed_,
@@ -542,6 +549,8 @@ void LstmParallel::WriteData(std::ostream &os, bool binary) const {   // lstm-la
 
 void LstmParallel::Params(eesen_b200_bilstm_params *p, eesen_b200_bilstm_grads *g) const {
   const int64 C = cell_dim_, I = input_dim_;
+  if (p) { p->ldwx = 0; p->ldwm = 0; }
+  if (g) { g->ldwx = 0; g->ldwm = 0; }
   for (int d = 0; d < 2; d++) {   // index 1 mirrors index 0 (unused by the uni-directional entry points)
     if (p) {
       const float *b = w_;
@@ -817,7 +826,7 @@ void Net::BindArena() {
                              cudaMemcpyHostToDevice, Stream()));
     tl->Bind(w_ + offs[i], g_ + offs[i]);
   }
-  CU_CHECK(cudaStreamSynchronize(Stream()));
+  CU_CHECK(SyncStream());
   segs_dirty_ = true;
   bool any_accu = false;
   for (size_t i = 0; i < layers_.size(); i++)
@@ -839,7 +848,7 @@ void Net::EnsureAccu(bool mark_all_layers) {
       CU_CHECK(cudaMemcpyAsync(accu_ + layer_offset_[i], tl->host_accu_.data(), sizeof(float) * tl->NumParams(),
                                cudaMemcpyHostToDevice, Stream()));
     }
-    CU_CHECK(cudaStreamSynchronize(Stream()));
+    CU_CHECK(SyncStream());
   }
   if (mark_all_layers)
     for (size_t i = 0; i < layers_.size(); i++)
@@ -851,7 +860,7 @@ void Net::GetParams(std::vector<float> *host) const { GetArena(w_, host); }
 void Net::GetArena(const float *arena, std::vector<float> *host) const {
   host->resize(num_params_);
   int64 o = 0;
-  CU_CHECK(cudaStreamSynchronize(Stream()));
+  CU_CHECK(SyncStream());
   for (size_t i = 0; i < layers_.size(); i++) {
     if (layer_offset_[i] < 0) continue;
     TrainableLayer *tl = dynamic_cast<TrainableLayer *>(layers_[i]);
@@ -864,7 +873,7 @@ void Net::GetArena(const float *arena, std::vector<float> *host) const {
 void Net::SetParams(const float *host, int64 n) {
   KALDI_ASSERT(n == num_params_);
   int64 o = 0;
-  CU_CHECK(cudaStreamSynchronize(Stream()));
+  CU_CHECK(SyncStream());
   for (size_t i = 0; i < layers_.size(); i++) {
     if (layer_offset_[i] < 0) continue;
     TrainableLayer *tl = dynamic_cast<TrainableLayer *>(layers_[i]);
@@ -894,7 +903,7 @@ void Net::Write(std::ostream &os, bool binary) {
 
 // refresh the host copies of parameters / accumulators from the device arenas
 void Net::RefreshHostCopies() {
-  CU_CHECK(cudaStreamSynchronize(Stream()));
+  CU_CHECK(SyncStream());
   for (size_t i = 0; i < layers_.size(); i++) {
     if (layer_offset_[i] < 0) continue;
     TrainableLayer *tl = dynamic_cast<TrainableLayer *>(layers_[i]);
@@ -1015,26 +1024,35 @@ void Net::Propagate(const CuMatrixBase<BaseFloat> &in, CuMatrix<BaseFloat> *out)
   (*out) = propagate_buf_[NumLayers()];
 }
 
-void Net::BackpropagateLayers(const CuMatrixBase<BaseFloat> &out_diff, CuMatrix<BaseFloat> *in_diff) {
-  if (!in_train_) KALDI_ERR << "Can't backpropagate in test mode";
-  const CuMatrixBase<BaseFloat> *diff = &out_diff;
-  for (int32 i = NumLayers() - 1; i >= 0; i--) {
-    layers_[i]->need_in_diff_ = (i > 0) || (in_diff != NULL);
-    layers_[i]->Backpropagate(propagate_buf_[i], propagate_buf_[i + 1], *diff, &backpropagate_buf_[i]);
-    diff = &backpropagate_buf_[i];
-  }
-}
-
-// data-parallel: one all-reduce of the raw gradient arena ...
-void Net::Reduce(int64 reduce_count) {
+// Data-parallel runs reduce the gradient block of a layer as soon as that layer has back-propagated (top-down, the
+// reference's update order net.cc:98-105): one NCCL all-reduce per trainable layer on the side stream, overlapped with
+// the layers below.  `zero` = this rank has no minibatch (BackpropagateShared): it contributes zeros in the same
+// sequence of collectives.
+void Net::BackpropagateLayers(const CuMatrixBase<BaseFloat> *out_diff, CuMatrix<BaseFloat> *in_diff) {
+  if (out_diff && !in_train_) KALDI_ERR << "Can't backpropagate in test mode";
   int rank, nranks;
   eesen_b200_world(ctx_, &rank, &nranks);
-  if (nranks > 1) CheckAbi(ctx_, eesen_b200_allreduce_sum(ctx_, g_, reduce_count), "eesen_b200_allreduce_sum");
+  const CuMatrixBase<BaseFloat> *diff = out_diff;
+  for (int32 i = NumLayers() - 1; i >= 0; i--) {
+    if (out_diff) {
+      layers_[i]->need_in_diff_ = (i > 0) || (in_diff != NULL);
+      layers_[i]->Backpropagate(propagate_buf_[i], propagate_buf_[i + 1], *diff, &backpropagate_buf_[i]);
+      diff = &backpropagate_buf_[i];
+    }
+    if (nranks > 1 && layer_offset_[i] >= 0) {
+      int64 end = arena_size_;
+      for (int32 k = i + 1; k < NumLayers(); k++)
+        if (layer_offset_[k] >= 0) { end = layer_offset_[k]; break; }
+      CheckAbi(ctx_, eesen_b200_allreduce_sum_overlapped(ctx_, g_ + layer_offset_[i], end - layer_offset_[i]),
+               "eesen_b200_allreduce_sum_overlapped");
+    }
+  }
 }
 
 // ... then the identical momentum / clip / SGD update on every rank
 void Net::Update() {
   if (segs_dirty_) UploadSegments();
+  ctx_->join_side();   // every gradient product and every per-layer all-reduce has to be in
   if (nseg_ > 0) {
     int pe = ctx_->prof_begin(eesen_b200_ctx::kSgd);
     if (update_algorithm_ != 0) EnsureAccu(true);
@@ -1051,8 +1069,7 @@ void Net::Update() {
 void Net::Backpropagate(const CuMatrixBase<BaseFloat> &out_diff, CuMatrix<BaseFloat> *in_diff) {
   g_ctx = ctx_;
   if (NumLayers() == 0) { if (in_diff) (*in_diff) = out_diff; return; }
-  BackpropagateLayers(out_diff, in_diff);
-  Reduce(arena_size_);
+  BackpropagateLayers(&out_diff, in_diff);
   Update();
   if (NULL != in_diff) (*in_diff) = backpropagate_buf_[0];
 }
@@ -1060,15 +1077,15 @@ void Net::Backpropagate(const CuMatrixBase<BaseFloat> &out_diff, CuMatrix<BaseFl
 int32 Net::BackpropagateShared(const CuMatrixBase<BaseFloat> *out_diff) {
   g_ctx = ctx_;
   if (NumLayers() == 0 || arena_size_ == 0) return out_diff ? 1 : 0;
-  if (out_diff) BackpropagateLayers(*out_diff, NULL);
-  else CU_CHECK(cudaMemsetAsync(g_, 0, sizeof(float) * arena_size_, Stream()));
-  // the 4 spare floats behind the arena carry the "I had a minibatch" vote through the same all-reduce
+  if (!out_diff) CU_CHECK(cudaMemsetAsync(g_, 0, sizeof(float) * arena_size_, Stream()));
+  BackpropagateLayers(out_diff, NULL);   // per-layer all-reduces (an idle rank contributes zeros)
+  // the 4 spare floats behind the arena carry the "I had a minibatch" vote through one more (tiny) all-reduce
   const float vote[4] = {out_diff ? 1.0f : 0.0f, 0.f, 0.f, 0.f};
   CU_CHECK(cudaMemcpyAsync(g_ + arena_size_, vote, sizeof(vote), cudaMemcpyHostToDevice, Stream()));
-  Reduce(arena_size_ + 4);
+  CheckAbi(ctx_, eesen_b200_allreduce_sum(ctx_, g_ + arena_size_, 4), "eesen_b200_allreduce_sum");
   float active = 0.f;
   CU_CHECK(cudaMemcpyAsync(&active, g_ + arena_size_, sizeof(float), cudaMemcpyDeviceToHost, Stream()));
-  CU_CHECK(cudaStreamSynchronize(Stream()));
+  CU_CHECK(SyncStream());
   const int32 n_active = (int32)(active + 0.5f);
   if (n_active > 0) Update();   // a step in which NO rank had data is not a training step: no momentum-only update
   return n_active;
@@ -1123,7 +1140,7 @@ std::string Net::InfoGradient() const {
 template <typename Tp>
 static void GrowDevice(Tp **p, size_t *cap, size_t need) {
   if (need <= *cap) return;
-  if (*p) { CU_CHECK(cudaStreamSynchronize(Stream())); CU_CHECK(cudaFree(*p)); }
+  if (*p) { CU_CHECK(SyncStream()); CU_CHECK(cudaFree(*p)); }
   size_t want = need + need / 4 + 16;
   CU_CHECK(cudaMalloc((void **)p, sizeof(Tp) * want));
   *cap = want;
@@ -1131,7 +1148,7 @@ static void GrowDevice(Tp **p, size_t *cap, size_t need) {
 template <typename Tp>
 static void GrowPinned(Tp **p, size_t *cap, size_t need) {
   if (need <= *cap) return;
-  if (*p) { CU_CHECK(cudaStreamSynchronize(Stream())); CU_CHECK(cudaFreeHost(*p)); }
+  if (*p) { CU_CHECK(SyncStream()); CU_CHECK(cudaFreeHost(*p)); }
   size_t want = need + need / 4 + 16;
   CU_CHECK(cudaMallocHost((void **)p, sizeof(Tp) * want));
   *cap = want;
@@ -1227,7 +1244,7 @@ static int32 LevenshteinEditDistance(const std::vector<int32> &a, const std::vec
 
 void Ctc::Finish(double stats[4]) {
   if (!pending_eval_ && !pending_err_) { if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0; return; }
-  CU_CHECK(cudaStreamSynchronize(Stream()));
+  CU_CHECK(SyncStream());
   double obj = 0, err_batch = 0, ref_batch = 0, frames_batch = 0;
   if (pending_eval_) {
     pzx_host_.assign(h_pzx_, h_pzx_ + p_S_);

@@ -313,8 +313,7 @@ class Net {
   void BindArena();
   void RefreshHostCopies();
   void UploadSegments();
-  void BackpropagateLayers(const CuMatrixBase<BaseFloat> &out_diff, CuMatrix<BaseFloat> *in_diff);
-  void Reduce(int64 reduce_count);
+  void BackpropagateLayers(const CuMatrixBase<BaseFloat> *out_diff, CuMatrix<BaseFloat> *in_diff);
   void Update();
   eesen_b200_ctx *ctx_;
   std::vector<Layer *> layers_;

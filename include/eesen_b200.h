@@ -33,7 +33,7 @@ extern "C" {
 #define EESEN_B200_ENOGPU 100002   /* no CUDA device / kernel image unusable on this device */
 #define EESEN_B200_ENCCL 100003    /* NCCL unavailable or failed */
 #define EESEN_B200_EIO 100004      /* model / archive I/O error */
-#define EESEN_B200_ESHAPE 100005   /* shape not supported by the resident-weight recurrent kernels */
+#define EESEN_B200_ESHAPE 100005   /* shape / capacity not supported (recurrent kernels, decoder token stores) */
 
 /* Arithmetic of the tensor-core contractions (storage is always fp32):
  *   0 = 3xTF32 split (fp32-faithful, default)   1 = TF32   2 = BF16 (dense GEMMs only) */
@@ -82,12 +82,18 @@ int eesen_b200_gemm(eesen_b200_ctx *ctx, int transA, int transB, int M, int N, i
 
 /* Parameters of one BiLSTM layer, both directions ([0] = forward cells, [1] = backward cells), in
  * the reference's shapes (src/net/bilstm-layer.h:187-210): wx[4C x I], wm[4C x C], bias[4C],
- * peepholes pi/pf/po[C]; gate row blocks in the order g, i, f, o. */
+ * peepholes pi/pf/po[C]; gate row blocks in the order g, i, f, o.
+ * ldwx / ldwm: row strides (in floats) of the wx / wm matrices, 0 = dense (I resp. C).  The reference's
+ * CuMatrix weights are cudaMallocPitch'ed (src/gpucompute/cuda-matrix.cc:46-79), so wei_gifo_x_fw_.Data()
+ * binds with ldwx = wei_gifo_x_fw_.Stride() without repacking.  Strides that are not a multiple of 4 floats
+ * (or bases not 16-byte aligned) cannot be addressed by TMA: such products run on the warp-level GEMM. */
 typedef struct {
   const float *wx[2], *wm[2], *bias[2], *pi[2], *pf[2], *po[2];
+  int ldwx, ldwm;
 } eesen_b200_bilstm_params;
 typedef struct {
   float *wx[2], *wm[2], *bias[2], *pi[2], *pf[2], *po[2];
+  int ldwx, ldwm;
 } eesen_b200_bilstm_grads;
 
 /* BiLstmParallel::PropagateFnc (reference src/net/bilstm-parallel-layer.h:379-420).
@@ -189,6 +195,11 @@ int eesen_b200_sgd_update(eesen_b200_ctx *ctx, float *w, float *corr, const floa
 int eesen_b200_nccl_unique_id(char id[128]);
 int eesen_b200_nccl_init(eesen_b200_ctx *ctx, int rank, int nranks, const char id[128]);
 int eesen_b200_allreduce_sum(eesen_b200_ctx *ctx, float *buf, int64_t n);
+/* Same reduction, issued on the library's low-priority side stream behind everything queued so far, so that it
+ * overlaps with the back-propagation of the layers below (per-layer gradient buckets; reference update order
+ * src/net/net.cc:98-105).  Consumers of the buffer (eesen_b200_sgd_update, eesen_b200_synchronize, ...) join the
+ * side stream themselves. */
+int eesen_b200_allreduce_sum_overlapped(eesen_b200_ctx *ctx, float *d_buf, int64_t n);
 int eesen_b200_world(const eesen_b200_ctx *ctx, int *rank, int *nranks);
 
 /* ---------------------------------------------------------------- level 2: the Net/Ctc host mirror
@@ -266,6 +277,31 @@ int eesen_b200_net_write_nonparallel(eesen_b200_net *net, const char *path, int 
  * rows/cols describe the logical matrix; data may be NULL to query the shape only. */
 int eesen_b200_net_get(eesen_b200_net *net, int which, float *data, int64_t capacity, int *rows, int *cols);
 int eesen_b200_net_set_params(eesen_b200_net *net, const float *flat, int64_t n);
+
+/* ---------------------------------------------------------------- decoding (first slice)
+ * One-best WFST token passing for a batch of utterances: the search core of `latgen-faster`
+ * (reference src/decoderbin/latgen-faster.cc:96-126 -> LatticeFasterDecoder::Decode
+ * src/decoder/lattice-faster-decoder.cc:77-97, ProcessEmitting :660-752, ProcessNonemitting :756-816, GetCutoff :594-658,
+ * ComputeFinalCosts :531-577; acoustic scores as DecodableMatrixScaled src/decoder/decodable-matrix.h:54-56).
+ * Output: the words (non-zero output labels) of the best path and its cost; lattices are not produced.
+ * The graph is handed over WITHOUT OpenFst: CSR over states, the arcs of a state stored emitting arcs first
+ * (ilabel = 1-based CTC token id), then epsilon-input arcs; all arrays on the HOST, copied once. */
+typedef struct eesen_b200_graph eesen_b200_graph;
+int eesen_b200_graph_create(eesen_b200_ctx *ctx, int num_states, int num_arcs, int start, const int *row /*[ns+1]*/,
+                            const int *eps /*[ns]*/, const int *ilabel, const int *olabel, const float *weight,
+                            const int *nextstate, const float *final_cost /*[ns], +inf = not final*/,
+                            eesen_b200_graph **out);
+void eesen_b200_graph_free(eesen_b200_graph *g);
+/* d_loglikes: device, packed time-major [T*S x K] (row t*S + s, ld floats per row) -- what eesen_b200_net_feedforward
+ * produces with apply_log; frames[S] (host): frames per utterance.  beam as --beam of latgen-faster; max_active /
+ * min_active are not implemented in this slice (the reference defaults are "no limit" / 200: pass 2147483647 / 0).
+ * frame_cap: most tokens one frame of one utterance may hold; tok_cap: most tokens one utterance may hold in total.
+ * out_labels [S x max_out], out_len [S] (-1: no surviving token), out_cost [S]: host arrays.
+ * stats (may be NULL): [0] closure rounds, [1] device milliseconds. */
+int eesen_b200_decode_best_path(eesen_b200_ctx *ctx, const eesen_b200_graph *g, int S, int T, const int *frames,
+                                const float *d_loglikes, int ld, int K, float acoustic_scale, float beam,
+                                int max_active, int min_active, int frame_cap, int tok_cap, int *out_labels,
+                                int max_out, int *out_len, float *out_cost, double *stats);
 
 #ifdef __cplusplus
 }

@@ -68,6 +68,52 @@ static void gemm_tn(int M, int N, int K, REAL alpha, const REAL *A, int lda, con
   }
 }
 
+/* ---- dense (input-side / affine) products with operands rounded to bf16 -----------------------------------
+ * BASELINE config 4 asks for a bf16 tensor-core gate GEMM; the product under test rounds BOTH operands of every
+ * dense contraction to bf16 (round to nearest even) and accumulates in fp32 (eesen_b200/csrc/gemm_tc.cu,
+ * kind::f16).  oracle_set_dense_rounding(1) makes this restatement do the same to the operands of exactly those
+ * products (x*Wx^T, DGIFO*Wx, DGIFO^T*x, DGIFO^T*m_prev, the affine layer's three) and leave the per-time-step
+ * recurrent products exact -- the "fp64 restatement fed bf16-rounded inputs" of SURVEY.md 7.4. */
+static int g_dense_round = 0;
+void oracle_set_dense_rounding(int mode) { g_dense_round = mode; }
+static REAL round_bf16(REAL x) {
+  float f = (float)x;
+  unsigned int u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return (REAL)f;
+  u += 0x7fffu + ((u >> 16) & 1u);
+  u &= 0xffff0000u;
+  memcpy(&f, &u, 4);
+  return (REAL)f;
+}
+static REAL *rounded_copy(const REAL *A, long rows, int cols, int ld) {
+  REAL *r = (REAL *)malloc(sizeof(REAL) * (size_t)(rows > 0 ? rows : 1) * (size_t)cols);
+  for (long i = 0; i < rows; i++)
+    for (int j = 0; j < cols; j++) r[i * cols + j] = round_bf16(A[i * ld + j]);
+  return r;
+}
+static void dense_nn(int M, int N, int K, REAL alpha, const REAL *A, int lda, const REAL *B, int ldb, REAL beta,
+                     REAL *Cm, int ldc) {
+  if (!g_dense_round) { gemm_nn(M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc); return; }
+  REAL *a = rounded_copy(A, M, K, lda), *b = rounded_copy(B, K, N, ldb);
+  gemm_nn(M, N, K, alpha, a, K, b, N, beta, Cm, ldc);
+  free(a); free(b);
+}
+static void dense_nt(int M, int N, int K, REAL alpha, const REAL *A, int lda, const REAL *B, int ldb, REAL beta,
+                     REAL *Cm, int ldc) {
+  if (!g_dense_round) { gemm_nt(M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc); return; }
+  REAL *a = rounded_copy(A, M, K, lda), *b = rounded_copy(B, N, K, ldb);
+  gemm_nt(M, N, K, alpha, a, K, b, K, beta, Cm, ldc);
+  free(a); free(b);
+}
+static void dense_tn(int M, int N, int K, REAL alpha, const REAL *A, int lda, const REAL *B, int ldb, REAL beta,
+                     REAL *Cm, int ldc) {
+  if (!g_dense_round) { gemm_tn(M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc); return; }
+  REAL *a = rounded_copy(A, K, M, lda), *b = rounded_copy(B, K, N, ldb);
+  gemm_tn(M, N, K, alpha, a, M, b, N, beta, Cm, ldc);
+  free(a); free(b);
+}
+
 /* cpucompute/vector.cc:820-840 (non-MKL Sigmoid) */
 static REAL sigmoid_ref(REAL x) {
   if (x > (REAL)0) return (REAL)1 / ((REAL)1 + r_exp(-x));
@@ -105,7 +151,7 @@ static void lstm_dir_forward_drop(int dir, int T, int S, int I, int C, const int
   const int W = 7 * C;
   memset(buf, 0, sizeof(REAL) * (size_t)(T + 2) * S * W); /* Resize(kSetZero) :393-394 */
   /* YGIFO[1S..(T+1)S) = in * Wx^T  (:109 / :163), then += bias (:110 / :164) */
-  gemm_nt(T * S, 4 * C, I, (REAL)1, x, I, wx, I, (REAL)0, buf + (long)S * W, W);
+  dense_nt(T * S, 4 * C, I, (REAL)1, x, I, wx, I, (REAL)0, buf + (long)S * W, W);
   for (long r = S; r < (long)(T + 1) * S; r++) {
     REAL *row = buf + r * W;
     for (int j = 0; j < 4 * C; j++) row[j] += bias[j];
@@ -228,12 +274,12 @@ static void lstm_dir_backward_drop(int dir, int T, int S, int I, int C, const RE
   }
   const REAL *DG = dbuf + (long)S * W; /* DGIFO rows 1S..(T+1)S */
   /* in_diff (=|+=) DGIFO * Wx  (:502 beta=0 / :593 beta=1) */
-  gemm_nn(T * S, I, 4 * C, (REAL)1, DG, W, wx, I, in_beta, in_diff, I);
+  dense_nn(T * S, I, 4 * C, (REAL)1, DG, W, wx, I, in_beta, in_diff, I);
   /* Wx_corr = DGIFO^T * in + mmt * Wx_corr (:505 / :596) */
-  gemm_tn(4 * C, I, T * S, (REAL)1, DG, W, x, I, mmt, corr[0], I);
+  dense_tn(4 * C, I, T * S, (REAL)1, DG, W, x, I, mmt, corr[0], I);
   /* Wm_corr = DGIFO^T * YM(prev slots) + mmt*...  fw: slots 0..T-1 (:506); bw: slots 2..T+1 (:597) */
   const REAL *Yprev = buf + (long)(dir > 0 ? 0 : 2) * S * W;
-  gemm_tn(4 * C, C, T * S, (REAL)1, DG, W, Yprev + 6 * C, W, mmt, corr[1], C);
+  dense_tn(4 * C, C, T * S, (REAL)1, DG, W, Yprev + 6 * C, W, mmt, corr[1], C);
   /* bias_corr = colsum(DGIFO) + mmt*... (:507 / :598) */
   for (int j = 0; j < 4 * C; j++) {
     REAL s_ = 0;
@@ -310,15 +356,15 @@ void oracle_lstm_backward(int T, int S, int I, int C, const REAL *x, const REAL 
 void oracle_affine_forward(int N, int D, int K, const REAL *in, const REAL *Wt, const REAL *b, REAL *out) {
   for (long r = 0; r < N; r++)
     for (int k = 0; k < K; k++) out[r * K + k] = b[k]; /* AddVecToRows(1.0, bias_, 0.0) :163 */
-  gemm_nt(N, K, D, (REAL)1, in, D, Wt, D, (REAL)1, out, K); /* :165 */
+  dense_nt(N, K, D, (REAL)1, in, D, Wt, D, (REAL)1, out, K); /* :165 */
 }
 
 void oracle_affine_backward(int N, int D, int K, const REAL *out_diff, const REAL *Wt, REAL *in_diff) {
-  gemm_nn(N, D, K, (REAL)1, out_diff, K, Wt, D, (REAL)0, in_diff, D); /* :171 */
+  dense_nn(N, D, K, (REAL)1, out_diff, K, Wt, D, (REAL)0, in_diff, D); /* :171 */
 }
 
 void oracle_affine_grad(int N, int D, int K, const REAL *in, const REAL *diff, REAL *Wc, REAL *bc, REAL mmt) {
-  gemm_tn(K, D, N, (REAL)1, diff, K, in, D, mmt, Wc, D); /* :182 */
+  dense_tn(K, D, N, (REAL)1, diff, K, in, D, mmt, Wc, D); /* :182 */
   for (int k = 0; k < K; k++) {                          /* :183 */
     REAL s_ = 0;
     for (long r = 0; r < N; r++) s_ += diff[r * K + k];

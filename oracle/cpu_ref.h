@@ -102,4 +102,8 @@ int oracle_real_size(void);
 #ifdef __cplusplus
 }
 #endif
+
+/* 1: round both operands of every dense (input-side / affine) product to bf16; 0: exact (default) */
+void oracle_set_dense_rounding(int mode);
+
 #endif

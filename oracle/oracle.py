@@ -65,6 +65,12 @@ def lib(dtype=np.float32) -> _Lib:
     return _LIBS[k]
 
 
+def set_dense_rounding(dtype, mode: int) -> None:
+    """mode 1: the restatement rounds both operands of every dense (input-side / affine) product to bf16, as the
+    product's bf16 arithmetic mode does (BASELINE config 4); 0 restores exact operands."""
+    lib(dtype).lib.oracle_set_dense_rounding(int(mode))
+
+
 def ctc_eval(y: np.ndarray, frames, labels: List[np.ndarray], S: int, dtype=np.float32, want_ab=False):
     L = lib(dtype)
     y = L.arr(y)
@@ -337,7 +343,7 @@ def have_reference(kind: str) -> bool:
 
 def run_reference(kind: str, model_path: str, batch_path: str, outdir: str, lr: float, momentum: float,
                   steps: int = 1, diff_in: Optional[str] = None, time_only: bool = False,
-                  threads: Optional[int] = None, timeout: int = 3600, opt: str = "SGD"):
+                  threads: Optional[int] = None, timeout: int = 3600, opt: str = "SGD", dump_layers: bool = True):
     """Run oracle/_ref/ref_dump_{cpu,gpu} (the unmodified reference objects) on one batch."""
     exe = os.path.join(REFDIR, f"ref_dump_{kind}")
     os.makedirs(outdir, exist_ok=True)
@@ -349,6 +355,8 @@ def run_reference(kind: str, model_path: str, batch_path: str, outdir: str, lr: 
         cmd += ["--diff-in", diff_in]
     if time_only:
         cmd += ["--time-only"]
+    if not dump_layers:
+        cmd += ["--no-dump-layers"]
     env = dict(os.environ)
     if threads is not None:
         env["OPENBLAS_NUM_THREADS"] = str(threads)
@@ -365,3 +373,34 @@ def load_dump(outdir: str) -> Dict[str, np.ndarray]:
         if f.endswith(".npy"):
             out[f[:-4]] = np.load(os.path.join(outdir, f))
     return out
+
+
+# --------------------------------------------------------------------------- WFST one-best search (row N3)
+_DEC = None
+
+
+def decode_best_path(g, loglikes: np.ndarray, acoustic_scale: float, beam: float, max_active: int = 2147483647,
+                     min_active: int = 0, max_out: int = 4096):
+    """oracle/decoder_ref.c: the restated LatticeFasterDecoder search, one utterance.  g: eesen_b200.wfst.Graph (plain
+    arrays); loglikes [T x K].  Returns (words | None, cost, frames_decoded, arcs_expanded)."""
+    global _DEC
+    if _DEC is None:
+        path = os.path.join(REFDIR, "liboracle_dec.so")
+        if not os.path.exists(path):
+            build()
+        _DEC = C.CDLL(path)
+        _DEC.oracle_decode_best_path.restype = C.c_int
+    ll = np.ascontiguousarray(loglikes, np.float32)
+    T, K = ll.shape
+    out = np.zeros(max_out, np.int32)
+    cost = C.c_float(0.0); nf = C.c_int(0); na = C.c_long(0)
+    P = lambda a, t: np.ascontiguousarray(a, t).ctypes.data_as(C.c_void_p)
+    keep = [np.ascontiguousarray(g.row, np.int32), np.ascontiguousarray(g.eps, np.int32), np.ascontiguousarray(g.ilabel, np.int32),
+            np.ascontiguousarray(g.olabel, np.int32), np.ascontiguousarray(g.weight, np.float32),
+            np.ascontiguousarray(g.nextstate, np.int32), np.ascontiguousarray(g.final, np.float32)]
+    p = [a.ctypes.data_as(C.c_void_p) for a in keep]
+    n = _DEC.oracle_decode_best_path(g.num_states, g.start, p[0], p[1], p[2], p[3], p[4], p[5], p[6], T, K,
+                                     ll.ctypes.data_as(C.c_void_p), C.c_float(acoustic_scale), C.c_float(beam),
+                                     int(max_active), int(min_active), out.ctypes.data_as(C.c_void_p), max_out,
+                                     C.byref(cost), C.byref(nf), C.byref(na))
+    return (out[:n].tolist() if n >= 0 else None), float(cost.value), int(nf.value), int(na.value)

@@ -17,8 +17,12 @@ assert ctx.lib.eesen_b200_debug_lstm_timing(ctx.h, buf, 1) == 1, "not built with
 net.train_step(b.feats, b.frames, b.labels, True)
 ctx.lib.eesen_b200_debug_lstm_timing(ctx.h, buf, 0)
 steps = (b.T - 1) * w.layers
-names_f = ["poll", "barA", "stage_ld", "barB", "mma", "scratch+barD", "elementwise+publish", "signal", "gate_stores+prefetch", "scratch reduce"]
-names_b = ["poll", "barA", "partials+elementwise", "barC", "mma+P stores", "signal"]
+if os.environ.get("EESEN_B200_LSTM_ENGINE") == "legacy":
+    names_f = ["poll", "barA", "stage_ld", "barB", "mma", "scratch+barD", "elementwise+publish", "signal", "gate_stores+prefetch", "scratch reduce"]
+    names_b = ["poll", "barA", "partials+elementwise", "barC", "mma+P stores", "signal"]
+else:   # tcgen05 engine (lstm_tc.cu)
+    names_f = ["stage (poll + B tile) + arrive", "MMA issue + commit wait", "TMEM ld + staging + barrier", "gates + publish", "saved-state stores + prefetch"]
+    names_b = ["gather partial d_m", "gate math + DG stores + B tile + arrive", "MMA issue + prefetch + commit wait", "TMEM ld + publish partials"]
 print(f"forward ({prec}) cycles/step (thread 0 of CTA 0; {steps} steps):")
 tot = 0
 for i, n in enumerate(names_f):

@@ -234,7 +234,155 @@ static void run(int NB, int afmt, int bfmt, int reps, int mode, const char *what
   cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dC);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// 5. A operand resident in TMEM (tcgen05.mma "TS" form): weights [128 x K] fp16 written once with tcgen05.st
+//    (lane = row, 2 halfs per 32-bit column, 8 columns per 16-wide k-slice), B from shared memory as before.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(128, 1)
+probe_ts_kernel(const float *A, const float *B, int NB, float *out, long long *cycles, int reps, int two) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *sB = smem;   // [64 x K]
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_sm;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 64 * K; i += 128) {
+    int r = i / K, k = i % K;
+    *reinterpret_cast<uint16_t *>(sB + sw128_off(64, r, k)) = r < NB ? cvt16(B[i], 0) : 0;
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_sm)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = tmem_base_sm;
+  // A -> TMEM columns [128, 128 + K/2) (and a second copy at [320, 320 + K/2) for the two-tile timing)
+  {
+    const int row = warp * 32 + lane;
+    for (int ks = 0; ks < K / 16; ks++) {
+      uint32_t w[8];
+      for (int j = 0; j < 8; j++) {
+        uint32_t lo = cvt16(A[(size_t)row * K + ks * 16 + 2 * j], 0), hi = cvt16(A[(size_t)row * K + ks * 16 + 2 * j + 1], 0);
+        w[j] = lo | (hi << 16);
+      }
+      for (int cpy = 0; cpy < 2; cpy++) {
+        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((cpy ? 320 : 128) + ks * 8);
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(ta), "r"(w[0]), "r"(w[1]),
+                     "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                     : "memory");
+      }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t idescN = (1u << 4) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t idescH = (1u << 4) | ((uint32_t)((NB / 2) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint64_t dB = umma_desc(smem_u32(sB), 16, 1024, 2);
+  uint32_t phase = 0;
+  long long t0 = 0;
+  if (tid == 0) t0 = clock64();
+  for (int rep = 0; rep < reps; rep++) {
+    if (warp == 0) {
+      uint32_t pe;
+      asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pe));
+      if (pe) {
+#pragma unroll
+        for (int kb = 0; kb < KB; kb++) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++) {
+            const uint64_t bd = dB + (uint64_t)((kb * (64 * 128) + ks * 32) >> 4);
+            umma_f16_ts(tmem_base, tmem_base + 128 + (kb * 4 + ks) * 8, bd, idescN, (kb | ks) != 0);
+            if (two) umma_f16_ts(tmem_base + 64, tmem_base + 320 + (kb * 4 + ks) * 8, bd, idescH, (kb | ks) != 0);
+          }
+        }
+        umma_commit(&bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  }
+  if (tid == 0) cycles[0] = clock64() - t0;
+  for (int c0 = 0; c0 < 128; c0 += 16) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+    for (int j = 0; j < 16; j++) out[(size_t)(warp * 32 + lane) * 128 + c0 + j] = __uint_as_float(r[j]);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+static void run_ts(int NB, int reps, int two, const char *what) {
+  const int M = 128;
+  std::vector<float> A((size_t)M * K), B((size_t)64 * K);
+  srand(7);
+  for (auto &v : A) v = (rand() / (float)RAND_MAX - 0.5f) * 0.4f;
+  for (auto &v : B) v = (rand() / (float)RAND_MAX - 0.5f) * 2.0f;
+  float *dA, *dB, *dO;
+  long long *dC;
+  CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dO, 128 * 128 * 4)); CK(cudaMalloc(&dC, 8));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dO, 0, 128 * 128 * 4));
+  size_t smem = 64 * K * 2 + 2048;
+  CK(cudaFuncSetAttribute(probe_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_ts_kernel<<<1, 128, smem>>>(dA, dB, NB, dO, dC, reps, two);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%-40s: LAUNCH/EXEC ERROR %s\n", what, cudaGetErrorString(e)); exit(2); }
+  std::vector<float> O(128 * 128);
+  long long cyc;
+  CK(cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost));
+  double maxerr = 0;
+  int bad = 0;
+  for (int r = 0; r < M; r++)
+    for (int n = 0; n < NB; n++) {
+      double s = 0;
+      for (int k = 0; k < K; k++) s += (double)round16(A[(size_t)r * K + k], 0) * (double)round16(B[(size_t)n * K + k], 0);
+      double err = fabs(O[(size_t)r * 128 + n] - s);
+      if (err > maxerr) maxerr = err;
+      if (err > 1e-3) bad++;
+      if (two && n < NB / 2 && fabs(O[(size_t)r * 128 + 64 + n] - s) > 1e-3) bad++;
+    }
+  printf("%-44s NB=%d two=%d: max|err|=%.3e bad=%d  cycles/rep=%.1f\n", what, NB, two, maxerr, bad, (double)cyc / reps);
+  cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dC);
+}
+
 int main() {
+  run_ts(32, 1, 0, "TS form (A in TMEM), single pass");
+  run_ts(32, 1, 1, "TS form, two accumulators");
+  run_ts(32, 200, 0, "timing TS: 20 MMA N=32");
+  run_ts(32, 200, 1, "timing TS: 20x(N=32 + N=16)");
+  run_ts(64, 200, 1, "timing TS: 20x(N=64 + N=32)");
   run<128>(32, 0, 0, 1, 0, "fp16 x fp16, single pass");
   run<128>(32, 1, 1, 1, 0, "bf16 x bf16, single pass");
   run<64>(32, 0, 0, 1, 0, "M=64 lane layout");
