@@ -97,16 +97,41 @@ __device__ __forceinline__ uint32_t idesc_f16(int M, int N) {
 __device__ __forceinline__ void st_word(uint32_t *p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.b32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t ld_word(const uint32_t *p) {
-  uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.b32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ uint4 ld_word4(const uint4 *p) {
   uint4 q;
   asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];\n"
                : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(p) : "memory");
   return q;
+}
+
+// A operand resident in TMEM ("TS" form): lane = row, two fp16 per 32-bit column, 8 columns per 16-wide k-slice
+// (layout and speed measured in tests/micro/umma_probe.cu: the 40 MMAs of one step complete in ~830 cycles with the
+// weights in TMEM against ~2700 with both operands in shared memory, where the 160 KB weight stream is the limit)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&w)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr), "r"(w[0]), "r"(w[1]),
+               "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+template <int KB>
+__device__ __forceinline__ void issue_fwd_mmas_ts(uint32_t tWhi, uint32_t tWlo, uint64_t dB, uint32_t tmem, uint32_t idN,
+                                                  uint32_t idH) {
+#pragma unroll
+  for (int kb = 0; kb < KB; kb++) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+      const uint64_t bd = dB + (uint64_t)((kb * 4096 + ks * 32) >> 4);
+      umma_f16_ts(tmem, tWhi + (kb * 4 + ks) * 8, bd, idN, (kb | ks) != 0);
+      umma_f16_ts(tmem + 32, tWlo + (kb * 4 + ks) * 8, bd, idH, (kb | ks) != 0);
+    }
+  }
 }
 
 // One recurrent step's MMAs from the elected lane: fully unrolled, descriptors = 64-bit base + constant
@@ -122,6 +147,16 @@ __device__ __forceinline__ void issue_fwd_mmas(uint64_t dWhi, uint64_t dWlo, uin
       umma_f16(tmem, dWhi + (uint64_t)((kb * 16384 + ks * 32) >> 4), bd, idN, (kb | ks) != 0);
       umma_f16(tmem + 32, dWlo + (uint64_t)((kb * 16384 + ks * 32) >> 4), bd, idH, (kb | ks) != 0);
     }
+  }
+}
+__device__ __forceinline__ void issue_bwd_tile_ts(uint32_t tAhi, uint32_t tAlo, uint64_t dB, uint32_t tmem) {
+  const uint32_t idN = idesc_f16(128, 32), idH = idesc_f16(128, 16);
+#pragma unroll
+  for (int ks = 0; ks < 8; ks++) {
+    const int kb = ks >> 2, k4 = ks & 3;
+    const uint64_t bd = dB + (uint64_t)((kb * 4096 + k4 * 32) >> 4);
+    umma_f16_ts(tmem, tAhi + ks * 8, bd, idN, ks != 0);
+    umma_f16_ts(tmem + 32, tAlo + ks * 8, bd, idH, ks != 0);
   }
 }
 template <int ROWS>
@@ -154,10 +189,10 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int C = a.C, S = a.S, T = a.T;
   const int KB = C >> 6;                                  // 64-wide k-blocks (C % 64 == 0)
-  uint8_t *Whi = smem;                                    // [KB][128 rows][128 B]
-  uint8_t *Wlo = Whi + (size_t)KB * 16384;
-  uint8_t *Bt = Wlo + (size_t)KB * 16384;                 // [KB][32 rows][128 B]: rows 0-15 hi, 16-31 lo'
+  uint8_t *Bt = smem;                                     // [KB][32 rows][128 B]: rows 0-15 hi, 16-31 lo'
   float *stg = reinterpret_cast<float *>(Bt + (size_t)KB * 4096);   // [4 gates][16 utts][32 cells]
+  // TMEM columns: [0,32) X accumulator, [32,48) Y accumulator, [64, 64 + C/2) W_hi, [64 + C/2, 64 + C) W_lo'
+  constexpr uint32_t kColW = 64;
   __shared__ uint64_t b_full, mma_done;
   __shared__ uint32_t tmem_base_sm;
 
@@ -167,28 +202,6 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
   uint32_t *xbuf = reinterpret_cast<uint32_t *>(a.xbuf);  // [2 parity][ndir][groups][16][C] 4-byte tagged words
   const int s0 = a.s_begin, s1 = a.s_begin + a.s_count;
 
-  // ---- resident weights: row = gate*32 + local cell, split into the two fp16 tiles (8 loads in flight per thread)
-  for (int base = 0; base < 128 * C; base += 8 * TCL_THREADS) {
-    float w[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const int idx = base + i * TCL_THREADS + tid;
-      const int r = idx / C, k = idx - r * C;
-      w[i] = idx < 128 * C ? __ldg(P.wm + ((size_t)(r >> 5) * C + slice * TCL_CS + (r & 31)) * P.ldwm + k) : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const int idx = base + i * TCL_THREADS + tid;
-      if (idx < 128 * C) {
-        const int r = idx / C, k = idx - r * C;
-        uint32_t h, l;
-        split_f16(w[i], h, l);
-        const uint32_t off = sw128_off(128, r, k);
-        *reinterpret_cast<uint16_t *>(Whi + off) = (uint16_t)h;
-        *reinterpret_cast<uint16_t *>(Wlo + off) = (uint16_t)l;
-      }
-    }
-  }
   for (int idx = tid; idx < KB * 1024; idx += TCL_THREADS) reinterpret_cast<uint32_t *>(Bt)[idx] = 0u;
   if (tid == 0) {
     mbar_init(&b_full, TCL_WORKERS);
@@ -196,7 +209,7 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_sm)), "n"(64)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_sm)), "n"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
@@ -205,6 +218,35 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = tmem_base_sm;
+
+  // ---- resident weights, in TMEM for the whole sequence: lane = gate*32 + local cell, the row's K = C values split
+  // into fp16 hi / lo' and packed two per column.  Warps w and w+4 own the same lane quadrant: they take alternate
+  // 16-wide k-slices.
+  {
+    const int r = (warp & 3) * 32 + lane;
+    const float *wrow = P.wm + ((size_t)(r >> 5) * C + slice * TCL_CS + (r & 31)) * P.ldwm;
+    const uint32_t tl = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kColW;
+    for (int ks = warp >> 2; ks < C / 16; ks += 2) {
+      float w[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) w[j] = __ldg(wrow + ks * 16 + j);
+      uint32_t wh[8], wl[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        uint32_t h0, l0, h1, l1;
+        split_f16(w[2 * j], h0, l0);
+        split_f16(w[2 * j + 1], h1, l1);
+        wh[j] = h0 | (h1 << 16);
+        wl[j] = l0 | (l1 << 16);
+      }
+      tmem_st8(tl + ks * 8, wh);
+      tmem_st8(tl + (C >> 1) + ks * 8, wl);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 
   {
     // ===== workers =====
@@ -237,8 +279,7 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
     load_pre(dir == 0 ? 0 : T - 1);
     const int c8n = C >> 3;                                // 8-cell chunks per utterance row
     const int quad = warp & 3, uh = warp >> 2;             // epilogue: TMEM lane quadrant (= gate), utterance half
-    const uint64_t dWhi = umma_desc(smem_u32(Whi), 16, 1024, 2), dWlo = umma_desc(smem_u32(Wlo), 16, 1024, 2),
-                   dBt = umma_desc(smem_u32(Bt), 16, 1024, 2);
+    const uint64_t dBt = umma_desc(smem_u32(Bt), 16, 1024, 2);
 
     TC_ACC_DECL();
     for (int step = 0; step < T; step++) {
@@ -297,13 +338,14 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           if (elect_one()) {
             const uint32_t idN = idesc_f16(128, 32), idH = idesc_f16(128, 16);
+            const uint32_t tWhi = tmem_base + kColW, tWlo = tmem_base + kColW + (uint32_t)(C >> 1);
             switch (KB) {
-              case 1: issue_fwd_mmas<1>(dWhi, dWlo, dBt, tmem_base, idN, idH); break;
-              case 2: issue_fwd_mmas<2>(dWhi, dWlo, dBt, tmem_base, idN, idH); break;
-              case 3: issue_fwd_mmas<3>(dWhi, dWlo, dBt, tmem_base, idN, idH); break;
-              case 4: issue_fwd_mmas<4>(dWhi, dWlo, dBt, tmem_base, idN, idH); break;
-              case 5: issue_fwd_mmas<5>(dWhi, dWlo, dBt, tmem_base, idN, idH); break;
-              default: issue_fwd_mmas<6>(dWhi, dWlo, dBt, tmem_base, idN, idH); break;
+              case 1: issue_fwd_mmas_ts<1>(tWhi, tWlo, dBt, tmem_base, idN, idH); break;
+              case 2: issue_fwd_mmas_ts<2>(tWhi, tWlo, dBt, tmem_base, idN, idH); break;
+              case 3: issue_fwd_mmas_ts<3>(tWhi, tWlo, dBt, tmem_base, idN, idH); break;
+              case 4: issue_fwd_mmas_ts<4>(tWhi, tWlo, dBt, tmem_base, idN, idH); break;
+              case 5: issue_fwd_mmas_ts<5>(tWhi, tWlo, dBt, tmem_base, idN, idH); break;
+              default: issue_fwd_mmas_ts<6>(tWhi, tWlo, dBt, tmem_base, idN, idH); break;
             }
             umma_commit(&mma_done);
           }
@@ -388,7 +430,7 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(64) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(512) : "memory");
   }
 }
 
@@ -407,6 +449,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
   uint8_t *Alo = Ahi + (size_t)C * 256;
   uint8_t *Bt = Alo + (size_t)C * 256;                    // [2 k-blocks][32 rows][128 B]
   float *scl = reinterpret_cast<float *>(Bt + 8192);      // [16] inverse column scales
+  float *gsm = scl + 16;                                   // [2 halves][16 utts][32 cells] gathered partial d_m
   __shared__ uint64_t b_full, mma_done[3];   // one commit barrier per M tile (C <= 384: at most 3 tiles)
   __shared__ uint32_t tmem_base_sm;
 
@@ -447,7 +490,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_sm)), "n"(256)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_sm)), "n"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
@@ -456,6 +499,40 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = tmem_base_sm;
+
+  // ---- the first two full M tiles of Wm^T also go to TMEM (columns [160, 160 + 128 * NTS): per tile 64 columns hi,
+  // 64 columns lo'; lane = output cell within the tile, 8 columns per 16-wide k-slice of this CTA's 128 gate rows):
+  // their MMAs read the weights from TMEM ("TS" form) instead of streaming 128 KB through shared memory per step.
+  // A third tile (C = 320: the 64-row one) keeps both operands in shared memory.
+  const int NTS = n128 < 2 ? n128 : 2;
+  constexpr uint32_t kColA = 160;
+  for (int mt = 0; mt < NTS; mt++) {
+    const int j = mt * 128 + (warp & 3) * 32 + lane;
+    const uint32_t tl = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kColA + (uint32_t)mt * 128;
+    for (int ks = warp >> 2; ks < 8; ks += 2) {
+      float w[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const int kk = ks * 16 + i;
+        w[i] = __ldg(P.wm + ((size_t)(kk >> 5) * C + slice * TCL_CS + (kk & 31)) * P.ldwm + j);
+      }
+      uint32_t wh[8], wl[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        uint32_t h0, l0, h1, l1;
+        split_f16(w[2 * i], h0, l0);
+        split_f16(w[2 * i + 1], h1, l1);
+        wh[i] = h0 | (h1 << 16);
+        wl[i] = l0 | (l1 << 16);
+      }
+      tmem_st8(tl + ks * 8, wh);
+      tmem_st8(tl + 64 + ks * 8, wl);
+    }
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 
   {
     // ===== workers: two (cell, utterance) items per thread =====
@@ -504,35 +581,36 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
       float dm[2] = {vd[0], vd[1]};
       if (step > 0) {
         // ---- d_m of this thread's items: the `slices` tagged partials, summed in fixed order (:470 / :561)
-        const uint32_t *pb = pbuf + ((size_t)((((step - 1) & 1) * ndir + dir) * groups + group) * slices) * pstride_slice + cell;
+        // Cooperative and wide: the CTA needs, from each of the `slices` producers, a [16 utterances x 32 cells] block of
+        // partials (128 contiguous bytes per utterance row).  Thread (half, u, c4) fetches 4 cells of utterance u from
+        // one half of the producers with 16-byte loads (<= 6 requests per thread instead of 2 x slices scalar ones),
+        // sums them in producer order, and the two halves meet in shared memory -- a fixed order: deterministic.
         const uint32_t want = (uint32_t)(((step - 1) >> 1) & 1);
-        uint32_t q[2][12];                                  // slices <= 12 (C <= 384, lstm_tc_plan)
-        // the loads of BOTH items go out together (one L2 round trip when everything is there) ...
+        const int c4 = tid & 7, gu = (tid >> 3) & 15, half = tid >> 7;
+        const int hs = (slices + 1) >> 1, sl0 = half * hs, sl1 = half ? slices : hs;
+        const bool uv = s0 + group * TCL_UG + gu < s1;
+        const uint4 *pv = reinterpret_cast<const uint4 *>(
+            pbuf + ((size_t)((((step - 1) & 1) * ndir + dir) * groups + group) * slices) * pstride_slice + (size_t)gu * C +
+            slice * TCL_CS + c4 * 4);
+        uint4 q[6];
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const uint32_t *pe = pb + (size_t)(2 * up + e) * C;
+        for (int i = 0; i < 6; i++)
+          if (uv && sl0 + i < sl1) q[i] = ld_word4(pv + (size_t)(sl0 + i) * (pstride_slice / 4));
+        float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int i = 0; i < 12; i++)
-            if (i < slices && ok[e]) q[e][i] = ld_word(pe + (size_t)i * pstride_slice);
+        for (int i = 0; i < 6; i++) {
+          if (uv && sl0 + i < sl1) {
+            while ((((q[i].x ^ want) | (q[i].y ^ want) | (q[i].z ^ want) | (q[i].w ^ want)) & 1u) != 0u)
+              q[i] = ld_word4(pv + (size_t)(sl0 + i) * (pstride_slice / 4));
+            acc4.x += __uint_as_float(q[i].x & 0xfffffffeu); acc4.y += __uint_as_float(q[i].y & 0xfffffffeu);   // tag bit cleared
+            acc4.z += __uint_as_float(q[i].z & 0xfffffffeu); acc4.w += __uint_as_float(q[i].w & 0xfffffffeu);
+          }
         }
-        // ... then only the words that have not arrived yet are polled again
+        *reinterpret_cast<float4 *>(gsm + ((size_t)(half * TCL_UG + gu) * 32 + c4 * 4)) = acc4;
+        named_bar_workers();
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const uint32_t *pe = pb + (size_t)(2 * up + e) * C;
-#pragma unroll
-          for (int i = 0; i < 12; i++)
-            if (i < slices && ok[e])
-              while ((q[e][i] & 1u) != want) q[e][i] = ld_word(pe + (size_t)i * pstride_slice);
-        }
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          if (!ok[e]) continue;
-          float s_ = 0.f;
-#pragma unroll
-          for (int i = 0; i < 12; i++)
-            if (i < slices) s_ += __uint_as_float(q[e][i] & 0xfffffffeu);   // tag bit cleared; fixed order: deterministic
-          dm[e] += s_;
-        }
+        for (int e = 0; e < 2; e++)
+          if (ok[e]) dm[e] += gsm[(size_t)(2 * up + e) * 32 + cl] + gsm[(size_t)(TCL_UG + 2 * up + e) * 32 + cl];   // :470 / :561
       }
       TC_TICK(1, 0);
       float dgt[4][2];
@@ -595,7 +673,8 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
           // still working on tile mt+1
           for (int mt = 0; mt < MT; mt++) {
             const uint64_t toff = (uint64_t)((mt * 128 * 256) >> 4);
-            if (mt < n128) issue_bwd_tile<128>(dAhi + toff, dAlo + toff, dBt, tmem_base + mt * 48);
+            if (mt < NTS) issue_bwd_tile_ts(tmem_base + kColA + mt * 128, tmem_base + kColA + mt * 128 + 64, dBt, tmem_base + mt * 48);
+            else if (mt < n128) issue_bwd_tile<128>(dAhi + toff, dAlo + toff, dBt, tmem_base + mt * 48);
             else issue_bwd_tile<64>(dAhi + toff, dAlo + toff, dBt, tmem_base + mt * 48);
             umma_commit(&mma_done[mt]);
           }
@@ -663,12 +742,18 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(256) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(512) : "memory");
   }
 }
 
-size_t tc_fwd_smem(int C) { return (size_t)(C / 64) * (2 * 16384 + 4096) + 4 * TCL_UG * 32 * sizeof(float) + 1024; }
-size_t tc_bwd_smem(int C) { return (size_t)C * 512 + 8192 + 64 + 1024; }
+// the forward kernel needs only the B tile and the gate staging in shared memory (the weights live in TMEM); it still
+// asks for most of the SM's shared memory so that no GEMM CTA of the side stream is placed next to it -- such a CTA
+// would sit in tcgen05.alloc until this kernel releases its 512 TMEM columns
+size_t tc_fwd_smem(int C) {
+  const size_t need = (size_t)(C / 64) * 4096 + 4 * TCL_UG * 32 * sizeof(float) + 1024;
+  return need > 180 * 1024 ? need : (size_t)180 * 1024;
+}
+size_t tc_bwd_smem(int C) { return (size_t)C * 512 + 8192 + 64 + 2 * TCL_UG * 32 * sizeof(float) + 1024; }
 
 }  // namespace
 
