@@ -18,6 +18,7 @@
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..9 = operand splitters during the main loop, then the epilogue (TMEM lane quadrant = warp%4, two warps per quadrant split the columns).
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 
@@ -26,6 +27,8 @@
 #include "tc_common.cuh"
 
 namespace eb {
+
+int pick_splits(long tiles, int kb, int num_sms);   // defined below (shared by the fp32 and the 16-bit paths)
 
 namespace {
 
@@ -41,7 +44,12 @@ struct TcArgs {
   float alpha, beta;
   int splits, kblocks_per_split;
   float *ws;
+  const int *kexp_a, *kexp_b;   // fp16x3 mode: the operands were scaled by 2^kexp before the split (device ints), else NULL
 };
+
+__device__ __forceinline__ float tc_alpha(const TcArgs &p) {
+  return p.kexp_a ? p.alpha * exp2f(-(float)(__ldg(p.kexp_a) + __ldg(p.kexp_b))) : p.alpha;
+}
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -57,6 +65,7 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 template <int BN>
 __device__ __forceinline__ void tc_epilogue(uint8_t *smem, uint64_t *accum_bar, uint32_t tmem_base, const TcArgs &p,
                                             int warp, int lane, int m0, int n0, int split) {
+    const float alpha = tc_alpha(p);   // (p.alpha, rescaled in the fp16x3 mode)
     mbar_wait(accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     // Epilogue: TMEM (lane = output row) -> registers -> this warp's private 32 x BN staging tile in
@@ -124,10 +133,10 @@ __device__ __forceinline__ void tc_epilogue(uint8_t *smem, uint64_t *accum_bar, 
             const int c = lane * 4 + q * 128;
             if (c < BNW && ncol0 + c < p.N) {
               float4 v = *reinterpret_cast<const float4 *>(srow + c);
-              v.x = p.alpha * v.x + bv[q].x + p.beta * old[j][q].x;
-              v.y = p.alpha * v.y + bv[q].y + p.beta * old[j][q].y;
-              v.z = p.alpha * v.z + bv[q].z + p.beta * old[j][q].z;
-              v.w = p.alpha * v.w + bv[q].w + p.beta * old[j][q].w;
+              v.x = alpha * v.x + bv[q].x + p.beta * old[j][q].x;
+              v.y = alpha * v.y + bv[q].y + p.beta * old[j][q].y;
+              v.z = alpha * v.z + bv[q].z + p.beta * old[j][q].z;
+              v.w = alpha * v.w + bv[q].w + p.beta * old[j][q].w;
               *reinterpret_cast<float4 *>(p.C + (size_t)row * p.ldc + ncol0 + c) = v;
             }
           }
@@ -145,7 +154,7 @@ __device__ __forceinline__ void tc_epilogue(uint8_t *smem, uint64_t *accum_bar, 
         float *crow = p.C + (size_t)row * p.ldc + ncol0;
         for (int c = lane * 4; c < BNW && ncol0 + c < p.N; c += 128) {
           float4 v = *reinterpret_cast<const float4 *>(srow + c);
-          v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
+          v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
           if (p.bias) {
             const float4 b = *reinterpret_cast<const float4 *>(p.bias + ncol0 + c);
             v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
@@ -159,7 +168,7 @@ __device__ __forceinline__ void tc_epilogue(uint8_t *smem, uint64_t *accum_bar, 
       } else {
         float *crow = p.C + (size_t)row * p.ldc + ncol0;
         for (int c = lane; c < BNW && ncol0 + c < p.N; c += 32) {
-          float v = p.alpha * srow[c];
+          float v = alpha * srow[c];
           if (p.bias) v += p.bias[ncol0 + c];
           if (p.beta != 0.f) v += p.beta * crow[c];
           crow[c] = v;
@@ -323,12 +332,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 //                     k-slice of 16 rows = +2048 B   (canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units)
 constexpr int TC16_BK = 64;
 
-template <int BN, int TA, int TB, int STAGES>
+// NT = 1: bf16 operands, one MMA per k-slice (FMT = 1).
+// NT = 3: fp32-faithful "fp16x3": every operand comes as TWO fp16 planes hi = fp16(s*x), lo = fp16(s*x - hi) with a
+//         per-matrix power-of-two scale s that puts max|s*x| into [2^13, 2^14) (convert_f16x2 below; 22 mantissa bits,
+//         exact scaling), three MMAs per k-slice lo*hi + hi*lo + hi*hi at the bf16/fp16 rate -- twice the rate of
+//         the kind::tf32 split, half its shared-memory bytes per MMA and no in-kernel splitter; the epilogue divides
+//         the scales out (tc_alpha).
+template <int BN, int TA, int TB, int STAGES, int NT, int FMT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs p) {
+gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, TcArgs p) {
   constexpr int A_BYTES = TC_BM * TC16_BK * 2;
   constexpr int B_BYTES = BN * TC16_BK * 2;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGE_BYTES = (NT == 3 ? 2 : 1) * (A_BYTES + B_BYTES);   // [A hi][B hi]([A lo][B lo])
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
@@ -368,28 +384,33 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (i >= STAGES) mbar_wait(&empty_bar[s], ((i / STAGES) - 1) & 1);
         uint8_t *sa = smem + (size_t)s * STAGE_BYTES;
         uint8_t *sb = sa + A_BYTES;
-        mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
         const int k0 = (kb_beg + i) * TC16_BK;
-        if (TA == 0) {
-          tma_load_2d(sa, &mapA, k0, m0, &full_bar[s]);              // box {64 k, 128 m}
-        } else {
 #pragma unroll
-          for (int g = 0; g < TC_BM / 64; g++)                        // box {64 m, 64 k} per 64-wide M group
-            tma_load_2d(sa + g * (TC16_BK * 128), &mapA, m0 + g * 64, k0, &full_bar[s]);
-        }
-        if (TB == 1) {
-          tma_load_2d(sb, &mapB, k0, n0, &full_bar[s]);              // box {64 k, BN n}
-        } else {
+        for (int pl = 0; pl < (NT == 3 ? 2 : 1); pl++) {              // plane 0: hi (or the bf16 copy), plane 1: lo
+          const CUtensorMap *ma = pl ? &mapA2 : &mapA, *mb = pl ? &mapB2 : &mapB;
+          uint8_t *pa = sa + pl * (A_BYTES + B_BYTES), *pb = sb + pl * (A_BYTES + B_BYTES);
+          if (TA == 0) {
+            tma_load_2d(pa, ma, k0, m0, &full_bar[s]);              // box {64 k, 128 m}
+          } else {
 #pragma unroll
-          for (int g = 0; g < BN / 64; g++)
-            tma_load_2d(sb + g * (TC16_BK * 128), &mapB, n0 + g * 64, k0, &full_bar[s]);
+            for (int g = 0; g < TC_BM / 64; g++)                      // box {64 m, 64 k} per 64-wide M group
+              tma_load_2d(pa + g * (TC16_BK * 128), ma, m0 + g * 64, k0, &full_bar[s]);
+          }
+          if (TB == 1) {
+            tma_load_2d(pb, mb, k0, n0, &full_bar[s]);              // box {64 k, BN n}
+          } else {
+#pragma unroll
+            for (int g = 0; g < BN / 64; g++)
+              tma_load_2d(pb + g * (TC16_BK * 128), mb, n0 + g * 64, k0, &full_bar[s]);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // instruction descriptor: D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), majors, N >> 3, M >> 4
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TA ? 1 : 0) << 15) |
+      // instruction descriptor: D = F32 (1 << 4), A = B = BF16 (1) or F16 (0) at bits 7 / 10, majors, N >> 3, M >> 4
+      const uint32_t idesc = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) | ((uint32_t)(TA ? 1 : 0) << 15) |
                              ((uint32_t)(TB ? 0 : 1) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       for (int i = 0; i < nkb; i++) {
         const int s = i % STAGES;
@@ -404,7 +425,15 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const uint32_t a_lbo = TA == 0 ? 16 : TC16_BK * 128, b_lbo = TB == 1 ? 16 : TC16_BK * 128;
           const uint64_t ad = umma_desc(sa + a_off, a_lbo, 1024, 2);
           const uint64_t bd = umma_desc(sb + b_off, b_lbo, 1024, 2);
-          umma_f16(tmem_base, ad, bd, idesc, (i | k) != 0);
+          if (NT == 3) {
+            const uint64_t al = umma_desc(sa + A_BYTES + B_BYTES + a_off, a_lbo, 1024, 2);
+            const uint64_t bl = umma_desc(sb + A_BYTES + B_BYTES + b_off, b_lbo, 1024, 2);
+            umma_f16(tmem_base, al, bd, idesc, (i | k) != 0);   // small terms first
+            umma_f16(tmem_base, ad, bl, idesc, 1);
+            umma_f16(tmem_base, ad, bd, idesc, 1);
+          } else {
+            umma_f16(tmem_base, ad, bd, idesc, (i | k) != 0);
+          }
         }
         umma_commit(&empty_bar[s]);
       }
@@ -419,6 +448,67 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+
+// fp16x3 operand preparation: max|x| of a matrix (bits of a non-negative float order like unsigned integers) ...
+__global__ void absmax_kernel(const float *__restrict__ src, long rows, int cols, long lds, unsigned *__restrict__ out) {
+  const int c4 = (cols + 3) / 4;
+  const long n = rows * c4;
+  const bool vec = (lds & 3) == 0 && (((uintptr_t)src) & 15) == 0;
+  unsigned m = 0u;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / c4;
+    const int c = (int)(i - r * c4) * 4;
+    const float *sp = src + r * lds + c;
+    if (vec && c + 4 <= cols) {
+      const float4 a = __ldg(reinterpret_cast<const float4 *>(sp));
+      m = max(max(m, __float_as_uint(fabsf(a.x))), max(__float_as_uint(fabsf(a.y)), max(__float_as_uint(fabsf(a.z)), __float_as_uint(fabsf(a.w)))));
+    } else {
+      for (int j = 0; j < 4 && c + j < cols; j++) m = max(m, __float_as_uint(fabsf(sp[j])));
+    }
+  }
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// ... then hi = fp16(s*x), lo = fp16(s*x - hi) with s = 2^k, k = 13 - floor(log2 max|x|) (0 for an all-zero matrix
+// or non-finite data, which then propagates as it is); k goes to *kexp for the epilogue
+__global__ void f32_to_f16x2_kernel(const float *__restrict__ src, long rows, int cols, long lds, uint16_t *__restrict__ hi,
+                                    uint16_t *__restrict__ lo, int ldd, const unsigned *__restrict__ maxbits,
+                                    int *__restrict__ kexp) {
+  const unsigned mb = *maxbits;
+  int k = 13 - ((int)(mb >> 23) - 127);
+  if (mb == 0u || mb >= 0x7f000000u) k = 0;
+  k = k > 100 ? 100 : (k < -100 ? -100 : k);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *kexp = k;
+  const float sc = __uint_as_float((uint32_t)(k + 127) << 23);
+  const int c8 = (cols + 7) / 8;
+  const long n = rows * c8;
+  const bool vec = (lds & 3) == 0 && (((uintptr_t)src) & 15) == 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / c8;
+    const int c = (int)(i - r * c8) * 8;
+    const float *sp = src + r * lds + c;
+    float v[8];
+    if (vec && c + 8 <= cols) {
+      const float4 a = __ldg(reinterpret_cast<const float4 *>(sp)), b = __ldg(reinterpret_cast<const float4 *>(sp) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = c + j < cols ? sp[j] : 0.f;
+    }
+    uint32_t wh[4], wl[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float x0 = v[2 * j] * sc, x1 = v[2 * j + 1] * sc;
+      const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+      const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+      wh[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      wl[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint4 *>(hi + r * ldd + c) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+    *reinterpret_cast<uint4 *>(lo + r * ldd + c) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
   }
 }
 
@@ -449,12 +539,13 @@ __global__ void f32_to_bf16_kernel(const float *__restrict__ src, long rows, int
 }
 
 __global__ void tc_splitk_reduce_kernel(TcArgs p) {
+  const float alpha = tc_alpha(p);
   size_t n = (size_t)p.M * p.N;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int k = 0; k < p.splits; k++) s += p.ws[k * n + i];
     int r = (int)(i / p.N), c = (int)(i % p.N);
-    float v = p.alpha * s;
+    float v = alpha * s;
     if (p.bias) v += p.bias[c];
     float *dst = p.C + (size_t)r * p.ldc + c;
     if (p.beta != 0.f) v += p.beta * (*dst);
@@ -561,24 +652,26 @@ cudaError_t launch_tc_layout(cudaStream_t st, const CUtensorMap &ma, const CUten
 }
 
 // ---- bf16 path (precision 2)
-bool make_map16(CUtensorMap *map, const void *base, long rows, long cols, long ld, int box_cols, int box_rows) {
+bool make_map16(CUtensorMap *map, const void *base, long rows, long cols, long ld, int box_cols, int box_rows,
+                bool fp16 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)base, dims, strides, box, estr,
+  CUresult r = enc(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
-template <int BN, int TA, int TB>
-cudaError_t launch_tc16(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const TcArgs &p) {
-  constexpr int STAGES = BN == 256 ? 4 : BN == 128 ? 6 : 8;
-  constexpr int SMEM = STAGES * (TC_BM * TC16_BK * 2 + BN * TC16_BK * 2) + 1024;
-  auto kern = gemm_tc16_kernel<BN, TA, TB, STAGES>;
+template <int BN, int TA, int TB, int NT>
+cudaError_t launch_tc16(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &ma2,
+                        const CUtensorMap &mb2, const TcArgs &p) {
+  constexpr int STAGES = NT == 3 ? (BN == 256 ? 2 : BN == 128 ? 3 : 4) : (BN == 256 ? 4 : BN == 128 ? 6 : 8);
+  constexpr int SMEM = STAGES * (NT == 3 ? 2 : 1) * (TC_BM * TC16_BK * 2 + BN * TC16_BK * 2) + 1024;
+  auto kern = gemm_tc16_kernel<BN, TA, TB, STAGES, NT, (NT == 3 ? 0 : 1)>;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -586,15 +679,54 @@ cudaError_t launch_tc16(cudaStream_t st, const CUtensorMap &ma, const CUtensorMa
     attr = true;
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + TC_BM - 1) / TC_BM, p.splits);
-  kern<<<grid, TC_THREADS, SMEM, st>>>(ma, mb, p);
+  kern<<<grid, TC_THREADS, SMEM, st>>>(ma, mb, ma2, mb2, p);
   return cudaGetLastError();
 }
 
-template <int TA, int TB>
-cudaError_t launch_tc16_layout(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const TcArgs &p, int bn) {
-  if (bn == 256) return launch_tc16<256, TA, TB>(st, ma, mb, p);
-  if (bn == 128) return launch_tc16<128, TA, TB>(st, ma, mb, p);
-  return launch_tc16<64, TA, TB>(st, ma, mb, p);
+template <int TA, int TB, int NT>
+cudaError_t launch_tc16_layout(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &ma2,
+                               const CUtensorMap &mb2, const TcArgs &p, int bn) {
+  if (bn == 256) return launch_tc16<256, TA, TB, NT>(st, ma, mb, ma2, mb2, p);
+  if (bn == 128) return launch_tc16<128, TA, TB, NT>(st, ma, mb, ma2, mb2, p);
+  return launch_tc16<64, TA, TB, NT>(st, ma, mb, ma2, mb2, p);
+}
+
+// common tail of the two 16-bit entry points
+cudaError_t run_tc16(cudaStream_t st, int num_sms, int transA, int transB, int M, int N, int K, const CUtensorMap &ma,
+                     const CUtensorMap &mb, const CUtensorMap &ma2, const CUtensorMap &mb2, TcArgs p, int bn, int nt,
+                     size_t ws_bytes) {
+  const int kb = (K + TC16_BK - 1) / TC16_BK;
+  p.splits = 1;
+  p.kblocks_per_split = kb;
+  long tiles = (long)((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn);
+  if (tiles < num_sms && K >= 4096 && p.ws) {
+    int splits = pick_splits(tiles, kb, num_sms);
+    while (splits > 1 && (size_t)splits * M * N * sizeof(float) > ws_bytes) splits--;
+    if (splits > 1) {
+      int per = (kb + splits - 1) / splits;
+      p.kblocks_per_split = per;
+      p.splits = (kb + per - 1) / per;
+    }
+  }
+  cudaError_t e;
+  if (nt == 3) {
+    if (transA == 0 && transB == 1) e = launch_tc16_layout<0, 1, 3>(st, ma, mb, ma2, mb2, p, bn);
+    else if (transA == 0 && transB == 0) e = launch_tc16_layout<0, 0, 3>(st, ma, mb, ma2, mb2, p, bn);
+    else e = launch_tc16_layout<1, 0, 3>(st, ma, mb, ma2, mb2, p, bn);
+  } else {
+    if (transA == 0 && transB == 1) e = launch_tc16_layout<0, 1, 1>(st, ma, mb, ma2, mb2, p, bn);
+    else if (transA == 0 && transB == 0) e = launch_tc16_layout<0, 0, 1>(st, ma, mb, ma2, mb2, p, bn);
+    else e = launch_tc16_layout<1, 0, 1>(st, ma, mb, ma2, mb2, p, bn);
+  }
+  if (e != cudaSuccess) return e;
+  if (p.splits > 1) {
+    size_t n = (size_t)M * N;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 4 * num_sms) blocks = 4 * num_sms;
+    tc_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p);
+    e = cudaGetLastError();
+  }
+  return e;
 }
 
 }  // namespace
@@ -656,6 +788,7 @@ cudaError_t gemm_tc(cudaStream_t st, int num_sms, int transA, int transB, int M,
   if (!ok) return cudaErrorInvalidValue;
   TcArgs p;
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.alpha = alpha; p.beta = beta; p.ws = ws;
+  p.kexp_a = nullptr; p.kexp_b = nullptr;
   const int kb = (K + TC_BK - 1) / TC_BK;
   p.splits = 1;
   p.kblocks_per_split = kb;
@@ -712,32 +845,53 @@ cudaError_t gemm_tc16(cudaStream_t st, int num_sms, int transA, int transB, int 
   if (!ok) return cudaErrorInvalidValue;
   TcArgs p;
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.alpha = alpha; p.beta = beta; p.ws = ws;
-  const int kb = (K + TC16_BK - 1) / TC16_BK;
-  p.splits = 1;
-  p.kblocks_per_split = kb;
-  long tiles = (long)((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn);
-  if (tiles < num_sms && K >= 4096 && ws) {
-    int splits = pick_splits(tiles, kb, num_sms);
-    while (splits > 1 && (size_t)splits * M * N * sizeof(float) > ws_bytes) splits--;
-    if (splits > 1) {
-      int per = (kb + splits - 1) / splits;
-      p.kblocks_per_split = per;
-      p.splits = (kb + per - 1) / per;
-    }
-  }
-  cudaError_t e;
-  if (transA == 0 && transB == 1) e = launch_tc16_layout<0, 1>(st, ma, mb, p, bn);
-  else if (transA == 0 && transB == 0) e = launch_tc16_layout<0, 0>(st, ma, mb, p, bn);
-  else e = launch_tc16_layout<1, 0>(st, ma, mb, p, bn);
+  p.kexp_a = nullptr; p.kexp_b = nullptr;
+  return run_tc16(st, num_sms, transA, transB, M, N, K, ma, mb, ma, mb, p, bn, 1, ws_bytes);
+}
+
+// ---- fp16x3 (precision 0 on the 16-bit pipe)
+size_t f16x2_plane_bytes(long rows, int cols) { return (size_t)rows * (size_t)((cols + 7) & ~7) * 2; }
+
+// src [rows x cols] (lds) -> planes hi / lo (dense, ld = cols rounded up to 8); scratch: one unsigned, kexp: one int (device)
+cudaError_t convert_f16x2(cudaStream_t st, int num_sms, const float *src, long rows, int cols, long lds, void *hi, void *lo,
+                          unsigned *scratch_max, int *kexp) {
+  cudaError_t e = cudaMemsetAsync(scratch_max, 0, sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  if (p.splits > 1) {
-    size_t n = (size_t)M * N;
-    int blocks = (int)((n + 255) / 256);
-    if (blocks > 4 * num_sms) blocks = 4 * num_sms;
-    tc_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p);
-    e = cudaGetLastError();
+  if (rows <= 0 || cols <= 0) return cudaMemsetAsync(kexp, 0, sizeof(int), st);
+  const int ldd = (cols + 7) & ~7;
+  long n = rows * ((cols + 3) / 4);
+  long blocks = (n + 255) / 256;
+  if (blocks > 8L * num_sms) blocks = 8L * num_sms;
+  absmax_kernel<<<(int)blocks, 256, 0, st>>>(src, rows, cols, lds, scratch_max);
+  n = rows * (ldd / 8);
+  blocks = (n + 255) / 256;
+  if (blocks > 16L * num_sms) blocks = 16L * num_sms;
+  f32_to_f16x2_kernel<<<(int)blocks, 256, 0, st>>>(src, rows, cols, lds, (uint16_t *)hi, (uint16_t *)lo, ldd, scratch_max, kexp);
+  return cudaGetLastError();
+}
+
+// A / B: views of converted matrices AS STORED (a view may be a sub-block of a larger converted matrix: pointer
+// offsets into both planes, ld of the whole)
+cudaError_t gemm_tc16x3(cudaStream_t st, int num_sms, int transA, int transB, int M, int N, int K, float alpha,
+                        const F16View &A, const F16View &B, float beta, float *C, int ldc, const float *bias, float *ws,
+                        size_t ws_bytes) {
+  if (transA && transB) return cudaErrorInvalidValue;
+  if ((A.ld & 7) || (B.ld & 7) || (((uintptr_t)A.hi | (uintptr_t)A.lo | (uintptr_t)B.hi | (uintptr_t)B.lo) & 15))
+    return cudaErrorInvalidValue;
+  const int bn = pick_bn(M, N, K);
+  CUtensorMap ma, mb, ma2, mb2;
+  bool ok = true;
+  for (int pl = 0; pl < 2 && ok; pl++) {
+    const void *a = pl ? A.lo : A.hi, *b = pl ? B.lo : B.hi;
+    CUtensorMap *pa = pl ? &ma2 : &ma, *pb = pl ? &mb2 : &mb;
+    ok = transA == 0 ? make_map16(pa, a, M, K, A.ld, TC16_BK, TC_BM, true) : make_map16(pa, a, K, M, A.ld, 64, TC16_BK, true);
+    ok = ok && (transB == 1 ? make_map16(pb, b, N, K, B.ld, TC16_BK, bn, true) : make_map16(pb, b, K, N, B.ld, 64, TC16_BK, true));
   }
-  return e;
+  if (!ok) return cudaErrorInvalidValue;
+  TcArgs p;
+  p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.alpha = alpha; p.beta = beta; p.ws = ws;
+  p.kexp_a = A.kexp; p.kexp_b = B.kexp;
+  return run_tc16(st, num_sms, transA, transB, M, N, K, ma, mb, ma2, mb2, p, bn, 3, ws_bytes);
 }
 
 }  // namespace eb

@@ -28,6 +28,20 @@ cudaError_t gemm_tc16(cudaStream_t st, int num_sms, int transA, int transB, int 
                       const void *A16, const void *B16, float beta, float *C, int ldc, const float *bias, float *ws,
                       size_t ws_bytes);
 
+// fp32-faithful arithmetic on the 16-bit tensor pipe ("fp16x3"): operands as two fp16 planes of the power-of-two
+// scaled matrix (22 mantissa bits), three kind::f16 MMAs per k-slice
+struct F16View {
+  const void *hi, *lo;   // planes of the matrix as stored (row-major), both with leading dimension ld (halfs)
+  int ld;
+  const int *kexp;       // device: the scale exponent the conversion chose
+};
+size_t f16x2_plane_bytes(long rows, int cols);
+cudaError_t convert_f16x2(cudaStream_t st, int num_sms, const float *src, long rows, int cols, long lds, void *hi, void *lo,
+                          unsigned *scratch_max, int *kexp);
+cudaError_t gemm_tc16x3(cudaStream_t st, int num_sms, int transA, int transB, int M, int N, int K, float alpha,
+                        const F16View &A, const F16View &B, float beta, float *C, int ldc, const float *bias, float *ws,
+                        size_t ws_bytes);
+
 // lstm.cu -- persistent recurrent kernels (both directions in one cooperative launch)
 struct LstmDirParams {
   const float *wm;  // [4C x C] recurrent weights, row blocks g,i,f,o

@@ -581,15 +581,17 @@ int lstm_debug_timing(long long *out32, int reset) {
 }
 
 // Engine per pass, read at every plan (not cached: the tests switch engines inside one process).
-//   EESEN_B200_LSTM_ENGINE unset : forward on tcgen05 (lstm_tc.cu) where the shape allows, backward on the warp-level
-//                                  kernels below (measured on C2: tcgen05 forward 7.4 ms vs 10.2 ms per step; the
-//                                  tcgen05 backward is correct but its reduce-scatter exchange is slower, 13 vs 10.8 ms)
-//   "legacy" : both passes here;  "tc" : both passes on tcgen05
+//   EESEN_B200_LSTM_ENGINE unset or "tc" : tcgen05 kernels (lstm_tc.cu) where the shape allows (cells % 64 == 0,
+//                                  <= 384), else the warp-level kernels below.  Measured on C2 (ms per step, 4 layers):
+//                                  forward 6.1 vs 10.2, backward 10.7 vs 10.8 -- and the tcgen05 grids occupy 80 SMs
+//                                  instead of 128, which leaves room for the weight-gradient GEMMs of the side stream
+//                                  (whole step 23.3 ms with both passes on tcgen05, 25.5 ms with the warp-level backward)
+//   "legacy"     : both passes here;  "tcfwd" : tcgen05 forward + warp-level backward
 static int engine_for_pass(int pass) {
   const char *e = getenv("EESEN_B200_LSTM_ENGINE");
   if (e && strcmp(e, "legacy") == 0) return 0;
-  if (e && strcmp(e, "tc") == 0) return 1;
-  return pass == 0 ? 1 : 0;
+  if (e && strcmp(e, "tcfwd") == 0) return pass == 0 ? 1 : 0;
+  return 1;
 }
 
 LstmPlan lstm_plan(int S, int C, int num_sms, size_t max_smem, int ndir, int pass) {

@@ -280,6 +280,19 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
     const int c8n = C >> 3;                                // 8-cell chunks per utterance row
     const int quad = warp & 3, uh = warp >> 2;             // epilogue: TMEM lane quadrant (= gate), utterance half
     const uint64_t dBt = umma_desc(smem_u32(Bt), 16, 1024, 2);
+    // exchange chunks of this thread (fixed for the whole sequence)
+    constexpr int MAXT = 3;                                // 16 * (C/8) / 256 <= 3 for C <= 384
+    uint4 q[MAXT][2];
+    size_t xoff[MAXT];
+    bool live[MAXT];
+#pragma unroll
+    for (int i = 0; i < MAXT; i++) {
+      const int v = tid + i * TCL_WORKERS;
+      const int u = v / c8n, c8 = v - u * c8n;
+      live[i] = v < TCL_UG * c8n && s0 + group * TCL_UG + u < s1;
+      xoff[i] = ((size_t)u * C + c8 * 8) / 4;
+      q[i][0] = make_uint4(0u, 0u, 0u, 0u); q[i][1] = q[i][0];
+    }
 
     TC_ACC_DECL();
     for (int step = 0; step < T; step++) {
@@ -293,21 +306,9 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
         const uint4 *xr = reinterpret_cast<const uint4 *>(
             xbuf + ((size_t)(((step - 1) & 1) * ndir + dir) * groups + group) * TCL_UG * C);
         const uint32_t want = (uint32_t)(((step - 1) >> 1) & 1) << 16;   // tag bit of the data produced at step-1
-        // every thread owns up to 3 chunks (utterance u, 8 cells): ALL their loads go out before the first check
-        // (a chunk-after-chunk loop would serialise one L2 round trip per chunk), then whatever is still missing
-        // is polled again
-        constexpr int MAXT = 3;                            // 16 * (C/8) / 256 <= 3 for C <= 384
-        uint4 q[MAXT][2];
-        const uint4 *src[MAXT];
-        bool live[MAXT];
-#pragma unroll
-        for (int i = 0; i < MAXT; i++) {
-          const int v = tid + i * TCL_WORKERS;
-          const int u = v / c8n, c8 = v - u * c8n;
-          live[i] = v < TCL_UG * c8n && s0 + group * TCL_UG + u < s1;
-          src[i] = xr + ((size_t)u * C + c8 * 8) / 4;
-          if (live[i]) { q[i][0] = ld_word4(src[i]); q[i][1] = ld_word4(src[i] + 1); }
-        }
+        // every thread owns up to 3 chunks (utterance u, 8 cells).  Their first loads went out at the end of the
+        // previous step, right behind the publish and in front of the saved-state stores (the words need a round trip
+        // through L2 anyway); whatever has not arrived by now is polled again
 #pragma unroll
         for (int i = 0; i < MAXT; i++) {
           const int v = tid + i * TCL_WORKERS;
@@ -317,7 +318,7 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
           if (live[i]) {
             while (((((q[i][0].x ^ want) | (q[i][0].y ^ want) | (q[i][0].z ^ want) | (q[i][0].w ^ want) |
                       (q[i][1].x ^ want) | (q[i][1].y ^ want) | (q[i][1].z ^ want) | (q[i][1].w ^ want)) & 0x10000u)) != 0u) {
-              q[i][0] = ld_word4(src[i]); q[i][1] = ld_word4(src[i] + 1);
+              q[i][0] = ld_word4(xr + xoff[i]); q[i][1] = ld_word4(xr + xoff[i] + 1);
             }
             hi4 = make_uint4(__byte_perm(q[i][0].x, q[i][0].y, 0x5410), __byte_perm(q[i][0].z, q[i][0].w, 0x5410),
                              __byte_perm(q[i][1].x, q[i][1].y, 0x5410), __byte_perm(q[i][1].z, q[i][1].w, 0x5410));
@@ -409,6 +410,12 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
           }
           __stcs(a.out + ((size_t)t * S + uidx[e]) * a.ldo + (size_t)dir * C + cell, sm[e]);
         }
+      }
+      if (step + 1 < T) {   // first poll of the words the group is publishing right now (consumed at the next step)
+        const uint4 *xn = reinterpret_cast<const uint4 *>(xbuf + ((size_t)((step & 1) * ndir + dir) * groups + group) * TCL_UG * C);
+#pragma unroll
+        for (int i = 0; i < MAXT; i++)
+          if (live[i]) { q[i][0] = ld_word4(xn + xoff[i]); q[i][1] = ld_word4(xn + xoff[i] + 1); }
       }
       TC_TICK(0, 3);
 #pragma unroll

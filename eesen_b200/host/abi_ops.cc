@@ -59,6 +59,8 @@ int eesen_b200_create(eesen_b200_ctx **out, int device) {
   {
     const char *ov = getenv("EESEN_B200_OVERLAP");
     ctx->overlap = (ov && ov[0] == '0') ? 0 : 1;
+    const char *fx = getenv("EESEN_B200_GEMM_FP32X3");
+    ctx->f16x3 = (fx && std::string(fx) == "tf32") ? 0 : 1;
   }
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // lo = numerically greatest = lowest priority
@@ -77,7 +79,9 @@ void eesen_b200_destroy(eesen_b200_ctx *ctx) {
   cudaSetDevice(ctx->device);
   ctx->join_side();
   cudaStreamSynchronize(ctx->stream);
-  eesen_b200_ctx::Buf *bufs[] = {&ctx->decode_ws, &ctx->gemm_ws_side, &ctx->bf16_a_side, &ctx->bf16_b_side,&ctx->gemm_ws, &ctx->lstm_pbuf, &ctx->lstm_gsum, &ctx->lstm_flags,
+  for (int i = 0; i < eesen_b200_ctx::kF16Slots; i++)
+    if (ctx->f16_slots[i].planes.p) cudaFree(ctx->f16_slots[i].planes.p);
+  eesen_b200_ctx::Buf *bufs[] = {&ctx->f16_meta, &ctx->f16_tmp[0], &ctx->f16_tmp[1], &ctx->f16_tmp[2], &ctx->f16_tmp[3], &ctx->decode_ws, &ctx->gemm_ws_side, &ctx->bf16_a_side, &ctx->bf16_b_side,&ctx->gemm_ws, &ctx->lstm_pbuf, &ctx->lstm_gsum, &ctx->lstm_flags,
                                  &ctx->ctc_ws, &ctx->colsum_ws, &ctx->seg_buf, &ctx->flag_buf, &ctx->bf16_a, &ctx->bf16_b};
   for (auto *b : bufs)
     if (b->p) cudaFree(b->p);
@@ -114,6 +118,69 @@ void *eesen_b200_stream(eesen_b200_ctx *ctx) { return (void *)ctx->stream; }
 int eesen_b200_sm_count(const eesen_b200_ctx *ctx) { return ctx->num_sms; }
 long eesen_b200_launch_count(const eesen_b200_ctx *ctx) { return ctx->launches; }
 
+// ---- fp16x3 operand planes --------------------------------------------------------------------------------------
+static int f16_meta(eesen_b200_ctx *ctx, int idx, unsigned **mx, int **kexp) {
+  void *m = nullptr;
+  int rc = ctx->reserve(ctx->f16_meta, 4096, &m);
+  if (rc) return rc;
+  *mx = (unsigned *)m + 2 * idx;
+  *kexp = (int *)m + 2 * idx + 1;
+  return 0;
+}
+
+// convert the whole matrix [rows x cols] (ld) on `stream` and remember it: later products find sub-blocks by address
+static int f16_register(eesen_b200_ctx *ctx, const float *base, long rows, int cols, int ld) {
+  if (!ctx->f16x3 || ctx->gemm_prec != 0 || ctx->gemm_engine != 0 || !base || rows <= 0 || cols <= 0) return 0;
+  if (ctx->f16_used >= eesen_b200_ctx::kF16Slots) return 0;   // (falls back to per-call conversion)
+  eesen_b200_ctx::F16Entry &e = ctx->f16_slots[ctx->f16_used];
+  const size_t pb = eb::f16x2_plane_bytes(rows, cols);
+  void *pl = nullptr;
+  int rc = ctx->reserve(e.planes, 2 * pb + 256, &pl);
+  if (rc) return rc;
+  unsigned *mx; int *kx;
+  if ((rc = f16_meta(ctx, ctx->f16_used, &mx, &kx))) return rc;
+  e.base = base; e.rows = rows; e.cols = cols; e.ld = ld; e.ldd = (cols + 7) & ~7;
+  e.view.hi = pl; e.view.lo = (char *)pl + ((pb + 255) & ~(size_t)255); e.view.ld = e.ldd; e.view.kexp = kx;
+  int pe = ctx->prof_begin(eesen_b200_ctx::kGemm);
+  cudaError_t ce = eb::convert_f16x2(ctx->stream, ctx->num_sms, base, rows, cols, ld, (void *)e.view.hi, (void *)e.view.lo, mx, kx);
+  ctx->prof_end(pe);
+  ctx->launches += 2;
+  if ((rc = ctx->check(ce, "convert_f16x2"))) return rc;
+  ctx->f16_used++;
+  return 0;
+}
+
+// a [r x c] block at P with leading dimension ld: inside a registered matrix?
+static bool f16_lookup(eesen_b200_ctx *ctx, const float *P, long r, int c, int ld, eb::F16View *out) {
+  for (int i = 0; i < ctx->f16_used; i++) {
+    const eesen_b200_ctx::F16Entry &e = ctx->f16_slots[i];
+    if (e.ld != ld || P < e.base) continue;
+    const long off = (long)(P - e.base), ro = off / ld, co = off % ld;
+    if (ro + r > e.rows || co + c > e.cols || (co & 7)) continue;
+    *out = e.view;
+    out->hi = (const char *)e.view.hi + ((size_t)ro * e.ldd + co) * 2;
+    out->lo = (const char *)e.view.lo + ((size_t)ro * e.ldd + co) * 2;
+    return true;
+  }
+  return false;
+}
+
+// view of an operand: registered, or converted on the spot into the stream's temporary planes (which = 0 A, 1 B)
+static int f16_operand(eesen_b200_ctx *ctx, bool on_side, int which, const float *P, long r, int c, int ld, eb::F16View *out) {
+  if (f16_lookup(ctx, P, r, c, ld, out)) return 0;
+  eesen_b200_ctx::Buf &b = ctx->f16_tmp[(on_side ? 2 : 0) + which];
+  const size_t pb = eb::f16x2_plane_bytes(r, c);
+  void *pl = nullptr;
+  int rc = ctx->reserve(b, 2 * pb + 256, &pl);
+  if (rc) return rc;
+  unsigned *mx; int *kx;
+  if ((rc = f16_meta(ctx, eesen_b200_ctx::kF16Slots + (on_side ? 2 : 0) + which, &mx, &kx))) return rc;
+  out->hi = pl; out->lo = (char *)pl + ((pb + 255) & ~(size_t)255); out->ld = (c + 7) & ~7; out->kexp = kx;
+  ctx->launches += 2;
+  return ctx->check(eb::convert_f16x2(on_side ? ctx->side : ctx->stream, ctx->num_sms, P, r, c, ld, (void *)out->hi,
+                                      (void *)out->lo, mx, kx), "convert_f16x2");
+}
+
 static int do_gemm(eesen_b200_ctx *ctx, int ta, int tb, int M, int N, int K, float alpha, const float *A, int lda,
                    long sA, const float *B, int ldb, long sB, float beta, float *C, int ldc, long sC,
                    const float *bias, long sBias, int batch, bool on_side = false) {
@@ -124,6 +191,31 @@ static int do_gemm(eesen_b200_ctx *ctx, int ta, int tb, int M, int N, int K, flo
   // tensor-core engine: tcgen05/TMEM/TMA (gemm_tc.cu) for every arithmetic mode -- kind::tf32 for fp32x3 / tf32,
   // kind::f16 on bf16 copies of the operands for bf16 (BASELINE config 4); the warp-level mma.sync kernel
   // (gemm.cu) is kept for EESEN_B200_GEMM_ENGINE=legacy (A/B measurements) and matrices TMA cannot address
+  if (ctx->gemm_engine == 0 && ctx->gemm_prec == 0 && ctx->f16x3 && !(ta && tb) && M > 0 && N > 0 && K > 0 &&
+      eb::gemm_tc_supported(ta, tb, M, N, K, A, 4, B, 4, 0)) {
+    // fp32-faithful arithmetic on the 16-bit tensor pipe: two fp16 planes per operand (registered whole-matrix
+    // conversions where the caller made them, else converted here), three kind::f16 MMAs per k-slice
+    size_t need_tc = eb::gemm_tc_workspace_bytes(M, N, K, ctx->num_sms);
+    if (need_tc) {
+      int rc = ctx->reserve(gemm_ws, need_tc, &ws);
+      if (rc) return rc;
+    }
+    const long ar = ta ? K : M, br = tb ? N : K;
+    const int ac = ta ? M : K, bc = tb ? K : N;
+    for (int b = 0; b < batch; b++) {
+      int pe = ctx->prof_begin(eesen_b200_ctx::kGemm, on_side);
+      eb::F16View va, vb;
+      int rc;
+      if ((rc = f16_operand(ctx, on_side, 0, A + b * sA, ar, ac, lda, &va))) return rc;
+      if ((rc = f16_operand(ctx, on_side, 1, B + b * sB, br, bc, ldb, &vb))) return rc;
+      cudaError_t e = eb::gemm_tc16x3(st, ctx->num_sms, ta, tb, M, N, K, alpha, va, vb, beta, C + b * sC, ldc,
+                                      bias ? bias + b * sBias : nullptr, (float *)ws, ws ? gemm_ws.bytes : 0);
+      ctx->prof_end(pe);
+      ctx->launches += 1;
+      if ((rc = ctx->check(e, "gemm_tc16x3"))) return rc;
+    }
+    return 0;
+  }
   if (ctx->gemm_engine == 0 && ctx->gemm_prec == 2 && !(ta && tb) && M > 0 && N > 0 && K > 0 &&
       eb::gemm_tc_supported(ta, tb, M, N, K, A, 4, B, 4, 0)) {
     size_t need_tc = eb::gemm_tc_workspace_bytes(M, N, K, ctx->num_sms);
@@ -235,6 +327,12 @@ static int lstm_forward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I,
   const int N = T * S, ldg = ndir * 4 * C;
   const int ldwx = p->ldwx > 0 ? p->ldwx : I, ldwm = p->ldwm > 0 ? p->ldwm : C;
   if (ldwx < I || ldwm < C) return ctx->fail(EESEN_B200_EINVAL, "ldwx / ldwm smaller than the matrix width");
+  // fp16x3: the layer input feeds the products of both directions -- one conversion
+  ctx->join_side();
+  ctx->f16_clear();
+  if ((rc = f16_register(ctx, x, N, I, ldx))) return rc;
+  for (int d = 0; d < ndir; d++)
+    if ((rc = f16_register(ctx, p->wx[d], 4 * C, I, ldwx))) return rc;
   if (ndir == 2 && sW > 0 && (sW & 3) == 0 && sB > 0) {
     rc = do_gemm(ctx, 0, 1, N, 4 * C, I, 1.f, x, ldx, 0, p->wx[0], ldwx, sW, 0.f, gates, ldg, 4 * C, p->bias[0], sB, 2);
     if (rc) return rc;
@@ -364,6 +462,17 @@ static int lstm_backward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I
     ctx->prof_end(pe);
     if ((rc = ctx->check(le, "lstm_reduce_gsum"))) return rc;
   }
+  // fp16x3: d(gates), the layer input, m and Wx each feed several of the products below -- one conversion each.
+  // The planes of the previous layer call may still be read by its weight-gradient products on the side stream:
+  // they have had the whole recurrent kernel above to finish, now they are waited for.
+  ctx->join_side();
+  ctx->f16_clear();
+  if ((rc = f16_register(ctx, dgates, N, ndir * 4 * C, ldg))) return rc;
+  if ((rc = f16_register(ctx, x, N, I, ldx))) return rc;
+  if (T > 1 && (rc = f16_register(ctx, out, N, ndir * C, ldo))) return rc;
+  if (dx)
+    for (int d = 0; d < ndir; d++)
+      if ((rc = f16_register(ctx, p->wx[d], 4 * C, I, ldwx))) return rc;
   // dx = DG_fw * Wx_fw + DG_bw * Wx_bw   (:502 beta=0, :593 beta=1)
   if (dx) {
     for (int d = 0; d < ndir; d++) {

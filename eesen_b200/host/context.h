@@ -30,6 +30,24 @@ struct eesen_b200_ctx {
   Buf gemm_ws_side, bf16_a_side, bf16_b_side;   // the side stream's own scratch
   Buf decode_ws;
 
+  // fp16x3 arithmetic (gemm_prec 0 on the 16-bit tensor pipe): converted operand planes.  Whole matrices that feed
+  // several products of one layer call (d(gates), the layer input, m, Wx) are converted ONCE and registered here;
+  // do_gemm finds sub-blocks of them by address.  Entries live until the next f16_clear().
+  struct F16Entry {
+    const float *base = nullptr;
+    long rows = 0;
+    int cols = 0, ld = 0, ldd = 0;
+    Buf planes;          // hi plane, then lo plane
+    eb::F16View view;
+  };
+  enum { kF16Slots = 6 };
+  F16Entry f16_slots[kF16Slots];
+  int f16_used = 0;
+  Buf f16_meta;          // per slot + per temp operand: {unsigned max scratch, int kexp}
+  Buf f16_tmp[4];        // ad-hoc operands: [0] A / [1] B on `stream`, [2] A / [3] B on the side stream
+  int f16x3 = 1;         // EESEN_B200_GEMM_FP32X3=tf32 : keep the kind::tf32 3-term split (A/B measurements)
+  void f16_clear() { f16_used = 0; }
+
   // Side stream (lower priority): work nothing on the critical path waits for -- the weight-gradient products of
   // layer l and the all-reduce of its gradient block run here while `stream` carries dX and the recurrent backward
   // of layer l-1 (the tcgen05 recurrent kernels occupy 80 of the 148 SMs).  fork_side(): side waits for everything

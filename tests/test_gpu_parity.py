@@ -146,13 +146,13 @@ def test_ctc_eval_vs_oracle(ctx, seed, S, T, K, maxlab):
 
 @pytest.mark.parametrize("S,T,I,C", [(4, 9, 8, 16), (2, 30, 40, 128), (20, 17, 40, 64), (16, 40, 40, 320), (3, 5, 64, 24),
                                      (100, 7, 40, 320), (1, 1, 40, 64)])   # 100 utts: two utterance chunks (64 + 36)
-@pytest.mark.parametrize("rec", ["fp32x3", "tf32", "legacy-engine", "tc-engine"])
+@pytest.mark.parametrize("rec", ["fp32x3", "tf32", "legacy-engine", "tcfwd-engine"])
 def test_bilstm_layer_vs_oracle(ctx, S, T, I, C, rec, monkeypatch):
     """Level-1 BiLSTM forward/backward of one layer against the fp64 oracle, ragged lengths.  Shapes with
     cells % 64 == 0 run on the tcgen05 recurrent kernels (lstm_tc.cu), the others -- and every shape under
     EESEN_B200_LSTM_ENGINE=legacy -- on the warp-level kernels (lstm.cu): same tolerances for both."""
     torch = torch_()
-    if rec in ("legacy-engine", "tc-engine"):   # default: tcgen05 forward + warp-level backward (lstm.cu:engine_for_pass)
+    if rec in ("legacy-engine", "tcfwd-engine"):   # default: tcgen05 for both passes (lstm.cu:engine_for_pass)
         if C % 64 != 0:
             pytest.skip("only the warp-level kernels take this shape")
         monkeypatch.setenv("EESEN_B200_LSTM_ENGINE", rec.split("-")[0])
