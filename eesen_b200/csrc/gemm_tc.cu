@@ -451,6 +451,129 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
 }
 
+// ---- CTA-pair variant of the kernel above (cta_group::2): the two CTAs of a (1,2,1) cluster own two adjacent
+// 128-row M tiles and ONE BN-wide N tile.  Each stages its own A rows and only HALF of the B tile (BN/2 of the N
+// rows); the pair's tensor cores run one M = 256, N = BN MMA per k-slice, issued by the even CTA.  Per CTA and
+// k-block that is (128 + BN/2) x 64 operand elements instead of (128 + BN): at BN = 256 a third less L2 -> SM traffic
+// and a third fewer shared-memory operand reads per MMA -- the two things the single-CTA kernel is bound by -- and the
+// stage shrinks from 96 to 64 KB (fp16x3), so three stages fit instead of two.
+template <int BN, int TA, int TB, int STAGES, int NT, int FMT>
+__global__ void __cluster_dims__(1, 2, 1) __launch_bounds__(TC_THREADS, 1)
+gemm_tc16_2sm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, TcArgs p) {
+  constexpr int BNH = BN / 2;                              // N rows of the pair's B tile staged by each CTA
+  constexpr int A_BYTES = TC_BM * TC16_BK * 2;
+  constexpr int B_BYTES = BNH * TC16_BK * 2;
+  constexpr int STAGE_BYTES = (NT == 3 ? 2 : 1) * (A_BYTES + B_BYTES);   // [A hi][B hi]([A lo][B lo])
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_sm;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                 // 0: leader (issues the MMAs), 1: peer
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int nh0 = n0 + (int)rank * BNH;                    // this CTA's half of the B tile
+  const int split = blockIdx.z;
+  const int kb_total = (p.K + TC16_BK - 1) / TC16_BK;
+  const int kb_beg = split * p.kblocks_per_split;
+  const int kb_end = min(kb_total, kb_beg + p.kblocks_per_split);
+  const int nkb = kb_end - kb_beg;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full_bar[s], 1);      // used in the leader only: its own arrive.expect_tx for the bytes of BOTH CTAs
+      mbar_init(&empty_bar[s], 1);     // multicast commit of the leader
+    }
+    mbar_init(&accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  cluster_sync_all();                  // the barriers of both CTAs exist before anything remote touches them
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_sm)),
+                 "n"(BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = tmem_base_sm;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % STAGES;
+        if (i >= STAGES) mbar_wait(&empty_bar[s], ((i / STAGES) - 1) & 1);
+        uint8_t *sa = smem + (size_t)s * STAGE_BYTES;
+        uint8_t *sb = sa + A_BYTES;
+        if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+        const int k0 = (kb_beg + i) * TC16_BK;
+#pragma unroll
+        for (int pl = 0; pl < (NT == 3 ? 2 : 1); pl++) {              // plane 0: hi (or the bf16 copy), plane 1: lo
+          const CUtensorMap *ma = pl ? &mapA2 : &mapA, *mb = pl ? &mapB2 : &mapB;
+          uint8_t *pa = sa + pl * (A_BYTES + B_BYTES), *pb = sb + pl * (A_BYTES + B_BYTES);
+          if (TA == 0) {
+            tma_load_2d_2sm(pa, ma, k0, m0, &full_bar[s]);          // box {64 k, 128 m}
+          } else {
+#pragma unroll
+            for (int g = 0; g < TC_BM / 64; g++)                      // box {64 m, 64 k} per 64-wide M group
+              tma_load_2d_2sm(pa + g * (TC16_BK * 128), ma, m0 + g * 64, k0, &full_bar[s]);
+          }
+          if (TB == 1) {
+            tma_load_2d_2sm(pb, mb, k0, nh0, &full_bar[s]);         // box {64 k, BN/2 n}
+          } else {
+#pragma unroll
+            for (int g = 0; g < BNH / 64; g++)
+              tma_load_2d_2sm(pb + g * (TC16_BK * 128), mb, nh0 + g * 64, k0, &full_bar[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // instruction descriptor as in the single-CTA kernel, M = 256 over the pair
+      const uint32_t idesc = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) | ((uint32_t)(TA ? 1 : 0) << 15) |
+                             ((uint32_t)(TB ? 0 : 1) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      for (int i = 0; i < nkb; i++) {
+        const int s = i % STAGES;
+        mbar_wait(&full_bar[s], (i / STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC16_BK / 16; k++) {
+          const uint32_t a_off = TA == 0 ? k * 32 : k * 2048;
+          const uint32_t b_off = TB == 1 ? k * 32 : k * 2048;
+          const uint32_t a_lbo = TA == 0 ? 16 : TC16_BK * 128, b_lbo = TB == 1 ? 16 : TC16_BK * 128;
+          const uint64_t ad = umma_desc(sa + a_off, a_lbo, 1024, 2);
+          const uint64_t bd = umma_desc(sb + b_off, b_lbo, 1024, 2);
+          if (NT == 3) {
+            const uint64_t al = umma_desc(sa + A_BYTES + B_BYTES + a_off, a_lbo, 1024, 2);
+            const uint64_t bl = umma_desc(sb + A_BYTES + B_BYTES + b_off, b_lbo, 1024, 2);
+            umma_f16_2sm(tmem_base, al, bd, idesc, (i | k) != 0);   // small terms first
+            umma_f16_2sm(tmem_base, ad, bl, idesc, 1);
+            umma_f16_2sm(tmem_base, ad, bd, idesc, 1);
+          } else {
+            umma_f16_2sm(tmem_base, ad, bd, idesc, (i | k) != 0);
+          }
+        }
+        umma_commit_2sm(&empty_bar[s]);
+      }
+      umma_commit_2sm(&accum_bar);
+    }
+  } else {
+    tc_epilogue<BN>(smem, &accum_bar, tmem_base, p, warp, lane, m0, n0, split);
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  cluster_sync_all();                  // neither CTA leaves (or frees TMEM) while the other may still use the pair's state
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+
 // fp16x3 operand preparation: max|x| of a matrix (bits of a non-negative float order like unsigned integers) ...
 __global__ void absmax_kernel(const float *__restrict__ src, long rows, int cols, long lds, unsigned *__restrict__ out) {
   const int c4 = (cols + 3) / 4;
@@ -683,6 +806,35 @@ cudaError_t launch_tc16(cudaStream_t st, const CUtensorMap &ma, const CUtensorMa
   return cudaGetLastError();
 }
 
+template <int BN, int TA, int TB, int NT>
+cudaError_t launch_tc16_2sm(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &ma2,
+                            const CUtensorMap &mb2, const TcArgs &p) {
+  constexpr int STAGES = (NT == 3 ? 1 : 2) * (BN == 256 ? 3 : 4);
+  constexpr int SMEM = STAGES * (NT == 3 ? 2 : 1) * (TC_BM * TC16_BK * 2 + (BN / 2) * TC16_BK * 2) + 1024;
+  auto kern = gemm_tc16_2sm_kernel<BN, TA, TB, STAGES, NT, (NT == 3 ? 0 : 1)>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const int mt = (p.M + TC_BM - 1) / TC_BM;
+  dim3 grid((p.N + BN - 1) / BN, (mt + 1) & ~1, p.splits);   // CTA pairs along M (cluster dims (1,2,1) are compiled in)
+  kern<<<grid, TC_THREADS, SMEM, st>>>(ma, mb, ma2, mb2, p);
+  return cudaGetLastError();
+}
+
+// CTA-pair kernel: 128- or 256-wide tiles and at least one full pair of M tiles.  EESEN_B200_GEMM_2SM=0 keeps the
+// single-CTA kernel (A/B measurements).
+bool use_2sm(int M, int bn) {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("EESEN_B200_GEMM_2SM");
+    on = (e && e[0] == '1') ? 1 : 0;   // (opt-in until it is validated on the device)
+  }
+  return on && bn >= 128 && M > TC_BM;
+}
+
 template <int TA, int TB, int NT>
 cudaError_t launch_tc16_layout(cudaStream_t st, const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &ma2,
                                const CUtensorMap &mb2, const TcArgs &p, int bn) {
@@ -694,7 +846,7 @@ cudaError_t launch_tc16_layout(cudaStream_t st, const CUtensorMap &ma, const CUt
 // common tail of the two 16-bit entry points
 cudaError_t run_tc16(cudaStream_t st, int num_sms, int transA, int transB, int M, int N, int K, const CUtensorMap &ma,
                      const CUtensorMap &mb, const CUtensorMap &ma2, const CUtensorMap &mb2, TcArgs p, int bn, int nt,
-                     size_t ws_bytes) {
+                     size_t ws_bytes, bool two_sm) {
   const int kb = (K + TC16_BK - 1) / TC16_BK;
   p.splits = 1;
   p.kblocks_per_split = kb;
@@ -709,7 +861,22 @@ cudaError_t run_tc16(cudaStream_t st, int num_sms, int transA, int transB, int M
     }
   }
   cudaError_t e;
-  if (nt == 3) {
+  if (two_sm) {
+#define EB_2SM(BNV)                                                                                   \
+    do {                                                                                              \
+      if (nt == 3) {                                                                                  \
+        if (transA == 0 && transB == 1) e = launch_tc16_2sm<BNV, 0, 1, 3>(st, ma, mb, ma2, mb2, p);   \
+        else if (transA == 0 && transB == 0) e = launch_tc16_2sm<BNV, 0, 0, 3>(st, ma, mb, ma2, mb2, p); \
+        else e = launch_tc16_2sm<BNV, 1, 0, 3>(st, ma, mb, ma2, mb2, p);                              \
+      } else {                                                                                        \
+        if (transA == 0 && transB == 1) e = launch_tc16_2sm<BNV, 0, 1, 1>(st, ma, mb, ma2, mb2, p);   \
+        else if (transA == 0 && transB == 0) e = launch_tc16_2sm<BNV, 0, 0, 1>(st, ma, mb, ma2, mb2, p); \
+        else e = launch_tc16_2sm<BNV, 1, 0, 1>(st, ma, mb, ma2, mb2, p);                              \
+      }                                                                                               \
+    } while (0)
+    if (bn == 256) EB_2SM(256); else EB_2SM(128);
+#undef EB_2SM
+  } else if (nt == 3) {
     if (transA == 0 && transB == 1) e = launch_tc16_layout<0, 1, 3>(st, ma, mb, ma2, mb2, p, bn);
     else if (transA == 0 && transB == 0) e = launch_tc16_layout<0, 0, 3>(st, ma, mb, ma2, mb2, p, bn);
     else e = launch_tc16_layout<1, 0, 3>(st, ma, mb, ma2, mb2, p, bn);
@@ -841,12 +1008,13 @@ cudaError_t gemm_tc16(cudaStream_t st, int num_sms, int transA, int transB, int 
   CUtensorMap ma, mb;
   bool ok;
   ok = transA == 0 ? make_map16(&ma, A16, M, K, (K + 7) & ~7, TC16_BK, TC_BM) : make_map16(&ma, A16, K, M, (M + 7) & ~7, 64, TC16_BK);
-  ok = ok && (transB == 1 ? make_map16(&mb, B16, N, K, (K + 7) & ~7, TC16_BK, bn) : make_map16(&mb, B16, K, N, (N + 7) & ~7, 64, TC16_BK));
+  const bool two_sm = use_2sm(M, bn);
+  ok = ok && (transB == 1 ? make_map16(&mb, B16, N, K, (K + 7) & ~7, TC16_BK, two_sm ? bn / 2 : bn) : make_map16(&mb, B16, K, N, (N + 7) & ~7, 64, TC16_BK));
   if (!ok) return cudaErrorInvalidValue;
   TcArgs p;
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.alpha = alpha; p.beta = beta; p.ws = ws;
   p.kexp_a = nullptr; p.kexp_b = nullptr;
-  return run_tc16(st, num_sms, transA, transB, M, N, K, ma, mb, ma, mb, p, bn, 1, ws_bytes);
+  return run_tc16(st, num_sms, transA, transB, M, N, K, ma, mb, ma, mb, p, bn, 1, ws_bytes, two_sm);
 }
 
 // ---- fp16x3 (precision 0 on the 16-bit pipe)
@@ -879,19 +1047,20 @@ cudaError_t gemm_tc16x3(cudaStream_t st, int num_sms, int transA, int transB, in
   if ((A.ld & 7) || (B.ld & 7) || (((uintptr_t)A.hi | (uintptr_t)A.lo | (uintptr_t)B.hi | (uintptr_t)B.lo) & 15))
     return cudaErrorInvalidValue;
   const int bn = pick_bn(M, N, K);
+  const bool two_sm = use_2sm(M, bn);
   CUtensorMap ma, mb, ma2, mb2;
   bool ok = true;
   for (int pl = 0; pl < 2 && ok; pl++) {
     const void *a = pl ? A.lo : A.hi, *b = pl ? B.lo : B.hi;
     CUtensorMap *pa = pl ? &ma2 : &ma, *pb = pl ? &mb2 : &mb;
     ok = transA == 0 ? make_map16(pa, a, M, K, A.ld, TC16_BK, TC_BM, true) : make_map16(pa, a, K, M, A.ld, 64, TC16_BK, true);
-    ok = ok && (transB == 1 ? make_map16(pb, b, N, K, B.ld, TC16_BK, bn, true) : make_map16(pb, b, K, N, B.ld, 64, TC16_BK, true));
+    ok = ok && (transB == 1 ? make_map16(pb, b, N, K, B.ld, TC16_BK, two_sm ? bn / 2 : bn, true) : make_map16(pb, b, K, N, B.ld, 64, TC16_BK, true));
   }
   if (!ok) return cudaErrorInvalidValue;
   TcArgs p;
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.alpha = alpha; p.beta = beta; p.ws = ws;
   p.kexp_a = A.kexp; p.kexp_b = B.kexp;
-  return run_tc16(st, num_sms, transA, transB, M, N, K, ma, mb, ma2, mb2, p, bn, 3, ws_bytes);
+  return run_tc16(st, num_sms, transA, transB, M, N, K, ma, mb, ma2, mb2, p, bn, 3, ws_bytes, two_sm);
 }
 
 }  // namespace eb

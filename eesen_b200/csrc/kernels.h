@@ -62,6 +62,12 @@ struct LstmFwdArgs {
   int drop = 0;
   const float *rmask = nullptr;  // scaled mask (0 | 1/(1-p)); dir d at col d*C; row t*S+s if per_step else s
   int ldr = 0, rmask_per_step = 0;
+  // Streamed input product (tcgen05 engine): G arrives in chunks of `gchunk` positions of each direction's OWN time
+  // order (chunk ci = rows t in [ci*gchunk, ..) for dir 0, mirrored from the end for dir 1); chunk ci may be read once
+  // gflag[ci] == gepoch, chunks < gready were complete before the launch.  gflag == nullptr: everything is there.
+  const unsigned *gflag = nullptr;
+  unsigned gepoch = 0;
+  int gchunk = 0, gready = 0;
 };
 struct LstmBwdArgs {
   int T, S, C;
@@ -103,6 +109,7 @@ int lstm_debug_timing(long long *out32, int reset);  // 1 if built with -DEB_LST
 LstmPlan lstm_tc_plan(int S, int C, int num_sms, size_t max_smem, int ndir);
 cudaError_t lstm_tc_forward(cudaStream_t st, const LstmPlan &plan, const LstmFwdArgs &a);
 cudaError_t lstm_tc_backward(cudaStream_t st, const LstmPlan &plan, const LstmBwdArgs &a);
+cudaError_t lstm_set_flag(cudaStream_t st, unsigned *flag, unsigned value);   // stream-ordered 4-byte store
 int lstm_tc_debug_timing(long long *out32, int reset);
 
 // ctc.cu

@@ -159,6 +159,17 @@ __device__ __forceinline__ void issue_bwd_tile_ts(uint32_t tAhi, uint32_t tAlo, 
     umma_f16_ts(tmem + 32, tAlo + ks * 8, bd, idH, ks != 0);
   }
 }
+// "stacked" tile for the last 64 rows when C % 128 == 64: ONE M = 128 operand in TMEM whose lanes 0-63 hold the hi
+// halves of the 64 rows and lanes 64-127 their lo' halves, so that a single N = 32 MMA per k-slice yields hi*hi | hi*lo'
+// (lanes 0-63) and lo'*hi (lanes 64-127, columns 0-15; columns 16-31 there are the dropped lo'*lo' term)
+__device__ __forceinline__ void issue_bwd_tile_stacked(uint32_t tA, uint64_t dB, uint32_t tmem) {
+  const uint32_t idN = idesc_f16(128, 32);
+#pragma unroll
+  for (int ks = 0; ks < 8; ks++) {
+    const int kb = ks >> 2, k4 = ks & 3;
+    umma_f16_ts(tmem, tA + ks * 8, dB + (uint64_t)((kb * 4096 + k4 * 32) >> 4), idN, ks != 0);
+  }
+}
 template <int ROWS>
 __device__ __forceinline__ void issue_bwd_tile(uint64_t dAhi, uint64_t dAlo, uint64_t dB, uint32_t tmem) {
   const uint32_t idN = idesc_f16(ROWS, 32), idH = idesc_f16(ROWS, 16);
@@ -169,6 +180,21 @@ __device__ __forceinline__ void issue_bwd_tile(uint64_t dAhi, uint64_t dAlo, uin
     umma_f16(tmem, dAhi + (uint64_t)((kb * ROWS * 128 + k4 * 32) >> 4), bd, idN, ks != 0);
     umma_f16(tmem + 32, dAlo + (uint64_t)((kb * ROWS * 128 + k4 * 32) >> 4), bd, idH, ks != 0);
   }
+}
+
+// spin until *p == v (acquire at gpu scope: what the stream that stored v wrote before is visible afterwards).
+// Bounded: a producer that never comes (a host-side sequencing bug) ends in a trap after ~4 s, not in a hung device.
+__device__ __forceinline__ void wait_flag(const unsigned *p, unsigned v) {
+  unsigned x;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(x) : "l"(p) : "memory");
+    if (x == v) break;
+    if (clock64() - t0 > (1ll << 33)) __trap();
+  }
+}
+__global__ void set_flag_kernel(unsigned *flag, unsigned value) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(flag), "r"(value) : "memory");
 }
 
 __device__ __forceinline__ void named_bar_workers() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
@@ -277,12 +303,13 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
       }
     };
     load_pre(dir == 0 ? 0 : T - 1);
+    int ghave = a.gready - 1;                              // last chunk of G known to be complete
     const int c8n = C >> 3;                                // 8-cell chunks per utterance row
     const int quad = warp & 3, uh = warp >> 2;             // epilogue: TMEM lane quadrant (= gate), utterance half
     const uint64_t dBt = umma_desc(smem_u32(Bt), 16, 1024, 2);
     // exchange chunks of this thread (fixed for the whole sequence)
     constexpr int MAXT = 3;                                // 16 * (C/8) / 256 <= 3 for C <= 384
-    uint4 q[MAXT][2];
+    uint4 xq[MAXT][2];
     size_t xoff[MAXT];
     bool live[MAXT];
 #pragma unroll
@@ -291,7 +318,7 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
       const int u = v / c8n, c8 = v - u * c8n;
       live[i] = v < TCL_UG * c8n && s0 + group * TCL_UG + u < s1;
       xoff[i] = ((size_t)u * C + c8 * 8) / 4;
-      q[i][0] = make_uint4(0u, 0u, 0u, 0u); q[i][1] = q[i][0];
+      xq[i][0] = make_uint4(0u, 0u, 0u, 0u); xq[i][1] = xq[i][0];
     }
 
     TC_ACC_DECL();
@@ -316,15 +343,15 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
           const int u = v / c8n, c8 = v - u * c8n;
           uint4 hi4 = make_uint4(0u, 0u, 0u, 0u), lo4 = hi4;
           if (live[i]) {
-            while (((((q[i][0].x ^ want) | (q[i][0].y ^ want) | (q[i][0].z ^ want) | (q[i][0].w ^ want) |
-                      (q[i][1].x ^ want) | (q[i][1].y ^ want) | (q[i][1].z ^ want) | (q[i][1].w ^ want)) & 0x10000u)) != 0u) {
-              q[i][0] = ld_word4(xr + xoff[i]); q[i][1] = ld_word4(xr + xoff[i] + 1);
+            while (((((xq[i][0].x ^ want) | (xq[i][0].y ^ want) | (xq[i][0].z ^ want) | (xq[i][0].w ^ want) |
+                      (xq[i][1].x ^ want) | (xq[i][1].y ^ want) | (xq[i][1].z ^ want) | (xq[i][1].w ^ want)) & 0x10000u)) != 0u) {
+              xq[i][0] = ld_word4(xr + xoff[i]); xq[i][1] = ld_word4(xr + xoff[i] + 1);
             }
-            hi4 = make_uint4(__byte_perm(q[i][0].x, q[i][0].y, 0x5410), __byte_perm(q[i][0].z, q[i][0].w, 0x5410),
-                             __byte_perm(q[i][1].x, q[i][1].y, 0x5410), __byte_perm(q[i][1].z, q[i][1].w, 0x5410));
+            hi4 = make_uint4(__byte_perm(xq[i][0].x, xq[i][0].y, 0x5410), __byte_perm(xq[i][0].z, xq[i][0].w, 0x5410),
+                             __byte_perm(xq[i][1].x, xq[i][1].y, 0x5410), __byte_perm(xq[i][1].z, xq[i][1].w, 0x5410));
             // the tag bit (LSB of every lo' half) is cleared again: a zero stays an exact zero
-            lo4 = make_uint4(__byte_perm(q[i][0].x, q[i][0].y, 0x7632) & 0xfffefffeu, __byte_perm(q[i][0].z, q[i][0].w, 0x7632) & 0xfffefffeu,
-                             __byte_perm(q[i][1].x, q[i][1].y, 0x7632) & 0xfffefffeu, __byte_perm(q[i][1].z, q[i][1].w, 0x7632) & 0xfffefffeu);
+            lo4 = make_uint4(__byte_perm(xq[i][0].x, xq[i][0].y, 0x7632) & 0xfffefffeu, __byte_perm(xq[i][0].z, xq[i][0].w, 0x7632) & 0xfffefffeu,
+                             __byte_perm(xq[i][1].x, xq[i][1].y, 0x7632) & 0xfffefffeu, __byte_perm(xq[i][1].z, xq[i][1].w, 0x7632) & 0xfffefffeu);
           }
           const int k0 = c8 * 8;
           *reinterpret_cast<uint4 *>(Bt + sw128_off(32, u, k0)) = hi4;
@@ -415,7 +442,7 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
         const uint4 *xn = reinterpret_cast<const uint4 *>(xbuf + ((size_t)((step & 1) * ndir + dir) * groups + group) * TCL_UG * C);
 #pragma unroll
         for (int i = 0; i < MAXT; i++)
-          if (live[i]) { q[i][0] = ld_word4(xn + xoff[i]); q[i][1] = ld_word4(xn + xoff[i] + 1); }
+          if (live[i]) { xq[i][0] = ld_word4(xn + xoff[i]); xq[i][1] = ld_word4(xn + xoff[i] + 1); }
       }
       TC_TICK(0, 3);
 #pragma unroll
@@ -427,7 +454,13 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
           __stcs(a.cell + ((size_t)t * S + uidx[e]) * a.ldc + (size_t)dir * C + cell, sc[e]);
         }
       }
-      if (step + 1 < T) load_pre(dir == 0 ? t + 1 : t - 1);
+      if (step + 1 < T) {
+        if (a.gflag) {   // streamed input product: the next position may lie in a chunk that is still being computed
+          const int need = (step + 1) / a.gchunk;
+          if (need > ghave) { wait_flag(a.gflag + need, a.gepoch); ghave = need; }
+        }
+        load_pre(dir == 0 ? t + 1 : t - 1);
+      }
       TC_TICK(0, 4);
     }
     TC_FLUSH(0);
@@ -443,8 +476,9 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
 
 // ------------------------------------------------------------------------------------ backward
 // Partial d_m of ALL C cells from this CTA's 128 gate rows:  P[j, u] = sum_r Wm[r, j] * D[u, r]
-// A = Wm^T tiles [j rows x 128 k] (hi, lo'), M tiles of 128 rows plus one of 64 when C % 128 == 64;
-// B = D (scaled per utterance, hi rows 0-15 | lo' rows 16-31) [32 x 128 k].
+// A = Wm^T tiles [j rows x 128 k] (hi, lo'): M tiles of 128 rows, the first two resident in TMEM, a third full one
+// (C = 384) in shared memory; the 64 rows left when C % 128 == 64 form a "stacked" TMEM tile (hi in lanes 0-63, lo' in
+// lanes 64-127);  B = D (scaled per utterance, hi rows 0-15 | lo' rows 16-31) [32 x 128 k].
 template <int DROP>
 __global__ void __launch_bounds__(TCL_THREADS, 1)
 lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
@@ -452,11 +486,14 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int C = a.C, S = a.S, T = a.T;
   const int n128 = C >> 7, rem64 = (C & 127) ? 1 : 0, MT = n128 + rem64;
-  uint8_t *Ahi = smem;                                    // per M tile: [2 k-blocks][rows][128 B]; tile mt at mt*128*256 B
-  uint8_t *Alo = Ahi + (size_t)C * 256;
-  uint8_t *Bt = Alo + (size_t)C * 256;                    // [2 k-blocks][32 rows][128 B]
+  const int NTS = n128 < 2 ? n128 : 2;                    // full tiles resident in TMEM
+  uint8_t *Bt = smem;                                     // [2 k-blocks][32 rows][128 B]
   float *scl = reinterpret_cast<float *>(Bt + 8192);      // [16] inverse column scales
-  float *gsm = scl + 16;                                   // [2 halves][16 utts][32 cells] gathered partial d_m
+  float *gsm = scl + 16;                                  // [2 halves][16 utts][32 cells] gathered partial d_m
+  float *ysm = gsm + 2 * TCL_UG * 32;                     // [16 utts][64 rows] lo'*hi part of the stacked tile
+  float *red = ysm + TCL_UG * 64;                         // [7][16 utts][32 cells] bias / peephole sums at the end
+  uint8_t *Ahi = smem + 32768;                            // full tiles beyond the TMEM-resident ones: [2 k-blocks][128][128 B] each
+  uint8_t *Alo = Ahi + (size_t)(n128 - NTS) * 32768;
   __shared__ uint64_t b_full, mma_done[3];   // one commit barrier per M tile (C <= 384: at most 3 tiles)
   __shared__ uint32_t tmem_base_sm;
 
@@ -467,24 +504,22 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
   const int s0 = a.s_begin, s1 = a.s_begin + a.s_count;
 
   // A[j, k = gate*32 + c] = Wm[gate*C + slice*32 + c][j]   (j fastest: coalesced reads of the Wm rows, 8 in flight)
-  for (int base = 0; base < 128 * C; base += 8 * TCL_THREADS) {
-    float w[8];
+  for (int mt = NTS; mt < n128; mt++) {
+    for (int base = 0; base < 128 * 128; base += 8 * TCL_THREADS) {
+      float w[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const int idx = base + i * TCL_THREADS + tid;
-      const int kk = idx / C, j = idx - kk * C;
-      w[i] = idx < 128 * C ? __ldg(P.wm + ((size_t)(kk >> 5) * C + slice * TCL_CS + (kk & 31)) * P.ldwm + j) : 0.f;
-    }
+      for (int i = 0; i < 8; i++) {
+        const int idx = base + i * TCL_THREADS + tid;
+        const int kk = idx >> 7, j = mt * 128 + (idx & 127);
+        w[i] = __ldg(P.wm + ((size_t)(kk >> 5) * C + slice * TCL_CS + (kk & 31)) * P.ldwm + j);
+      }
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const int idx = base + i * TCL_THREADS + tid;
-      if (idx < 128 * C) {
-        const int kk = idx / C, j = idx - kk * C;
+      for (int i = 0; i < 8; i++) {
+        const int idx = base + i * TCL_THREADS + tid;
+        const int kk = idx >> 7;
         uint32_t h, l;
         split_f16(w[i], h, l);
-        const int mt = j >> 7;
-        const int rows = mt < n128 ? 128 : 64;
-        const uint32_t off = (uint32_t)mt * 128 * 256 + sw128_off(rows, j & 127, kk);
+        const uint32_t off = (uint32_t)(mt - NTS) * 32768 + sw128_off(128, idx & 127, kk);
         *reinterpret_cast<uint16_t *>(Ahi + off) = (uint16_t)h;
         *reinterpret_cast<uint16_t *>(Alo + off) = (uint16_t)l;
       }
@@ -510,8 +545,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
   // ---- the first two full M tiles of Wm^T also go to TMEM (columns [160, 160 + 128 * NTS): per tile 64 columns hi,
   // 64 columns lo'; lane = output cell within the tile, 8 columns per 16-wide k-slice of this CTA's 128 gate rows):
   // their MMAs read the weights from TMEM ("TS" form) instead of streaming 128 KB through shared memory per step.
-  // A third tile (C = 320: the 64-row one) keeps both operands in shared memory.
-  const int NTS = n128 < 2 ? n128 : 2;
+  // A third FULL tile (C = 384) keeps both operands in shared memory.
   constexpr uint32_t kColA = 160;
   for (int mt = 0; mt < NTS; mt++) {
     const int j = mt * 128 + (warp & 3) * 32 + lane;
@@ -534,6 +568,30 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
       }
       tmem_st8(tl + ks * 8, wh);
       tmem_st8(tl + 64 + ks * 8, wl);
+    }
+  }
+  // the stacked tile of the last 64 rows (columns [160 + 128 * NTS, + 64)): lane quadrants 0-1 hold hi, 2-3 lo'
+  const uint32_t colS = kColA + (uint32_t)NTS * 128;
+  if (rem64) {
+    const int j = n128 * 128 + (warp & 1) * 32 + lane;
+    const bool lo_half = (warp & 2) != 0;
+    const uint32_t tl = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + colS;
+    for (int ks = warp >> 2; ks < 8; ks += 2) {
+      float w[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const int kk = ks * 16 + i;
+        w[i] = __ldg(P.wm + ((size_t)(kk >> 5) * C + slice * TCL_CS + (kk & 31)) * P.ldwm + j);
+      }
+      uint32_t wv[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        uint32_t h0, l0, h1, l1;
+        split_f16(w[2 * i], h0, l0);
+        split_f16(w[2 * i + 1], h1, l1);
+        wv[i] = lo_half ? (l0 | (l1 << 16)) : (h0 | (h1 << 16));
+      }
+      tmem_st8(tl + ks * 8, wv);
     }
   }
   asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
@@ -580,6 +638,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
     const int quad = warp & 3, uh = warp >> 2;
     const uint64_t dAhi = umma_desc(smem_u32(Ahi), 16, 1024, 2), dAlo = umma_desc(smem_u32(Alo), 16, 1024, 2),
                    dBt = umma_desc(smem_u32(Bt), 16, 1024, 2);
+    const uint32_t accS = (uint32_t)n128 * 48;   // accumulator columns: full tile mt at mt * 48, the stacked tile behind them
 
     TC_ACC_DECL();
     for (int step = 0; step < T; step++) {
@@ -676,14 +735,18 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
         mbar_wait(&b_full, (uint32_t)(step & 1));
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         if (elect_one()) {
-          // one commit per M tile: the epilogue (TMEM -> tagged words) of tile mt runs while the tensor pipe is
-          // still working on tile mt+1
-          for (int mt = 0; mt < MT; mt++) {
-            const uint64_t toff = (uint64_t)((mt * 128 * 256) >> 4);
+          // one commit per M tile: the epilogue (TMEM -> tagged words) of a tile runs while the tensor pipe is
+          // still working on the next one.  The stacked tile goes first: its epilogue has one more hand-over.
+          int nb = 0;
+          if (rem64) {
+            issue_bwd_tile_stacked(tmem_base + colS, dBt, tmem_base + accS);
+            umma_commit(&mma_done[nb++]);
+          }
+          for (int mt = 0; mt < n128; mt++) {
+            const uint64_t toff = (uint64_t)(((mt - NTS) * 32768) >> 4);
             if (mt < NTS) issue_bwd_tile_ts(tmem_base + kColA + mt * 128, tmem_base + kColA + mt * 128 + 64, dBt, tmem_base + mt * 48);
-            else if (mt < n128) issue_bwd_tile<128>(dAhi + toff, dAlo + toff, dBt, tmem_base + mt * 48);
-            else issue_bwd_tile<64>(dAhi + toff, dAlo + toff, dBt, tmem_base + mt * 48);
-            umma_commit(&mma_done[mt]);
+            else issue_bwd_tile<128>(dAhi + toff, dAlo + toff, dBt, tmem_base + mt * 48);
+            umma_commit(&mma_done[nb++]);
           }
         }
         __syncwarp();
@@ -694,29 +757,53 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
         uint32_t *pw = pbuf + ((size_t)((((step & 1) * ndir + dir) * groups + group) * slices + slice)) * pstride_slice;
         const uint32_t tagw = (uint32_t)((step >> 1) & 1);
         float inv[8];
-        for (int mt = 0; mt < MT; mt++) {
-          mbar_wait(&mma_done[mt], (uint32_t)(step & 1));
+        for (int bi = 0; bi < MT; bi++) {
+          mbar_wait(&mma_done[bi], (uint32_t)(step & 1));
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          if (mt == 0) {   // the column scales were written by the other warps before they arrived on b_full: read
+          if (bi == 0) {   // the column scales were written by the other warps before they arrived on b_full: read
                            // them only behind the first commit (which is behind b_full)
 #pragma unroll
             for (int j = 0; j < 8; j++) inv[j] = scl[8 * uh + j];
           }
-          const bool full = mt < n128;
+          if (rem64 && bi == 0) {
+            // stacked tile: lanes 0-63 (quadrants 0-1) carry hi*hi | hi*lo', lanes 64-127 the lo'*hi term of the same
+            // rows -- it crosses to the other warps through shared memory
+            const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16) + accS;
+            const int r = (quad & 1) * 32 + lane;
+            if (quad >= 2) {
+              uint32_t y0[8];
+              tmem_ld8(tl + 8 * uh, y0);
+              tmem_ld_wait();
+#pragma unroll
+              for (int jj = 0; jj < 8; jj++) ysm[(8 * uh + jj) * 64 + r] = u2f(y0[jj]);
+              asm volatile("bar.arrive 2, 256;\n" ::: "memory");
+            } else {
+              uint32_t x0[8], x1[8];
+              tmem_ld8(tl + 8 * uh, x0);
+              tmem_ld8(tl + 16 + 8 * uh, x1);
+              tmem_ld_wait();
+              asm volatile("bar.sync 2, 256;\n" ::: "memory");
+              const int j = n128 * 128 + r;
+#pragma unroll
+              for (int jj = 0; jj < 8; jj++) {
+                const float pv = (u2f(x0[jj]) + (u2f(x1[jj]) + ysm[(8 * uh + jj) * 64 + r]) * kLoUnscale) * inv[jj];
+                st_word(pw + (size_t)(8 * uh + jj) * C + j, (__float_as_uint(pv) & 0xfffffffeu) | tagw);   // tag = LSB
+              }
+            }
+            continue;
+          }
+          const int mt = bi - rem64;
           uint32_t x0[8], x1[8], y0[8];
           const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 48);
           tmem_ld8(tl + 8 * uh, x0);
           tmem_ld8(tl + 16 + 8 * uh, x1);
           tmem_ld8(tl + 32 + 8 * uh, y0);
           tmem_ld_wait();
-          // M = 128: lane = row; M = 64: rows 16*quad .. +15 sit in lanes 0-15 of every quadrant
-          const int j = full ? mt * 128 + quad * 32 + lane : mt * 128 + quad * 16 + lane;
-          if (full || lane < 16) {
+          const int j = mt * 128 + quad * 32 + lane;   // M = 128: lane = row
 #pragma unroll
-            for (int jj = 0; jj < 8; jj++) {
-              const float pv = (u2f(x0[jj]) + (u2f(x1[jj]) + u2f(y0[jj])) * kLoUnscale) * inv[jj];
-              st_word(pw + (size_t)(8 * uh + jj) * C + j, (__float_as_uint(pv) & 0xfffffffeu) | tagw);   // tag = LSB
-            }
+          for (int jj = 0; jj < 8; jj++) {
+            const float pv = (u2f(x0[jj]) + (u2f(x1[jj]) + u2f(y0[jj])) * kLoUnscale) * inv[jj];
+            st_word(pw + (size_t)(8 * uh + jj) * C + j, (__float_as_uint(pv) & 0xfffffffeu) | tagw);   // tag = LSB
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -727,8 +814,6 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
     TC_FLUSH(1);
     // ---- bias / peephole gradient partial sums of this (dir, group): reduce over the CTA's 16 utterances
     named_bar_workers();
-    float *red = reinterpret_cast<float *>(smem);   // [7][16 utts][32 cells] (the weights are no longer needed:
-                                                    //  every MMA was committed and waited for)
 #pragma unroll
     for (int e = 0; e < 2; e++) {
       const int u = 2 * up + e;
@@ -760,9 +845,20 @@ size_t tc_fwd_smem(int C) {
   const size_t need = (size_t)(C / 64) * 4096 + 4 * TCL_UG * 32 * sizeof(float) + 1024;
   return need > 180 * 1024 ? need : (size_t)180 * 1024;
 }
-size_t tc_bwd_smem(int C) { return (size_t)C * 512 + 8192 + 64 + 2 * TCL_UG * 32 * sizeof(float) + 1024; }
+// backward: B tile + small scratch in the first 32 KB, then the full M tiles that do not fit TMEM (C = 384: one);
+// like the forward kernel it asks for most of the SM so that no TMEM-allocating GEMM CTA lands beside it
+size_t tc_bwd_smem(int C) {
+  const int n128 = C >> 7, nts = n128 < 2 ? n128 : 2;
+  const size_t need = 32768 + (size_t)(n128 - nts) * 65536 + 1024;
+  return need > 180 * 1024 ? need : (size_t)180 * 1024;
+}
 
 }  // namespace
+
+cudaError_t lstm_set_flag(cudaStream_t st, unsigned *flag, unsigned value) {
+  set_flag_kernel<<<1, 1, 0, st>>>(flag, value);
+  return cudaGetLastError();
+}
 
 int lstm_tc_debug_timing(long long *out32, int reset) {
 #ifdef EB_LSTM_TIMING

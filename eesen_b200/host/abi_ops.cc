@@ -59,6 +59,8 @@ int eesen_b200_create(eesen_b200_ctx **out, int device) {
   {
     const char *ov = getenv("EESEN_B200_OVERLAP");
     ctx->overlap = (ov && ov[0] == '0') ? 0 : 1;
+    const char *sg = getenv("EESEN_B200_STREAM_GEMM");
+    ctx->stream_gemm = (sg && sg[0] == '0') ? 0 : 1;
     const char *fx = getenv("EESEN_B200_GEMM_FP32X3");
     ctx->f16x3 = (fx && std::string(fx) == "tf32") ? 0 : 1;
   }
@@ -82,7 +84,7 @@ void eesen_b200_destroy(eesen_b200_ctx *ctx) {
   for (int i = 0; i < eesen_b200_ctx::kF16Slots; i++)
     if (ctx->f16_slots[i].planes.p) cudaFree(ctx->f16_slots[i].planes.p);
   eesen_b200_ctx::Buf *bufs[] = {&ctx->f16_meta, &ctx->f16_tmp[0], &ctx->f16_tmp[1], &ctx->f16_tmp[2], &ctx->f16_tmp[3], &ctx->decode_ws, &ctx->gemm_ws_side, &ctx->bf16_a_side, &ctx->bf16_b_side,&ctx->gemm_ws, &ctx->lstm_pbuf, &ctx->lstm_gsum, &ctx->lstm_flags,
-                                 &ctx->ctc_ws, &ctx->colsum_ws, &ctx->seg_buf, &ctx->flag_buf, &ctx->bf16_a, &ctx->bf16_b};
+                                 &ctx->ctc_ws, &ctx->colsum_ws, &ctx->seg_buf, &ctx->flag_buf, &ctx->bf16_a, &ctx->bf16_b, &ctx->lstm_gflags};
   for (auto *b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->nccl_comm && ctx->nccl_lib) {
@@ -333,7 +335,42 @@ static int lstm_forward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I,
   if ((rc = f16_register(ctx, x, N, I, ldx))) return rc;
   for (int d = 0; d < ndir; d++)
     if ((rc = f16_register(ctx, p->wx[d], 4 * C, I, ldwx))) return rc;
-  if (ndir == 2 && sW > 0 && (sW & 3) == 0 && sB > 0) {
+  // Streamed: with the tcgen05 engine (80 of 148 SMs, latency-bound) the product is cut along time into chunks in the
+  // order the two directions consume G -- direction 0 from t = 0 upwards, direction 1 from t = T-1 downwards.  The
+  // first kReady chunks run here, the others on the side stream next to the recurrent kernel, which checks
+  // gflag[chunk] before the first read of a chunk.
+  constexpr int kReady = 2;
+  int gchunk = 0, nchunks_g = 0;
+  unsigned *gflags = nullptr;
+  if (plan.engine == 1 && chunk == S && ctx->overlap && ctx->stream_gemm && T >= 256) {
+    gchunk = std::max(32, (T + 9) / 10);
+    nchunks_g = (T + gchunk - 1) / gchunk;
+    if (nchunks_g <= kReady || nchunks_g > 64) nchunks_g = 0;
+  }
+  if (nchunks_g) {
+    void *gf = nullptr;
+    const bool fresh = ctx->lstm_gflags.bytes == 0;
+    if ((rc = ctx->reserve(ctx->lstm_gflags, 64 * sizeof(unsigned), &gf))) return rc;
+    gflags = (unsigned *)gf;
+    if (fresh && (rc = ctx->check(cudaMemsetAsync(gf, 0, 64 * sizeof(unsigned), ctx->stream), "cudaMemsetAsync"))) return rc;
+    ctx->gepoch += 1;
+    if (ctx->gepoch == 0u) ctx->gepoch = 1;     // 0 = "never set"
+    ctx->fork_side();                           // the side stream waits for the operand conversions above
+    for (int ci = 0; ci < nchunks_g; ci++) {
+      const bool on_side = ci >= kReady;
+      const int t0 = ci * gchunk, nt = std::min(gchunk, T - t0);
+      for (int d = 0; d < ndir; d++) {
+        const long r0 = (long)(d == 0 ? t0 : T - t0 - nt) * S;
+        rc = do_gemm(ctx, 0, 1, nt * S, 4 * C, I, 1.f, x + r0 * ldx, ldx, 0, p->wx[d], ldwx, 0, 0.f,
+                     gates + r0 * ldg + (size_t)d * 4 * C, ldg, 0, p->bias[d], 0, 1, on_side);
+        if (rc) return rc;
+      }
+      if (on_side) {
+        ctx->launches += 1;
+        if ((rc = ctx->check(eb::lstm_set_flag(ctx->side, gflags + ci, ctx->gepoch), "lstm_set_flag"))) return rc;
+      }
+    }
+  } else if (ndir == 2 && sW > 0 && (sW & 3) == 0 && sB > 0) {
     rc = do_gemm(ctx, 0, 1, N, 4 * C, I, 1.f, x, ldx, 0, p->wx[0], ldwx, sW, 0.f, gates, ldg, 4 * C, p->bias[0], sB, 2);
     if (rc) return rc;
   } else {
@@ -355,6 +392,7 @@ static int lstm_forward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I,
   a.xbuf = xbuf;
   a.precision = ctx->rec_prec;
   a.drop = drop; a.rmask = rmask; a.ldr = ldr; a.rmask_per_step = per_step;
+  if (nchunks_g) { a.gflag = gflags; a.gepoch = ctx->gepoch; a.gchunk = gchunk; a.gready = kReady; }
   for (int s0 = 0; s0 < S; s0 += chunk) {
     a.s_begin = s0;
     a.s_count = std::min(chunk, S - s0);

@@ -26,7 +26,7 @@ struct eesen_b200_ctx {
     void *p = nullptr;
     size_t bytes = 0;
   };
-  Buf gemm_ws, lstm_pbuf, lstm_gsum, lstm_flags, ctc_ws, colsum_ws, seg_buf, flag_buf, bf16_a, bf16_b;
+  Buf gemm_ws, lstm_pbuf, lstm_gsum, lstm_flags, ctc_ws, colsum_ws, seg_buf, flag_buf, bf16_a, bf16_b, lstm_gflags;
   Buf gemm_ws_side, bf16_a_side, bf16_b_side;   // the side stream's own scratch
   Buf decode_ws;
 
@@ -57,6 +57,11 @@ struct eesen_b200_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool side_pending = false;
   int overlap = 1;   // EESEN_B200_OVERLAP=0: everything on `stream` (A/B measurements)
+  // Streamed input product of the recurrent forward pass: x*Wx^T is cut into chunks of time steps in the order the
+  // two directions consume them; the first chunks run on `stream`, the rest on the side stream WHILE the recurrent
+  // kernel runs (it checks a per-chunk flag before it reads a chunk).  EESEN_B200_STREAM_GEMM=0 turns it off.
+  int stream_gemm = 1;
+  unsigned gepoch = 0;
   void fork_side() {
     cudaEventRecord(ev_fork, stream);
     cudaStreamWaitEvent(side, ev_fork, 0);

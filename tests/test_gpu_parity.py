@@ -145,7 +145,9 @@ def test_ctc_eval_vs_oracle(ctx, seed, S, T, K, maxlab):
 
 
 @pytest.mark.parametrize("S,T,I,C", [(4, 9, 8, 16), (2, 30, 40, 128), (20, 17, 40, 64), (16, 40, 40, 320), (3, 5, 64, 24),
-                                     (100, 7, 40, 320), (1, 1, 40, 64)])   # 100 utts: two utterance chunks (64 + 36)
+                                     (100, 7, 40, 320), (1, 1, 40, 64),    # 100 utts: two utterance chunks (64 + 36)
+                                     (4, 11, 40, 192), (3, 9, 40, 384),    # backward tile mixes: 128 + stacked 64; 3 x 128
+                                     (8, 300, 40, 64), (6, 290, 40, 320)]) # T >= 256: input product streamed in chunks
 @pytest.mark.parametrize("rec", ["fp32x3", "tf32", "legacy-engine", "tcfwd-engine"])
 def test_bilstm_layer_vs_oracle(ctx, S, T, I, C, rec, monkeypatch):
     """Level-1 BiLSTM forward/backward of one layer against the fp64 oracle, ragged lengths.  Shapes with
