@@ -68,6 +68,7 @@ struct LstmFwdArgs {
   const unsigned *gflag = nullptr;
   unsigned gepoch = 0;
   int gchunk = 0, gready = 0;
+  int tune = 0;   // debug knobs (EESEN_B200_TUNE): bit 0 = first exchange poll behind the saved-state stores
 };
 struct LstmBwdArgs {
   int T, S, C;
@@ -83,6 +84,7 @@ struct LstmBwdArgs {
   int drop = 0;                 // as LstmFwdArgs (:604-879)
   const float *rmask = nullptr;
   int ldr = 0, rmask_per_step = 0;
+  int tune = 0;                 // debug knobs (EESEN_B200_TUNE): bit 1 = 64-row remainder tile from shared memory (SS form)
 };
 struct LstmPlan {
   int engine;            // 0: warp-level mma.sync kernels (lstm.cu), 1: tcgen05 kernels (lstm_tc.cu)

@@ -55,6 +55,7 @@ __device__ long long g_lstm_tc_timing[2][16];
       tk_ = n_;                                                                     \
     }                                                                               \
   } while (0)
+#define TC_COUNT(i) tacc_[i] += 1
 #define TC_FLUSH(kernel)                                                            \
   do {                                                                              \
     if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)          \
@@ -64,6 +65,7 @@ __device__ long long g_lstm_tc_timing[2][16];
 #define TC_T0()
 #define TC_ACC_DECL()
 #define TC_TICK(kernel, i)
+#define TC_COUNT(i)
 #define TC_FLUSH(kernel)
 #endif
 
@@ -120,16 +122,21 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&w)[8])
                "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
                : "memory");
 }
-template <int KB>
-__device__ __forceinline__ void issue_fwd_mmas_ts(uint32_t tWhi, uint32_t tWlo, uint64_t dB, uint32_t tmem, uint32_t idN,
-                                                  uint32_t idH) {
+// NLO = number of leading k-slices whose W_lo' sits in TMEM; the remaining ones (C = 512: TMEM is full) are read from
+// the shared-memory tile dWloS ("SS" form)
+template <int KB, int NLO>
+__device__ __forceinline__ void issue_fwd_mmas_ts(uint32_t tWhi, uint32_t tWlo, uint64_t dWloS, uint64_t dB, uint32_t tmem,
+                                                  uint32_t idN, uint32_t idH) {
 #pragma unroll
   for (int kb = 0; kb < KB; kb++) {
 #pragma unroll
     for (int ks = 0; ks < 4; ks++) {
       const uint64_t bd = dB + (uint64_t)((kb * 4096 + ks * 32) >> 4);
       umma_f16_ts(tmem, tWhi + (kb * 4 + ks) * 8, bd, idN, (kb | ks) != 0);
-      umma_f16_ts(tmem + 32, tWlo + (kb * 4 + ks) * 8, bd, idH, (kb | ks) != 0);
+      if (kb * 4 + ks < NLO)
+        umma_f16_ts(tmem + 32, tWlo + (kb * 4 + ks) * 8, bd, idH, (kb | ks) != 0);
+      else
+        umma_f16(tmem + 32, dWloS + (uint64_t)((((kb * 4 + ks - NLO) >> 2) * 16384 + ks * 32) >> 4), bd, idH, (kb | ks) != 0);
     }
   }
 }
@@ -208,7 +215,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 
 // ------------------------------------------------------------------------------------ forward
-template <int DROP>
+// WIDE = 1: 384 < C <= 512 (4 exchange chunks per thread; at C = 512 the last 8 k-slices of W_lo' in shared memory)
+template <int DROP, int WIDE>
 __global__ void __launch_bounds__(TCL_THREADS, 1)
 lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -217,8 +225,12 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
   const int KB = C >> 6;                                  // 64-wide k-blocks (C % 64 == 0)
   uint8_t *Bt = smem;                                     // [KB][32 rows][128 B]: rows 0-15 hi, 16-31 lo'
   float *stg = reinterpret_cast<float *>(Bt + (size_t)KB * 4096);   // [4 gates][16 utts][32 cells]
-  // TMEM columns: [0,32) X accumulator, [32,48) Y accumulator, [64, 64 + C/2) W_hi, [64 + C/2, 64 + C) W_lo'
+  // TMEM columns: [0,32) X accumulator, [32,48) Y accumulator, [64, 64 + C/2) W_hi, [64 + C/2, ..) W_lo' of the first
+  // nlo k-slices (all of them up to C = 448; 24 of 32 at C = 512, the other 8 in the shared-memory tile WloS)
   constexpr uint32_t kColW = 64;
+  const int nks = C >> 4;
+  const int nlo = (WIDE && nks > 28) ? 24 : nks;
+  uint8_t *WloS = Bt + (size_t)KB * 4096 + 8192;                     // [k-blocks from slice nlo on][128 rows][128 B]
   __shared__ uint64_t b_full, mma_done;
   __shared__ uint32_t tmem_base_sm;
 
@@ -266,9 +278,16 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
         wl[j] = l0 | (l1 << 16);
       }
       tmem_st8(tl + ks * 8, wh);
-      tmem_st8(tl + (C >> 1) + ks * 8, wl);
+      if (ks < nlo) {
+        tmem_st8(tl + (C >> 1) + ks * 8, wl);
+      } else {
+        const int k0 = (ks - nlo) * 16;
+        *reinterpret_cast<uint4 *>(WloS + sw128_off(128, r, k0)) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+        *reinterpret_cast<uint4 *>(WloS + sw128_off(128, r, k0 + 8)) = make_uint4(wl[4], wl[5], wl[6], wl[7]);
+      }
     }
     asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // (WloS: generic-proxy writes -> UMMA reads)
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
@@ -308,7 +327,7 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
     const int quad = warp & 3, uh = warp >> 2;             // epilogue: TMEM lane quadrant (= gate), utterance half
     const uint64_t dBt = umma_desc(smem_u32(Bt), 16, 1024, 2);
     // exchange chunks of this thread (fixed for the whole sequence)
-    constexpr int MAXT = 3;                                // 16 * (C/8) / 256 <= 3 for C <= 384
+    constexpr int MAXT = WIDE ? 4 : 3;                     // 16 * (C/8) / 256 <= 3 for C <= 384, 4 for C <= 512
     uint4 xq[MAXT][2];
     size_t xoff[MAXT];
     bool live[MAXT];
@@ -346,6 +365,7 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
             while (((((xq[i][0].x ^ want) | (xq[i][0].y ^ want) | (xq[i][0].z ^ want) | (xq[i][0].w ^ want) |
                       (xq[i][1].x ^ want) | (xq[i][1].y ^ want) | (xq[i][1].z ^ want) | (xq[i][1].w ^ want)) & 0x10000u)) != 0u) {
               xq[i][0] = ld_word4(xr + xoff[i]); xq[i][1] = ld_word4(xr + xoff[i] + 1);
+              TC_COUNT(5);   // (debug build: re-polls of thread 0)
             }
             hi4 = make_uint4(__byte_perm(xq[i][0].x, xq[i][0].y, 0x5410), __byte_perm(xq[i][0].z, xq[i][0].w, 0x5410),
                              __byte_perm(xq[i][1].x, xq[i][1].y, 0x5410), __byte_perm(xq[i][1].z, xq[i][1].w, 0x5410));
@@ -367,13 +387,19 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
           if (elect_one()) {
             const uint32_t idN = idesc_f16(128, 32), idH = idesc_f16(128, 16);
             const uint32_t tWhi = tmem_base + kColW, tWlo = tmem_base + kColW + (uint32_t)(C >> 1);
-            switch (KB) {
-              case 1: issue_fwd_mmas_ts<1>(tWhi, tWlo, dBt, tmem_base, idN, idH); break;
-              case 2: issue_fwd_mmas_ts<2>(tWhi, tWlo, dBt, tmem_base, idN, idH); break;
-              case 3: issue_fwd_mmas_ts<3>(tWhi, tWlo, dBt, tmem_base, idN, idH); break;
-              case 4: issue_fwd_mmas_ts<4>(tWhi, tWlo, dBt, tmem_base, idN, idH); break;
-              case 5: issue_fwd_mmas_ts<5>(tWhi, tWlo, dBt, tmem_base, idN, idH); break;
-              default: issue_fwd_mmas_ts<6>(tWhi, tWlo, dBt, tmem_base, idN, idH); break;
+            const uint64_t dWloS = umma_desc(smem_u32(WloS), 16, 1024, 2);
+            if (WIDE) {
+              if (KB == 7) issue_fwd_mmas_ts<7, 28>(tWhi, tWlo, dWloS, dBt, tmem_base, idN, idH);
+              else issue_fwd_mmas_ts<8, 24>(tWhi, tWlo, dWloS, dBt, tmem_base, idN, idH);
+            } else {
+              switch (KB) {
+                case 1: issue_fwd_mmas_ts<1, 4>(tWhi, tWlo, dWloS, dBt, tmem_base, idN, idH); break;
+                case 2: issue_fwd_mmas_ts<2, 8>(tWhi, tWlo, dWloS, dBt, tmem_base, idN, idH); break;
+                case 3: issue_fwd_mmas_ts<3, 12>(tWhi, tWlo, dWloS, dBt, tmem_base, idN, idH); break;
+                case 4: issue_fwd_mmas_ts<4, 16>(tWhi, tWlo, dWloS, dBt, tmem_base, idN, idH); break;
+                case 5: issue_fwd_mmas_ts<5, 20>(tWhi, tWlo, dWloS, dBt, tmem_base, idN, idH); break;
+                default: issue_fwd_mmas_ts<6, 24>(tWhi, tWlo, dWloS, dBt, tmem_base, idN, idH); break;
+              }
             }
             umma_commit(&mma_done);
           }
@@ -438,12 +464,13 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
           __stcs(a.out + ((size_t)t * S + uidx[e]) * a.ldo + (size_t)dir * C + cell, sm[e]);
         }
       }
-      if (step + 1 < T) {   // first poll of the words the group is publishing right now (consumed at the next step)
+      auto first_poll = [&]() {   // first poll of the words the group is publishing right now (consumed at the next step)
         const uint4 *xn = reinterpret_cast<const uint4 *>(xbuf + ((size_t)((step & 1) * ndir + dir) * groups + group) * TCL_UG * C);
 #pragma unroll
         for (int i = 0; i < MAXT; i++)
           if (live[i]) { xq[i][0] = ld_word4(xn + xoff[i]); xq[i][1] = ld_word4(xn + xoff[i] + 1); }
-      }
+      };
+      if (step + 1 < T && !(a.tune & 1)) first_poll();
       TC_TICK(0, 3);
 #pragma unroll
       for (int e = 0; e < 2; e++) {
@@ -454,6 +481,7 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
           __stcs(a.cell + ((size_t)t * S + uidx[e]) * a.ldc + (size_t)dir * C + cell, sc[e]);
         }
       }
+      if (step + 1 < T && (a.tune & 1)) first_poll();
       if (step + 1 < T) {
         if (a.gflag) {   // streamed input product: the next position may lie in a chunk that is still being computed
           const int need = (step + 1) / a.gchunk;
@@ -479,13 +507,16 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
 // A = Wm^T tiles [j rows x 128 k] (hi, lo'): M tiles of 128 rows, the first two resident in TMEM, a third full one
 // (C = 384) in shared memory; the 64 rows left when C % 128 == 64 form a "stacked" TMEM tile (hi in lanes 0-63, lo' in
 // lanes 64-127);  B = D (scaled per utterance, hi rows 0-15 | lo' rows 16-31) [32 x 128 k].
-template <int DROP>
+// WIDE = 1: 384 < C <= 512 (up to 4 M tiles: 192 accumulator columns, two tiles in shared memory; 16 producers)
+template <int DROP, int WIDE>
 __global__ void __launch_bounds__(TCL_THREADS, 1)
 lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int C = a.C, S = a.S, T = a.T;
   const int n128 = C >> 7, rem64 = (C & 127) ? 1 : 0, MT = n128 + rem64;
+  const bool ss64 = rem64 && (a.tune & 2);                // debug: the 64-row tile as an M = 64 SS-form tile, issued last
+  const bool stk = rem64 && !ss64;                        // default: stacked TMEM tile, issued first
   const int NTS = n128 < 2 ? n128 : 2;                    // full tiles resident in TMEM
   uint8_t *Bt = smem;                                     // [2 k-blocks][32 rows][128 B]
   float *scl = reinterpret_cast<float *>(Bt + 8192);      // [16] inverse column scales
@@ -494,7 +525,9 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
   float *red = ysm + TCL_UG * 64;                         // [7][16 utts][32 cells] bias / peephole sums at the end
   uint8_t *Ahi = smem + 32768;                            // full tiles beyond the TMEM-resident ones: [2 k-blocks][128][128 B] each
   uint8_t *Alo = Ahi + (size_t)(n128 - NTS) * 32768;
-  __shared__ uint64_t b_full, mma_done[3];   // one commit barrier per M tile (C <= 384: at most 3 tiles)
+  uint8_t *Ahi64 = Alo + (size_t)(n128 - NTS) * 32768;    // (ss64 only) [2 k-blocks][64 rows][128 B], hi then lo'
+  uint8_t *Alo64 = Ahi64 + 16384;
+  __shared__ uint64_t b_full, mma_done[4];   // one commit barrier per M tile (at most 4 tiles)
   __shared__ uint32_t tmem_base_sm;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -525,10 +558,20 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
       }
     }
   }
+  if (ss64) {
+    for (int idx = tid; idx < 128 * 64; idx += TCL_THREADS) {
+      const int kk = idx >> 6, r = idx & 63;
+      const float w = __ldg(P.wm + ((size_t)(kk >> 5) * C + slice * TCL_CS + (kk & 31)) * P.ldwm + n128 * 128 + r);
+      uint32_t h, l;
+      split_f16(w, h, l);
+      *reinterpret_cast<uint16_t *>(Ahi64 + sw128_off(64, r, kk)) = (uint16_t)h;
+      *reinterpret_cast<uint16_t *>(Alo64 + sw128_off(64, r, kk)) = (uint16_t)l;
+    }
+  }
   for (int idx = tid; idx < 2048; idx += TCL_THREADS) reinterpret_cast<uint32_t *>(Bt)[idx] = 0u;
   if (tid == 0) {
     mbar_init(&b_full, TCL_WORKERS);
-    for (int i = 0; i < 3; i++) mbar_init(&mma_done[i], 1);
+    for (int i = 0; i < 4; i++) mbar_init(&mma_done[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
@@ -546,7 +589,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
   // 64 columns lo'; lane = output cell within the tile, 8 columns per 16-wide k-slice of this CTA's 128 gate rows):
   // their MMAs read the weights from TMEM ("TS" form) instead of streaming 128 KB through shared memory per step.
   // A third FULL tile (C = 384) keeps both operands in shared memory.
-  constexpr uint32_t kColA = 160;
+  constexpr uint32_t kColA = WIDE ? 192 : 160;   // behind the accumulators: 48 columns per full tile, 32 for the stacked one
   for (int mt = 0; mt < NTS; mt++) {
     const int j = mt * 128 + (warp & 3) * 32 + lane;
     const uint32_t tl = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kColA + (uint32_t)mt * 128;
@@ -572,7 +615,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
   }
   // the stacked tile of the last 64 rows (columns [160 + 128 * NTS, + 64)): lane quadrants 0-1 hold hi, 2-3 lo'
   const uint32_t colS = kColA + (uint32_t)NTS * 128;
-  if (rem64) {
+  if (stk) {
     const int j = n128 * 128 + (warp & 1) * 32 + lane;
     const bool lo_half = (warp & 2) != 0;
     const uint32_t tl = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + colS;
@@ -658,16 +701,19 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
         const uint4 *pv = reinterpret_cast<const uint4 *>(
             pbuf + ((size_t)((((step - 1) & 1) * ndir + dir) * groups + group) * slices) * pstride_slice + (size_t)gu * C +
             slice * TCL_CS + c4 * 4);
-        uint4 q[6];
+        constexpr int NQ = WIDE ? 8 : 6;   // producers per half
+        uint4 q[NQ];
 #pragma unroll
-        for (int i = 0; i < 6; i++)
+        for (int i = 0; i < NQ; i++)
           if (uv && sl0 + i < sl1) q[i] = ld_word4(pv + (size_t)(sl0 + i) * (pstride_slice / 4));
         float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 6; i++) {
+        for (int i = 0; i < NQ; i++) {
           if (uv && sl0 + i < sl1) {
-            while ((((q[i].x ^ want) | (q[i].y ^ want) | (q[i].z ^ want) | (q[i].w ^ want)) & 1u) != 0u)
+            while ((((q[i].x ^ want) | (q[i].y ^ want) | (q[i].z ^ want) | (q[i].w ^ want)) & 1u) != 0u) {
               q[i] = ld_word4(pv + (size_t)(sl0 + i) * (pstride_slice / 4));
+              TC_COUNT(5);   // (debug build: re-polls of thread 0)
+            }
             acc4.x += __uint_as_float(q[i].x & 0xfffffffeu); acc4.y += __uint_as_float(q[i].y & 0xfffffffeu);   // tag bit cleared
             acc4.z += __uint_as_float(q[i].z & 0xfffffffeu); acc4.w += __uint_as_float(q[i].w & 0xfffffffeu);
           }
@@ -738,7 +784,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
           // one commit per M tile: the epilogue (TMEM -> tagged words) of a tile runs while the tensor pipe is
           // still working on the next one.  The stacked tile goes first: its epilogue has one more hand-over.
           int nb = 0;
-          if (rem64) {
+          if (stk) {
             issue_bwd_tile_stacked(tmem_base + colS, dBt, tmem_base + accS);
             umma_commit(&mma_done[nb++]);
           }
@@ -746,6 +792,10 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
             const uint64_t toff = (uint64_t)(((mt - NTS) * 32768) >> 4);
             if (mt < NTS) issue_bwd_tile_ts(tmem_base + kColA + mt * 128, tmem_base + kColA + mt * 128 + 64, dBt, tmem_base + mt * 48);
             else issue_bwd_tile<128>(dAhi + toff, dAlo + toff, dBt, tmem_base + mt * 48);
+            umma_commit(&mma_done[nb++]);
+          }
+          if (ss64) {
+            issue_bwd_tile<64>(umma_desc(smem_u32(Ahi64), 16, 1024, 2), umma_desc(smem_u32(Alo64), 16, 1024, 2), dBt, tmem_base + accS);
             umma_commit(&mma_done[nb++]);
           }
         }
@@ -765,7 +815,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
 #pragma unroll
             for (int j = 0; j < 8; j++) inv[j] = scl[8 * uh + j];
           }
-          if (rem64 && bi == 0) {
+          if (stk && bi == 0) {
             // stacked tile: lanes 0-63 (quadrants 0-1) carry hi*hi | hi*lo', lanes 64-127 the lo'*hi term of the same
             // rows -- it crosses to the other warps through shared memory
             const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16) + accS;
@@ -792,18 +842,22 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
             }
             continue;
           }
-          const int mt = bi - rem64;
+          const int mt = bi - (stk ? 1 : 0);
+          const bool full = mt < n128;              // (ss64: the last one is the M = 64 tile)
           uint32_t x0[8], x1[8], y0[8];
           const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 48);
           tmem_ld8(tl + 8 * uh, x0);
           tmem_ld8(tl + 16 + 8 * uh, x1);
           tmem_ld8(tl + 32 + 8 * uh, y0);
           tmem_ld_wait();
-          const int j = mt * 128 + quad * 32 + lane;   // M = 128: lane = row
+          // M = 128: lane = row; M = 64: rows 16*quad .. +15 sit in lanes 0-15 of every quadrant
+          const int j = full ? mt * 128 + quad * 32 + lane : mt * 128 + quad * 16 + lane;
+          if (full || lane < 16) {
 #pragma unroll
-          for (int jj = 0; jj < 8; jj++) {
-            const float pv = (u2f(x0[jj]) + (u2f(x1[jj]) + u2f(y0[jj])) * kLoUnscale) * inv[jj];
-            st_word(pw + (size_t)(8 * uh + jj) * C + j, (__float_as_uint(pv) & 0xfffffffeu) | tagw);   // tag = LSB
+            for (int jj = 0; jj < 8; jj++) {
+              const float pv = (u2f(x0[jj]) + (u2f(x1[jj]) + u2f(y0[jj])) * kLoUnscale) * inv[jj];
+              st_word(pw + (size_t)(8 * uh + jj) * C + j, (__float_as_uint(pv) & 0xfffffffeu) | tagw);   // tag = LSB
+            }
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -842,14 +896,14 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
 // asks for most of the SM's shared memory so that no GEMM CTA of the side stream is placed next to it -- such a CTA
 // would sit in tcgen05.alloc until this kernel releases its 512 TMEM columns
 size_t tc_fwd_smem(int C) {
-  const size_t need = (size_t)(C / 64) * 4096 + 4 * TCL_UG * 32 * sizeof(float) + 1024;
+  const size_t need = (size_t)(C / 64) * 4096 + 4 * TCL_UG * 32 * sizeof(float) + (C > 448 ? 32768 : 0) + 1024;
   return need > 180 * 1024 ? need : (size_t)180 * 1024;
 }
 // backward: B tile + small scratch in the first 32 KB, then the full M tiles that do not fit TMEM (C = 384: one);
 // like the forward kernel it asks for most of the SM so that no TMEM-allocating GEMM CTA lands beside it
 size_t tc_bwd_smem(int C) {
   const int n128 = C >> 7, nts = n128 < 2 ? n128 : 2;
-  const size_t need = 32768 + (size_t)(n128 - nts) * 65536 + 1024;
+  const size_t need = 32768 + (size_t)(n128 - nts) * 65536 + 32768 + 1024;   // (+ 32 KB: the debug SS form of the 64-row tile)
   return need > 180 * 1024 ? need : (size_t)180 * 1024;
 }
 
@@ -883,7 +937,7 @@ LstmPlan lstm_tc_plan(int S, int C, int num_sms, size_t max_smem, int ndir) {
   if (C % 64 != 0 || C < 64 || S <= 0 || ndir < 1 || ndir > 2) return pl;
   const int groups = (S + TCL_UG - 1) / TCL_UG, slices = C / TCL_CS;
   const size_t sf = tc_fwd_smem(C), sb = tc_bwd_smem(C);
-  if ((long)ndir * groups * slices > num_sms || sf > max_smem || sb > max_smem || slices > 12) return pl;
+  if ((long)ndir * groups * slices > num_sms || sf > max_smem || sb > max_smem || slices > 16) return pl;
   pl.engine = 1;
   pl.nut = 2; pl.nct = 4; pl.ksplit = 1;
   pl.groups = groups; pl.slices = slices;
@@ -905,8 +959,11 @@ cudaError_t lstm_tc_forward(cudaStream_t st, const LstmPlan &pl, const LstmFwdAr
   int groups = pl.groups, ndir = pl.ndir;
   LstmFwdArgs args = a;
   void *kargs[] = {&args, &groups, &ndir};
-  const void *fn = a.drop == 0 ? (const void *)lstm_tc_fwd_kernel<0>
-                   : a.drop == 1 ? (const void *)lstm_tc_fwd_kernel<1> : (const void *)lstm_tc_fwd_kernel<2>;
+  const bool wide = a.C > 384;
+  const void *fn = wide ? (a.drop == 0 ? (const void *)lstm_tc_fwd_kernel<0, 1>
+                                       : a.drop == 1 ? (const void *)lstm_tc_fwd_kernel<1, 1> : (const void *)lstm_tc_fwd_kernel<2, 1>)
+                        : (a.drop == 0 ? (const void *)lstm_tc_fwd_kernel<0, 0>
+                                       : a.drop == 1 ? (const void *)lstm_tc_fwd_kernel<1, 0> : (const void *)lstm_tc_fwd_kernel<2, 0>);
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_fwd);
   if (e != cudaSuccess) return e;
   return cudaLaunchCooperativeKernel(fn, grid, block, kargs, pl.smem_fwd, st);
@@ -921,8 +978,11 @@ cudaError_t lstm_tc_backward(cudaStream_t st, const LstmPlan &pl, const LstmBwdA
   int groups = pl.groups, slices = pl.slices, ndir = pl.ndir;
   LstmBwdArgs args = a;
   void *kargs[] = {&args, &groups, &slices, &ndir};
-  const void *fn = a.drop == 0 ? (const void *)lstm_tc_bwd_kernel<0>
-                   : a.drop == 1 ? (const void *)lstm_tc_bwd_kernel<1> : (const void *)lstm_tc_bwd_kernel<2>;
+  const bool wide = a.C > 384;
+  const void *fn = wide ? (a.drop == 0 ? (const void *)lstm_tc_bwd_kernel<0, 1>
+                                       : a.drop == 1 ? (const void *)lstm_tc_bwd_kernel<1, 1> : (const void *)lstm_tc_bwd_kernel<2, 1>)
+                        : (a.drop == 0 ? (const void *)lstm_tc_bwd_kernel<0, 0>
+                                       : a.drop == 1 ? (const void *)lstm_tc_bwd_kernel<1, 0> : (const void *)lstm_tc_bwd_kernel<2, 0>);
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bwd);
   if (e != cudaSuccess) return e;
   return cudaLaunchCooperativeKernel(fn, grid, block, kargs, pl.smem_bwd, st);

@@ -392,6 +392,7 @@ static int lstm_forward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I,
   a.xbuf = xbuf;
   a.precision = ctx->rec_prec;
   a.drop = drop; a.rmask = rmask; a.ldr = ldr; a.rmask_per_step = per_step;
+  { const char *tn = getenv("EESEN_B200_TUNE"); a.tune = tn ? atoi(tn) : 0; }
   if (nchunks_g) { a.gflag = gflags; a.gepoch = ctx->gepoch; a.gchunk = gchunk; a.gready = kReady; }
   for (int s0 = 0; s0 < S; s0 += chunk) {
     a.s_begin = s0;
@@ -482,6 +483,7 @@ static int lstm_backward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I
   a.pbuf = pbuf; a.gsum = gsum;
   a.precision = ctx->rec_prec;
   a.drop = drop; a.rmask = rmask; a.ldr = ldr; a.rmask_per_step = per_step;
+  { const char *tn = getenv("EESEN_B200_TUNE"); a.tune = tn ? atoi(tn) : 0; }
   for (int ci = 0; ci < nchunks; ci++) {
     a.s_begin = ci * chunk;
     a.s_count = std::min(chunk, S - a.s_begin);

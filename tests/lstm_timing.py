@@ -21,15 +21,19 @@ if os.environ.get("EESEN_B200_LSTM_ENGINE") == "legacy":
     names_f = ["poll", "barA", "stage_ld", "barB", "mma", "scratch+barD", "elementwise+publish", "signal", "gate_stores+prefetch", "scratch reduce"]
     names_b = ["poll", "barA", "partials+elementwise", "barC", "mma+P stores", "signal"]
 else:   # tcgen05 engine (lstm_tc.cu)
-    names_f = ["stage (poll + B tile) + arrive", "MMA issue + commit wait", "TMEM ld + staging + barrier", "gates + publish", "saved-state stores + prefetch"]
-    names_b = ["gather partial d_m", "gate math + DG stores + B tile + arrive", "MMA issue + prefetch + commit wait", "TMEM ld + publish partials"]
+    names_f = ["stage (poll + B tile) + arrive", "MMA issue + commit wait", "TMEM ld + staging + barrier", "gates + publish", "saved-state stores + prefetch", "(re-polls of thread 0, count)"]
+    names_b = ["gather partial d_m", "gate math + DG stores + B tile + arrive", "MMA issue + prefetch + commit wait", "TMEM ld + publish partials", "(unused)", "(re-polls of thread 0, count)"]
 print(f"forward ({prec}) cycles/step (thread 0 of CTA 0; {steps} steps):")
 tot = 0
 for i, n in enumerate(names_f):
+    if n.startswith("("):
+        print(f"  {n:24s} {buf[i] / steps:9.2f}"); continue
     print(f"  {n:24s} {buf[i] / steps:9.0f}"); tot += buf[i] / steps
 print(f"  {'total':24s} {tot:9.0f}")
 print("backward cycles/step:")
 tot = 0
 for i, n in enumerate(names_b):
+    if n.startswith("("):
+        print(f"  {n:24s} {buf[16 + i] / steps:9.2f}"); continue
     print(f"  {n:24s} {buf[16 + i] / steps:9.0f}"); tot += buf[16 + i] / steps
 print(f"  {'total':24s} {tot:9.0f}")

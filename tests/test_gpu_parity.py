@@ -147,6 +147,7 @@ def test_ctc_eval_vs_oracle(ctx, seed, S, T, K, maxlab):
 @pytest.mark.parametrize("S,T,I,C", [(4, 9, 8, 16), (2, 30, 40, 128), (20, 17, 40, 64), (16, 40, 40, 320), (3, 5, 64, 24),
                                      (100, 7, 40, 320), (1, 1, 40, 64),    # 100 utts: two utterance chunks (64 + 36)
                                      (4, 11, 40, 192), (3, 9, 40, 384),    # backward tile mixes: 128 + stacked 64; 3 x 128
+                                     (3, 7, 40, 512), (18, 6, 40, 448),    # wide plans (C4's 512 cells): W_lo' partly / tiles 3-4 in smem
                                      (8, 300, 40, 64), (6, 290, 40, 320)]) # T >= 256: input product streamed in chunks
 @pytest.mark.parametrize("rec", ["fp32x3", "tf32", "legacy-engine", "tcfwd-engine"])
 def test_bilstm_layer_vs_oracle(ctx, S, T, I, C, rec, monkeypatch):
@@ -168,7 +169,10 @@ def test_bilstm_layer_vs_oracle(ctx, S, T, I, C, rec, monkeypatch):
     for s in range(S):
         x[np.arange(frames[s], T) * S + s] = 0
     l = kaldi_io.LayerSpec("bilstm", I, 2 * C)
-    params = [rng.uniform(-0.3, 0.3, size=l.param_shapes()[n]).astype(np.float32) for n in l.param_names()]
+    # U(-0.3, 0.3) is 3x the model's init range; over hundreds of steps a 320-cell recurrence with such weights is
+    # chaotic (rounding differences grow exponentially in ANY fp32 implementation), so the long shapes use the init range
+    wr = 0.3 if T <= 100 else 0.1
+    params = [rng.uniform(-wr, wr, size=l.param_shapes()[n]).astype(np.float32) for n in l.param_names()]
     dout = rng.standard_normal((T * S, 2 * C)).astype(np.float32)
     for s in range(S):
         dout[np.arange(frames[s], T) * S + s] = 0   # upper layers hand back zero gradient on padded rows
