@@ -222,14 +222,14 @@ def gpu_reference_leg(w, tmp: str, steps: int = 2):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
-def rooflines_from_profile(ms, counts, w, batches, peaks, steps, prec, wall_ms):
+def rooflines_from_profile(ms, counts, w, batches, peaks, steps, prec, wall_ms, engines=(1, 1)):
     """Per-kernel rooflines from the library's per-launch CUDA events (eesen_b200_profile).
     Algorithmic figures (SURVEY.md section 8d split by kernel):
       recurrent forward  : 20*C floats per valid frame and layer (read pre-acts 8C, write g,i,f,o,c,m 12C)
       recurrent backward : 22*C floats per valid frame and layer (read saved 12C + dout 2C, write DGIFO 8C)
       dense GEMMs        : 48*C*I + 16*C*C per layer + 12*C*K flops per PADDED frame (all rows are multiplied)
     `traffic` = dram__bytes_read+write per launch from the committed ncu --set full capture
-    (profiles/r01_traffic.json), or null."""
+    (profiles/traffic.json), or null.  engines = (forward, backward): 1 = tcgen05 recurrent kernels, 0 = warp-level."""
     # shares are taken against the measured wall time of the timed steps: the weight-gradient products and the
     # per-layer all-reduces run on a side stream concurrently with the recurrent kernels, so the per-category
     # CUDA-event sums may add up to more than the step
@@ -237,7 +237,7 @@ def rooflines_from_profile(ms, counts, w, batches, peaks, steps, prec, wall_ms):
     valid = float(np.mean([b.valid_frames for b in batches]))
     padded = float(np.mean([b.feats.shape[0] for b in batches]))
     traffic = {}
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
             traffic = json.load(open(tp)).get(w.name, {})
@@ -250,8 +250,10 @@ def rooflines_from_profile(ms, counts, w, batches, peaks, steps, prec, wall_ms):
         by = (20.0 if k == "lstm_fwd" else 22.0) * w.cells * 4.0 * valid   # bytes per launch (one layer)
         dur = ms[k] / counts[k] * 1e-3
         ach = by / dur / 1e9
-        out[k] = {"kernel": k + "_kernel", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                  "frac": ach / peaks["hbm_gbs"], "traffic": traffic.get(k), "peak_source": peaks["source"],
+        eng = engines[0 if k == "lstm_fwd" else 1]
+        kname = ("lstm_tc_" if eng == 1 else "lstm_") + ("fwd" if k == "lstm_fwd" else "bwd") + "_kernel"
+        out[k] = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                  "frac": ach / peaks["hbm_gbs"], "traffic": traffic.get(kname), "peak_source": peaks["source"],
                   "algorithmic_bytes_per_launch": by, "avg_launch_ms": dur * 1e3, "launches_per_step": counts[k] / steps,
                   "share_of_step": ms[k] / tot,
                   "note": "latency-bound at 64 utterances/GPU: T dependent steps per launch (SURVEY.md 7.1)"}
@@ -265,14 +267,20 @@ def rooflines_from_profile(ms, counts, w, batches, peaks, steps, prec, wall_ms):
         flops = fl * padded
         dur = ms["gemm"] / steps * 1e-3
         ach = flops / dur / 1e12
-        mult = {"fp32x3": 6.0, "tf32": 2.0, "bf16": 1.0}[prec]   # tensor-pipe work per algorithmic flop, in bf16 units
-        out["gemm"] = {"kernel": "gemm_tc_kernel (all dense contractions of a step)", "bound": "tensor", "achieved": ach,
+        tf32x3 = os.environ.get("EESEN_B200_GEMM_FP32X3") == "tf32"
+        mult = {"fp32x3": 6.0 if tf32x3 else 3.0, "tf32": 2.0, "bf16": 1.0}[prec]   # tensor-pipe work per algorithmic flop, in bf16 units
+        gnote = {"fp32x3": "arithmetic fp32x3: 3 tcgen05 kind::f16 MMAs per product on fp16 hi/lo planes (3 bf16-equivalent flops per algorithmic flop)",
+                 "tf32": "arithmetic tf32: 1 tcgen05 kind::tf32 MMA per product (tf32 runs at half the bf16 rate)",
+                 "bf16": "arithmetic bf16: 1 tcgen05 kind::f16 MMA per product"}[prec]
+        if os.environ.get("EESEN_B200_GEMM_FP32X3") == "tf32" and prec == "fp32x3":
+            gnote = "arithmetic fp32x3 on kind::tf32 (3 MMAs per product at half the bf16 rate)"
+        out["gemm"] = {"kernel": "gemm_tc16_kernel (all dense contractions of a step, operand conversions included)", "bound": "tensor", "achieved": ach,
                        "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                        "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic.get("gemm"),
                        "peak_source": peaks["source"], "algorithmic_flops_per_step": flops,
                        "launches_per_step": counts["gemm"] / steps, "share_of_step": ms["gemm"] / tot,
                        "tensor_pipe_frac_bf16_equiv": ach * mult / peaks["bf16_tflops_sustained"],
-                       "note": f"arithmetic {prec}: {int(mult / 2)} tcgen05 kind::tf32 MMAs per product (tf32 runs at half the bf16 rate)"}
+                       "note": gnote}
     return out
 
 
@@ -433,7 +441,8 @@ def run_ours(args, w):
                                  "launches on the side stream overlap the recurrent kernels, so the sum can exceed ms_per_step",
             "last_step_stats": stats,
         }
-        allr = rooflines_from_profile(prof_ms, prof_cnt, w, pool, peaks, args.steps, args.gemm_precision, ms_dev)
+        engines = (ctx.lstm_engine(w.S, w.cells, 2, False), ctx.lstm_engine(w.S, w.cells, 2, True))
+        allr = rooflines_from_profile(prof_ms, prof_cnt, w, pool, peaks, args.steps, args.gemm_precision, ms_dev, engines)
         # dominant kernel = the single kernel function with the largest share of the step; the dense
         # contractions are one kernel template launched ~25x per step and are reported next to it
         dom = max((k for k in allr if k != "gemm"), key=lambda k: allr[k]["share_of_step"], default="gemm")

@@ -110,6 +110,10 @@ class Context:
     def sm_count(self) -> int:
         return int(self.lib.eesen_b200_sm_count(self.h))
 
+    def lstm_engine(self, num_utts: int, cells: int, ndir: int = 2, backward: bool = False) -> int:
+        """1 = tcgen05 recurrent kernels, 0 = warp-level kernels, -1 = no plan (eesen_b200_lstm_engine)."""
+        return int(self.lib.eesen_b200_lstm_engine(self.h, C.c_int(num_utts), C.c_int(cells), C.c_int(ndir), C.c_int(1 if backward else 0)))
+
     PROFILE_CATEGORIES = ("gemm", "lstm_fwd", "lstm_bwd", "softmax", "ctc", "sgd", "allreduce", "misc")
 
     def profile(self, enable: int = -1):

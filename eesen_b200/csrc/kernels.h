@@ -94,6 +94,7 @@ struct LstmPlan {
   int threads;
   size_t smem_fwd, smem_bwd;
   size_t pbuf_floats, gsum_floats, xbuf_bytes;
+  int cluster;           // (engine 1) 1: the CTAs of a (dir, group) form a thread-block cluster and exchange through DSMEM
   int valid;
 };
 // pass: 0 = forward, 1 = backward (the engines are chosen per pass, lstm.cu:engine_for_pass)

@@ -602,6 +602,7 @@ LstmPlan lstm_plan(int S, int C, int num_sms, size_t max_smem, int ndir, int pas
   LstmPlan best;
   best.valid = 0;
   best.engine = 0;
+  best.cluster = 0;
   best.ndir = ndir;
   long best_work = -1;
   if (C % 8 != 0 || C <= 0 || S <= 0 || ndir < 1 || ndir > 2) return best;

@@ -46,7 +46,7 @@ namespace eb {
 // trip five times per step)
 __device__ long long g_lstm_tc_timing[2][16];
 #define TC_T0() long long tk_ = clock64()
-#define TC_ACC_DECL() long long tacc_[6] = {0, 0, 0, 0, 0, 0}
+#define TC_ACC_DECL() long long tacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define TC_TICK(kernel, i)                                                          \
   do {                                                                              \
     if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {        \
@@ -59,7 +59,7 @@ __device__ long long g_lstm_tc_timing[2][16];
 #define TC_FLUSH(kernel)                                                            \
   do {                                                                              \
     if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)          \
-      for (int i_ = 0; i_ < 6; i_++) g_lstm_tc_timing[kernel][i_] += tacc_[i_];     \
+      for (int i_ = 0; i_ < 8; i_++) g_lstm_tc_timing[kernel][i_] += tacc_[i_];     \
   } while (0)
 #else
 #define TC_T0()
@@ -123,7 +123,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&w)[8])
                : "memory");
 }
 // NLO = number of leading k-slices whose W_lo' sits in TMEM; the remaining ones (C = 512: TMEM is full) are read from
-// the shared-memory tile dWloS ("SS" form)
+// the shared-memory tile dWloS ("SS" form).
+// (Measured, tests/micro/umma_probe.cu + profiles/r02_d_chains.txt: these small MMAs are ISSUE-bound, ~22-27 cycles per
+// instruction whatever N (16..64) and whether or not consecutive ones hit the same accumulator -- splitting K over four
+// independent accumulator chains, or interleaving the tiles of the backward step, changed nothing and was removed.)
 template <int KB, int NLO>
 __device__ __forceinline__ void issue_fwd_mmas_ts(uint32_t tWhi, uint32_t tWlo, uint64_t dWloS, uint64_t dB, uint32_t tmem,
                                                   uint32_t idN, uint32_t idH) {
@@ -200,6 +203,23 @@ __device__ __forceinline__ void wait_flag(const unsigned *p, unsigned v) {
     if (clock64() - t0 > (1ll << 33)) __trap();
   }
 }
+// mbarrier wait on bytes that peers of the cluster push (st.async complete_tx); bounded like wait_flag
+__device__ __forceinline__ void mbar_wait_peers(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  long long t0 = 0;
+  for (;;) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (t0 == 0) t0 = clock64();
+    else if (clock64() - t0 > (1ll << 33)) __trap();
+  }
+}
 __global__ void set_flag_kernel(unsigned *flag, unsigned value) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(flag), "r"(value) : "memory");
 }
@@ -216,22 +236,31 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // ------------------------------------------------------------------------------------ forward
 // WIDE = 1: 384 < C <= 512 (4 exchange chunks per thread; at C = 512 the last 8 k-slices of W_lo' in shared memory)
-template <int DROP, int WIDE>
+// CL = 1: the `slices` CTAs of one (dir, group) are ONE thread-block cluster and exchange m_t through distributed shared
+// memory instead of L2: every warp pushes the hi / lo' halves of its 2 utterances x 32 cells as 16-byte st.async stores
+// straight into the (double-buffered) B tile of all CTAs of the cluster, complete_tx on the destination's mbarrier; the
+// MMA-issuing warp sleeps on that mbarrier -- no polling, no staging pass, no grid-wide co-residency requirement.
+// Measured ping-pong (tests/micro/cluster_exchange2.cu, 8 clusters of 10 CTAs): 1.63 k cycles per step against 2.80 k
+// (mean; slowest CTA 4.0 k) for the tagged words through L2.
+template <int DROP, int WIDE, int CL>
 __global__ void __launch_bounds__(TCL_THREADS, 1)
 lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int C = a.C, S = a.S, T = a.T;
   const int KB = C >> 6;                                  // 64-wide k-blocks (C % 64 == 0)
-  uint8_t *Bt = smem;                                     // [KB][32 rows][128 B]: rows 0-15 hi, 16-31 lo'
-  float *stg = reinterpret_cast<float *>(Bt + (size_t)KB * 4096);   // [4 gates][16 utts][32 cells]
+  uint8_t *Bt = smem;                                     // [CL ? 2 : 1][KB][32 rows][128 B]: rows 0-15 hi, 16-31 lo'
+  const uint32_t bt_bytes = (uint32_t)KB * 4096u;
+  float *stg = reinterpret_cast<float *>(Bt + (size_t)(CL ? 2 : 1) * bt_bytes);   // [4 gates][16 utts][32 cells]
+  uint8_t *pub = reinterpret_cast<uint8_t *>(stg) + 8192;  // (CL) [8 warps][hi | lo'][2 utts][32 cells] fp16: 256 B per warp
   // TMEM columns: [0,32) X accumulator, [32,48) Y accumulator, [64, 64 + C/2) W_hi, [64 + C/2, ..) W_lo' of the first
   // nlo k-slices (all of them up to C = 448; 24 of 32 at C = 512, the other 8 in the shared-memory tile WloS)
   constexpr uint32_t kColW = 64;
   const int nks = C >> 4;
   const int nlo = (WIDE && nks > 28) ? 24 : nks;
   uint8_t *WloS = Bt + (size_t)KB * 4096 + 8192;                     // [k-blocks from slice nlo on][128 rows][128 B]
-  __shared__ uint64_t b_full, mma_done;
+  __shared__ uint64_t b_full, mma_done, xfull[2];
+  const uint32_t slices = gridDim.x, xbytes = slices * 2048u;        // (CL) bytes a CTA receives per step
   __shared__ uint32_t tmem_base_sm;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -240,11 +269,17 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
   uint32_t *xbuf = reinterpret_cast<uint32_t *>(a.xbuf);  // [2 parity][ndir][groups][16][C] 4-byte tagged words
   const int s0 = a.s_begin, s1 = a.s_begin + a.s_count;
 
-  for (int idx = tid; idx < KB * 1024; idx += TCL_THREADS) reinterpret_cast<uint32_t *>(Bt)[idx] = 0u;
+  for (int idx = tid; idx < (CL ? 2 : 1) * KB * 1024; idx += TCL_THREADS) reinterpret_cast<uint32_t *>(Bt)[idx] = 0u;
   if (tid == 0) {
     mbar_init(&b_full, TCL_WORKERS);
     mbar_init(&mma_done, 1);
+    mbar_init(&xfull[0], 1);
+    mbar_init(&xfull[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    if (CL) {   // m_0 lands in tile 0, m_1 in tile 1; each tile is re-armed when its MMAs have been issued
+      mbar_expect_tx(&xfull[0], xbytes);
+      mbar_expect_tx(&xfull[1], xbytes);
+    }
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_sm)), "n"(512)
@@ -256,6 +291,7 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = tmem_base_sm;
+  if (CL) cluster_sync_all();   // every CTA of the cluster has its barriers armed and its tiles zeroed before anyone pushes
 
   // ---- resident weights, in TMEM for the whole sequence: lane = gate*32 + local cell, the row's K = C values split
   // into fp16 hi / lo' and packed two per column.  Warps w and w+4 own the same lane quadrant: they take alternate
@@ -325,8 +361,8 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
     int ghave = a.gready - 1;                              // last chunk of G known to be complete
     const int c8n = C >> 3;                                // 8-cell chunks per utterance row
     const int quad = warp & 3, uh = warp >> 2;             // epilogue: TMEM lane quadrant (= gate), utterance half
-    const uint64_t dBt = umma_desc(smem_u32(Bt), 16, 1024, 2);
-    // exchange chunks of this thread (fixed for the whole sequence)
+    const uint64_t dBt0 = umma_desc(smem_u32(Bt), 16, 1024, 2);
+    // exchange chunks of this thread (fixed for the whole sequence; L2 path)
     constexpr int MAXT = WIDE ? 4 : 3;                     // 16 * (C/8) / 256 <= 3 for C <= 384, 4 for C <= 512
     uint4 xq[MAXT][2];
     size_t xoff[MAXT];
@@ -348,6 +384,7 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
       for (int q = 0; q < 4; q++) { acc[q][0] = 0.f; acc[q][1] = 0.f; }
       TC_T0();
       if (step > 0) {
+        if (!CL) {
         // ---- stage m_{t-1} of the group: spin on the tagged words, write the hi / lo' rows of the B tile
         const uint4 *xr = reinterpret_cast<const uint4 *>(
             xbuf + ((size_t)(((step - 1) & 1) * ndir + dir) * groups + group) * TCL_UG * C);
@@ -379,12 +416,21 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
         }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
         mbar_arrive(&b_full);
+        }
         TC_TICK(0, 0);
         if (warp == 0) {
           // ===== MMA issue: 2 instructions per 16-wide k-slice, one commit =====
-          mbar_wait(&b_full, (uint32_t)((step - 1) & 1));
+          if (CL) {
+            // m_{t-1} of the whole group has landed in tile (step-1)&1 when the bytes armed on its mbarrier are complete
+            mbar_wait_peers(&xfull[(step - 1) & 1], (uint32_t)(((step - 1) >> 1) & 1));
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // remote generic-proxy stores -> UMMA reads
+            if (lane == 0) mbar_expect_tx(&xfull[(step - 1) & 1], xbytes);      // armed again for m_{t+1}
+          } else {
+            mbar_wait(&b_full, (uint32_t)((step - 1) & 1));
+          }
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           if (elect_one()) {
+            const uint64_t dBt = dBt0 + (uint64_t)(CL ? ((uint32_t)((step - 1) & 1) * (bt_bytes >> 4)) : 0u);
             const uint32_t idN = idesc_f16(128, 32), idH = idesc_f16(128, 16);
             const uint32_t tWhi = tmem_base + kColW, tWlo = tmem_base + kColW + (uint32_t)(C >> 1);
             const uint64_t dWloS = umma_desc(smem_u32(WloS), 16, 1024, 2);
@@ -451,7 +497,32 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
         sc[e] = keep ? c : 0.f; sm[e] = keep ? m : 0.f;
         cprev[e] = sc[e];
       }
-      // only m is on the inter-CTA critical path: publish it first (already split, tagged word, no fence)
+      // only m is on the inter-CTA critical path: publish it first
+      if (CL) {
+        if (step + 1 < T) {
+          // the warp's [hi | lo'][2 utts][32 cells] halves -> 16 chunks of 16 bytes in its own staging area, then lane
+          // (chunk, half of the destinations) pushes its chunk into tile `step & 1` of every CTA of the cluster
+          uint16_t *pw = reinterpret_cast<uint16_t *>(pub + warp * 256);
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            uint32_t h, l;
+            split_f16(sm[e], h, l);          // (sm = 0 for padded / absent utterances: the rows are zeros)
+            pw[e * 32 + cl] = (uint16_t)h;
+            pw[(2 + e) * 32 + cl] = (uint16_t)l;
+          }
+          __syncwarp();
+          const int ch = lane & 15;                        // chunk = (kind, e, 8-cell group)
+          const uint4 v = *reinterpret_cast<const uint4 *>(pub + warp * 256 + ch * 16);
+          const int row = (ch >> 3) * 16 + 2 * up + ((ch >> 2) & 1);
+          const uint32_t la = smem_u32(Bt) + (uint32_t)(step & 1) * bt_bytes + sw128_off(32, row, slice * TCL_CS + (ch & 3) * 8);
+          const uint32_t lb = smem_u32(&xfull[step & 1]);
+          for (uint32_t d = (uint32_t)(lane >> 4); d < slices; d += 2) st_async16(mapa_u32(la, d), v, mapa_u32(lb, d));
+          __syncwarp();   // (the staging area is rewritten at the next step)
+        }
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+          if (valid[e]) __stcs(a.out + ((size_t)t * S + uidx[e]) * a.ldo + (size_t)dir * C + cell, sm[e]);
+      } else {
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         if (valid[e]) {
@@ -464,13 +535,14 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
           __stcs(a.out + ((size_t)t * S + uidx[e]) * a.ldo + (size_t)dir * C + cell, sm[e]);
         }
       }
+      }
       auto first_poll = [&]() {   // first poll of the words the group is publishing right now (consumed at the next step)
         const uint4 *xn = reinterpret_cast<const uint4 *>(xbuf + ((size_t)((step & 1) * ndir + dir) * groups + group) * TCL_UG * C);
 #pragma unroll
         for (int i = 0; i < MAXT; i++)
           if (live[i]) { xq[i][0] = ld_word4(xn + xoff[i]); xq[i][1] = ld_word4(xn + xoff[i] + 1); }
       };
-      if (step + 1 < T && !(a.tune & 1)) first_poll();
+      if (!CL && step + 1 < T && !(a.tune & 1)) first_poll();
       TC_TICK(0, 3);
 #pragma unroll
       for (int e = 0; e < 2; e++) {
@@ -481,7 +553,7 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
           __stcs(a.cell + ((size_t)t * S + uidx[e]) * a.ldc + (size_t)dir * C + cell, sc[e]);
         }
       }
-      if (step + 1 < T && (a.tune & 1)) first_poll();
+      if (!CL && step + 1 < T && (a.tune & 1)) first_poll();
       if (step + 1 < T) {
         if (a.gflag) {   // streamed input product: the next position may lie in a chunk that is still being computed
           const int need = (step + 1) / a.gchunk;
@@ -496,6 +568,7 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
 
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  if (CL) cluster_sync_all();   // no CTA leaves while a peer could still address its shared memory
   if (warp == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(512) : "memory");
@@ -508,14 +581,18 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
 // (C = 384) in shared memory; the 64 rows left when C % 128 == 64 form a "stacked" TMEM tile (hi in lanes 0-63, lo' in
 // lanes 64-127);  B = D (scaled per utterance, hi rows 0-15 | lo' rows 16-31) [32 x 128 k].
 // WIDE = 1: 384 < C <= 512 (up to 4 M tiles: 192 accumulator columns, two tiles in shared memory; 16 producers)
-template <int DROP, int WIDE>
+// CL = 1: the `slices` CTAs of one (dir, group) are one thread-block cluster (see lstm_tc_fwd_kernel); the partial d_m
+// rows a CTA computed for the cells of CTA d go straight into d's receive buffer R[parity][producer][32 cells][16 utts]
+// (row stride 80 bytes) as two 16-byte st.async stores per thread and tile -- the 32 accumulator rows of a warp's TMEM lane
+// quadrant are exactly the 32 cells of ONE destination -- and the owner adds the `slices` blocks in producer order.
+template <int DROP, int WIDE, int CL>
 __global__ void __launch_bounds__(TCL_THREADS, 1)
 lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int C = a.C, S = a.S, T = a.T;
   const int n128 = C >> 7, rem64 = (C & 127) ? 1 : 0, MT = n128 + rem64;
-  const bool ss64 = rem64 && (a.tune & 2);                // debug: the 64-row tile as an M = 64 SS-form tile, issued last
+  const bool ss64 = !CL && rem64 && (a.tune & 2);         // debug: the 64-row tile as an M = 64 SS-form tile, issued last
   const bool stk = rem64 && !ss64;                        // default: stacked TMEM tile, issued first
   const int NTS = n128 < 2 ? n128 : 2;                    // full tiles resident in TMEM
   uint8_t *Bt = smem;                                     // [2 k-blocks][32 rows][128 B]
@@ -527,7 +604,10 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
   uint8_t *Alo = Ahi + (size_t)(n128 - NTS) * 32768;
   uint8_t *Ahi64 = Alo + (size_t)(n128 - NTS) * 32768;    // (ss64 only) [2 k-blocks][64 rows][128 B], hi then lo'
   uint8_t *Alo64 = Ahi64 + 16384;
-  __shared__ uint64_t b_full, mma_done[4];   // one commit barrier per M tile (at most 4 tiles)
+  constexpr int kRRow = 20, kRBlk = 32 * kRRow;           // (CL) floats per cell row (16 utts + pad: 80 B) / per producer block
+  float *R = reinterpret_cast<float *>(Alo64 + 16384);    // (CL) [2 parity][slices][32 cells][kRRow]
+  const uint32_t rbytes = (uint32_t)slices * 2048u;       // (CL) payload bytes a CTA receives per step
+  __shared__ uint64_t b_full, mma_done[4], rfull[2];   // one commit barrier per M tile (at most 4 tiles)
   __shared__ uint32_t tmem_base_sm;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -572,7 +652,13 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
   if (tid == 0) {
     mbar_init(&b_full, TCL_WORKERS);
     for (int i = 0; i < 4; i++) mbar_init(&mma_done[i], 1);
+    mbar_init(&rfull[0], 1);
+    mbar_init(&rfull[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    if (CL) {   // the partials of step 0 land in buffer 0, of step 1 in buffer 1; re-armed after every gather
+      mbar_expect_tx(&rfull[0], rbytes);
+      mbar_expect_tx(&rfull[1], rbytes);
+    }
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_sm)), "n"(512)
@@ -584,6 +670,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = tmem_base_sm;
+  if (CL) cluster_sync_all();   // barriers of every CTA of the cluster armed before anyone pushes
 
   // ---- the first two full M tiles of Wm^T also go to TMEM (columns [160, 160 + 128 * NTS): per tile 64 columns hi,
   // 64 columns lo'; lane = output cell within the tile, 8 columns per 16-wide k-slice of this CTA's 128 gate rows):
@@ -688,7 +775,23 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
       const int t = dir == 0 ? T - 1 - step : step;
       TC_T0();
       float dm[2] = {vd[0], vd[1]};
-      if (step > 0) {
+      if (CL && step > 0) {
+        // ---- d_m of this thread's items: the `slices` blocks that landed in buffer (step-1)&1, added in producer order
+        const int par = (step - 1) & 1;
+        mbar_wait_peers(&rfull[par], (uint32_t)(((step - 1) >> 1) & 1));
+        const float *rb = R + (size_t)par * slices * kRBlk + cl * kRRow + 2 * up;
+        float s0_ = 0.f, s1_ = 0.f;
+        for (int p = 0; p < slices; p++) {
+          const float2 v = *reinterpret_cast<const float2 *>(rb + (size_t)p * kRBlk);
+          s0_ += v.x; s1_ += v.y;
+        }
+        if (ok[0]) dm[0] += s0_;
+        if (ok[1]) dm[1] += s1_;
+        // armed again for the partials of step + 1 (they cannot arrive before this CTA has published step's partials,
+        // which it does behind the b_full barrier all its threads reach after this gather)
+        if (tid == 0) mbar_expect_tx(&rfull[par], rbytes);
+      }
+      if (!CL && step > 0) {
         // ---- d_m of this thread's items: the `slices` tagged partials, summed in fixed order (:470 / :561)
         // Cooperative and wide: the CTA needs, from each of the `slices` producers, a [16 utterances x 32 cells] block of
         // partials (128 contiguous bytes per utterance row).  Thread (half, u, c4) fetches 4 cells of utterance u from
@@ -781,7 +884,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
         mbar_wait(&b_full, (uint32_t)(step & 1));
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         if (elect_one()) {
-          // one commit per M tile: the epilogue (TMEM -> tagged words) of a tile runs while the tensor pipe is
+          // one commit per M tile: the epilogue (TMEM -> partial words) of a tile runs while the tensor pipe is
           // still working on the next one.  The stacked tile goes first: its epilogue has one more hand-over.
           int nb = 0;
           if (stk) {
@@ -801,15 +904,25 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
         }
         __syncwarp();
       }
-      prefetch(t + tstep);
       TC_TICK(1, 2);
+      prefetch(t + tstep);
+      TC_TICK(1, 4);
       {
         uint32_t *pw = pbuf + ((size_t)((((step & 1) * ndir + dir) * groups + group) * slices + slice)) * pstride_slice;
         const uint32_t tagw = (uint32_t)((step >> 1) & 1);
         float inv[8];
+        // (CL) the 8 utterance values of accumulator row `row` of the 32-row block that belongs to CTA d of the cluster:
+        // two 16-byte stores into d's receive buffer (step & 1), block `slice` (= this producer), complete_tx on d's barrier
+        auto push8 = [&](uint32_t d, int row, const float (&pv)[8]) {
+          const uint32_t la = smem_u32(R) + (uint32_t)((((step & 1) * slices + slice) * kRBlk + row * kRRow + 8 * uh) * 4);
+          const uint32_t ra = mapa_u32(la, d), rbar = mapa_u32(smem_u32(&rfull[step & 1]), d);
+          st_async16(ra, make_uint4(__float_as_uint(pv[0]), __float_as_uint(pv[1]), __float_as_uint(pv[2]), __float_as_uint(pv[3])), rbar);
+          st_async16(ra + 16, make_uint4(__float_as_uint(pv[4]), __float_as_uint(pv[5]), __float_as_uint(pv[6]), __float_as_uint(pv[7])), rbar);
+        };
         for (int bi = 0; bi < MT; bi++) {
           mbar_wait(&mma_done[bi], (uint32_t)(step & 1));
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          TC_TICK(1, 6);   // (debug build: time spent waiting for the tiles' commits)
           if (bi == 0) {   // the column scales were written by the other warps before they arrived on b_full: read
                            // them only behind the first commit (which is behind b_full)
 #pragma unroll
@@ -834,12 +947,18 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
               tmem_ld_wait();
               asm volatile("bar.sync 2, 256;\n" ::: "memory");
               const int j = n128 * 128 + r;
+              float pv[8];
 #pragma unroll
-              for (int jj = 0; jj < 8; jj++) {
-                const float pv = (u2f(x0[jj]) + (u2f(x1[jj]) + ysm[(8 * uh + jj) * 64 + r]) * kLoUnscale) * inv[jj];
-                st_word(pw + (size_t)(8 * uh + jj) * C + j, (__float_as_uint(pv) & 0xfffffffeu) | tagw);   // tag = LSB
+              for (int jj = 0; jj < 8; jj++) pv[jj] = (u2f(x0[jj]) + (u2f(x1[jj]) + ysm[(8 * uh + jj) * 64 + r]) * kLoUnscale) * inv[jj];
+              if (CL) {
+                push8((uint32_t)(n128 * 4 + (quad & 1)), lane, pv);
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++)
+                  st_word(pw + (size_t)(8 * uh + jj) * C + j, (__float_as_uint(pv[jj]) & 0xfffffffeu) | tagw);   // tag = LSB
               }
             }
+            TC_TICK(1, 3);
             continue;
           }
           const int mt = bi - (stk ? 1 : 0);
@@ -853,12 +972,18 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
           // M = 128: lane = row; M = 64: rows 16*quad .. +15 sit in lanes 0-15 of every quadrant
           const int j = full ? mt * 128 + quad * 32 + lane : mt * 128 + quad * 16 + lane;
           if (full || lane < 16) {
+            float pv[8];
 #pragma unroll
-            for (int jj = 0; jj < 8; jj++) {
-              const float pv = (u2f(x0[jj]) + (u2f(x1[jj]) + u2f(y0[jj])) * kLoUnscale) * inv[jj];
-              st_word(pw + (size_t)(8 * uh + jj) * C + j, (__float_as_uint(pv) & 0xfffffffeu) | tagw);   // tag = LSB
+            for (int jj = 0; jj < 8; jj++) pv[jj] = (u2f(x0[jj]) + (u2f(x1[jj]) + u2f(y0[jj])) * kLoUnscale) * inv[jj];
+            if (CL) {
+              push8((uint32_t)(mt * 4 + quad), lane, pv);   // (CL: full tiles only)
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 8; jj++)
+                st_word(pw + (size_t)(8 * uh + jj) * C + j, (__float_as_uint(pv[jj]) & 0xfffffffeu) | tagw);   // tag = LSB
             }
           }
+          TC_TICK(1, 3);
         }
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       }
@@ -886,6 +1011,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
 
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  if (CL) cluster_sync_all();   // no CTA leaves while a peer could still address its shared memory
   if (warp == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(512) : "memory");
@@ -896,15 +1022,77 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
 // asks for most of the SM's shared memory so that no GEMM CTA of the side stream is placed next to it -- such a CTA
 // would sit in tcgen05.alloc until this kernel releases its 512 TMEM columns
 size_t tc_fwd_smem(int C) {
-  const size_t need = (size_t)(C / 64) * 4096 + 4 * TCL_UG * 32 * sizeof(float) + (C > 448 ? 32768 : 0) + 1024;
+  // (cluster exchange, C <= 384: two B tiles + the warps' 2 KB publish staging)
+  const size_t need = (size_t)(C <= 384 ? 2 : 1) * (C / 64) * 4096 + 4 * TCL_UG * 32 * sizeof(float) + 2048 + (C > 448 ? 32768 : 0) + 1024;
   return need > 180 * 1024 ? need : (size_t)180 * 1024;
 }
-// backward: B tile + small scratch in the first 32 KB, then the full M tiles that do not fit TMEM (C = 384: one);
+// backward: B tile + small scratch in the first 32 KB, then the full M tiles that do not fit TMEM (C = 384: one), then
+// (cluster exchange, C <= 384) the receive buffers [2][slices][32 cells][80 B];
 // like the forward kernel it asks for most of the SM so that no TMEM-allocating GEMM CTA lands beside it
 size_t tc_bwd_smem(int C) {
   const int n128 = C >> 7, nts = n128 < 2 ? n128 : 2;
-  const size_t need = 32768 + (size_t)(n128 - nts) * 65536 + 32768 + 1024;   // (+ 32 KB: the debug SS form of the 64-row tile)
+  const size_t need = 32768 + (size_t)(n128 - nts) * 65536 + 32768 + 1024 +   // (+ 32 KB: the debug SS form of the 64-row tile)
+                      (C <= 384 ? (size_t)2 * (C / TCL_CS) * 32 * 80 : 0);
   return need > 180 * 1024 ? need : (size_t)180 * 1024;
+}
+
+const void *tc_fwd_fn(int drop, bool wide, bool cl) {
+  if (wide) return drop == 0 ? (const void *)lstm_tc_fwd_kernel<0, 1, 0> : drop == 1 ? (const void *)lstm_tc_fwd_kernel<1, 1, 0> : (const void *)lstm_tc_fwd_kernel<2, 1, 0>;
+  if (cl) return drop == 0 ? (const void *)lstm_tc_fwd_kernel<0, 0, 1> : drop == 1 ? (const void *)lstm_tc_fwd_kernel<1, 0, 1> : (const void *)lstm_tc_fwd_kernel<2, 0, 1>;
+  return drop == 0 ? (const void *)lstm_tc_fwd_kernel<0, 0, 0> : drop == 1 ? (const void *)lstm_tc_fwd_kernel<1, 0, 0> : (const void *)lstm_tc_fwd_kernel<2, 0, 0>;
+}
+const void *tc_bwd_fn(int drop, bool wide, bool cl) {
+  if (wide) return drop == 0 ? (const void *)lstm_tc_bwd_kernel<0, 1, 0> : drop == 1 ? (const void *)lstm_tc_bwd_kernel<1, 1, 0> : (const void *)lstm_tc_bwd_kernel<2, 1, 0>;
+  if (cl) return drop == 0 ? (const void *)lstm_tc_bwd_kernel<0, 0, 1> : drop == 1 ? (const void *)lstm_tc_bwd_kernel<1, 0, 1> : (const void *)lstm_tc_bwd_kernel<2, 0, 1>;
+  return drop == 0 ? (const void *)lstm_tc_bwd_kernel<0, 0, 0> : drop == 1 ? (const void *)lstm_tc_bwd_kernel<1, 0, 0> : (const void *)lstm_tc_bwd_kernel<2, 0, 0>;
+}
+
+// launch configuration of the cluster variant: one cluster = the `slices` CTAs of one (dir, group)
+struct ClusterLaunch {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute at[1];
+  ClusterLaunch(const LstmPlan &pl, size_t smem, cudaStream_t st) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = dim3(pl.slices, pl.groups, pl.ndir);
+    cfg.blockDim = dim3(pl.threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = pl.slices; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+  }
+};
+cudaError_t tc_prepare_fn(const void *fn, size_t smem, int slices, bool cl) {
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess && cl && slices > 8) e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  return e;
+}
+
+// 1 when every (dir, group) cluster of `slices` CTAs of both passes can be resident at the same time (else the clusters
+// would run in waves and the tagged-word exchange through L2 is the better plan).  EESEN_B200_LSTM_EXCHANGE=l2 forces
+// the L2 exchange (A/B measurements).
+int tc_cluster_ok(const LstmPlan &pl, int C) {
+  const char *ex = getenv("EESEN_B200_LSTM_EXCHANGE");
+  if (ex && strcmp(ex, "l2") == 0) return 0;
+  if (C > 384 || pl.slices > 16 || pl.slices < 1) return 0;
+  static int cache[2][17][17];   // [ndir - 1][groups][slices]: 0 unknown, 1 no, 2 yes
+  if (pl.groups > 16) return 0;
+  int &c = cache[pl.ndir - 1][pl.groups][pl.slices];
+  if (c == 0) {
+    bool ok = true;
+    for (int pass = 0; pass < 2 && ok; pass++) {
+      const void *fn = pass == 0 ? tc_fwd_fn(0, false, true) : tc_bwd_fn(0, false, true);
+      const size_t smem = pass == 0 ? pl.smem_fwd : pl.smem_bwd;
+      if (tc_prepare_fn(fn, smem, pl.slices, true) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+      ClusterLaunch cl(pl, smem, 0);
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, fn, &cl.cfg) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+      ok = n >= pl.ndir * pl.groups;
+    }
+    c = ok ? 2 : 1;
+  }
+  return c == 2;
 }
 
 }  // namespace
@@ -946,6 +1134,7 @@ LstmPlan lstm_tc_plan(int S, int C, int num_sms, size_t max_smem, int ndir) {
   pl.pbuf_floats = (size_t)2 * ndir * groups * slices * TCL_UG * C;       // 4-byte words, tag in the LSB
   pl.xbuf_bytes = (size_t)2 * ndir * groups * TCL_UG * C * 4;
   pl.gsum_floats = (size_t)2 * groups * 7 * C;
+  pl.cluster = tc_cluster_ok(pl, C);
   pl.valid = 1;
   return pl;
 }
@@ -953,38 +1142,40 @@ LstmPlan lstm_tc_plan(int S, int C, int num_sms, size_t max_smem, int ndir) {
 cudaError_t lstm_tc_forward(cudaStream_t st, const LstmPlan &pl, const LstmFwdArgs &a) {
   if (!pl.valid || pl.engine != 1) return cudaErrorInvalidConfiguration;
   if (a.drop < 0 || a.drop > 2 || (a.drop != 0 && !a.rmask)) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(a.xbuf, 0xff, pl.xbuf_bytes, st);   // tag bit 1 = "not the data of steps 0 / 1"
+  const bool wide = a.C > 384, cl = pl.cluster && !wide;
+  const void *fn = tc_fwd_fn(a.drop, wide, cl);
+  cudaError_t e = tc_prepare_fn(fn, pl.smem_fwd, pl.slices, cl);
   if (e != cudaSuccess) return e;
-  dim3 grid(pl.slices, pl.groups, pl.ndir), block(pl.threads);
   int groups = pl.groups, ndir = pl.ndir;
   LstmFwdArgs args = a;
   void *kargs[] = {&args, &groups, &ndir};
-  const bool wide = a.C > 384;
-  const void *fn = wide ? (a.drop == 0 ? (const void *)lstm_tc_fwd_kernel<0, 1>
-                                       : a.drop == 1 ? (const void *)lstm_tc_fwd_kernel<1, 1> : (const void *)lstm_tc_fwd_kernel<2, 1>)
-                        : (a.drop == 0 ? (const void *)lstm_tc_fwd_kernel<0, 0>
-                                       : a.drop == 1 ? (const void *)lstm_tc_fwd_kernel<1, 0> : (const void *)lstm_tc_fwd_kernel<2, 0>);
-  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_fwd);
+  if (cl) {   // clusters are self-contained: no tagged-word buffer, no grid-wide co-residency
+    ClusterLaunch c(pl, pl.smem_fwd, st);
+    return cudaLaunchKernelExC(&c.cfg, fn, kargs);
+  }
+  e = cudaMemsetAsync(a.xbuf, 0xff, pl.xbuf_bytes, st);   // tag bit 1 = "not the data of steps 0 / 1"
   if (e != cudaSuccess) return e;
+  dim3 grid(pl.slices, pl.groups, pl.ndir), block(pl.threads);
   return cudaLaunchCooperativeKernel(fn, grid, block, kargs, pl.smem_fwd, st);
 }
 
 cudaError_t lstm_tc_backward(cudaStream_t st, const LstmPlan &pl, const LstmBwdArgs &a) {
   if (!pl.valid || pl.engine != 1) return cudaErrorInvalidConfiguration;
   if (a.drop < 0 || a.drop > 2 || (a.drop != 0 && !a.rmask)) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(a.pbuf, 0xff, pl.pbuf_floats * sizeof(float), st);
+  const bool wide = a.C > 384, cl = pl.cluster && !wide;
+  const void *fn = tc_bwd_fn(a.drop, wide, cl);
+  cudaError_t e = tc_prepare_fn(fn, pl.smem_bwd, pl.slices, cl);
   if (e != cudaSuccess) return e;
-  dim3 grid(pl.slices, pl.groups, pl.ndir), block(pl.threads);
   int groups = pl.groups, slices = pl.slices, ndir = pl.ndir;
   LstmBwdArgs args = a;
   void *kargs[] = {&args, &groups, &slices, &ndir};
-  const bool wide = a.C > 384;
-  const void *fn = wide ? (a.drop == 0 ? (const void *)lstm_tc_bwd_kernel<0, 1>
-                                       : a.drop == 1 ? (const void *)lstm_tc_bwd_kernel<1, 1> : (const void *)lstm_tc_bwd_kernel<2, 1>)
-                        : (a.drop == 0 ? (const void *)lstm_tc_bwd_kernel<0, 0>
-                                       : a.drop == 1 ? (const void *)lstm_tc_bwd_kernel<1, 0> : (const void *)lstm_tc_bwd_kernel<2, 0>);
-  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bwd);
+  if (cl) {
+    ClusterLaunch c(pl, pl.smem_bwd, st);
+    return cudaLaunchKernelExC(&c.cfg, fn, kargs);
+  }
+  e = cudaMemsetAsync(a.pbuf, 0xff, pl.pbuf_floats * sizeof(float), st);
   if (e != cudaSuccess) return e;
+  dim3 grid(pl.slices, pl.groups, pl.ndir), block(pl.threads);
   return cudaLaunchCooperativeKernel(fn, grid, block, kargs, pl.smem_bwd, st);
 }
 

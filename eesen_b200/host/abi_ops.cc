@@ -774,6 +774,12 @@ int eesen_b200_profile(eesen_b200_ctx *ctx, int enable, double *ms, long *counts
   return 0;
 }
 
+int eesen_b200_lstm_engine(eesen_b200_ctx *ctx, int num_utts, int cells, int ndir, int pass) {
+  if (!ctx) return -1;
+  const eb::LstmPlan pl = eb::lstm_plan(num_utts, cells, ctx->num_sms, ctx->max_smem, ndir, pass);
+  return pl.valid ? pl.engine : -1;
+}
+
 int eesen_b200_debug_lstm_timing(eesen_b200_ctx *ctx, long long *out32, int reset) {
   if (ctx) cudaStreamSynchronize(ctx->stream);
   return eb::lstm_debug_timing(out32, reset);

@@ -67,6 +67,11 @@ int eesen_b200_profile(eesen_b200_ctx *ctx, int enable, double *ms, long *counts
  * (forward, backward); returns 1 when compiled in, else 0. */
 int eesen_b200_debug_lstm_timing(eesen_b200_ctx *ctx, long long *out32, int reset);
 
+/* Which recurrent kernels a layer of `cells` cells per direction, `ndir` directions and `num_utts` parallel
+ * utterances runs on (pass 0 = forward, 1 = backward): 1 = tcgen05 kernels (lstm_tc_{fwd,bwd}_kernel),
+ * 0 = warp-level kernels (lstm_{fwd,bwd}_kernel), -1 = no plan for this shape.  For bench.py's labels. */
+int eesen_b200_lstm_engine(eesen_b200_ctx *ctx, int num_utts, int cells, int ndir, int pass);
+
 /* ---------------------------------------------------------------- level 1: device operators */
 
 /* NaN/Inf scan of a device array: *flags = bit 0 (a NaN) | bit 1 (an Inf).  Replaces the host-side sum test of

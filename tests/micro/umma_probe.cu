@@ -252,7 +252,7 @@ probe_ts_kernel(const float *A, const float *B, int NB, float *out, long long *c
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *sB = smem;   // [64 x K]
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2;
   __shared__ uint32_t tmem_base_sm;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < 64 * K; i += 128) {
@@ -261,6 +261,7 @@ probe_ts_kernel(const float *A, const float *B, int NB, float *out, long long *c
   }
   if (tid == 0) {
     mbar_init(&bar, 1);
+    mbar_init(&bar2, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
@@ -301,7 +302,7 @@ probe_ts_kernel(const float *A, const float *B, int NB, float *out, long long *c
   long long t0 = 0;
   if (tid == 0) t0 = clock64();
   for (int rep = 0; rep < reps; rep++) {
-    if (warp == 0) {
+    if (warp == 0 && two < 10) {
       uint32_t pe;
       asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pe));
       if (pe) {
@@ -311,14 +312,50 @@ probe_ts_kernel(const float *A, const float *B, int NB, float *out, long long *c
           for (int ks = 0; ks < 4; ks++) {
             const uint64_t bd = dB + (uint64_t)((kb * (64 * 128) + ks * 32) >> 4);
             umma_f16_ts(tmem_base, tmem_base + 128 + (kb * 4 + ks) * 8, bd, idescN, (kb | ks) != 0);
-            if (two) umma_f16_ts(tmem_base + 64, tmem_base + 320 + (kb * 4 + ks) * 8, bd, idescH, (kb | ks) != 0);
+            if (two == 1) umma_f16_ts(tmem_base + 64, tmem_base + 320 + (kb * 4 + ks) * 8, bd, idescH, (kb | ks) != 0);
           }
         }
         umma_commit(&bar);
       }
       __syncwarp();
     }
-    mbar_wait(&bar, phase);
+    if (warp == 1 && two >= 10) {   // K split over (two - 10) independent accumulator chains (X: N = NB at column c*NB; Y: N = NB/2 behind them)
+      uint32_t pe;
+      asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pe));
+      if (pe) {
+        const int nch = two % 10, withy = two >= 30;
+#pragma unroll
+        for (int kb = 0; kb < KB; kb++) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++) {
+            const int s = kb * 4 + ks, c = s % nch;
+            const uint64_t bd = dB + (uint64_t)((kb * (64 * 128) + ks * 32) >> 4);
+            umma_f16_ts(tmem_base + 512 - 128 + c * 16, tmem_base + 128 + s * 8, bd, idescH, s >= nch);
+            if (withy) umma_f16_ts(tmem_base + 64 + c * 16, tmem_base + 128 + s * 8, bd, idescH, s >= nch);
+          }
+        }
+        umma_commit(&bar2);
+      }
+      __syncwarp();
+    }
+    if (warp == 1 && two == 2) {   // second accumulator chain issued by a second warp (own commit)
+      uint32_t pe;
+      asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pe));
+      if (pe) {
+#pragma unroll
+        for (int kb = 0; kb < KB; kb++) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++) {
+            const uint64_t bd = dB + (uint64_t)((kb * (64 * 128) + ks * 32) >> 4);
+            umma_f16_ts(tmem_base + 64, tmem_base + 320 + (kb * 4 + ks) * 8, bd, idescH, (kb | ks) != 0);
+          }
+        }
+        umma_commit(&bar2);
+      }
+      __syncwarp();
+    }
+    if (two < 10) mbar_wait(&bar, phase);
+    if (two == 2 || two >= 10) mbar_wait(&bar2, phase);
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   }
@@ -383,6 +420,17 @@ int main() {
   run_ts(32, 200, 0, "timing TS: 20 MMA N=32");
   run_ts(32, 200, 1, "timing TS: 20x(N=32 + N=16)");
   run_ts(64, 200, 1, "timing TS: 20x(N=64 + N=32)");
+  run_ts(32, 1, 2, "TS form, two accumulators, two issuing warps");
+  run_ts(32, 200, 2, "timing TS: 20x N=32 | 20x N=16, 2 issuers");
+  run_ts(16, 200, 0, "timing TS: 20 MMA N=16");
+  // (results of the K-split timings are not checked: the accumulators sit in other columns)
+  run_ts(32, 200, 11, "timing TS: 20 MMA N=16, 1 chain (ref)");
+  run_ts(32, 200, 12, "timing TS: 20 MMA N=16, 2 chains");
+  run_ts(32, 200, 14, "timing TS: 20 MMA N=16, 4 chains");
+  run_ts(32, 200, 18, "timing TS: 20 MMA N=16, 8 chains");
+  run_ts(32, 200, 32, "timing TS: 40 MMA N=16, 2+2 chains");
+  run_ts(32, 200, 34, "timing TS: 40 MMA N=16, 4+4 chains");
+  run_ts(64, 200, 0, "timing TS: 20 MMA N=64");
   run<128>(32, 0, 0, 1, 0, "fp16 x fp16, single pass");
   run<128>(32, 1, 1, 1, 0, "bf16 x bf16, single pass");
   run<64>(32, 0, 0, 1, 0, "M=64 lane layout");
