@@ -46,7 +46,7 @@ namespace eb {
 // trip five times per step)
 __device__ long long g_lstm_tc_timing[2][16];
 #define TC_T0() long long tk_ = clock64()
-#define TC_ACC_DECL() long long tacc_[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define TC_ACC_DECL() long long tacc_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
 #define TC_TICK(kernel, i)                                                          \
   do {                                                                              \
     if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {        \
@@ -56,10 +56,16 @@ __device__ long long g_lstm_tc_timing[2][16];
     }                                                                               \
   } while (0)
 #define TC_COUNT(i) tacc_[i] += 1
+// second observer (thread 128 = warp 4 of CTA (0,0,0)): cycles from the moment thread 0 starts issuing the MMAs of a step
+// (TC_MARK) to the moment this thread sees the commit of tile bi (TC_SEEN), accumulated in slots 12 + bi
+#define TC_MARK_DECL() __shared__ long long tc_mark_; long long tseen_[4] = {0, 0, 0, 0}
+#define TC_MARK() do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *(volatile long long *)&tc_mark_ = clock64(); } while (0)
+#define TC_SEEN(bi) do { if (tid == 128 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) tseen_[bi] += clock64() - *(volatile long long *)&tc_mark_; } while (0)
+#define TC_SEEN_FLUSH(kernel) do { if (tid == 128 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) for (int i_ = 0; i_ < 4; i_++) g_lstm_tc_timing[kernel][12 + i_] += tseen_[i_]; } while (0)
 #define TC_FLUSH(kernel)                                                            \
   do {                                                                              \
     if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)          \
-      for (int i_ = 0; i_ < 8; i_++) g_lstm_tc_timing[kernel][i_] += tacc_[i_];     \
+      for (int i_ = 0; i_ < 12; i_++) g_lstm_tc_timing[kernel][i_] += tacc_[i_];     \
   } while (0)
 #else
 #define TC_T0()
@@ -67,6 +73,10 @@ __device__ long long g_lstm_tc_timing[2][16];
 #define TC_TICK(kernel, i)
 #define TC_COUNT(i)
 #define TC_FLUSH(kernel)
+#define TC_MARK_DECL()
+#define TC_MARK()
+#define TC_SEEN(bi)
+#define TC_SEEN_FLUSH(kernel)
 #endif
 
 namespace {
@@ -596,8 +606,13 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
   const bool stk = rem64 && !ss64;                        // default: stacked TMEM tile, issued first
   const int NTS = n128 < 2 ? n128 : 2;                    // full tiles resident in TMEM
   uint8_t *Bt = smem;                                     // [2 k-blocks][32 rows][128 B]
-  float *scl = reinterpret_cast<float *>(Bt + 8192);      // [16] inverse column scales
-  float *gsm = scl + 16;                                  // [2 halves][16 utts][32 cells] gathered partial d_m
+  // [2 step parities][16] inverse column scales.  Two sets: a warp may write the scales of step s+1 while another warp of
+  // the CTA has not yet read those of step s in its epilogue -- with the cluster exchange a warp's gather depends only on
+  // the two warps of every CTA that own its cells' accumulator rows, not on all warps of its own CTA (found by
+  // compute-sanitizer timing on C = 256 / 384, where no stacked-tile barrier hides it; two sets suffice: step s+2's scales
+  // are written behind b_full of step s+1, which every thread reaches after its epilogue of step s)
+  float *scl = reinterpret_cast<float *>(Bt + 8192);
+  float *gsm = scl + 32;                                  // [2 halves][16 utts][32 cells] gathered partial d_m
   float *ysm = gsm + 2 * TCL_UG * 32;                     // [16 utts][64 rows] lo'*hi part of the stacked tile
   float *red = ysm + TCL_UG * 64;                         // [7][16 utts][32 cells] bias / peephole sums at the end
   uint8_t *Ahi = smem + 32768;                            // full tiles beyond the TMEM-resident ones: [2 k-blocks][128][128 B] each
@@ -768,9 +783,13 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
     const int quad = warp & 3, uh = warp >> 2;
     const uint64_t dAhi = umma_desc(smem_u32(Ahi), 16, 1024, 2), dAlo = umma_desc(smem_u32(Alo), 16, 1024, 2),
                    dBt = umma_desc(smem_u32(Bt), 16, 1024, 2);
-    const uint32_t accS = (uint32_t)n128 * 48;   // accumulator columns: full tile mt at mt * 48, the stacked tile behind them
+    // accumulator columns: full tile mt at mt * 48, the stacked tile behind them (a 64-column stride, X on a 32-column
+    // boundary, measured no faster)
+    auto acc_col = [&](int mt) -> uint32_t { return (uint32_t)mt * 48u; };
+    const uint32_t accS = (uint32_t)n128 * 48u;
 
     TC_ACC_DECL();
+    TC_MARK_DECL();
     for (int step = 0; step < T; step++) {
       const int t = dir == 0 ? T - 1 - step : step;
       TC_T0();
@@ -866,7 +885,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
         kexp = kexp > 120 ? 120 : (kexp < -120 ? -120 : kexp);
         if (mb == 0u || mb >= 0x7f800000u) kexp = 0;       // all-zero column, or inf/nan (propagates as it is)
         const float sc = __uint_as_float((uint32_t)(kexp + 127) << 23);
-        if (lane == 0) scl[2 * up + e] = __uint_as_float((uint32_t)(127 - kexp) << 23);
+        if (lane == 0) scl[(step & 1) * 16 + 2 * up + e] = __uint_as_float((uint32_t)(127 - kexp) << 23);
         const int u = 2 * up + e;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -883,6 +902,8 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
         // ===== MMA issue (the last step's partial is never consumed: T-1 products) =====
         mbar_wait(&b_full, (uint32_t)(step & 1));
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        TC_TICK(1, 10);   // (debug build: waiting for the other warps' part of the B tile)
+        TC_MARK();
         if (elect_one()) {
           // one commit per M tile: the epilogue (TMEM -> partial words) of a tile runs while the tensor pipe is
           // still working on the next one.  The stacked tile goes first: its epilogue has one more hand-over.
@@ -893,8 +914,8 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
           }
           for (int mt = 0; mt < n128; mt++) {
             const uint64_t toff = (uint64_t)(((mt - NTS) * 32768) >> 4);
-            if (mt < NTS) issue_bwd_tile_ts(tmem_base + kColA + mt * 128, tmem_base + kColA + mt * 128 + 64, dBt, tmem_base + mt * 48);
-            else issue_bwd_tile<128>(dAhi + toff, dAlo + toff, dBt, tmem_base + mt * 48);
+            if (mt < NTS) issue_bwd_tile_ts(tmem_base + kColA + mt * 128, tmem_base + kColA + mt * 128 + 64, dBt, tmem_base + acc_col(mt));
+            else issue_bwd_tile<128>(dAhi + toff, dAlo + toff, dBt, tmem_base + acc_col(mt));
             umma_commit(&mma_done[nb++]);
           }
           if (ss64) {
@@ -922,11 +943,12 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
         for (int bi = 0; bi < MT; bi++) {
           mbar_wait(&mma_done[bi], (uint32_t)(step & 1));
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          TC_TICK(1, 6);   // (debug build: time spent waiting for the tiles' commits)
+          TC_TICK(1, 6 + bi);   // (debug build: time spent waiting for the commit of tile bi)
+          TC_SEEN(bi);
           if (bi == 0) {   // the column scales were written by the other warps before they arrived on b_full: read
                            // them only behind the first commit (which is behind b_full)
 #pragma unroll
-            for (int j = 0; j < 8; j++) inv[j] = scl[8 * uh + j];
+            for (int j = 0; j < 8; j++) inv[j] = scl[(step & 1) * 16 + 8 * uh + j];
           }
           if (stk && bi == 0) {
             // stacked tile: lanes 0-63 (quadrants 0-1) carry hi*hi | hi*lo', lanes 64-127 the lo'*hi term of the same
@@ -964,7 +986,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
           const int mt = bi - (stk ? 1 : 0);
           const bool full = mt < n128;              // (ss64: the last one is the M = 64 tile)
           uint32_t x0[8], x1[8], y0[8];
-          const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * 48);
+          const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_col(mt);
           tmem_ld8(tl + 8 * uh, x0);
           tmem_ld8(tl + 16 + 8 * uh, x1);
           tmem_ld8(tl + 32 + 8 * uh, y0);
@@ -991,6 +1013,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
     }
 
     TC_FLUSH(1);
+    TC_SEEN_FLUSH(1);
     // ---- bias / peephole gradient partial sums of this (dir, group): reduce over the CTA's 16 utterances
     named_bar_workers();
 #pragma unroll

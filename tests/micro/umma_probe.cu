@@ -414,7 +414,120 @@ static void run_ts(int NB, int reps, int two, const char *what) {
   cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dC);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// 6. The backward step of lstm_tc_bwd_kernel at C = 320 in isolation: a stacked tile (8 MMAs, N = 32, one accumulator) and two
+//    full tiles (8 x (N = 32 + N = 16) each), all operands A resident in TMEM, K = 128 (B tile [32 x 128]); one commit per
+//    tile.  Reports when the elected thread is done issuing and when each tile's commit is observed (cycles from the
+//    start of the issue, mean over reps).  order = 0: tile after tile (as the kernel), 1: all tiles k-slice by k-slice.
+__global__ void __launch_bounds__(128, 1) probe_bwd_kernel(long long *cycles, int reps, int order) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *sB = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // [32 x 128] fp16
+  __shared__ uint64_t bar[3];
+  __shared__ uint32_t tmem_base_sm;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 32 * 128; i += 128) *reinterpret_cast<uint16_t *>(sB + sw128_off(32, i / 128, i % 128)) = cvt16(0.01f * (i % 37), 0);
+  if (tid == 0) {
+    for (int i = 0; i < 3; i++) mbar_init(&bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_sm)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tm = tmem_base_sm;
+  {   // some fp16 pattern in the weight columns [160, 480)
+    for (int c0 = 160; c0 < 480; c0 += 8) {
+      const uint32_t ta = tm + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      const uint32_t w = 0x2c002c00u;   // 2 x fp16 0.0625
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};\n" ::"r"(ta), "r"(w) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t idN = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t idH = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint64_t dB = umma_desc(smem_u32(sB), 16, 1024, 2);
+  long long tissue = 0, tw[3] = {0, 0, 0};
+  for (int rep = 0; rep < reps; rep++) {
+    __syncthreads();
+    const long long t0 = clock64();
+    if (warp == 0) {
+      uint32_t pe;
+      asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pe));
+      if (pe) {
+        if (order == 0) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ks++)
+            umma_f16_ts(tm + 96, tm + 416 + ks * 8, dB + (uint64_t)(((ks >> 2) * 4096 + (ks & 3) * 32) >> 4), idN, ks != 0);
+          umma_commit(&bar[0]);
+#pragma unroll
+          for (int mt = 0; mt < 2; mt++) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++) {
+              const uint64_t bd = dB + (uint64_t)(((ks >> 2) * 4096 + (ks & 3) * 32) >> 4);
+              umma_f16_ts(tm + mt * 48, tm + 160 + mt * 128 + ks * 8, bd, idN, ks != 0);
+              umma_f16_ts(tm + mt * 48 + 32, tm + 160 + mt * 128 + 64 + ks * 8, bd, idH, ks != 0);
+            }
+            umma_commit(&bar[1 + mt]);
+          }
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < 8; ks++) {
+            const uint64_t bd = dB + (uint64_t)(((ks >> 2) * 4096 + (ks & 3) * 32) >> 4);
+            umma_f16_ts(tm + 96, tm + 416 + ks * 8, bd, idN, ks != 0);
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) {
+              umma_f16_ts(tm + mt * 48, tm + 160 + mt * 128 + ks * 8, bd, idN, ks != 0);
+              umma_f16_ts(tm + mt * 48 + 32, tm + 160 + mt * 128 + 64 + ks * 8, bd, idH, ks != 0);
+            }
+          }
+          for (int i = 0; i < 3; i++) umma_commit(&bar[i]);
+        }
+      }
+      __syncwarp();
+    }
+    const long long t1 = clock64();
+    tissue += t1 - t0;
+    for (int i = 0; i < 3; i++) {
+      mbar_wait(&bar[i], (uint32_t)(rep & 1));
+      tw[i] += clock64() - t0;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  }
+  if (tid == 0) { cycles[0] = tissue; cycles[1] = tw[0]; cycles[2] = tw[1]; cycles[3] = tw[2]; }
+  if (tid == 64) { cycles[4] = tissue; cycles[5] = tw[0]; cycles[6] = tw[1]; cycles[7] = tw[2]; }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "n"(512) : "memory");
+  }
+}
+static void run_bwd(int order) {
+  long long *dC, h[8];
+  CK(cudaMalloc(&dC, 64));
+  const int reps = 200;
+  CK(cudaFuncSetAttribute(probe_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384));
+  probe_bwd_kernel<<<1, 128, 16384>>>(dC, reps, order);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("bwd step probe: LAUNCH/EXEC ERROR %s\n", cudaGetErrorString(e)); exit(2); }
+  CK(cudaMemcpy(h, dC, 64, cudaMemcpyDeviceToHost));
+  printf("bwd step (8 stacked + 2 x 16 MMAs), %s: issuing warp: issue done %.0f, commits seen at %.0f / %.0f / %.0f;  a waiting warp: %.0f / %.0f / %.0f cycles\n",
+         order ? "k-slice interleaved" : "tile after tile    ", (double)h[0] / reps, (double)h[1] / reps, (double)h[2] / reps, (double)h[3] / reps,
+         (double)h[5] / reps, (double)h[6] / reps, (double)h[7] / reps);
+  cudaFree(dC);
+}
+
 int main() {
+  run_bwd(0);
+  run_bwd(1);
   run_ts(32, 1, 0, "TS form (A in TMEM), single pass");
   run_ts(32, 1, 1, "TS form, two accumulators");
   run_ts(32, 200, 0, "timing TS: 20 MMA N=32");

@@ -148,17 +148,25 @@ def test_ctc_eval_vs_oracle(ctx, seed, S, T, K, maxlab):
                                      (100, 7, 40, 320), (1, 1, 40, 64),    # 100 utts: two utterance chunks (64 + 36)
                                      (4, 11, 40, 192), (3, 9, 40, 384),    # backward tile mixes: 128 + stacked 64; 3 x 128
                                      (3, 7, 40, 512), (18, 6, 40, 448),    # wide plans (C4's 512 cells): W_lo' partly / tiles 3-4 in smem
-                                     (8, 300, 40, 64), (6, 290, 40, 320)]) # T >= 256: input product streamed in chunks
-@pytest.mark.parametrize("rec", ["fp32x3", "tf32", "legacy-engine", "tcfwd-engine"])
+                                     (8, 300, 40, 64), (6, 290, 40, 320),  # T >= 256: input product streamed in chunks
+                                     (3, 9, 40, 256), (40, 21, 40, 256)])  # full tiles only + ragged last group (cluster exchange)
+@pytest.mark.parametrize("rec", ["fp32x3", "tf32", "legacy-engine", "tcfwd-engine", "l2-exchange"])
 def test_bilstm_layer_vs_oracle(ctx, S, T, I, C, rec, monkeypatch):
     """Level-1 BiLSTM forward/backward of one layer against the fp64 oracle, ragged lengths.  Shapes with
     cells % 64 == 0 run on the tcgen05 recurrent kernels (lstm_tc.cu), the others -- and every shape under
     EESEN_B200_LSTM_ENGINE=legacy -- on the warp-level kernels (lstm.cu): same tolerances for both."""
     torch = torch_()
+    monkeypatch.delenv("EESEN_B200_LSTM_EXCHANGE", raising=False)
     if rec in ("legacy-engine", "tcfwd-engine"):   # default: tcgen05 for both passes (lstm.cu:engine_for_pass)
         if C % 64 != 0:
             pytest.skip("only the warp-level kernels take this shape")
         monkeypatch.setenv("EESEN_B200_LSTM_ENGINE", rec.split("-")[0])
+        rec = "fp32x3"
+    elif rec == "l2-exchange":   # default for cells <= 384: thread-block clusters exchanging through DSMEM (lstm_tc.cu, CL = 1)
+        if C % 64 != 0 or C > 384:
+            pytest.skip("the cluster exchange does not apply to this shape")
+        monkeypatch.delenv("EESEN_B200_LSTM_ENGINE", raising=False)
+        monkeypatch.setenv("EESEN_B200_LSTM_EXCHANGE", "l2")
         rec = "fp32x3"
     else:
         monkeypatch.delenv("EESEN_B200_LSTM_ENGINE", raising=False)
