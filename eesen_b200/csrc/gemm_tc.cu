@@ -187,7 +187,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   constexpr int STAGE_BYTES = NTERMS == 3 ? 2 * (A_BYTES + B_BYTES) : (A_BYTES + B_BYTES);
   // stage layout: [A hi][B hi]([A lo][B lo])
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic ON the __shared__ array: a round trip through uintptr_t loses the address
+  // space and every access below would compile to generic LD.E / ST.E instead of LDS / STS
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t full_bar[STAGES], conv_bar[STAGES], empty_bar[STAGES], accum_bar;
   __shared__ uint32_t tmem_base_sm;
 
@@ -346,7 +348,9 @@ gemm_tc16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   constexpr int B_BYTES = BN * TC16_BK * 2;
   constexpr int STAGE_BYTES = (NT == 3 ? 2 : 1) * (A_BYTES + B_BYTES);   // [A hi][B hi]([A lo][B lo])
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic ON the __shared__ array: a round trip through uintptr_t loses the address
+  // space and every access below would compile to generic LD.E / ST.E instead of LDS / STS
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
   __shared__ uint32_t tmem_base_sm;
 
@@ -466,7 +470,9 @@ gemm_tc16_2sm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   constexpr int B_BYTES = BNH * TC16_BK * 2;
   constexpr int STAGE_BYTES = (NT == 3 ? 2 : 1) * (A_BYTES + B_BYTES);   // [A hi][B hi]([A lo][B lo])
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic ON the __shared__ array: a round trip through uintptr_t loses the address
+  // space and every access below would compile to generic LD.E / ST.E instead of LDS / STS
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
   __shared__ uint32_t tmem_base_sm;
 

@@ -256,7 +256,9 @@ template <int DROP, int WIDE, int CL>
 __global__ void __launch_bounds__(TCL_THREADS, 1)
 lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic ON the __shared__ array: a round trip through uintptr_t loses the address
+  // space and every access below would compile to generic LD.E / ST.E instead of LDS / STS
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int C = a.C, S = a.S, T = a.T;
   const int KB = C >> 6;                                  // 64-wide k-blocks (C % 64 == 0)
   uint8_t *Bt = smem;                                     // [CL ? 2 : 1][KB][32 rows][128 B]: rows 0-15 hi, 16-31 lo'
@@ -599,7 +601,9 @@ template <int DROP, int WIDE, int CL>
 __global__ void __launch_bounds__(TCL_THREADS, 1)
 lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic ON the __shared__ array: a round trip through uintptr_t loses the address
+  // space and every access below would compile to generic LD.E / ST.E instead of LDS / STS
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int C = a.C, S = a.S, T = a.T;
   const int n128 = C >> 7, rem64 = (C & 127) ? 1 : 0, MT = n128 + rem64;
   const bool ss64 = !CL && rem64 && (a.tune & 2);         // debug: the 64-row tile as an M = 64 SS-form tile, issued last
@@ -926,6 +930,8 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
         __syncwarp();
       }
       TC_TICK(1, 2);
+      // the saved state of the next position (measured: issuing these loads in front of the MMA issue instead costs
+      // 0.2 ms per C2 step -- it delays the product; behind it their latency hides under the tensor pipe's work)
       prefetch(t + tstep);
       TC_TICK(1, 4);
       {
@@ -943,7 +949,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
         for (int bi = 0; bi < MT; bi++) {
           mbar_wait(&mma_done[bi], (uint32_t)(step & 1));
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          TC_TICK(1, 6 + bi);   // (debug build: time spent waiting for the commit of tile bi)
+          TC_TICK(1, 6);   // (debug build: time spent waiting for the tiles' commits)
           TC_SEEN(bi);
           if (bi == 0) {   // the column scales were written by the other warps before they arrived on b_full: read
                            // them only behind the first commit (which is behind b_full)

@@ -22,7 +22,7 @@ if os.environ.get("EESEN_B200_LSTM_ENGINE") == "legacy":
     names_b = ["poll", "barA", "partials+elementwise", "barC", "mma+P stores", "signal"]
 else:   # tcgen05 engine (lstm_tc.cu)
     names_f = ["stage (poll + B tile) + arrive", "MMA issue + commit wait", "TMEM ld + staging + barrier", "gates + publish", "saved-state stores + prefetch", "(re-polls of thread 0, count)"]
-    names_b = ["gather partial d_m", "gate math + DG stores + B tile + arrive", "MMA issue", "TMEM ld + publish partials", "prefetch issue", "(re-polls of thread 0, count)", "waiting for commit of tile 0", "waiting for commit of tile 1", "waiting for commit of tile 2", "waiting for commit of tile 3", "waiting for the other warps (b_full)", "(unused)", "(warp 4: cycles from MMA issue start to commit 0 seen)", "(warp 4: ... commit 1 seen)", "(warp 4: ... commit 2 seen)", "(warp 4: ... commit 3 seen)"]
+    names_b = ["gather partial d_m", "gate math + DG stores + B tile + arrive", "MMA issue", "TMEM ld + publish partials", "prefetch issue", "(re-polls of thread 0, count)", "waiting for the tiles' commits", "(unused)", "(unused)", "(unused)", "waiting for the other warps (b_full)", "(unused)", "(warp 4: cycles from MMA issue start to commit 0 seen)", "(warp 4: ... commit 1 seen)", "(warp 4: ... commit 2 seen)", "(warp 4: ... commit 3 seen)"]
 print(f"forward ({prec}) cycles/step (thread 0 of CTA 0; {steps} steps):")
 tot = 0
 for i, n in enumerate(names_f):
