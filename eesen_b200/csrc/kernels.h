@@ -85,6 +85,12 @@ struct LstmBwdArgs {
   const float *rmask = nullptr;
   int ldr = 0, rmask_per_step = 0;
   int tune = 0;                 // debug knobs (EESEN_B200_TUNE): bit 1 = 64-row remainder tile from shared memory (SS form)
+  // Streamed dout (tcgen05 engine): dout arrives in PAIRS of time chunks of `dchunk` positions, pair ci = chunk ci from
+  // the start and chunk ci from the end of the sequence (dnck chunks in all); pair ci may be read once dflag[ci] ==
+  // depoch, pairs < dready were complete before the launch.  dflag == nullptr: everything is there.
+  const unsigned *dflag = nullptr;
+  unsigned depoch = 0;
+  int dchunk = 0, dnck = 0, dready = 0;
 };
 struct LstmPlan {
   int engine;            // 0: warp-level mma.sync kernels (lstm.cu), 1: tcgen05 kernels (lstm_tc.cu)

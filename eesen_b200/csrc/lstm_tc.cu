@@ -767,7 +767,12 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
     for (int q = 0; q < 4; q++) { sb[q][0] = 0.f; sb[q][1] = 0.f; }
     float vg[2], vi[2], vf[2], vo[2], vc[2], vcp[2], vd[2], vr[2] = {1.f, 1.f};
     const int tstep = dir == 0 ? -1 : 1;   // time order of the forward pass: c_prev lives at t + tstep
+    int dhave = a.dready - 1;                              // last pair of dout chunks known to be complete
     auto prefetch = [&](int t) {
+      if (a.dflag) {   // streamed dX of the layer above: position t may lie in a pair of chunks still being computed
+        const int k = t / a.dchunk, need = min(k, a.dnck - 1 - k);
+        if (need > dhave) { wait_flag(a.dflag + need, a.depoch); dhave = need; }
+      }
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         if (!ok[e]) { vg[e] = vi[e] = vf[e] = vo[e] = vc[e] = vcp[e] = vd[e] = 0.f; continue; }

@@ -61,6 +61,12 @@ int eesen_b200_create(eesen_b200_ctx **out, int device) {
     ctx->overlap = (ov && ov[0] == '0') ? 0 : 1;
     const char *sg = getenv("EESEN_B200_STREAM_GEMM");
     ctx->stream_gemm = (sg && sg[0] == '0') ? 0 : 1;
+    const char *sx = getenv("EESEN_B200_STREAM_DX");
+    ctx->stream_dx = (sx && sx[0] == '1') ? 1 : 0;
+    const char *dr = getenv("EESEN_B200_DX_READY");
+    ctx->dx_ready_pairs = dr ? std::max(1, atoi(dr)) : 1;
+    const char *ec = getenv("EESEN_B200_EARLY_CONV");
+    ctx->early_conv = (ec && ec[0] == '0') ? 0 : 1;
     const char *fx = getenv("EESEN_B200_GEMM_FP32X3");
     ctx->f16x3 = (fx && std::string(fx) == "tf32") ? 0 : 1;
   }
@@ -131,7 +137,7 @@ static int f16_meta(eesen_b200_ctx *ctx, int idx, unsigned **mx, int **kexp) {
 }
 
 // convert the whole matrix [rows x cols] (ld) on `stream` and remember it: later products find sub-blocks by address
-static int f16_register(eesen_b200_ctx *ctx, const float *base, long rows, int cols, int ld) {
+static int f16_register(eesen_b200_ctx *ctx, const float *base, long rows, int cols, int ld, bool on_side = false) {
   if (!ctx->f16x3 || ctx->gemm_prec != 0 || ctx->gemm_engine != 0 || !base || rows <= 0 || cols <= 0) return 0;
   if (ctx->f16_used >= eesen_b200_ctx::kF16Slots) return 0;   // (falls back to per-call conversion)
   eesen_b200_ctx::F16Entry &e = ctx->f16_slots[ctx->f16_used];
@@ -143,8 +149,9 @@ static int f16_register(eesen_b200_ctx *ctx, const float *base, long rows, int c
   if ((rc = f16_meta(ctx, ctx->f16_used, &mx, &kx))) return rc;
   e.base = base; e.rows = rows; e.cols = cols; e.ld = ld; e.ldd = (cols + 7) & ~7;
   e.view.hi = pl; e.view.lo = (char *)pl + ((pb + 255) & ~(size_t)255); e.view.ld = e.ldd; e.view.kexp = kx;
-  int pe = ctx->prof_begin(eesen_b200_ctx::kGemm);
-  cudaError_t ce = eb::convert_f16x2(ctx->stream, ctx->num_sms, base, rows, cols, ld, (void *)e.view.hi, (void *)e.view.lo, mx, kx);
+  int pe = ctx->prof_begin(eesen_b200_ctx::kGemm, on_side);
+  cudaError_t ce = eb::convert_f16x2(on_side ? ctx->side : ctx->stream, ctx->num_sms, base, rows, cols, ld, (void *)e.view.hi,
+                                     (void *)e.view.lo, mx, kx);
   ctx->prof_end(pe);
   ctx->launches += 2;
   if ((rc = ctx->check(ce, "convert_f16x2"))) return rc;
@@ -484,6 +491,29 @@ static int lstm_backward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I
   a.precision = ctx->rec_prec;
   a.drop = drop; a.rmask = rmask; a.ldr = ldr; a.rmask_per_step = per_step;
   { const char *tn = getenv("EESEN_B200_TUNE"); a.tune = tn ? atoi(tn) : 0; }
+  // dout may be the dX the previous call is still streaming on the side stream (ctx->dxs): the tcgen05 kernel reads it
+  // chunk pair by chunk pair behind flags; any other consumer waits for all of it first
+  if (ctx->dxs.active) {
+    const eesen_b200_ctx::DxStream &dxs = ctx->dxs;
+    if (dout == dxs.ptr && ldd == dxs.ld && T == dxs.T && S == dxs.S && plan.engine == 1 && chunk == S) {
+      a.dflag = dxs.flags; a.depoch = dxs.epoch; a.dchunk = dxs.chunk; a.dnck = dxs.nck; a.dready = dxs.ready;
+    } else {
+      ctx->join_side();
+    }
+    ctx->dxs.active = false;
+  }
+  // fp16x3: the layer input and m feed the weight-gradient products; they are forward activations, so their planes are
+  // made on the side stream (behind the weight-gradient products of the layer above, which still read the previous
+  // planes) WHILE the recurrent kernel below runs.  d(gates) and Wx follow on `stream` behind the kernel.
+  const int N = T * S;
+  const bool sd = ctx->overlap != 0;
+  const bool early = sd && ctx->early_conv;
+  ctx->f16_clear();
+  if (early) {
+    ctx->fork_side();
+    if ((rc = f16_register(ctx, x, N, I, ldx, true))) return rc;
+    if (T > 1 && (rc = f16_register(ctx, out, N, ndir * C, ldo, true))) return rc;
+  }
   for (int ci = 0; ci < nchunks; ci++) {
     a.s_begin = ci * chunk;
     a.s_count = std::min(chunk, S - a.s_begin);
@@ -494,7 +524,6 @@ static int lstm_backward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I
     ctx->prof_end(pe);
     if ((rc = ctx->check(le, "lstm_backward"))) return rc;
   }
-  const int N = T * S;
   for (int d = 0; d < ndir; d++) {
     ctx->launches += 1;
     int pe = ctx->prof_begin(eesen_b200_ctx::kMisc);
@@ -506,26 +535,70 @@ static int lstm_backward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I
   // The planes of the previous layer call may still be read by its weight-gradient products on the side stream:
   // they have had the whole recurrent kernel above to finish, now they are waited for.
   ctx->join_side();
-  ctx->f16_clear();
+  if (!early) {
+    if ((rc = f16_register(ctx, x, N, I, ldx))) return rc;
+    if (T > 1 && (rc = f16_register(ctx, out, N, ndir * C, ldo))) return rc;
+  }
   if ((rc = f16_register(ctx, dgates, N, ndir * 4 * C, ldg))) return rc;
-  if ((rc = f16_register(ctx, x, N, I, ldx))) return rc;
-  if (T > 1 && (rc = f16_register(ctx, out, N, ndir * C, ldo))) return rc;
   if (dx)
     for (int d = 0; d < ndir; d++)
       if ((rc = f16_register(ctx, p->wx[d], 4 * C, I, ldwx))) return rc;
-  // dx = DG_fw * Wx_fw + DG_bw * Wx_bw   (:502 beta=0, :593 beta=1)
-  if (dx) {
+  // dx = DG_fw * Wx_fw + DG_bw * Wx_bw   (:502 beta=0, :593 beta=1), rows [r0, r0 + nr)
+  auto dx_rows = [&](long r0, long nr, bool on_side) -> int {
     for (int d = 0; d < ndir; d++) {
-      rc = do_gemm(ctx, 0, 0, N, I, 4 * C, 1.f, dgates + (size_t)d * 4 * C, ldg, 0, p->wx[d], ldwx, 0,
-                   d == 0 ? 0.f : 1.f, dx, lddx, 0, nullptr, 0, 1);
-      if (rc) return rc;
+      int rc2 = do_gemm(ctx, 0, 0, (int)nr, I, 4 * C, 1.f, dgates + (size_t)r0 * ldg + (size_t)d * 4 * C, ldg, 0, p->wx[d], ldwx, 0,
+                        d == 0 ? 0.f : 1.f, dx + (size_t)r0 * lddx, lddx, 0, nullptr, 0, 1, on_side);
+      if (rc2) return rc2;
     }
+    return 0;
+  };
+  // Streamed (see context.h:DxStream): Net announced that dx goes straight into the recurrent backward of the layer
+  // below.  Time chunks of g positions; pair ci = chunk ci and chunk nck-1-ci -- direction 0 of the layer below starts at
+  // t = T-1, direction 1 at t = 0.  Pair 0 here, the others on the side stream in front of the weight-gradient products.
+  bool stream_dx = false;
+  int dg = 0, dnck = 0, dnpairs = 0;
+  if (dx && sd && ctx->dx_stream_hint && ctx->stream_dx && ctx->stream_gemm && plan.engine == 1 && chunk == S && T >= 256) {
+    dg = std::max(16, (T + 9) / 10);
+    dnck = (T + dg - 1) / dg;
+    dnpairs = (dnck + 1) / 2;
+    stream_dx = dnpairs > ctx->dx_ready_pairs && dnpairs <= 64;
+  }
+  unsigned *dflags = nullptr;
+  if (stream_dx) {
+    void *df = nullptr;
+    const bool fresh = ctx->lstm_dflags.bytes == 0;
+    if ((rc = ctx->reserve(ctx->lstm_dflags, 64 * sizeof(unsigned), &df))) return rc;
+    dflags = (unsigned *)df;
+    if (fresh && (rc = ctx->check(cudaMemsetAsync(df, 0, 64 * sizeof(unsigned), ctx->stream), "cudaMemsetAsync"))) return rc;
+    ctx->depoch += 1;
+    if (ctx->depoch == 0u) ctx->depoch = 1;
+  }
+  auto dx_pair = [&](int ci, bool on_side) -> int {
+    const int k1 = ci, k2 = dnck - 1 - ci;
+    int rc2 = dx_rows((long)k1 * dg * S, (long)std::min(dg, T - k1 * dg) * S, on_side);
+    if (!rc2 && k2 > k1) rc2 = dx_rows((long)k2 * dg * S, (long)std::min(dg, T - k2 * dg) * S, on_side);
+    return rc2;
+  };
+  if (dx && !stream_dx) {
+    if ((rc = dx_rows(0, N, false))) return rc;
+  } else if (dx) {
+    for (int ci = 0; ci < ctx->dx_ready_pairs; ci++)
+      if ((rc = dx_pair(ci, false))) return rc;
   }
   // The weight-gradient products below are consumed only by the all-reduce / update at the end of the step: they go
   // to the side stream (forked here, after the recurrent kernel and the bias / peephole sums) and overlap with the
   // dX product above and with the recurrent backward of the layer below.
-  const bool sd = ctx->overlap != 0;
   if (sd) ctx->fork_side();
+  if (stream_dx) {
+    for (int ci = ctx->dx_ready_pairs; ci < dnpairs; ci++) {
+      if ((rc = dx_pair(ci, true))) return rc;
+      ctx->launches += 1;
+      if ((rc = ctx->check(eb::lstm_set_flag(ctx->side, dflags + ci, ctx->depoch), "lstm_set_flag"))) return rc;
+    }
+    eesen_b200_ctx::DxStream &dxs = ctx->dxs;
+    dxs.active = true; dxs.ptr = dx; dxs.ld = lddx; dxs.T = T; dxs.S = S; dxs.chunk = dg; dxs.nck = dnck; dxs.ready = ctx->dx_ready_pairs;
+    dxs.flags = dflags; dxs.epoch = ctx->depoch;
+  }
   long sGW = ndir == 2 ? gr->wx[1] - gr->wx[0] : 0, sGM = ndir == 2 ? gr->wm[1] - gr->wm[0] : 0;
   bool batched = ndir == 2 && sGW > 0 && (sGW & 3) == 0 && sGM > 0 && (sGM & 3) == 0;
   // Wx grad = DG^T * x   (:505 / :596), both directions batched
@@ -543,8 +616,10 @@ static int lstm_backward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I
   //                          bw pairs DG rows [0, N-S) with out rows [S, N) (:597)
   if (T > 1) {
     const int Nm = N - S;
+    // (no layer below -- dx == NULL: nothing waits on `stream`, so the forward cells' product runs there, next to the
+    // backward cells' on the side stream; it shortens the tail of the step in front of the optimiser)
     rc = do_gemm(ctx, 1, 0, 4 * C, C, Nm, 1.f, dgates + (size_t)S * ldg, ldg, 0, out, ldo, 0, 0.f, gr->wm[0], gldwm, 0,
-                 nullptr, 0, 1, sd);
+                 nullptr, 0, 1, sd && (dx != nullptr || ndir == 1));
     if (rc) return rc;
     if (ndir == 2) {
       rc = do_gemm(ctx, 1, 0, 4 * C, C, Nm, 1.f, dgates + 4 * C, ldg, 0, out + (size_t)S * ldo + C, ldo, 0, 0.f,

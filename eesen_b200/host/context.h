@@ -7,6 +7,8 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -62,6 +64,25 @@ struct eesen_b200_ctx {
   // kernel runs (it checks a per-chunk flag before it reads a chunk).  EESEN_B200_STREAM_GEMM=0 turns it off.
   int stream_gemm = 1;
   unsigned gepoch = 0;
+  // Streamed dX of the recurrent backward pass (the same idea, other direction): when the caller (Net) says that the
+  // in_diff of this layer goes straight into the recurrent backward of the layer below (dx_stream_hint), DG*Wx is cut
+  // into pairs of time chunks -- the two ends of the sequence first, where the two directions of the layer below
+  // start -- the first pair runs on `stream`, the others on the side stream while the recurrent kernel of the layer
+  // below already runs; it checks dflags[pair] before it reads a chunk of its dout.  `dxs` describes the matrix being
+  // streamed; the next recurrent backward call matches it by address (anything else first joins the side stream).
+  int dx_stream_hint = 0;
+  int stream_dx = 0;       // EESEN_B200_STREAM_DX=1 turns the streamed dX on (measured: the side stream has no room for it)
+  int dx_ready_pairs = 1;  // EESEN_B200_DX_READY: chunk pairs computed on `stream` before the layer below starts
+  int early_conv = 1;      // EESEN_B200_EARLY_CONV=0: planes of x / m made behind the recurrent backward kernel, on `stream`
+  struct DxStream {
+    bool active = false;
+    const float *ptr = nullptr;
+    int ld = 0, T = 0, S = 0, chunk = 0, nck = 0, ready = 0;
+    unsigned *flags = nullptr;
+    unsigned epoch = 0;
+  } dxs;
+  Buf lstm_dflags;
+  unsigned depoch = 0;
   void fork_side() {
     cudaEventRecord(ev_fork, stream);
     cudaStreamWaitEvent(side, ev_fork, 0);
@@ -99,11 +120,22 @@ struct eesen_b200_ctx {
   void prof_collect() {
     join_side();
     cudaStreamSynchronize(stream);
+    // EESEN_B200_TRACE_FILE=<path>: one line per launch since the last collect -- stream (0 main, 1 side), category,
+    // start and duration in ms relative to the first launch: the timeline of a step without a profiler attached
+    FILE *tf = nullptr;
+    if (const char *tp = getenv("EESEN_B200_TRACE_FILE")) tf = fopen(tp, "a");
+    if (tf) fprintf(tf, "# collect: %zu launches\n", prof_events.size());
     for (auto &e : prof_events) {
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) { prof_ms[e.cat] += ms; prof_count[e.cat] += 1; }
+      if (tf) {
+        float t0 = 0.f;
+        cudaEventElapsedTime(&t0, prof_events[0].a, e.a);
+        fprintf(tf, "%d %d %.4f %.4f\n", e.st == side ? 1 : 0, e.cat, t0, ms);
+      }
       prof_pool.push_back(e);
     }
+    if (tf) fclose(tf);
     prof_events.clear();
   }
 

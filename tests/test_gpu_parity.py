@@ -663,6 +663,30 @@ def test_c2_full_size_deterministic(ctx, c2_run):
     n2.close()
 
 
+def test_c2_stream_knobs_give_the_same_step(ctx, c2_run, monkeypatch):
+    """The stream-level schedules are pure reorderings: the streamed dX of the recurrent backward pass (opt-in,
+    EESEN_B200_STREAM_DX=1: chunk pairs behind flags on the side stream, the kernel of the layer below waits per chunk),
+    planes of x / m made early on the side stream (default) or behind the kernel, everything on one stream
+    (EESEN_B200_OVERLAP=0) -- all give the parameters of the default schedule after one C2 step (row-chunked GEMMs
+    compute every output row exactly as the whole product does; only the split-K weight-gradient sums are shared)."""
+    w, net, b, n, st = c2_run
+    ref = n.params()
+    for env in ({"EESEN_B200_STREAM_DX": "1"}, {"EESEN_B200_STREAM_DX": "1", "EESEN_B200_DX_READY": "2", "EESEN_B200_EARLY_CONV": "0"},
+                {"EESEN_B200_OVERLAP": "0"}):
+        for k in ("EESEN_B200_STREAM_DX", "EESEN_B200_DX_READY", "EESEN_B200_EARLY_CONV", "EESEN_B200_OVERLAP"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        c2 = binding.Context(0)          # the knobs are read when a context is created
+        n2 = binding.Net(c2, model_file(net))
+        n2.set_train_options(w.learn_rate, w.momentum)
+        st2 = n2.train_step(b.feats, b.frames, b.labels, True)
+        assert st2["obj"] == st["obj"], env
+        assert np.abs(n2.params() - ref).max() <= 1e-7, (env, np.abs(n2.params() - ref).max())
+        n2.close()
+        c2.close()
+
+
 @pytest.mark.skipif(not oracle.have_reference("gpu"), reason="oracle/_ref/ref_dump_gpu not built")
 def test_c2_full_size_vs_reference_gpucompute(ctx):
     """BASELINE configs[1] at full size against the reference's own gpucompute run on the same inputs:
