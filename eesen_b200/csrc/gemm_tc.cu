@@ -1028,15 +1028,20 @@ size_t f16x2_plane_bytes(long rows, int cols) { return (size_t)rows * (size_t)((
 
 // src [rows x cols] (lds) -> planes hi / lo (dense, ld = cols rounded up to 8); scratch: one unsigned, kexp: one int (device)
 cudaError_t convert_f16x2(cudaStream_t st, int num_sms, const float *src, long rows, int cols, long lds, void *hi, void *lo,
-                          unsigned *scratch_max, int *kexp) {
-  cudaError_t e = cudaMemsetAsync(scratch_max, 0, sizeof(unsigned), st);
-  if (e != cudaSuccess) return e;
+                          unsigned *scratch_max, int *kexp, const unsigned *known_max) {
   if (rows <= 0 || cols <= 0) return cudaMemsetAsync(kexp, 0, sizeof(int), st);
   const int ldd = (cols + 7) & ~7;
-  long n = rows * ((cols + 3) / 4);
-  long blocks = (n + 255) / 256;
-  if (blocks > 8L * num_sms) blocks = 8L * num_sms;
-  absmax_kernel<<<(int)blocks, 256, 0, st>>>(src, rows, cols, lds, scratch_max);
+  long n, blocks;
+  if (!known_max) {
+    cudaError_t e = cudaMemsetAsync(scratch_max, 0, sizeof(unsigned), st);
+    if (e != cudaSuccess) return e;
+    n = rows * ((cols + 3) / 4);
+    blocks = (n + 255) / 256;
+    if (blocks > 8L * num_sms) blocks = 8L * num_sms;
+    absmax_kernel<<<(int)blocks, 256, 0, st>>>(src, rows, cols, lds, scratch_max);
+  } else {
+    scratch_max = const_cast<unsigned *>(known_max);
+  }
   n = rows * (ldd / 8);
   blocks = (n + 255) / 256;
   if (blocks > 16L * num_sms) blocks = 16L * num_sms;

@@ -36,8 +36,9 @@ struct F16View {
   const int *kexp;       // device: the scale exponent the conversion chose
 };
 size_t f16x2_plane_bytes(long rows, int cols);
+// known_max != NULL: the bits of max |src| are already there (device) -- no scan of the matrix
 cudaError_t convert_f16x2(cudaStream_t st, int num_sms, const float *src, long rows, int cols, long lds, void *hi, void *lo,
-                          unsigned *scratch_max, int *kexp);
+                          unsigned *scratch_max, int *kexp, const unsigned *known_max = nullptr);
 cudaError_t gemm_tc16x3(cudaStream_t st, int num_sms, int transA, int transB, int M, int N, int K, float alpha,
                         const F16View &A, const F16View &B, float beta, float *C, int ldc, const float *bias, float *ws,
                         size_t ws_bytes);
@@ -69,6 +70,11 @@ struct LstmFwdArgs {
   unsigned gepoch = 0;
   int gchunk = 0, gready = 0;
   int tune = 0;   // debug knobs (EESEN_B200_TUNE): bit 0 = first exchange poll behind the saved-state stores
+  // (tcgen05 engine) fp16 planes of the layer output for the dense products that read it next (the input product of the
+  // layer above, the weight gradients): hi = fp16(2^13 * m), lo = fp16(2^13 * m - hi) -- |m| < 1, so the scale is fixed
+  // and the kernel can write them next to m itself; [T*S x ldh] halfs each, dir d at col d*C.  NULL: not wanted.
+  void *out_hi = nullptr, *out_lo = nullptr;
+  int ldh = 0;
 };
 struct LstmBwdArgs {
   int T, S, C;
@@ -91,6 +97,7 @@ struct LstmBwdArgs {
   const unsigned *dflag = nullptr;
   unsigned depoch = 0;
   int dchunk = 0, dnck = 0, dready = 0;
+  unsigned *dgmax = nullptr;    // (tcgen05 engine) atomicMax of the bits of max |DG| over the launch, or NULL
 };
 struct LstmPlan {
   int engine;            // 0: warp-level mma.sync kernels (lstm.cu), 1: tcgen05 kernels (lstm_tc.cu)

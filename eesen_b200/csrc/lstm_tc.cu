@@ -509,6 +509,16 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
         sc[e] = keep ? c : 0.f; sm[e] = keep ? m : 0.f;
         cprev[e] = sc[e];
       }
+      // fp16 planes of m for the dense products that read the layer output (LstmFwdArgs::out_hi): fixed scale 2^13
+      auto store_planes = [&](int e, int tt) {
+        if (a.out_hi) {
+          const float xs = sm[e] * 8192.f;
+          const __half h = __float2half_rn(xs);
+          const size_t o = ((size_t)tt * S + uidx[e]) * a.ldh + (size_t)dir * C + cell;
+          reinterpret_cast<__half *>(a.out_hi)[o] = h;
+          reinterpret_cast<__half *>(a.out_lo)[o] = __float2half_rn(xs - __half2float(h));
+        }
+      };
       // only m is on the inter-CTA critical path: publish it first
       if (CL) {
         if (step + 1 < T) {
@@ -533,7 +543,7 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
         }
 #pragma unroll
         for (int e = 0; e < 2; e++)
-          if (valid[e]) __stcs(a.out + ((size_t)t * S + uidx[e]) * a.ldo + (size_t)dir * C + cell, sm[e]);
+          if (valid[e]) { __stcs(a.out + ((size_t)t * S + uidx[e]) * a.ldo + (size_t)dir * C + cell, sm[e]); store_planes(e, t); }
       } else {
 #pragma unroll
       for (int e = 0; e < 2; e++) {
@@ -545,6 +555,7 @@ lstm_tc_fwd_kernel(LstmFwdArgs a, int groups, int ndir) {
                     h | ((l & 0xfffeu) << 16) | ((uint32_t)((step >> 1) & 1) << 16));   // tag = LSB of lo'
           }
           __stcs(a.out + ((size_t)t * S + uidx[e]) * a.ldo + (size_t)dir * C + cell, sm[e]);
+          store_planes(e, t);
         }
       }
       }
@@ -766,6 +777,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
 #pragma unroll
     for (int q = 0; q < 4; q++) { sb[q][0] = 0.f; sb[q][1] = 0.f; }
     float vg[2], vi[2], vf[2], vo[2], vc[2], vcp[2], vd[2], vr[2] = {1.f, 1.f};
+    float runmax = 0.f;
     const int tstep = dir == 0 ? -1 : 1;   // time order of the forward pass: c_prev lives at t + tstep
     int dhave = a.dready - 1;                              // last pair of dout chunks known to be complete
     auto prefetch = [&](int t) {
@@ -856,7 +868,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
           if (ok[e]) dm[e] += gsm[(size_t)(2 * up + e) * 32 + cl] + gsm[(size_t)(TCL_UG + 2 * up + e) * 32 + cl];   // :470 / :561
       }
       TC_TICK(1, 0);
-      float dgt[4][2];
+      float dgt[4][2], mxe[2];
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         float dg = 0.f, di = 0.f, df = 0.f, dO = 0.f;
@@ -882,12 +894,14 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
           spi[e] += di * vcp[e]; spf[e] += df * vcp[e]; spo[e] += dO * vc[e];     // :508-510 / :599-601
         }
         dgt[0][e] = dg; dgt[1][e] = di; dgt[2][e] = df; dgt[3][e] = dO;
+        mxe[e] = fmaxf(fmaxf(fabsf(dg), fabsf(di)), fmaxf(fabsf(df), fabsf(dO)));
+        runmax = fmaxf(runmax, mxe[e]);   // max |d(gates)| of everything this thread writes (-> a.dgmax)
       }
       if (step + 1 == T) break;   // the last step's recurrent contribution is never consumed
       // ---- D operand: every utterance column scaled by its own power of two into [2^13, 2^14), fp16 hi / lo'
 #pragma unroll
       for (int e = 0; e < 2; e++) {
-        float mx = fmaxf(fmaxf(fabsf(dgt[0][e]), fabsf(dgt[1][e])), fmaxf(fabsf(dgt[2][e]), fabsf(dgt[3][e])));
+        const float mx = mxe[e];
         const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));   // non-negative floats order like their bits
         int ex = (int)(mb >> 23) - 127;                    // floor(log2(max)); -127 for zero / subnormal columns
         int kexp = 13 - ex;
@@ -1025,6 +1039,13 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
 
     TC_FLUSH(1);
     TC_SEEN_FLUSH(1);
+    // max |d(gates)| over the launch: the scale of the fp16 planes the dense products read DG through (gemm_tc.cu) --
+    // saves them a pass over the 393 MB matrix (NaN / inf order above every finite value as bit patterns: they reach the
+    // conversion as they would have through its own scan)
+    if (a.dgmax) {
+      const unsigned mbits = __reduce_max_sync(0xffffffffu, __float_as_uint(runmax));
+      if (lane == 0 && mbits) atomicMax(a.dgmax, mbits);
+    }
     // ---- bias / peephole gradient partial sums of this (dir, group): reduce over the CTA's 16 utterances
     named_bar_workers();
 #pragma unroll

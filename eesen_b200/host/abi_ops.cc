@@ -65,6 +65,8 @@ int eesen_b200_create(eesen_b200_ctx **out, int device) {
     ctx->stream_dx = (sx && sx[0] == '1') ? 1 : 0;
     const char *dr = getenv("EESEN_B200_DX_READY");
     ctx->dx_ready_pairs = dr ? std::max(1, atoi(dr)) : 1;
+    const char *fr = getenv("EESEN_B200_FWD_READY");
+    ctx->fwd_ready_chunks = fr ? std::max(1, atoi(fr)) : 1;
     const char *ec = getenv("EESEN_B200_EARLY_CONV");
     ctx->early_conv = (ec && ec[0] == '0') ? 0 : 1;
     const char *fx = getenv("EESEN_B200_GEMM_FP32X3");
@@ -136,9 +138,36 @@ static int f16_meta(eesen_b200_ctx *ctx, int idx, unsigned **mx, int **kexp) {
   return 0;
 }
 
+static bool f16_lookup(eesen_b200_ctx *ctx, const float *P, long r, int c, int ld, eb::F16View *out);
+
 // convert the whole matrix [rows x cols] (ld) on `stream` and remember it: later products find sub-blocks by address
-static int f16_register(eesen_b200_ctx *ctx, const float *base, long rows, int cols, int ld, bool on_side = false) {
+// persist (only while a Net drives a training forward pass, ctx->act_enable): the planes go to an ActPlanes slot and stay
+// valid until the next forward pass -- the input weights Wx, which the dX product of the backward pass reads again
+static int f16_register(eesen_b200_ctx *ctx, const float *base, long rows, int cols, int ld, bool on_side = false,
+                        const unsigned *known_max = nullptr, bool persist = false) {
   if (!ctx->f16x3 || ctx->gemm_prec != 0 || ctx->gemm_engine != 0 || !base || rows <= 0 || cols <= 0) return 0;
+  { eb::F16View have; if (f16_lookup(ctx, base, rows, cols, ld, &have)) return 0; }   // (e.g. planes the forward kernel wrote)
+  if (persist && ctx->act_enable) {
+    int slot = -1;
+    for (int i = 0; i < eesen_b200_ctx::kActSlots; i++)
+      if (ctx->act[i].base == base) slot = i;
+    if (slot < 0) { slot = ctx->act_next; ctx->act_next = (ctx->act_next + 1) % eesen_b200_ctx::kActSlots; }
+    eesen_b200_ctx::ActPlanes &e = ctx->act[slot];
+    const size_t pb = eb::f16x2_plane_bytes(rows, cols);
+    void *pl = nullptr;
+    int rc = ctx->reserve(e.planes, 2 * pb + 256, &pl);
+    if (rc) return rc;
+    unsigned *mx; int *kx;
+    if ((rc = f16_meta(ctx, eesen_b200_ctx::kF16Slots + 8 + slot, &mx, &kx))) return rc;
+    e.base = base; e.rows = rows; e.cols = cols; e.ld = ld; e.ldd = (cols + 7) & ~7; e.gen = ctx->act_gen;
+    e.view.hi = pl; e.view.lo = (char *)pl + ((pb + 255) & ~(size_t)255); e.view.ld = e.ldd; e.view.kexp = kx;
+    int pe = ctx->prof_begin(eesen_b200_ctx::kGemm, on_side);
+    cudaError_t ce = eb::convert_f16x2(on_side ? ctx->side : ctx->stream, ctx->num_sms, base, rows, cols, ld, (void *)e.view.hi,
+                                       (void *)e.view.lo, mx, kx, known_max);
+    ctx->prof_end(pe);
+    ctx->launches += known_max ? 1 : 2;
+    return ctx->check(ce, "convert_f16x2");
+  }
   if (ctx->f16_used >= eesen_b200_ctx::kF16Slots) return 0;   // (falls back to per-call conversion)
   eesen_b200_ctx::F16Entry &e = ctx->f16_slots[ctx->f16_used];
   const size_t pb = eb::f16x2_plane_bytes(rows, cols);
@@ -151,15 +180,16 @@ static int f16_register(eesen_b200_ctx *ctx, const float *base, long rows, int c
   e.view.hi = pl; e.view.lo = (char *)pl + ((pb + 255) & ~(size_t)255); e.view.ld = e.ldd; e.view.kexp = kx;
   int pe = ctx->prof_begin(eesen_b200_ctx::kGemm, on_side);
   cudaError_t ce = eb::convert_f16x2(on_side ? ctx->side : ctx->stream, ctx->num_sms, base, rows, cols, ld, (void *)e.view.hi,
-                                     (void *)e.view.lo, mx, kx);
+                                     (void *)e.view.lo, mx, kx, known_max);
   ctx->prof_end(pe);
-  ctx->launches += 2;
+  ctx->launches += known_max ? 1 : 2;
   if ((rc = ctx->check(ce, "convert_f16x2"))) return rc;
   ctx->f16_used++;
   return 0;
 }
 
-// a [r x c] block at P with leading dimension ld: inside a registered matrix?
+// a [r x c] block at P with leading dimension ld: inside a registered matrix (or a layer output whose planes the
+// recurrent forward kernel wrote during this forward pass)?
 static bool f16_lookup(eesen_b200_ctx *ctx, const float *P, long r, int c, int ld, eb::F16View *out) {
   for (int i = 0; i < ctx->f16_used; i++) {
     const eesen_b200_ctx::F16Entry &e = ctx->f16_slots[i];
@@ -171,7 +201,42 @@ static bool f16_lookup(eesen_b200_ctx *ctx, const float *P, long r, int c, int l
     out->lo = (const char *)e.view.lo + ((size_t)ro * e.ldd + co) * 2;
     return true;
   }
+  for (int i = 0; i < eesen_b200_ctx::kActSlots; i++) {
+    const eesen_b200_ctx::ActPlanes &e = ctx->act[i];
+    if (!e.base || e.gen != ctx->act_gen || e.ld != ld || P < e.base) continue;
+    const long off = (long)(P - e.base), ro = off / ld, co = off % ld;
+    if (ro + r > e.rows || co + c > e.cols || (co & 7)) continue;
+    *out = e.view;
+    out->hi = (const char *)e.view.hi + ((size_t)ro * e.ldd + co) * 2;
+    out->lo = (const char *)e.view.lo + ((size_t)ro * e.ldd + co) * 2;
+    return true;
+  }
   return false;
+}
+
+// planes for the layer output `out` [rows x cols] (ld) that the tcgen05 forward kernel is about to write (fixed scale 2^13)
+static int act_planes_for(eesen_b200_ctx *ctx, const float *out, long rows, int cols, int ld, eb::LstmFwdArgs *a) {
+  if (!ctx->act_enable || !ctx->f16x3 || ctx->gemm_prec != 0 || ctx->gemm_engine != 0 || (cols & 7)) return 0;
+  int slot = -1;
+  for (int i = 0; i < eesen_b200_ctx::kActSlots; i++)
+    if (ctx->act[i].base == out) slot = i;
+  if (slot < 0) { slot = ctx->act_next; ctx->act_next = (ctx->act_next + 1) % eesen_b200_ctx::kActSlots; }
+  eesen_b200_ctx::ActPlanes &e = ctx->act[slot];
+  const size_t pb = eb::f16x2_plane_bytes(rows, cols);
+  void *pl = nullptr;
+  int rc = ctx->reserve(e.planes, 2 * pb + 256, &pl);
+  if (rc) return rc;
+  if (!ctx->act_kexp) {
+    unsigned *mx; int *kx;
+    if ((rc = f16_meta(ctx, eesen_b200_ctx::kF16Slots + 5, &mx, &kx))) return rc;
+    static const int k13 = 13;
+    if ((rc = ctx->check(cudaMemcpyAsync(kx, &k13, sizeof(int), cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync"))) return rc;
+    ctx->act_kexp = kx;
+  }
+  e.base = out; e.rows = rows; e.cols = cols; e.ld = ld; e.ldd = cols; e.gen = ctx->act_gen;
+  e.view.hi = pl; e.view.lo = (char *)pl + ((pb + 255) & ~(size_t)255); e.view.ld = e.ldd; e.view.kexp = ctx->act_kexp;
+  a->out_hi = (void *)e.view.hi; a->out_lo = (void *)e.view.lo; a->ldh = e.ldd;
+  return 0;
 }
 
 // view of an operand: registered, or converted on the spot into the stream's temporary planes (which = 0 A, 1 B)
@@ -341,12 +406,12 @@ static int lstm_forward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I,
   ctx->f16_clear();
   if ((rc = f16_register(ctx, x, N, I, ldx))) return rc;
   for (int d = 0; d < ndir; d++)
-    if ((rc = f16_register(ctx, p->wx[d], 4 * C, I, ldwx))) return rc;
+    if ((rc = f16_register(ctx, p->wx[d], 4 * C, I, ldwx, false, nullptr, true))) return rc;
   // Streamed: with the tcgen05 engine (80 of 148 SMs, latency-bound) the product is cut along time into chunks in the
   // order the two directions consume G -- direction 0 from t = 0 upwards, direction 1 from t = T-1 downwards.  The
   // first kReady chunks run here, the others on the side stream next to the recurrent kernel, which checks
   // gflag[chunk] before the first read of a chunk.
-  constexpr int kReady = 2;
+  const int kReady = ctx->fwd_ready_chunks;   // (EESEN_B200_FWD_READY, default 1: measured 14.86 vs 15.13 (2) vs 15.45 ms (3) per C2 step)
   int gchunk = 0, nchunks_g = 0;
   unsigned *gflags = nullptr;
   if (plan.engine == 1 && chunk == S && ctx->overlap && ctx->stream_gemm && T >= 256) {
@@ -400,6 +465,7 @@ static int lstm_forward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I,
   a.precision = ctx->rec_prec;
   a.drop = drop; a.rmask = rmask; a.ldr = ldr; a.rmask_per_step = per_step;
   { const char *tn = getenv("EESEN_B200_TUNE"); a.tune = tn ? atoi(tn) : 0; }
+  if (plan.engine == 1 && (rc = act_planes_for(ctx, out, N, ndir * C, ldo, &a))) return rc;
   if (nchunks_g) { a.gflag = gflags; a.gepoch = ctx->gepoch; a.gchunk = gchunk; a.gready = kReady; }
   for (int s0 = 0; s0 < S; s0 += chunk) {
     a.s_begin = s0;
@@ -509,6 +575,14 @@ static int lstm_backward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I
   const bool sd = ctx->overlap != 0;
   const bool early = sd && ctx->early_conv;
   ctx->f16_clear();
+  // max |DG| comes out of the tcgen05 kernel itself (a.dgmax): the conversion of DG below needs no scan of its own
+  unsigned *dgmax = nullptr;
+  if (plan.engine == 1 && ctx->f16x3 && ctx->gemm_prec == 0 && ctx->gemm_engine == 0) {
+    int *unused_k;
+    if ((rc = f16_meta(ctx, eesen_b200_ctx::kF16Slots + 4, &dgmax, &unused_k))) return rc;
+    if ((rc = ctx->check(cudaMemsetAsync(dgmax, 0, sizeof(unsigned), ctx->stream), "cudaMemsetAsync"))) return rc;
+    a.dgmax = dgmax;
+  }
   if (early) {
     ctx->fork_side();
     if ((rc = f16_register(ctx, x, N, I, ldx, true))) return rc;
@@ -539,7 +613,7 @@ static int lstm_backward_impl(eesen_b200_ctx *ctx, int ndir, int T, int S, int I
     if ((rc = f16_register(ctx, x, N, I, ldx))) return rc;
     if (T > 1 && (rc = f16_register(ctx, out, N, ndir * C, ldo))) return rc;
   }
-  if ((rc = f16_register(ctx, dgates, N, ndir * 4 * C, ldg))) return rc;
+  if ((rc = f16_register(ctx, dgates, N, ndir * 4 * C, ldg, false, dgmax))) return rc;
   if (dx)
     for (int d = 0; d < ndir; d++)
       if ((rc = f16_register(ctx, p->wx[d], 4 * C, I, ldwx))) return rc;

@@ -49,6 +49,24 @@ struct eesen_b200_ctx {
   Buf f16_tmp[4];        // ad-hoc operands: [0] A / [1] B on `stream`, [2] A / [3] B on the side stream
   int f16x3 = 1;         // EESEN_B200_GEMM_FP32X3=tf32 : keep the kind::tf32 3-term split (A/B measurements)
   void f16_clear() { f16_used = 0; }
+  // Planes of layer outputs written by the recurrent forward kernel itself (LstmFwdArgs::out_hi): they outlive
+  // f16_clear() -- the next layer's input product, and both weight-gradient products of the backward pass, find them by
+  // address and convert nothing.  Only while a Net drives the step (act_enable, set by Net::Propagate in training mode;
+  // act_gen: one generation per forward pass, older entries are dead), so that callers of the level-1 operators who reuse
+  // buffers never meet planes of other data.
+  struct ActPlanes {
+    const float *base = nullptr;
+    long rows = 0;
+    int cols = 0, ld = 0, ldd = 0;
+    unsigned gen = 0;
+    Buf planes;
+    eb::F16View view;
+  };
+  enum { kActSlots = 32 };
+  ActPlanes act[kActSlots];
+  int act_next = 0, act_enable = 0;
+  unsigned act_gen = 1;
+  int *act_kexp = nullptr;   // device: the constant 13
 
   // Side stream (lower priority): work nothing on the critical path waits for -- the weight-gradient products of
   // layer l and the all-reduce of its gradient block run here while `stream` carries dX and the recurrent backward
@@ -63,6 +81,7 @@ struct eesen_b200_ctx {
   // two directions consume them; the first chunks run on `stream`, the rest on the side stream WHILE the recurrent
   // kernel runs (it checks a per-chunk flag before it reads a chunk).  EESEN_B200_STREAM_GEMM=0 turns it off.
   int stream_gemm = 1;
+  int fwd_ready_chunks = 1;   // chunks of the streamed input product computed on `stream` before the kernel starts
   unsigned gepoch = 0;
   // Streamed dX of the recurrent backward pass (the same idea, other direction): when the caller (Net) says that the
   // in_diff of this layer goes straight into the recurrent backward of the layer below (dx_stream_hint), DG*Wx is cut

@@ -1020,7 +1020,12 @@ void Net::Propagate(const CuMatrixBase<BaseFloat> &in, CuMatrix<BaseFloat> *out)
   if (NumLayers() == 0) { (*out) = in; return; }
   propagate_buf_[0].Resize(in.NumRows(), in.NumCols(), kUndefined);
   propagate_buf_[0].CopyFromMat(in);
+  // in training mode the recurrent forward kernels also write the fp16 planes of their outputs (context.h:ActPlanes):
+  // one generation per forward pass
+  ctx_->act_gen += 1;
+  ctx_->act_enable = in_train_ ? 1 : 0;
   for (int32 i = 0; i < NumLayers(); i++) layers_[i]->Propagate(propagate_buf_[i], &propagate_buf_[i + 1]);
+  ctx_->act_enable = 0;
   (*out) = propagate_buf_[NumLayers()];
 }
 
