@@ -226,6 +226,7 @@ def rooflines_from_profile(ms, counts, w, batches, peaks, steps, prec, wall_ms, 
     """Per-kernel rooflines from the library's per-launch CUDA events (eesen_b200_profile).
     Algorithmic figures (SURVEY.md section 8d split by kernel):
       recurrent forward  : 20*C floats per valid frame and layer (read pre-acts 8C, write g,i,f,o,c,m 12C)
+                           + 2*C floats' worth for the fp16 hi/lo planes of m the tcgen05 kernel writes
       recurrent backward : 22*C floats per valid frame and layer (read saved 12C + dout 2C, write DGIFO 8C)
       dense GEMMs        : 48*C*I + 16*C*C per layer + 12*C*K flops per PADDED frame (all rows are multiplied)
     `traffic` = dram__bytes_read+write per launch from the committed ncu --set full capture
@@ -247,7 +248,8 @@ def rooflines_from_profile(ms, counts, w, batches, peaks, steps, prec, wall_ms, 
     for k in ("lstm_fwd", "lstm_bwd"):
         if counts.get(k, 0) == 0:
             continue
-        by = (20.0 if k == "lstm_fwd" else 22.0) * w.cells * 4.0 * valid   # bytes per launch (one layer)
+        # bytes per launch (one layer); the tcgen05 forward kernel also writes the two fp16 planes of m (2C x 2 x 2 bytes)
+        by = ((22.0 if engines[0] == 1 else 20.0) if k == "lstm_fwd" else 22.0) * w.cells * 4.0 * valid
         dur = ms[k] / counts[k] * 1e-3
         ach = by / dur / 1e9
         eng = engines[0 if k == "lstm_fwd" else 1]
@@ -257,7 +259,9 @@ def rooflines_from_profile(ms, counts, w, batches, peaks, steps, prec, wall_ms, 
                   "algorithmic_bytes_per_launch": by, "avg_launch_ms": dur * 1e3, "launches_per_step": counts[k] / steps,
                   "share_of_step": ms[k] / tot,
                   "note": "latency-bound at 64 utterances/GPU: T dependent steps per launch (SURVEY.md 7.1)"}
-    if counts.get("gemm", 0):
+    g_ms = ms.get("gemm", 0.0) + ms.get("gemm_side", 0.0)
+    g_cnt = counts.get("gemm", 0) + counts.get("gemm_side", 0)
+    if g_cnt:
         d = w.in_dim
         fl = 0.0
         for _ in range(w.layers):
@@ -265,7 +269,7 @@ def rooflines_from_profile(ms, counts, w, batches, peaks, steps, prec, wall_ms, 
             d = 2 * w.cells
         fl += 12.0 * w.cells * w.classes
         flops = fl * padded
-        dur = ms["gemm"] / steps * 1e-3
+        dur = g_ms / steps * 1e-3
         ach = flops / dur / 1e12
         tf32x3 = os.environ.get("EESEN_B200_GEMM_FP32X3") == "tf32"
         mult = {"fp32x3": 6.0 if tf32x3 else 3.0, "tf32": 2.0, "bf16": 1.0}[prec]   # tensor-pipe work per algorithmic flop, in bf16 units
@@ -278,7 +282,8 @@ def rooflines_from_profile(ms, counts, w, batches, peaks, steps, prec, wall_ms, 
                        "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                        "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic.get("gemm"),
                        "peak_source": peaks["source"], "algorithmic_flops_per_step": flops,
-                       "launches_per_step": counts["gemm"] / steps, "share_of_step": ms["gemm"] / tot,
+                       "launches_per_step": g_cnt / steps, "share_of_step": ms.get("gemm", 0.0) / tot,
+                       "share_note": "share_of_step counts the launches of the main stream only; the side stream's products (gemm_side in per_category_ms_per_step) overlap the recurrent kernels",
                        "tensor_pipe_frac_bf16_equiv": ach * mult / peaks["bf16_tflops_sustained"],
                        "note": gnote}
     return out
@@ -437,8 +442,9 @@ def run_ours(args, w):
                 "tolerance": "log p(z|x) rel 1e-4, per-frame gradient abs 5e-3 (not the headline; fp32x3 is)"},
             "clocks": clocks,
             "per_category_ms_per_step": {k: v / args.steps for k, v in prof_ms.items() if v > 0},
-            "per_category_note": "CUDA-event time of each launch on its own stream; gemm (weight gradients) and all-reduce "
-                                 "launches on the side stream overlap the recurrent kernels, so the sum can exceed ms_per_step",
+            "per_category_note": "CUDA-event time of each launch on its own stream; gemm = dense products and conversions of the "
+                                 "main stream, gemm_side (weight gradients, streamed chunks) and allreduce run on the side stream "
+                                 "and overlap the recurrent kernels, so the sum can exceed ms_per_step",
             "last_step_stats": stats,
         }
         engines = (ctx.lstm_engine(w.S, w.cells, 2, False), ctx.lstm_engine(w.S, w.cells, 2, True))

@@ -114,12 +114,12 @@ class Context:
         """1 = tcgen05 recurrent kernels, 0 = warp-level kernels, -1 = no plan (eesen_b200_lstm_engine)."""
         return int(self.lib.eesen_b200_lstm_engine(self.h, C.c_int(num_utts), C.c_int(cells), C.c_int(ndir), C.c_int(1 if backward else 0)))
 
-    PROFILE_CATEGORIES = ("gemm", "lstm_fwd", "lstm_bwd", "softmax", "ctc", "sgd", "allreduce", "misc")
+    PROFILE_CATEGORIES = ("gemm", "lstm_fwd", "lstm_bwd", "softmax", "ctc", "sgd", "allreduce", "misc", "gemm_side")
 
     def profile(self, enable: int = -1):
         """Returns ({category: ms}, {category: launches}) since the last reset; enable=1/0 switches+resets."""
-        ms = (C.c_double * 8)()
-        cnt = (C.c_long * 8)()
+        ms = (C.c_double * 9)()
+        cnt = (C.c_long * 9)()
         self.check(self.lib.eesen_b200_profile(self.h, int(enable), ms, cnt), "profile")
         return ({k: ms[i] for i, k in enumerate(self.PROFILE_CATEGORIES)},
                 {k: cnt[i] for i, k in enumerate(self.PROFILE_CATEGORIES)})

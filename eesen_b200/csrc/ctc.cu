@@ -203,8 +203,14 @@ ctc_kernel(int T, int S, int K, int max_lab, const int *__restrict__ len, const 
             for (int r = 0; r < R; r++) cur[r] = nxt[r];
           }
           float *dst = dstbuf + (size_t)t * LP + lane * R;
+          if (R % 4 == 0) {   // 16-byte row stores (the workspace rows are 128-float multiples)
 #pragma unroll
-          for (int r = 0; r < R; r++) dst[r] = cur[r];
+            for (int r = 0; r < R; r += 4)
+              *reinterpret_cast<float4 *>(dst + r) = make_float4(cur[r], cur[r + 1 < R ? r + 1 : 0], cur[r + 2 < R ? r + 2 : 0], cur[r + 3 < R ? r + 3 : 0]);
+          } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) dst[r] = cur[r];
+          }
           if (n + PF < Ts) emis(e[i], t0 + dt * (n + PF));
         }
       }
@@ -248,14 +254,29 @@ ctc_kernel(int T, int S, int K, int max_lab, const int *__restrict__ len, const 
     const float *yrow = probs + ((size_t)t * S + s) * ldp;
     float blank = 0.f;
     const float lb = logprob(yrow[0]);
-    for (int j = lane; j < L; j += 32) {
-      float ab = arow[j] + brow[j];
-      if (j & 1) {
-        int c = lab_at(j >> 1);
-        float gam = ex2_approx(ab - pzx - logprob(yrow[c]));    // exp(log(a*b) - pzx - 2 log y) * y  (:1624 then MulElements)
-        atomicAdd(&occ[c], (unsigned long long)(fminf(gam, 1048576.f) * kFix));   // each term <= 1 up to rounding
-      } else {
-        blank += ex2_approx(ab - pzx - lb);
+    // all loads of the row first (alpha, beta, the labels' posteriors: up to R of each per lane), then the arithmetic --
+    // one round trip to L2/HBM per row instead of one per 32 lattice positions
+    float abv[R], yv[R];
+    int cv[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int j = lane + 32 * r;
+      abv[r] = 0.f; yv[r] = 1.f; cv[r] = 0;
+      if (j < L) {
+        abv[r] = arow[j] + brow[j];
+        if (j & 1) { cv[r] = lab_at(j >> 1); yv[r] = yrow[cv[r]]; }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int j = lane + 32 * r;
+      if (j < L) {
+        if (j & 1) {
+          float gam = ex2_approx(abv[r] - pzx - logprob(yv[r]));    // exp(log(a*b) - pzx - 2 log y) * y  (:1624 then MulElements)
+          atomicAdd(&occ[cv[r]], (unsigned long long)(fminf(gam, 1048576.f) * kFix));   // each term <= 1 up to rounding
+        } else {
+          blank += ex2_approx(abv[r] - pzx - lb);
+        }
       }
     }
     blank = warp_sum(blank);

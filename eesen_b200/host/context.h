@@ -115,7 +115,7 @@ struct eesen_b200_ctx {
   }
 
   // optional per-category kernel timing with CUDA events on `stream` (bench.py roofline)
-  enum { kGemm = 0, kLstmFwd, kLstmBwd, kSoftmax, kCtc, kSgd, kAllReduce, kMisc, kNumCat };
+  enum { kGemm = 0, kLstmFwd, kLstmBwd, kSoftmax, kCtc, kSgd, kAllReduce, kMisc, kGemmSide, kNumCat };   // kGemmSide: dense products / conversions of the side stream
   struct ProfEv { cudaEvent_t a, b; int cat; cudaStream_t st; };
   bool prof_on = false;
   std::vector<ProfEv> prof_events;
@@ -127,7 +127,7 @@ struct eesen_b200_ctx {
     ProfEv e;
     if (!prof_pool.empty()) { e = prof_pool.back(); prof_pool.pop_back(); }
     else { cudaEventCreate(&e.a); cudaEventCreate(&e.b); }
-    e.cat = cat;
+    e.cat = (cat == kGemm && on_side) ? (int)kGemmSide : cat;
     e.st = on_side ? side : stream;
     cudaEventRecord(e.a, e.st);
     prof_events.push_back(e);

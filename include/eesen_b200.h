@@ -57,10 +57,11 @@ int eesen_b200_sm_count(const eesen_b200_ctx *ctx);
 long eesen_b200_launch_count(const eesen_b200_ctx *ctx);
 
 /* Per-category device timing with CUDA events on the context's stream (for bench.py's roofline).
- * Categories: 0 gemm, 1 lstm_forward, 2 lstm_backward, 3 softmax/argmax, 4 ctc, 5 sgd, 6 all-reduce, 7 misc.
+ * Categories: 0 gemm (main stream), 1 lstm_forward, 2 lstm_backward, 3 softmax/argmax, 4 ctc, 5 sgd, 6 all-reduce, 7 misc,
+ * 8 gemm on the side stream (weight gradients, streamed chunks, conversions: they overlap the recurrent kernels).
  * Synchronises, returns the milliseconds / launch counts accumulated since the last reset in
- * ms[8] / counts[8] (either may be NULL); enable = 1/0 switches recording and resets, -1 only reads. */
-#define EESEN_B200_NUM_PROFILE_CATEGORIES 8
+ * ms[9] / counts[9] (either may be NULL); enable = 1/0 switches recording and resets, -1 only reads. */
+#define EESEN_B200_NUM_PROFILE_CATEGORIES 9
 int eesen_b200_profile(eesen_b200_ctx *ctx, int enable, double *ms, long *counts);
 
 /* Debug builds only (make TIMING=1): clock64 deltas per phase of the recurrent kernels, [2][16]

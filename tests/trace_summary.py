@@ -1,7 +1,7 @@
 """Reads an EESEN_B200_TRACE_FILE (context.h:prof_collect) and prints the timeline of the LAST collected block: launches of
 the main stream in order (start, duration, gap to the previous one), per-category busy time per stream, idle time."""
 import sys
-CATS = ("gemm", "lstm_fwd", "lstm_bwd", "softmax", "ctc", "sgd", "allreduce", "misc")
+CATS = ("gemm", "lstm_fwd", "lstm_bwd", "softmax", "ctc", "sgd", "allreduce", "misc", "gemm_side")
 blocks, cur = [], None
 for ln in open(sys.argv[1]):
     if ln.startswith("#"):
