@@ -148,7 +148,8 @@ ctc_kernel(int T, int S, int K, int max_lab, const int *__restrict__ len, const 
     auto emis = [&](float (&dst)[R], int t) {
       const float *row = probs + ((size_t)t * S + s) * ldp;
 #pragma unroll
-      for (int r = 0; r < R; r++) dst[r] = cls[r] >= 0 ? logprob(__ldg(row + cls[r])) : kLogZero;
+      for (int r = 0; r < R; r++) dst[r] = cls[r] >= 0 ? __ldg(row + cls[r]) : 0.f;   // RAW posteriors: the log is taken
+      // where the value is used, PF steps later -- taking it here makes the in-order warp wait for the load it just issued
     };
 #pragma unroll
     for (int i = 0; i < PF; i++)
@@ -165,7 +166,7 @@ ctc_kernel(int T, int S, int K, int max_lab, const int *__restrict__ len, const 
             for (int r = 0; r < R; r++) {
               int j = lane * R + r;
               bool init = warp == 0 ? (j < 2) : (j > L - 3);   // cuda-kernels.cu:1392-1394 / 1526-1528
-              cur[r] = (cls[r] >= 0 && init) ? e[i][r] : kLogZero;
+              cur[r] = (cls[r] >= 0 && init) ? logprob(e[i][r]) : kLogZero;
             }
           } else {
             float nb1, nb2;  // neighbour chunk values: alpha <- previous lane's last two, beta <- next lane's first two
@@ -196,7 +197,7 @@ ctc_kernel(int T, int S, int K, int max_lab, const int *__restrict__ len, const 
                 if (R == 1) x2 = nb2;
               }
               float v = skip[r] ? lse3(x0, x1, x2) : lse2(x0, x1);
-              v = e[i][r] + v;                       // AddAB(prob, LogAPlusB(..)) :1397-1406 / 1531-1541
+              v = logprob(e[i][r]) + v;              // AddAB(prob, LogAPlusB(..)) :1397-1406 / 1531-1541
               nxt[r] = (cls[r] >= 0 && v > kLogZero) ? v : kLogZero;
             }
 #pragma unroll
