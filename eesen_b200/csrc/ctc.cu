@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256, 1)
 ctc_kernel(int T, int S, int K, int max_lab, const int *__restrict__ len, const int *__restrict__ labels,
            const int *__restrict__ lab_len, const float *__restrict__ probs, int ldp,
            float *__restrict__ pzx_out, float *__restrict__ diff, int ldd, float *__restrict__ ws) {
-  constexpr int PF = R <= 8 ? 4 : 2;   // emission prefetch distance (time steps)
+  constexpr int PF = R <= 4 ? 8 : (R <= 8 ? 4 : 2);   // emission prefetch distance (time steps)
   constexpr int LP = 32 * R;           // padded lattice width
   // per-warp class occupancies, accumulated as 24.40 fixed point: integer addition is associative, so
   // the shared-memory atomics below give the same bits whatever order the lanes of a pass are served in
@@ -196,7 +196,9 @@ ctc_kernel(int T, int S, int K, int max_lab, const int *__restrict__ len, const 
                 x2 = r + 2 < R ? cur[r + 2 < R ? r + 2 : 0] : (r + 1 < R ? nb1 : nb2);
                 if (R == 1) x2 = nb2;
               }
-              float v = skip[r] ? lse3(x0, x1, x2) : lse2(x0, x1);
+              // branch-free: a forbidden j-2 / j+2 transition enters as log 0 (2^(-1e30 - m) == 0 exactly, so the sum is
+              // the two-term one bit for bit); without the per-lane branch the R chains of a lane interleave
+              float v = lse3(x0, x1, skip[r] ? x2 : kLogZero);
               v = logprob(e[i][r]) + v;              // AddAB(prob, LogAPlusB(..)) :1397-1406 / 1531-1541
               nxt[r] = (cls[r] >= 0 && v > kLogZero) ? v : kLogZero;
             }
