@@ -951,30 +951,40 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
       TC_TICK(1, 2);
       // the saved state of the next position (measured: issuing these loads in front of the MMA issue instead costs
       // 0.2 ms per C2 step -- it delays the product; behind it their latency hides under the tensor pipe's work)
-      prefetch(t + tstep);
+      if (!(a.tune & 256)) prefetch(t + tstep);   // (A/B knob bit 8: the loads behind the epilogue instead)
       TC_TICK(1, 4);
       {
         uint32_t *pw = pbuf + ((size_t)((((step & 1) * ndir + dir) * groups + group) * slices + slice)) * pstride_slice;
         const uint32_t tagw = (uint32_t)((step >> 1) & 1);
-        float inv[8];
+        // Warp 0 issues the MMAs and is the last to get to the epilogue; every consumer of the cluster waits for ITS
+        // pushes (ncu stall samples, profiles/r02_p_lstm_tc_hotspots.txt: 27 % of all warp time in the wait for the peers'
+        // partials).  So warp 0 takes no part in the epilogue: warp 4, which owns the same TMEM lane quadrant, handles
+        // both utterance halves while warp 0 is still issuing.  (EESEN_B200_TUNE bit 6: the old split, A/B.)
+        const bool relieve = !(a.tune & 64);
+        const bool w0 = relieve && warp == 0;
+        const int nhalves = (relieve && warp == 4) ? 2 : 1;
+        const int nbar2 = relieve ? 224 : 256;   // threads on the stacked tile's hand-over barrier
         // (CL) the 8 utterance values of accumulator row `row` of the 32-row block that belongs to CTA d of the cluster:
         // two 16-byte stores into d's receive buffer (step & 1), block `slice` (= this producer), complete_tx on d's barrier
-        auto push8 = [&](uint32_t d, int row, const float (&pv)[8]) {
-          const uint32_t la = smem_u32(R) + (uint32_t)((((step & 1) * slices + slice) * kRBlk + row * kRRow + 8 * uh) * 4);
+        auto push8 = [&](uint32_t d, int row, int uhh, const float (&pv)[8]) {
+          const uint32_t la = smem_u32(R) + (uint32_t)((((step & 1) * slices + slice) * kRBlk + row * kRRow + 8 * uhh) * 4);
           const uint32_t ra = mapa_u32(la, d), rbar = mapa_u32(smem_u32(&rfull[step & 1]), d);
           st_async16(ra, make_uint4(__float_as_uint(pv[0]), __float_as_uint(pv[1]), __float_as_uint(pv[2]), __float_as_uint(pv[3])), rbar);
           st_async16(ra + 16, make_uint4(__float_as_uint(pv[4]), __float_as_uint(pv[5]), __float_as_uint(pv[6]), __float_as_uint(pv[7])), rbar);
         };
+        if (a.tune & 128) {   // (A/B knob bit 7: no epilogue work while the tensor pipe is still busy)
+          mbar_wait(&mma_done[MT - 1], (uint32_t)(step & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        }
         for (int bi = 0; bi < MT; bi++) {
+          if (w0 && bi + 1 < MT) continue;   // warp 0 only makes sure the last tile is done (the B tile is rewritten next step)
           mbar_wait(&mma_done[bi], (uint32_t)(step & 1));
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           TC_TICK(1, 6);   // (debug build: time spent waiting for the tiles' commits)
           TC_SEEN(bi);
-          if (bi == 0) {   // the column scales were written by the other warps before they arrived on b_full: read
-                           // them only behind the first commit (which is behind b_full)
-#pragma unroll
-            for (int j = 0; j < 8; j++) inv[j] = scl[(step & 1) * 16 + 8 * uh + j];
-          }
+          if (w0) continue;
+          // (the column scales were written by the other warps before they arrived on b_full: they are read only behind a
+          // commit, which is behind b_full; two sets by step parity, see the declaration of scl)
           if (stk && bi == 0) {
             // stacked tile: lanes 0-63 (quadrants 0-1) carry hi*hi | hi*lo', lanes 64-127 the lo'*hi term of the same
             // rows -- it crosses to the other warps through shared memory
@@ -986,23 +996,27 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
               tmem_ld_wait();
 #pragma unroll
               for (int jj = 0; jj < 8; jj++) ysm[(8 * uh + jj) * 64 + r] = u2f(y0[jj]);
-              asm volatile("bar.arrive 2, 256;\n" ::: "memory");
+              asm volatile("bar.arrive 2, %0;\n" ::"r"(nbar2) : "memory");
             } else {
-              uint32_t x0[8], x1[8];
-              tmem_ld8(tl + 8 * uh, x0);
-              tmem_ld8(tl + 16 + 8 * uh, x1);
-              tmem_ld_wait();
-              asm volatile("bar.sync 2, 256;\n" ::: "memory");
-              const int j = n128 * 128 + r;
-              float pv[8];
-#pragma unroll
-              for (int jj = 0; jj < 8; jj++) pv[jj] = (u2f(x0[jj]) + (u2f(x1[jj]) + ysm[(8 * uh + jj) * 64 + r]) * kLoUnscale) * inv[jj];
-              if (CL) {
-                push8((uint32_t)(n128 * 4 + (quad & 1)), lane, pv);
-              } else {
+              for (int hh = 0; hh < nhalves; hh++) {
+                const int uhh = nhalves == 2 ? 1 - hh : uh;
+                uint32_t x0[8], x1[8];
+                tmem_ld8(tl + 8 * uhh, x0);
+                tmem_ld8(tl + 16 + 8 * uhh, x1);
+                tmem_ld_wait();
+                if (hh == 0) asm volatile("bar.sync 2, %0;\n" ::"r"(nbar2) : "memory");
+                const int j = n128 * 128 + r;
+                float pv[8];
 #pragma unroll
                 for (int jj = 0; jj < 8; jj++)
-                  st_word(pw + (size_t)(8 * uh + jj) * C + j, (__float_as_uint(pv[jj]) & 0xfffffffeu) | tagw);   // tag = LSB
+                  pv[jj] = (u2f(x0[jj]) + (u2f(x1[jj]) + ysm[(8 * uhh + jj) * 64 + r]) * kLoUnscale) * scl[(step & 1) * 16 + 8 * uhh + jj];
+                if (CL) {
+                  push8((uint32_t)(n128 * 4 + (quad & 1)), lane, uhh, pv);
+                } else {
+#pragma unroll
+                  for (int jj = 0; jj < 8; jj++)
+                    st_word(pw + (size_t)(8 * uhh + jj) * C + j, (__float_as_uint(pv[jj]) & 0xfffffffeu) | tagw);   // tag = LSB
+                }
               }
             }
             TC_TICK(1, 3);
@@ -1010,30 +1024,35 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
           }
           const int mt = bi - (stk ? 1 : 0);
           const bool full = mt < n128;              // (ss64: the last one is the M = 64 tile)
-          uint32_t x0[8], x1[8], y0[8];
           const uint32_t tl = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_col(mt);
-          tmem_ld8(tl + 8 * uh, x0);
-          tmem_ld8(tl + 16 + 8 * uh, x1);
-          tmem_ld8(tl + 32 + 8 * uh, y0);
-          tmem_ld_wait();
-          // M = 128: lane = row; M = 64: rows 16*quad .. +15 sit in lanes 0-15 of every quadrant
-          const int j = full ? mt * 128 + quad * 32 + lane : mt * 128 + quad * 16 + lane;
-          if (full || lane < 16) {
-            float pv[8];
-#pragma unroll
-            for (int jj = 0; jj < 8; jj++) pv[jj] = (u2f(x0[jj]) + (u2f(x1[jj]) + u2f(y0[jj])) * kLoUnscale) * inv[jj];
-            if (CL) {
-              push8((uint32_t)(mt * 4 + quad), lane, pv);   // (CL: full tiles only)
-            } else {
+          for (int hh = 0; hh < nhalves; hh++) {
+            const int uhh = nhalves == 2 ? 1 - hh : uh;
+            uint32_t x0[8], x1[8], y0[8];
+            tmem_ld8(tl + 8 * uhh, x0);
+            tmem_ld8(tl + 16 + 8 * uhh, x1);
+            tmem_ld8(tl + 32 + 8 * uhh, y0);
+            tmem_ld_wait();
+            // M = 128: lane = row; M = 64: rows 16*quad .. +15 sit in lanes 0-15 of every quadrant
+            const int j = full ? mt * 128 + quad * 32 + lane : mt * 128 + quad * 16 + lane;
+            if (full || lane < 16) {
+              float pv[8];
 #pragma unroll
               for (int jj = 0; jj < 8; jj++)
-                st_word(pw + (size_t)(8 * uh + jj) * C + j, (__float_as_uint(pv[jj]) & 0xfffffffeu) | tagw);   // tag = LSB
+                pv[jj] = (u2f(x0[jj]) + (u2f(x1[jj]) + u2f(y0[jj])) * kLoUnscale) * scl[(step & 1) * 16 + 8 * uhh + jj];
+              if (CL) {
+                push8((uint32_t)(mt * 4 + quad), lane, uhh, pv);   // (CL: full tiles only)
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++)
+                  st_word(pw + (size_t)(8 * uhh + jj) * C + j, (__float_as_uint(pv[jj]) & 0xfffffffeu) | tagw);   // tag = LSB
+              }
             }
           }
           TC_TICK(1, 3);
         }
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       }
+      if (a.tune & 256) prefetch(t + tstep);
       TC_TICK(1, 3);
     }
 
