@@ -951,7 +951,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
       TC_TICK(1, 2);
       // the saved state of the next position (measured: issuing these loads in front of the MMA issue instead costs
       // 0.2 ms per C2 step -- it delays the product; behind it their latency hides under the tensor pipe's work)
-      if (!(a.tune & 256)) prefetch(t + tstep);   // (A/B knob bit 8: the loads behind the epilogue instead)
+      prefetch(t + tstep);
       TC_TICK(1, 4);
       {
         uint32_t *pw = pbuf + ((size_t)((((step & 1) * ndir + dir) * groups + group) * slices + slice)) * pstride_slice;
@@ -972,10 +972,8 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
           st_async16(ra, make_uint4(__float_as_uint(pv[0]), __float_as_uint(pv[1]), __float_as_uint(pv[2]), __float_as_uint(pv[3])), rbar);
           st_async16(ra + 16, make_uint4(__float_as_uint(pv[4]), __float_as_uint(pv[5]), __float_as_uint(pv[6]), __float_as_uint(pv[7])), rbar);
         };
-        if (a.tune & 128) {   // (A/B knob bit 7: no epilogue work while the tensor pipe is still busy)
-          mbar_wait(&mma_done[MT - 1], (uint32_t)(step & 1));
-          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        }
+        // (measured, profiles/r02_w_ab.txt: holding the epilogue back until the last tile has committed costs 0.3 ms per
+        // C2 step, moving the prefetch loads behind the epilogue 0.8 ms: the overlap below is what pays)
         for (int bi = 0; bi < MT; bi++) {
           if (w0 && bi + 1 < MT) continue;   // warp 0 only makes sure the last tile is done (the B tile is rewritten next step)
           mbar_wait(&mma_done[bi], (uint32_t)(step & 1));
@@ -1052,7 +1050,6 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
         }
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       }
-      if (a.tune & 256) prefetch(t + tstep);
       TC_TICK(1, 3);
     }
 
