@@ -115,7 +115,11 @@ int eesen_b200_bilstm_forward(eesen_b200_ctx *ctx, int T, int S, int I, int C, c
 /* BiLstmParallel::BackpropagateFnc (reference :881-913, :422-602).  dgates [T*S x 8C] is scratch/out
  * (the DGIFO blocks of backpropagate_buf_); dx may be NULL (first layer).  grads receives the RAW
  * gradient sums over all rows (no momentum: corr = grad + momentum*corr is applied by
- * eesen_b200_sgd_update after the data-parallel all-reduce). */
+ * eesen_b200_sgd_update after the data-parallel all-reduce).
+ * Stream order: dgates and dx are complete in the order of eesen_b200_stream when the call returns its work to it; the
+ * weight gradients (grads->wx, ->wm) are produced on the library's side stream, overlapped with whatever the caller
+ * queues next, and are complete for eesen_b200_sgd_update / eesen_b200_allreduce_sum* / eesen_b200_synchronize (each
+ * joins the side stream) -- a caller reading them with its own kernels synchronizes first. */
 int eesen_b200_bilstm_backward(eesen_b200_ctx *ctx, int T, int S, int I, int C, const float *x, int ldx,
                                const eesen_b200_bilstm_params *p, const float *gates, const float *cell,
                                const float *out, int ldo, const float *dout, int ldd, float *dgates,
