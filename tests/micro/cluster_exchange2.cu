@@ -88,6 +88,55 @@ __global__ void __launch_bounds__(THREADS, 1) dsmem_kernel(int iters, int SL, in
   if (tid == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+
+// ---- (c) DSMEM bulk copies: the slab is staged locally (generic stores), then ONE elected thread per destination issues a
+// 2 KB cp.async.bulk shared::cta -> shared::cluster with complete_tx on the destination's mbarrier
+__device__ __forceinline__ void bulk_s2s(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t rbar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(rbar)
+               : "memory");
+}
+__global__ void __launch_bounds__(THREADS, 1) bulk_kernel(int iters, int SL, int delay, unsigned *out, long long *cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  cluster_sync_all();
+  const uint32_t tile = smem_u32(smem), slab = 2048u, tile_bytes = (uint32_t)SL * slab;
+  uint8_t *stage = smem + 2 * tile_bytes;   // [2 parity][2 KB] local staging
+  unsigned acc = 0;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; it++) {
+    const int par = it & 1;
+    if (tid == 0) mbar_expect_tx(&bar[par], tile_bytes);
+    // every thread writes its 8 bytes of the slab (it, rank, ...), then the proxy fence and a CTA barrier
+    *reinterpret_cast<uint2 *>(stage + par * slab + tid * 8) = make_uint2((uint32_t)it, rank);
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    if (tid < SL)
+      bulk_s2s(mapa(tile + (uint32_t)par * tile_bytes + rank * slab, (uint32_t)tid), smem_u32(stage + par * slab), slab,
+               mapa(smem_u32(&bar[par]), (uint32_t)tid));
+    mbar_wait(&bar[par], (uint32_t)((it >> 1) & 1));
+    for (int i = tid; i < SL * 128; i += THREADS) {
+      const uint4 q = *reinterpret_cast<const uint4 *>(smem + (size_t)par * tile_bytes + (size_t)i * 16);
+      acc += (q.x == (uint32_t)it) ? 1u : 1000000u;
+    }
+    if (delay) { long long t = clock64(); while (clock64() - t < delay) {} }
+  }
+  long long t1 = clock64();
+  cluster_sync_all();
+  out[blockIdx.x * THREADS + tid] = acc;
+  if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+  (void)lane; (void)warp;
+}
+
 // ---- (a) L2 tagged words, as lstm_tc_fwd_kernel: xbuf [2 parity][groups][16][C] words
 __device__ __forceinline__ void st_word(uint32_t *p, uint32_t v) { asm volatile("st.relaxed.gpu.global.b32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ uint4 ld_word4(const uint4 *p) {
@@ -131,6 +180,8 @@ int main() {
   cudaFuncSetAttribute(dsmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(dsmem_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   cudaFuncSetAttribute(l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(bulk_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   const int iters = 4000;
   unsigned *out; long long *cyc; uint32_t *xbuf;
   cudaMalloc(&out, sizeof(unsigned) * 148 * THREADS); cudaMalloc(&cyc, sizeof(long long) * 148);
@@ -159,6 +210,17 @@ int main() {
         double s = 0; long long mx = 0; for (int i = 0; i < blocks; i++) { s += h[i]; if (h[i] > mx) mx = h[i]; }
         unsigned long long tot = 0; for (int i = 0; i < blocks * THREADS; i++) tot += ho[i];
         printf("   DSMEM st.async + mbarrier, delay %4d: %.0f clk per step (max CTA %.0f)  payload %s  (%s / %s)\n", delay, s / blocks / iters,
+               (double)mx / iters, tot == (unsigned long long)blocks * c.SL * 128 * iters ? "ok" : "WRONG", cudaGetErrorString(e), cudaGetErrorString(e2));
+      }
+      if (qe == cudaSuccess && maxc >= 1) {
+        int SL = c.SL;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, bulk_kernel, iters, SL, delay, out, cyc);
+        cudaError_t e2 = cudaDeviceSynchronize();
+        long long h[148]; cudaMemcpy(h, cyc, sizeof(long long) * blocks, cudaMemcpyDeviceToHost);
+        unsigned ho[148 * THREADS]; cudaMemcpy(ho, out, sizeof(unsigned) * blocks * THREADS, cudaMemcpyDeviceToHost);
+        double s = 0; long long mx = 0; for (int i = 0; i < blocks; i++) { s += h[i]; if (h[i] > mx) mx = h[i]; }
+        unsigned long long tot = 0; for (int i = 0; i < blocks * THREADS; i++) tot += ho[i];
+        printf("   DSMEM bulk copies (2 KB each), delay %4d: %.0f clk per step (max CTA %.0f)  payload %s  (%s / %s)\n", delay, s / blocks / iters,
                (double)mx / iters, tot == (unsigned long long)blocks * c.SL * 128 * iters ? "ok" : "WRONG", cudaGetErrorString(e), cudaGetErrorString(e2));
       }
       {
