@@ -62,6 +62,12 @@ __device__ long long g_lstm_tc_timing[2][16];
 #define TC_MARK() do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *(volatile long long *)&tc_mark_ = clock64(); } while (0)
 #define TC_SEEN(bi) do { if (tid == 128 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) tseen_[bi] += clock64() - *(volatile long long *)&tc_mark_; } while (0)
 #define TC_SEEN_FLUSH(kernel) do { if (tid == 128 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) for (int i_ = 0; i_ < 4; i_++) g_lstm_tc_timing[kernel][12 + i_] += tseen_[i_]; } while (0)
+// the same observer's own epilogue phases (backward kernel; slots 12..15 of the FORWARD table, which that kernel leaves
+// alone): 0 commit wait, 1 TMEM loads, 2 arithmetic, 3 pushes
+#define TC_OBS_DECL() long long tobs_[4] = {0, 0, 0, 0}, tol_ = 0
+#define TC_OBS_START() do { if (tid == 128) tol_ = clock64(); } while (0)
+#define TC_OBS(i) do { if (tid == 128) { long long n_ = clock64(); tobs_[i] += n_ - tol_; tol_ = n_; } } while (0)
+#define TC_OBS_FLUSH() do { if (tid == 128 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) for (int i_ = 0; i_ < 4; i_++) g_lstm_tc_timing[0][12 + i_] += tobs_[i_]; } while (0)
 #define TC_FLUSH(kernel)                                                            \
   do {                                                                              \
     if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)          \
@@ -77,6 +83,10 @@ __device__ long long g_lstm_tc_timing[2][16];
 #define TC_MARK()
 #define TC_SEEN(bi)
 #define TC_SEEN_FLUSH(kernel)
+#define TC_OBS_DECL()
+#define TC_OBS_START()
+#define TC_OBS(i)
+#define TC_OBS_FLUSH()
 #endif
 
 namespace {
@@ -811,6 +821,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
 
     TC_ACC_DECL();
     TC_MARK_DECL();
+    TC_OBS_DECL();
     for (int step = 0; step < T; step++) {
       const int t = dir == 0 ? T - 1 - step : step;
       TC_T0();
@@ -948,6 +959,10 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
         }
         __syncwarp();
       }
+      // (Measured and dropped, profiles/r02_ac_ab.txt: letting the other warps sleep until warp 0 has issued the whole
+      // product.  In isolation the elected thread issues the 40 MMAs in 0.64 k cycles alone and in 1.8 k next to four
+      // warps of global loads (tests/micro/umma_probe.cu, profiles/r02_ab_umma_noise.txt), but inside the kernel the
+      // wait costs 0.9 ms per C2 step: the overlap of prefetch and epilogue with the product is worth more.)
       TC_TICK(1, 2);
       // the saved state of the next position (measured: issuing these loads in front of the MMA issue instead costs
       // 0.2 ms per C2 step -- it delays the product; behind it their latency hides under the tensor pipe's work)
@@ -976,10 +991,12 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
         // C2 step, moving the prefetch loads behind the epilogue 0.8 ms: the overlap below is what pays)
         for (int bi = 0; bi < MT; bi++) {
           if (w0 && bi + 1 < MT) continue;   // warp 0 only makes sure the last tile is done (the B tile is rewritten next step)
+          TC_OBS_START();
           mbar_wait(&mma_done[bi], (uint32_t)(step & 1));
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           TC_TICK(1, 6);   // (debug build: time spent waiting for the tiles' commits)
           TC_SEEN(bi);
+          TC_OBS(0);
           if (w0) continue;
           // (the column scales were written by the other warps before they arrived on b_full: they are read only behind a
           // commit, which is behind b_full; two sets by step parity, see the declaration of scl)
@@ -1003,13 +1020,16 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
                 tmem_ld8(tl + 16 + 8 * uhh, x1);
                 tmem_ld_wait();
                 if (hh == 0) asm volatile("bar.sync 2, %0;\n" ::"r"(nbar2) : "memory");
+                TC_OBS(1);
                 const int j = n128 * 128 + r;
                 float pv[8];
 #pragma unroll
                 for (int jj = 0; jj < 8; jj++)
                   pv[jj] = (u2f(x0[jj]) + (u2f(x1[jj]) + ysm[(8 * uhh + jj) * 64 + r]) * kLoUnscale) * scl[(step & 1) * 16 + 8 * uhh + jj];
+                TC_OBS(2);
                 if (CL) {
                   push8((uint32_t)(n128 * 4 + (quad & 1)), lane, uhh, pv);
+                  TC_OBS(3);
                 } else {
 #pragma unroll
                   for (int jj = 0; jj < 8; jj++)
@@ -1030,6 +1050,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
             tmem_ld8(tl + 16 + 8 * uhh, x1);
             tmem_ld8(tl + 32 + 8 * uhh, y0);
             tmem_ld_wait();
+            TC_OBS(1);
             // M = 128: lane = row; M = 64: rows 16*quad .. +15 sit in lanes 0-15 of every quadrant
             const int j = full ? mt * 128 + quad * 32 + lane : mt * 128 + quad * 16 + lane;
             if (full || lane < 16) {
@@ -1037,8 +1058,10 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
 #pragma unroll
               for (int jj = 0; jj < 8; jj++)
                 pv[jj] = (u2f(x0[jj]) + (u2f(x1[jj]) + u2f(y0[jj])) * kLoUnscale) * scl[(step & 1) * 16 + 8 * uhh + jj];
+              TC_OBS(2);
               if (CL) {
                 push8((uint32_t)(mt * 4 + quad), lane, uhh, pv);   // (CL: full tiles only)
+                TC_OBS(3);
               } else {
 #pragma unroll
                 for (int jj = 0; jj < 8; jj++)
@@ -1055,6 +1078,7 @@ lstm_tc_bwd_kernel(LstmBwdArgs a, int groups, int slices, int ndir) {
 
     TC_FLUSH(1);
     TC_SEEN_FLUSH(1);
+    TC_OBS_FLUSH();
     // max |d(gates)| over the launch: the scale of the fp16 planes the dense products read DG through (gemm_tc.cu) --
     // saves them a pass over the 393 MB matrix (NaN / inf order above every finite value as bit patterns: they reach the
     // conversion as they would have through its own scan)

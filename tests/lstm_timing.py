@@ -30,6 +30,8 @@ for i, n in enumerate(names_f):
         print(f"  {n:24s} {buf[i] / steps:9.2f}"); continue
     print(f"  {n:24s} {buf[i] / steps:9.0f}"); tot += buf[i] / steps
 print(f"  {'total':24s} {tot:9.0f}")
+print("backward, second observer (warp 4, both utterance halves of its quadrant): cycles/step in commit waits / TMEM loads (+ hand-over barrier) / arithmetic / pushes:")
+print("  ", "  ".join(f"{buf[12 + i] / steps:8.0f}" for i in range(4)))
 print("backward cycles/step:")
 tot = 0
 for i, n in enumerate(names_b):

@@ -420,13 +420,14 @@ static void run_ts(int NB, int reps, int two, const char *what) {
 //    full tiles (8 x (N = 32 + N = 16) each), all operands A resident in TMEM, K = 128 (B tile [32 x 128]); one commit per
 //    tile.  Reports when the elected thread is done issuing and when each tile's commit is observed (cycles from the
 //    start of the issue, mean over reps).  order = 0: tile after tile (as the kernel), 1: all tiles k-slice by k-slice.
-__global__ void __launch_bounds__(128, 1) probe_bwd_kernel(long long *cycles, int reps, int order) {
+__global__ void __launch_bounds__(256, 1) probe_bwd_kernel(long long *cycles, int reps, int order, int noise, const float *gsrc) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *sB = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // [32 x 128] fp16
   __shared__ uint64_t bar[3];
   __shared__ uint32_t tmem_base_sm;
   const int tid = threadIdx.x, warp = tid >> 5;
-  for (int i = tid; i < 32 * 128; i += 128) *reinterpret_cast<uint16_t *>(sB + sw128_off(32, i / 128, i % 128)) = cvt16(0.01f * (i % 37), 0);
+  for (int i = tid; i < 32 * 128; i += 256) *reinterpret_cast<uint16_t *>(sB + sw128_off(32, i / 128, i % 128)) = cvt16(0.01f * (i % 37), 0);
+  float nacc = 0.f;
   if (tid == 0) {
     for (int i = 0; i < 3; i++) mbar_init(&bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -441,7 +442,7 @@ __global__ void __launch_bounds__(128, 1) probe_bwd_kernel(long long *cycles, in
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tm = tmem_base_sm;
   {   // some fp16 pattern in the weight columns [160, 480)
-    for (int c0 = 160; c0 < 480; c0 += 8) {
+    for (int c0 = 160; c0 < 480 && warp < 4; c0 += 8) {
       const uint32_t ta = tm + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
       const uint32_t w = 0x2c002c00u;   // 2 x fp16 0.0625
       asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};\n" ::"r"(ta), "r"(w) : "memory");
@@ -495,6 +496,30 @@ __global__ void __launch_bounds__(128, 1) probe_bwd_kernel(long long *cycles, in
     }
     const long long t1 = clock64();
     tissue += t1 - t0;
+    if (warp >= 4 && noise) {
+      // warps 4-7 keep the SM busy while the tensor pipe works (until the last commit): 1 = tcgen05.ld of the accumulator
+      // columns, 2 = shared-memory stores, 3 = global loads, 4 = FMA chains
+      uint32_t done = 0;
+      int guard = 0;
+      while (!done && guard++ < 100000) {
+        if (noise == 1) {
+          uint32_t r[8];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                       : "r"(tm + ((uint32_t)((warp & 3) * 32) << 16) + 96u));
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+          nacc += __uint_as_float(r[0]);
+        } else if (noise == 2) {
+          for (int k = 0; k < 16; k++) *reinterpret_cast<volatile uint16_t *>(sB + 9216 + ((tid * 66 + k * 130) & 4095)) = (uint16_t)k;
+        } else if (noise == 3) {
+          for (int k = 0; k < 8; k++) nacc += __ldcs(gsrc + ((size_t)(rep * 8 + k) * 65536 + tid * 32) % (1u << 24));
+        } else {
+          for (int k = 0; k < 64; k++) nacc = fmaf(nacc, 1.0001f, 0.5f);
+        }
+        asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(smem_u32(&bar[2])), "r"((uint32_t)(rep & 1)) : "memory");
+      }
+    }
     for (int i = 0; i < 3; i++) {
       mbar_wait(&bar[i], (uint32_t)(rep & 1));
       tw[i] += clock64() - t0;
@@ -503,6 +528,7 @@ __global__ void __launch_bounds__(128, 1) probe_bwd_kernel(long long *cycles, in
   }
   if (tid == 0) { cycles[0] = tissue; cycles[1] = tw[0]; cycles[2] = tw[1]; cycles[3] = tw[2]; }
   if (tid == 64) { cycles[4] = tissue; cycles[5] = tw[0]; cycles[6] = tw[1]; cycles[7] = tw[2]; }
+  if (nacc == 12345.678f) cycles[8] = 1;
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   if (warp == 0) {
@@ -510,24 +536,28 @@ __global__ void __launch_bounds__(128, 1) probe_bwd_kernel(long long *cycles, in
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "n"(512) : "memory");
   }
 }
-static void run_bwd(int order) {
+static void run_bwd(int order, int noise = 0) {
   long long *dC, h[8];
-  CK(cudaMalloc(&dC, 64));
+  float *gsrc;
+  CK(cudaMalloc(&dC, 128));
+  CK(cudaMalloc(&gsrc, (size_t)(1u << 24) * 4 + 4096));
+  CK(cudaMemset(gsrc, 0, (size_t)(1u << 24) * 4 + 4096));
   const int reps = 200;
   CK(cudaFuncSetAttribute(probe_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384));
-  probe_bwd_kernel<<<1, 128, 16384>>>(dC, reps, order);
+  probe_bwd_kernel<<<1, 256, 16384>>>(dC, reps, order, noise, gsrc);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("bwd step probe: LAUNCH/EXEC ERROR %s\n", cudaGetErrorString(e)); exit(2); }
   CK(cudaMemcpy(h, dC, 64, cudaMemcpyDeviceToHost));
-  printf("bwd step (8 stacked + 2 x 16 MMAs), %s: issuing warp: issue done %.0f, commits seen at %.0f / %.0f / %.0f;  a waiting warp: %.0f / %.0f / %.0f cycles\n",
-         order ? "k-slice interleaved" : "tile after tile    ", (double)h[0] / reps, (double)h[1] / reps, (double)h[2] / reps, (double)h[3] / reps,
+  printf("[noise %d] bwd step (8 stacked + 2 x 16 MMAs), %s: issuing warp: issue done %.0f, commits seen at %.0f / %.0f / %.0f;  a waiting warp: %.0f / %.0f / %.0f cycles\n",
+         noise, order ? "k-slice interleaved" : "tile after tile    ", (double)h[0] / reps, (double)h[1] / reps, (double)h[2] / reps, (double)h[3] / reps,
          (double)h[5] / reps, (double)h[6] / reps, (double)h[7] / reps);
-  cudaFree(dC);
+  cudaFree(dC); cudaFree(gsrc);
 }
 
 int main() {
   run_bwd(0);
   run_bwd(1);
+  for (int nz = 1; nz <= 4; nz++) run_bwd(0, nz);
   run_ts(32, 1, 0, "TS form (A in TMEM), single pass");
   run_ts(32, 1, 1, "TS form, two accumulators");
   run_ts(32, 200, 0, "timing TS: 20 MMA N=32");
