@@ -2,16 +2,16 @@
 //
 // Same contract as lstm.cu (reference BiLstmParallel::PropagateFncVanillaPass{Forward,Backward}
 // bilstm-parallel-layer.h:112-149,166-205 and BackpropagateFncVanillaPass* :450-499,541-590 plus the
-// bias / peephole reductions :507-510,598-601): ONE cooperative launch per layer and pass runs all T
+// bias / peephole reductions :507-510,598-601): ONE launch per layer and pass runs all T
 // steps of both directions.  What changes is the per-step product m_{t-1} * Wm^T (forward) and
 // d(gates) * Wm (backward): it runs as tcgen05.mma kind::f16 with the accumulator in TMEM instead
 // of 60 warp-level mma.sync per warp and step.
 //
 // Decomposition: CTA(dir, group, slice) owns 32 cells (= 128 gate rows = one M=128 tile) of one direction
-// for a group of 16 utterances.  Its rows of Wm stay resident in shared memory for the whole sequence as
-// TWO fp16 tiles in the canonical K-major SWIZZLE_128B layout the tensor core reads directly:
+// for a group of 16 utterances.  Its rows of Wm stay resident in TENSOR MEMORY for the whole sequence ("TS" form MMAs;
+// the tiles that do not fit at 384 / 512 cells stay in shared memory) as fp16 pairs
 //   W = W_hi + 2^-11 * W_lo'        W_hi = fp16(W),  W_lo' = fp16((W - W_hi) * 2^11)
-// and the per-step activations are split the same way, stacked along N:
+// and the per-step activations are split the same way, stacked along N in a K-major SWIZZLE_128B tile:
 //   B = [ x_hi (16 utterances) ; x_lo' (16 utterances) ]          (32 x K, K-major)
 // Two MMAs per 16-wide k-slice:  X += W_hi * B  (N = 32: hi*hi | hi*lo'),  Y += W_lo' * B[0:16]  (N = 16:
 // lo'*hi); result = X[:, u] + 2^-11 * (X[:, 16+u] + Y[:, u]) -- the dropped lo'*lo' term is 2^-22 relative,
@@ -21,14 +21,17 @@
 // [2^13, 2^14) before the split and scaled back in the epilogue.  (One instruction cannot mix fp16 and bf16
 // operands on sm_100a -- measured, tests/micro/umma_probe.cu -- hence the scaling instead of a bf16 split.)
 //
-// Exchange between the CTAs of one (dir, group): "LL" style tagged words as in lstm.cu, but 4 bytes wide -- the
-// step tag is ONE bit that replaces the least significant bit of the payload (of lo' forward: 2^-21 relative; of
-// the fp32 partial d_m backward: 2^-24 relative), so a step moves half the bytes of an 8-byte word protocol through
-// L2.  A buffer is reused every second step with the bit flipped ((step >> 1) & 1); buffers start as 0xFF bytes.
-// The forward payload is the already split pair (hi | lo' << 16): the ten consumers of a word do no arithmetic.
-// 256 threads: every warp stages the exchanged words into the B tile, evaluates the gates (two (cell, utterance)
-// pairs per thread) and owns a part of the TMEM -> register epilogue (lane quadrant = warp % 4); warp 0
-// additionally allocates TMEM and issues the MMAs from one elected lane while the others wait for the commit.
+// Exchange between the CTAs of one (dir, group), two implementations behind the template parameter CL:
+//   CL = 1 (default up to 384 cells): the CTAs form ONE thread-block cluster and push m_t / the partial d_m straight into
+//          each other's shared memory -- st.async with complete_tx on the destination's mbarrier, receive tiles
+//          double-buffered by step parity; no polling, no grid-wide co-residency (see the kernels' comments);
+//   CL = 0 (512 cells, or when the clusters of a pass are not all co-resident): "LL" style tagged words through L2 as
+//          in lstm.cu, but 4 bytes wide -- the step tag is ONE bit that replaces the least significant bit of the
+//          payload (of lo' forward: 2^-21 relative; of the fp32 partial d_m backward: 2^-24 relative); a buffer is
+//          reused every second step with the bit flipped ((step >> 1) & 1), buffers start as 0xFF bytes; cooperative launch.
+// 256 threads: every warp evaluates the gates (two (cell, utterance) pairs per thread) and owns a part of the TMEM ->
+// register epilogue (lane quadrant = warp % 4); warp 0 additionally allocates TMEM and issues the MMAs from one elected
+// lane (and, in the backward kernel, leaves its share of the epilogue to warp 4).
 #include <cuda_fp16.h>
 
 #include <cstdlib>
