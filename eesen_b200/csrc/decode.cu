@@ -2,7 +2,7 @@
 // BASELINE config 5: latgen-faster over TLG.fst, 64 utterances in parallel).
 //
 // Replaces the search core of the reference's LatticeFasterDecoder (src/decoder/lattice-faster-decoder.cc):
-//   InitDecoding :53-71, Decode :77-97, GetCutoff :594-658 (beam part), ProcessEmitting :660-752,
+//   InitDecoding :53-71, Decode :77-97, GetCutoff :594-658 (beam, max_active, min_active), ProcessEmitting :660-752,
 //   ProcessNonemitting :756-816, ComputeFinalCosts :531-577, with the acoustic scores of DecodableMatrixScaled
 //   (src/decoder/decodable-matrix.h:54-56) read straight from the packed posterior matrix.
 // First slice: the best path (words = non-zero olabels, and its cost); lattices are out of scope.
@@ -51,6 +51,7 @@ struct DecodeState {
   int *n_touched, *n_wl_a, *n_wl_b;   // [S]
   uint32_t *frame_best;       // [S] ordered bits of the best token cost of the frame just finished
   uint32_t *build_best;       // [S] same for the frame under construction (before the closure)
+  float *cutoff;              // [S] GetCutoff of the frame being expanded (beam, max_active, min_active)
   double *offset_sum;         // [S]
   int *err;                   // bit 0: frame_cap overflow, bit 1: work-list overflow, bit 2: token store overflow
   // token store, per utterance [S][tok_cap]
@@ -82,14 +83,67 @@ __global__ void decode_init_kernel(DecodeState d, int S, int start) {
   d.n_wl_a[u] = 0; d.n_wl_b[u] = 0;
 }
 
+// GetCutoff :594-658 -- one CTA per utterance.  best + beam, tightened to the cost of the max_active-th best token when
+// more than max_active tokens are alive (:626-631), loosened to the min_active-th best when the beam would keep fewer
+// (:632-650).  The k-th smallest cost is found EXACTLY (the reference uses std::nth_element): a most-significant-byte-
+// first radix select over the order-preserving bit patterns of the costs, four 256-bin histogram passes in shared memory.
+__device__ uint32_t kth_smallest_bits(const float *cost, int n, int k, unsigned *hist, uint32_t *sh_prefix, int *sh_k) {
+  // (all threads of the CTA call this; returns the ordered bits of the k-th smallest, 0-based)
+  uint32_t prefix = 0, mask = 0;
+  for (int pass = 3; pass >= 0; pass--) {
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0u;
+    __syncthreads();
+    const int shift = pass * 8;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint32_t key = ord_bits(cost[i]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int kk = k, b = 0;
+      for (; b < 255; b++) {
+        if (kk < (int)hist[b]) break;
+        kk -= (int)hist[b];
+      }
+      *sh_prefix = prefix | ((uint32_t)b << shift);
+      *sh_k = kk;
+    }
+    __syncthreads();
+    prefix = *sh_prefix;
+    k = *sh_k;
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  return prefix;
+}
+
+__global__ void decode_cutoff_kernel(DecodeState d, int S, int t, const int *frames, const int *f0v, const int *nv,
+                                     float beam, int max_active, int min_active) {
+  __shared__ unsigned hist[256];
+  __shared__ uint32_t sh_prefix;
+  __shared__ int sh_k;
+  const int u = blockIdx.x;
+  if (t >= frames[u]) return;
+  const int n = nv[u];
+  const float best = ord_float(d.frame_best[u]);
+  float cut = best + beam;                                                       // :604-609 / :646
+  const float *cost = d.tok_cost + (size_t)u * d.tok_cap + f0v[u];
+  float max_c = INFINITY, min_c = INFINITY;
+  if (n > max_active) max_c = ord_float(kth_smallest_bits(cost, n, max_active, hist, &sh_prefix, &sh_k));     // :626-631
+  if (n > min_active) min_c = min_active == 0 ? best : ord_float(kth_smallest_bits(cost, n, min_active, hist, &sh_prefix, &sh_k));   // :636-644
+  if (max_c < cut) cut = max_c;                                                  // :632-635
+  else if (min_c > cut) cut = min_c;                                             // :645-650
+  if (threadIdx.x == 0) d.cutoff[u] = cut;
+}
+
 // ProcessEmitting :660-752 -- one thread per token of frame t (tokens [f0, f0 + n) of utterance u)
 __global__ void decode_expand_kernel(DecodeState d, int S, int t, const int *frames, const int *f0v, const int *nv,
-                                     const float *loglikes, int ld, float scale, float beam) {
+                                     const float *loglikes, int ld, float scale, float beam, int limits) {
   const int u = blockIdx.y;
   if (t >= frames[u]) return;
   const int n = nv[u], f0 = f0v[u];
   const float best = ord_float(d.frame_best[u]);
-  const float cutoff = best + beam, cost_offset = -best;                       // :604-609 (beam only), :689
+  const float cutoff = limits ? d.cutoff[u] : best + beam, cost_offset = -best;   // GetCutoff (decode_cutoff_kernel) / :604-609, :689
   if (blockIdx.x == 0 && threadIdx.x == 0) d.offset_sum[u] += (double)cost_offset;
   const float *ll = loglikes + ((size_t)t * S + u) * ld;
   unsigned long long *cell = d.cell + (size_t)u * d.num_states;
@@ -229,16 +283,16 @@ size_t decode_workspace_bytes(int S, int num_states, int frame_cap, int wl_cap, 
   b += (size_t)S * num_states * 4 * 2;             // slot maps
   b += (size_t)S * frame_cap * 4;                  // touched
   b += (size_t)S * wl_cap * 4 * 2;                 // work lists
-  b += (size_t)S * 4 * 16 + 256;                   // counters, bests, offsets, err
+  b += (size_t)S * 4 * 16 + 1024;                  // counters, bests, offsets, cutoffs, err
   b += (size_t)S * tok_cap * 16;                   // token store
   return b + 4096;
 }
 
 // Everything device-side; `frames` etc. are small host arrays.  Returns the error bits of DecodeState::err in *err_bits.
 cudaError_t decode_best_path(cudaStream_t st, int num_sms, const DecodeGraph &g, int S, int T, const int *h_frames,
-                             const float *d_loglikes, int ld, float scale, float beam, void *ws, int frame_cap,
-                             int wl_cap, int tok_cap, int *d_out_labels, int max_out, int *d_out_len, float *d_out_cost,
-                             int *err_bits, long *closure_rounds) {
+                             const float *d_loglikes, int ld, float scale, float beam, int max_active, int min_active,
+                             void *ws, int frame_cap, int wl_cap, int tok_cap, int *d_out_labels, int max_out,
+                             int *d_out_len, float *d_out_cost, int *err_bits, long *closure_rounds) {
   if (S <= 0) return cudaSuccess;
   // carve the workspace
   char *p = (char *)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
@@ -255,6 +309,7 @@ cudaError_t decode_best_path(cudaStream_t st, int num_sms, const DecodeGraph &g,
   d.n_touched = (int *)take((size_t)S * 4); d.n_wl_a = (int *)take((size_t)S * 4); d.n_wl_b = (int *)take((size_t)S * 4);
   d.frame_best = (uint32_t *)take((size_t)S * 4); d.build_best = (uint32_t *)take((size_t)S * 4);
   d.offset_sum = (double *)take((size_t)S * 8);
+  d.cutoff = (float *)take((size_t)S * 4);
   d.err = (int *)take(4);
   int *d_frames = (int *)take((size_t)S * 4), *d_f0 = (int *)take((size_t)S * 4), *d_f1 = (int *)take((size_t)S * 4),
       *d_n = (int *)take((size_t)S * 4);
@@ -288,7 +343,9 @@ cudaError_t decode_best_path(cudaStream_t st, int num_sms, const DecodeGraph &g,
       if ((e = cudaMemsetAsync(d.n_touched, 0, sizeof(int) * S, st)) != cudaSuccess) break;
       int n_max = 0;
       for (int u = 0; u < S; u++) if (t < h_frames[u] && h_n[u] > n_max) n_max = h_n[u];
-      decode_expand_kernel<<<grid_for(n_max, 1), blk, 0, st>>>(d, S, t, d_frames, d_f0, d_n, d_loglikes, ld, scale, beam);
+      const int limits = !(max_active == 2147483647 && min_active == 0);
+      if (limits) decode_cutoff_kernel<<<S, 1024, 0, st>>>(d, S, t, d_frames, d_f0, d_n, beam, max_active, min_active);
+      decode_expand_kernel<<<grid_for(n_max, 1), blk, 0, st>>>(d, S, t, d_frames, d_f0, d_n, d_loglikes, ld, scale, beam, limits);
     }
     fill_u32_kernel<<<1, 64, 0, st>>>(d.build_best, (size_t)S, 0xffffffffu);
     // closure of the frame under construction (frame index t + 1; utterances with frames > t take part)

@@ -151,9 +151,9 @@ struct DecodeGraph {      // device pointers; CSR over states, emitting arcs of 
 };
 size_t decode_workspace_bytes(int S, int num_states, int frame_cap, int wl_cap, int tok_cap);
 cudaError_t decode_best_path(cudaStream_t st, int num_sms, const DecodeGraph &g, int S, int T, const int *h_frames,
-                             const float *d_loglikes, int ld, float scale, float beam, void *ws, int frame_cap,
-                             int wl_cap, int tok_cap, int *d_out_labels, int max_out, int *d_out_len, float *d_out_cost,
-                             int *err_bits, long *closure_rounds);
+                             const float *d_loglikes, int ld, float scale, float beam, int max_active, int min_active,
+                             void *ws, int frame_cap, int wl_cap, int tok_cap, int *d_out_labels, int max_out,
+                             int *d_out_len, float *d_out_cost, int *err_bits, long *closure_rounds);
 
 // optim.cu
 struct SgdSegment {

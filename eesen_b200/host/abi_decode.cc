@@ -75,9 +75,8 @@ int eesen_b200_decode_best_path(eesen_b200_ctx *ctx, const eesen_b200_graph *g, 
   if (!ctx || !g || S < 1 || T < 0 || !frames || !d_loglikes || ld < K || K < 1 || !out_labels || !out_len || !out_cost ||
       max_out < 1 || frame_cap < 1 || tok_cap < frame_cap || !(beam > 0.f))
     return EESEN_B200_EINVAL;
-  if (max_active != 2147483647 || min_active != 0)
-    return ctx->fail(EESEN_B200_EINVAL, "decode: max_active / min_active pruning is not implemented in this slice "
-                                        "(pass 2147483647 / 0: beam pruning only)");
+  if (max_active < 1 || min_active < 0 || min_active > max_active)
+    return ctx->fail(EESEN_B200_EINVAL, "decode: need 1 <= max_active, 0 <= min_active <= max_active (no limit: 2147483647 / 0)");
   for (int s = 0; s < S; s++)
     if (frames[s] < 0 || frames[s] > T) return ctx->fail(EESEN_B200_EINVAL, "decode: frames[] out of range");
   ctx->join_side();
@@ -97,10 +96,10 @@ int eesen_b200_decode_best_path(eesen_b200_ctx *ctx, const eesen_b200_graph *g, 
   cudaEventRecord(e0, ctx->stream);
   int err_bits = 0;
   long rounds = 0;
-  cudaError_t ce = eb::decode_best_path(ctx->stream, ctx->num_sms, g->g, S, T, frames, d_loglikes, ld, acoustic_scale, beam, ws,
-                                        frame_cap, wl_cap, tok_cap, d_labels, max_out, d_len, d_cost, &err_bits, &rounds);
+  cudaError_t ce = eb::decode_best_path(ctx->stream, ctx->num_sms, g->g, S, T, frames, d_loglikes, ld, acoustic_scale, beam, max_active,
+                                        min_active, ws, frame_cap, wl_cap, tok_cap, d_labels, max_out, d_len, d_cost, &err_bits, &rounds);
   cudaEventRecord(e1, ctx->stream);
-  ctx->launches += 4 * (long)(T + 1) + rounds;
+  ctx->launches += ((max_active == 2147483647 && min_active == 0) ? 4 : 5) * (long)(T + 1) + rounds;
   if ((rc = ctx->check(ce, "decode_best_path"))) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
   cudaError_t c2 = cudaMemcpyAsync(out_labels, d_labels, (size_t)S * max_out * 4, cudaMemcpyDeviceToHost, ctx->stream);
   if (c2 == cudaSuccess) c2 = cudaMemcpyAsync(out_len, d_len, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->stream);

@@ -142,7 +142,8 @@ class DeviceGraph:
                                               p[6], C.byref(self.h)), "graph_create")
 
     def decode(self, d_loglikes, ld: int, K: int, frames: Sequence[int], T: int, acoustic_scale: float, beam: float,
-               frame_cap: int = 1 << 15, tok_cap: int | None = None, max_out: int = 512):
+               frame_cap: int = 1 << 15, tok_cap: int | None = None, max_out: int = 512,
+               max_active: int = 2147483647, min_active: int = 0):
         S = len(frames)
         tok_cap = tok_cap or min(frame_cap * (T + 1), 1 << 24)
         fr = np.ascontiguousarray(frames, np.int32)
@@ -150,7 +151,7 @@ class DeviceGraph:
         stats = (C.c_double * 2)()
         self.ctx.check(self.ctx.lib.eesen_b200_decode_best_path(
             self.ctx.h, self.h, S, T, fr.ctypes.data_as(C.c_void_p), C.c_void_p(d_loglikes.data_ptr()), ld, K,
-            C.c_float(acoustic_scale), C.c_float(beam), 2147483647, 0, frame_cap, tok_cap,
+            C.c_float(acoustic_scale), C.c_float(beam), int(max_active), int(min_active), frame_cap, tok_cap,
             labels.ctypes.data_as(C.c_void_p), max_out, n.ctypes.data_as(C.c_void_p), cost.ctypes.data_as(C.c_void_p), stats),
             "decode_best_path")
         return [labels[s, :max(0, n[s])].tolist() if n[s] >= 0 else None for s in range(S)], cost, \

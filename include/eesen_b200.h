@@ -303,8 +303,9 @@ int eesen_b200_graph_create(eesen_b200_ctx *ctx, int num_states, int num_arcs, i
                             eesen_b200_graph **out);
 void eesen_b200_graph_free(eesen_b200_graph *g);
 /* d_loglikes: device, packed time-major [T*S x K] (row t*S + s, ld floats per row) -- what eesen_b200_net_feedforward
- * produces with apply_log; frames[S] (host): frames per utterance.  beam as --beam of latgen-faster; max_active /
- * min_active are not implemented in this slice (the reference defaults are "no limit" / 200: pass 2147483647 / 0).
+ * produces with apply_log; frames[S] (host): frames per utterance.  beam, max_active, min_active as the options of
+ * latgen-faster (GetCutoff, lattice-faster-decoder.cc:594-658: the k-th best cost is selected exactly, as nth_element
+ * does); 2147483647 / 0 = beam pruning only.
  * frame_cap: most tokens one frame of one utterance may hold; tok_cap: most tokens one utterance may hold in total.
  * out_labels [S x max_out], out_len [S] (-1: no surviving token), out_cost [S]: host arrays.
  * stats (may be NULL): [0] closure rounds, [1] device milliseconds. */

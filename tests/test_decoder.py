@@ -179,6 +179,32 @@ def test_gpu_search_vs_restatement_random_graphs(ctx, seed, states, beam):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("seed,states,beam,max_active,min_active", [(4, 2000, 1e4, 25, 0), (5, 2000, 0.5, 2147483647, 40),
+                                                                     (6, 3000, 9.0, 60, 20), (7, 300, 6.0, 7, 3)])
+def test_gpu_search_max_and_min_active_follow_get_cutoff(ctx, seed, states, beam, max_active, min_active):
+    """GetCutoff with --max-active / --min-active (lattice-faster-decoder.cc:594-658): the CUDA search selects the k-th best
+    cost exactly (radix select), so words agree bit for bit with the restatement and costs to rounding."""
+    rng = np.random.default_rng(seed)
+    K, S, T = 9, 12, 24
+    g = wfst.random_graph(rng, states, K, 50)
+    frames = np.sort(rng.integers(T // 2, T + 1, size=S))[::-1].copy(); frames[0] = T
+    ll, d_ll, ld = _batch_loglikes(rng, S, T, K, frames)
+    dg = wfst.DeviceGraph(ctx, g)
+    words, cost, st = dg.decode(d_ll, ld, K, frames, T, 0.9, beam, frame_cap=1 << 13, max_active=max_active, min_active=min_active)
+    limited = 0
+    for s in range(S):
+        rows = np.arange(frames[s]) * S + s
+        w, c, nf, a_lim = oracle.decode_best_path(g, ll[rows], 0.9, beam, max_active=max_active, min_active=min_active)
+        _, _, _, a_free = oracle.decode_best_path(g, ll[rows], 0.9, beam)
+        limited += a_lim != a_free
+        assert words[s] == w, (s, words[s], w)
+        if w is not None:
+            assert abs(cost[s] - c) <= 2e-5 * max(1.0, abs(c)), (s, cost[s], c)
+    assert limited > 0          # the limits actually changed the search
+    dg.close()
+
+
+@pytest.mark.gpu
 def test_gpu_search_synthetic_tlg_64_utterances(ctx):
     """CTC-topology lexicon graph (20 k words, ~0.5 M arcs), 64 utterances of noisy realisations of word sequences."""
     rng = np.random.default_rng(5)
