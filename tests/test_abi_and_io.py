@@ -220,3 +220,28 @@ def test_reference_driver_reads_our_archives_and_reports_the_same_accuracy():
         e, n = oracle.greedy_token_errors(y, [utts[i].shape[0]], [np.asarray(labels[i])], 1)
         err += e; ref += n
     assert abs(acc - 100.0 * (1.0 - err / ref)) < 1e-3
+
+
+def test_profile_categories_agree_between_header_and_binding():
+    """include/eesen_b200.h and the ctypes stub must size the eesen_b200_profile arrays alike (9 categories: index 8 is
+    the dense work of the side stream)."""
+    src = open(HEADER).read()
+    n = int(re.search(r"#define\s+EESEN_B200_NUM_PROFILE_CATEGORIES\s+(\d+)", src).group(1))
+    assert n == len(binding.Context.PROFILE_CATEGORIES) == 9
+    assert binding.Context.PROFILE_CATEGORIES[0] == "gemm" and binding.Context.PROFILE_CATEGORIES[8] == "gemm_side"
+
+
+def test_trace_summary_reads_a_launch_trace(tmp_path):
+    """tests/trace_summary.py on a hand-written EESEN_B200_TRACE_FILE block (host/context.h:prof_collect format:
+    stream, category, start ms, duration ms): busy time per stream and category, idle time of the main stream."""
+    import sys
+    p = tmp_path / "trace.txt"
+    p.write_text("# collect: 2 launches\n0 0 0.0 0.1\n1 8 0.0 0.5\n"
+                 "# collect: 4 launches\n0 0 0.000 0.100\n0 1 0.150 1.000\n1 8 0.120 0.700\n0 2 1.200 1.500\n")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "trace_summary.py"), str(p)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout
+    assert "4 launches, span 2.700 ms" in out                      # only the LAST block counts
+    assert "'gemm': 0.1" in out and "'lstm_fwd': 1.0" in out and "'lstm_bwd': 1.5" in out
+    assert "side busy: {'gemm_side': 0.7}" in out
+    assert "idle between launches 0.100 ms" in out                 # 0.05 before lstm_fwd + 0.05 before lstm_bwd
